@@ -1,0 +1,665 @@
+/* oracle_impl.h -- TEST INFRASTRUCTURE ONLY (never linked into / called from the product path).
+ *
+ * Plain-C, scalar CPU restatement of the reference's gridded pair-counting path, included twice
+ * by pairs_oracle.c with REAL = float and REAL = double (the reference does the same with its
+ * `DOUBLE` sed templates, rules.mk:23-49).  Every routine cites the reference lines it follows.
+ * Pinned against: the reference itself compiled here (oracle/_ref, see build_ref.sh), the
+ * reference's golden file mocks/tests/Mr19_mock_wtheta.DD, and the data-free known-answer tests
+ * of Corrfunc/tests/test_theory.py (tests/test_oracle_*.py).
+ *
+ * What is restated bit-for-bit: bin edges and their squares, lattice geometry (nmesh, bin size,
+ * inverse, truncating cell index with the ix-- clamp), the cell-pair set with periodic wrap,
+ * first/second roles, duplicate suppression and the autocorr icell2<=icell filter, the per-pair
+ * arithmetic in the AVX-512 kernels' FMA association, the 2-D bin index evaluated in floating
+ * point, and the epilogues.  What is NOT restated: the z-sorted early exits inside a cell pair
+ * (pure pruning aids; the reference's own sweep tests show results do not depend on them).
+ */
+
+#define CAT_(a, b) a##_##b
+#define CAT(a, b) CAT_(a, b)
+#define FN(name) CAT(name, SUFFIX)
+
+#if REAL_IS_DOUBLE
+#define FMA_R(a, b, c) fma((a), (b), (c))
+#define SQRT_R(a) sqrt(a)
+#define FABS_R(a) fabs(a)
+#define ACOS_R(a) acos(a)
+#define ASIN_R(a) asin(a)
+#define COSD_R(X) cos((X) * ORC_PI_OVER_180)
+#define SIND_R(X) sin((X) * ORC_PI_OVER_180)
+#define MAXPOS_R DBL_MAX
+#else
+#define FMA_R(a, b, c) fmaf((a), (b), (c))
+#define SQRT_R(a) sqrtf(a)
+#define FABS_R(a) fabsf(a)
+#define ACOS_R(a) acosf(a)
+#define ASIN_R(a) asinf(a)
+#define COSD_R(X) cosf((X) * ORC_PI_OVER_180)
+#define SIND_R(X) sinf((X) * ORC_PI_OVER_180)
+#define MAXPOS_R FLT_MAX
+#endif
+
+typedef struct {
+    int64_t n;     /* particles in this cell */
+    int64_t start; /* offset into the cell-sorted arrays */
+    REAL xb[2], yb[2], zb[2];
+    REAL rab[2], decb[2]; /* theta lattice only */
+} FN(ocell);
+
+/* utils/gridlink_utils.c.src:31-49 */
+static int FN(o_get_binsize)(const REAL xdiff, const REAL xwrap, const REAL rmax, const int refine_factor,
+                            const int max_ncells, REAL *xbinsize, int *nlattice)
+{
+    int nmesh = (int)(refine_factor * xdiff / rmax);
+    nmesh = nmesh < 1 ? 1 : nmesh;
+    if (xwrap > 0 && rmax >= xwrap / 2) {
+        fprintf(stderr, "oracle> rmax=%f must be less than half of periodic boxsize=%f\n", (double)rmax, (double)xwrap);
+        return EXIT_FAILURE;
+    }
+    if (nmesh > max_ncells) nmesh = max_ncells;
+    if (nmesh < 2) nmesh = 2;
+    *xbinsize = xdiff / nmesh;
+    *nlattice = nmesh;
+    return EXIT_SUCCESS;
+}
+
+typedef struct {
+    int nmesh[3];
+    int64_t totncells;
+    FN(ocell) * cells;
+    REAL *x, *y, *z, *w; /* cell-sorted copies */
+} FN(olattice);
+
+static void FN(o_free_lattice)(FN(olattice) * L)
+{
+    if (!L) return;
+    free(L->cells);
+    free(L->x);
+    free(L->y);
+    free(L->z);
+    free(L->w);
+    free(L);
+}
+
+/* utils/gridlink_impl.c.src:65-436 (copy_particles=1 branch; per-cell z sort omitted: pruning aid) */
+static FN(olattice) * FN(o_gridlink)(const int64_t N, const REAL *X, const REAL *Y, const REAL *Z, const REAL *W,
+                                      const REAL xmin, const REAL xmax, const REAL ymin, const REAL ymax,
+                                      const REAL zmin, const REAL zmax, const REAL max_x, const REAL max_y,
+                                      const REAL max_z, const REAL xwrap, const REAL ywrap, const REAL zwrap,
+                                      const int rfx, const int rfy, const int rfz, const int max_cells)
+{
+    REAL xbin = 0, ybin = 0, zbin = 0;
+    int nx, ny, nz;
+    if (FN(o_get_binsize)(xmax - xmin, xwrap, max_x, rfx, max_cells, &xbin, &nx) ||
+        FN(o_get_binsize)(ymax - ymin, ywrap, max_y, rfy, max_cells, &ybin, &ny) ||
+        FN(o_get_binsize)(zmax - zmin, zwrap, max_z, rfz, max_cells, &zbin, &nz))
+        return NULL;
+    const int64_t tot = (int64_t)nx * ny * nz;
+    FN(olattice) *L = calloc(1, sizeof(*L));
+    L->nmesh[0] = nx;
+    L->nmesh[1] = ny;
+    L->nmesh[2] = nz;
+    L->totncells = tot;
+    L->cells = calloc(tot, sizeof(*L->cells));
+    L->x = malloc(sizeof(REAL) * (N > 0 ? N : 1));
+    L->y = malloc(sizeof(REAL) * (N > 0 ? N : 1));
+    L->z = malloc(sizeof(REAL) * (N > 0 ? N : 1));
+    L->w = W ? malloc(sizeof(REAL) * (N > 0 ? N : 1)) : NULL;
+    int64_t *idx = malloc(sizeof(int64_t) * (N > 0 ? N : 1));
+    /* gridlink_impl.c.src:156-158 */
+    const REAL xinv = xbin > 0 ? 1.0 / xbin : 0.;
+    const REAL yinv = ybin > 0 ? 1.0 / ybin : 0.;
+    const REAL zinv = zbin > 0 ? 1.0 / zbin : 0.;
+    int64_t oob = 0;
+    for (int64_t i = 0; i < N; i++) { /* gridlink_impl.c.src:165-181 */
+        int ix = (int)((X[i] - xmin) * xinv);
+        int iy = (int)((Y[i] - ymin) * yinv);
+        int iz = (int)((Z[i] - zmin) * zinv);
+        if (ix > nx - 1) ix--;
+        if (iy > ny - 1) iy--;
+        if (iz > nz - 1) iz--;
+        oob += ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz;
+        idx[i] = (int64_t)ix * ny * nz + (int64_t)iy * nz + iz;
+        if (oob == 0) L->cells[idx[i]].n++;
+    }
+    if (oob) {
+        fprintf(stderr, "oracle> %" PRId64 " particles are out of bounds\n", oob);
+        free(idx);
+        FN(o_free_lattice)(L);
+        return NULL;
+    }
+    int64_t off = 0;
+    for (int64_t c = 0; c < tot; c++) {
+        L->cells[c].start = off;
+        off += L->cells[c].n;
+        L->cells[c].n = 0;
+        L->cells[c].xb[0] = L->cells[c].yb[0] = L->cells[c].zb[0] = MAXPOS_R;
+        L->cells[c].xb[1] = L->cells[c].yb[1] = L->cells[c].zb[1] = -MAXPOS_R;
+    }
+    for (int64_t i = 0; i < N; i++) { /* gridlink_impl.c.src:289-315 */
+        FN(ocell) *c = &L->cells[idx[i]];
+        const int64_t p = c->start + c->n++;
+        L->x[p] = X[i];
+        L->y[p] = Y[i];
+        L->z[p] = Z[i];
+        if (W) L->w[p] = W[i];
+        if (X[i] < c->xb[0]) c->xb[0] = X[i];
+        if (Y[i] < c->yb[0]) c->yb[0] = Y[i];
+        if (Z[i] < c->zb[0]) c->zb[0] = Z[i];
+        if (X[i] > c->xb[1]) c->xb[1] = X[i];
+        if (Y[i] > c->yb[1]) c->yb[1] = Y[i];
+        if (Z[i] > c->zb[1]) c->zb[1] = Z[i];
+    }
+    free(idx);
+    return L;
+}
+
+typedef struct {
+    int64_t c1, c2;
+    REAL xw, yw, zw;
+    int same;
+} FN(opair);
+
+/* utils/gridlink_impl.c.src:439-625 */
+static FN(opair) * FN(o_cell_pairs)(const FN(olattice) * L1, const FN(olattice) * L2, int64_t *npairs_out,
+                                     const int rfx, const int rfy, const int rfz, const REAL xwrap,
+                                     const REAL ywrap, const REAL zwrap, const REAL max_3D, const REAL max_2D,
+                                     const REAL max_1D, const int enable_min_sep, const int autocorr, const int px,
+                                     const int py, const int pz)
+{
+    const int nx = L1->nmesh[0], ny = L1->nmesh[1], nz = L1->nmesh[2];
+    const int64_t tot = L1->totncells;
+    const int64_t max_ngb = (int64_t)(2 * rfx + 1) * (2 * rfy + 1) * (2 * rfz + 1);
+    FN(opair) *P = malloc(sizeof(*P) * (size_t)(tot * max_ngb > 0 ? tot * max_ngb : 1));
+    int64_t np = 0;
+    const int any_periodic = px || py || pz;
+    const int check_dup = (any_periodic && (nx < 2 * rfx + 1 || ny < 2 * rfy + 1 || nz < 2 * rfz + 1)) ? 1 : 0;
+    for (int64_t icell = 0; icell < tot; icell++) {
+        const FN(ocell) *first = &L1->cells[icell];
+        if (first->n == 0) continue;
+        const int iz = icell % nz;
+        const int ix = icell / ((int64_t)ny * nz);
+        const int iy = (icell - iz - (int64_t)ix * nz * ny) / nz;
+        int64_t nthis = 0;
+        for (int iix = -rfx; iix <= rfx; iix++) {
+            const int pix = (ix + iix + nx) % nx;
+            const int iiix = px ? pix : ix + iix;
+            if (iiix < 0 || iiix >= nx) continue;
+            const REAL offx = ((ix + iix) >= 0) && ((ix + iix) < nx) ? 0.0 : ((ix + iix) < 0 ? xwrap : -xwrap);
+            for (int iiy = -rfy; iiy <= rfy; iiy++) {
+                const int piy = (iy + iiy + ny) % ny;
+                const int iiiy = py ? piy : iy + iiy;
+                if (iiiy < 0 || iiiy >= ny) continue;
+                const REAL offy = ((iy + iiy) >= 0) && ((iy + iiy) < ny) ? 0.0 : ((iy + iiy) < 0 ? ywrap : -ywrap);
+                for (int iiz = -rfz; iiz <= rfz; iiz++) {
+                    const int piz = (iz + iiz + nz) % nz;
+                    const int iiiz = pz ? piz : iz + iiz;
+                    if (iiiz < 0 || iiiz >= nz) continue;
+                    const REAL offz = ((iz + iiz) >= 0) && ((iz + iiz) < nz) ? 0.0 : ((iz + iiz) < 0 ? zwrap : -zwrap);
+                    const int64_t icell2 = iiiz + (int64_t)nz * iiiy + (int64_t)nz * ny * iiix;
+                    if ((autocorr == 1 && icell2 > icell) || L2->cells[icell2].n == 0) continue;
+                    if (check_dup) { /* gridlink_utils.h.src:46-72 */
+                        int dup = 0;
+                        for (int64_t jj = 0; jj < nthis; jj++) {
+                            const FN(opair) *q = &P[np - jj - 1];
+                            if (q->c2 == icell2 && q->xw == offx && q->yw == offy && q->zw == offz) {
+                                dup = 1;
+                                break;
+                            }
+                        }
+                        if (dup) continue;
+                    }
+                    const FN(ocell) *second = &L2->cells[icell2];
+                    if (enable_min_sep) { /* gridlink_impl.c.src:538-589 */
+                        const REAL x_low = first->xb[0] + offx, x_hi = first->xb[1] + offx;
+                        const REAL y_low = first->yb[0] + offy, y_hi = first->yb[1] + offy;
+                        const REAL z_low = first->zb[0] + offz, z_hi = first->zb[1] + offz;
+                        const REAL first_x = iix < 0 ? x_low : x_hi;
+                        const REAL second_x = iix < 0 ? second->xb[1] : second->xb[0];
+                        const REAL min_dx = iix != 0 ? (first_x - second_x) : 0;
+                        const REAL first_y = iiy < 0 ? y_low : y_hi;
+                        const REAL second_y = iiy < 0 ? second->yb[1] : second->yb[0];
+                        const REAL min_dy = iiy != 0 ? (first_y - second_y) : 0;
+                        const REAL first_z = iiz < 0 ? z_low : z_hi;
+                        const REAL second_z = iiz < 0 ? second->zb[1] : second->zb[0];
+                        const REAL min_dz = iiz != 0 ? (first_z - second_z) : 0;
+                        if (max_3D > 0) {
+                            const REAL s = min_dx * min_dx + min_dy * min_dy + min_dz * min_dz;
+                            if (s >= max_3D * max_3D) continue;
+                        }
+                        if (max_2D > 0) {
+                            const REAL s = min_dx * min_dx + min_dy * min_dy;
+                            if (s >= max_2D * max_2D) continue;
+                        }
+                        if (max_1D > 0 && iiz != 0) {
+                            const REAL s = min_dz * min_dz;
+                            if (s >= max_1D * max_1D) continue;
+                        }
+                    }
+                    P[np].c1 = icell;
+                    P[np].c2 = icell2;
+                    P[np].xw = offx;
+                    P[np].yw = offy;
+                    P[np].zw = offz;
+                    P[np].same = (autocorr == 1 && icell2 == icell) ? 1 : 0;
+                    np++;
+                    nthis++;
+                }
+            }
+        }
+    }
+    *npairs_out = np;
+    return P;
+}
+
+/* The per-pair arithmetic of the AVX-512 kernels, for one cell pair.
+ *   DD / xi : theory/DD/countpairs_kernels.c.src:178-254   r2 = fma(dz,dz, fma(dy,dy, dx*dx))
+ *   wp      : theory/wp/wp_kernels.c.src:186-262           r2 = fma(dy,dy, dx*dx), -pimax < dz < pimax
+ *   DDrppi  : theory/DDrppi/countpairs_rp_pi_kernels.c.src:191-267
+ *   DDsmu   : theory/DDsmu/countpairs_s_mu_kernels.c.src:207-290   s2 = fma(dx,dx, fma(dy,dy, dz*dz))
+ *   DDtheta : mocks/DDtheta_mocks/countpairs_theta_mocks_kernels.c.src:1052-1128
+ */
+typedef struct {
+    int mode;
+    int nbin;             /* number of edges (= reference's nbin) */
+    const REAL *edges;    /* rupp_sqr[] (theory) or costheta_upp[] (theta) */
+    REAL pimax;           /* wp / rppi */
+    int npibin;           /* rppi */
+    REAL inv_dpi;         /* rppi */
+    REAL sqr_mumax;       /* smu */
+    int nmu;              /* smu */
+    REAL inv_dmu;         /* smu */
+    int need_avg, need_w; /* accumulate sums? */
+    int fast_acos;
+    uint64_t *npairs;
+    double *avg;  /* reference accumulates in REAL; the oracle keeps double sums (order-robust) */
+    double *wavg;
+} FN(okern);
+
+static inline REAL FN(o_fast_acos)(const REAL x)
+{ /* utils/fast_acos.h:57-101 (degree-8 estimate) */
+    const REAL xa = FABS_R(x);
+    const REAL one = (REAL)1.0;
+    REAL poly = (REAL) + 7.1796493341480527e-04;
+    poly = (REAL)-4.1160981058965262e-03 + poly * xa;
+    poly = (REAL) + 1.1272900916992512e-02 + poly * xa;
+    poly = (REAL)-2.0949278766238422e-02 + poly * xa;
+    poly = (REAL) + 3.2683762943179318e-02 + poly * xa;
+    poly = (REAL)-5.0625279962389413e-02 + poly * xa;
+    poly = (REAL) + 8.9034700107934128e-02 + poly * xa;
+    poly = (REAL)-2.1460143648688035e-01 + poly * xa;
+    poly = (REAL) + 1.5707963267948966 + poly * xa;
+    poly = poly * SQRT_R(one - xa);
+    return (x < 0) ? (REAL)(M_PI - poly) : poly;
+}
+
+static void FN(o_count_cellpair)(const FN(okern) * K, const int64_t N0, const REAL *x0, const REAL *y0,
+                                 const REAL *z0, const REAL *w0, const int64_t N1, const REAL *x1, const REAL *y1,
+                                 const REAL *z1, const REAL *w1, const int same, const REAL offx, const REAL offy,
+                                 const REAL offz)
+{
+    const int nbin = K->nbin;
+    const REAL *E = K->edges;
+    for (int64_t i = 0; i < N0; i++) {
+        const REAL xpos = x0[i] + offx, ypos = y0[i] + offy, zpos = z0[i] + offz;
+        for (int64_t j = same ? i + 1 : 0; j < N1; j++) {
+            const REAL dx = x1[j] - xpos, dy = y1[j] - ypos, dz = z1[j] - zpos;
+            int64_t slot = -1;
+            REAL sep = 0;
+            switch (K->mode) {
+            case ORC_DD:
+            case ORC_XI: {
+                const REAL r2 = FMA_R(dz, dz, FMA_R(dy, dy, dx * dx));
+                if (!(r2 < E[nbin - 1] && r2 >= E[0])) continue;
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (r2 >= E[k - 1]) break;
+                slot = k;
+                if (K->need_avg) sep = SQRT_R(r2);
+            } break;
+            case ORC_WP: {
+                const REAL r2 = FMA_R(dy, dy, dx * dx);
+                if (!(dz > -K->pimax && dz < K->pimax)) continue;
+                if (!(r2 < E[nbin - 1] && r2 >= E[0])) continue;
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (r2 >= E[k - 1]) break;
+                slot = k;
+                if (K->need_avg) sep = SQRT_R(r2);
+            } break;
+            case ORC_RPPI: {
+                const REAL r2 = FMA_R(dy, dy, dx * dx);
+                if (!(dz > -K->pimax)) continue;
+                const REAL adz = FABS_R(dz);
+                if (!(adz < K->pimax)) continue;
+                if (!(r2 < E[nbin - 1] && r2 >= E[0])) continue;
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (r2 >= E[k - 1]) break;
+                /* finalbin evaluated in REAL floating point, then truncated (rp_pi_kernels:249-256) */
+                const REAL pibin = adz * K->inv_dpi;
+                const REAL lin = (REAL)k * (REAL)(K->npibin + 1);
+                slot = (int64_t)(int)(lin + pibin);
+                if (K->need_avg) sep = SQRT_R(r2);
+            } break;
+            case ORC_SMU: {
+                const REAL sqr_dz = dz * dz;
+                const REAL s2 = FMA_R(dx, dx, FMA_R(dy, dy, sqr_dz));
+                const REAL max_sqr_dz = s2 * K->sqr_mumax;
+                if (!(sqr_dz < max_sqr_dz)) continue;
+                if (!(s2 < E[nbin - 1] && s2 >= E[0])) continue;
+                const REAL sqr_mu = sqr_dz / s2; /* fast_divide_and_NR_steps == 0: true divide */
+                const REAL mu = SQRT_R(sqr_mu);
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (s2 >= E[k - 1]) break;
+                const REAL mubin = mu * K->inv_dmu;
+                const REAL lin = (REAL)k * (REAL)(K->nmu + 1);
+                slot = (int64_t)(int)(lin + mubin);
+                if (K->need_avg) sep = SQRT_R(s2);
+            } break;
+            case ORC_THETA: {
+                const REAL chord2 = FMA_R(dz, dz, FMA_R(dy, dy, dx * dx));
+                const REAL costheta = (REAL)1.0 - (REAL)0.5 * chord2;
+                /* costhetamax < costheta <= costhetamin ; E[] = cos(theta_upp[]) is decreasing */
+                if (!(costheta > E[nbin - 1] && costheta <= E[0])) continue;
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (costheta <= E[k - 1]) break;
+                slot = k;
+                if (K->need_avg) {
+                    const REAL c = costheta >= (REAL)1.0 ? (REAL)1.0 : costheta; /* avx512_calls.h:333-338 */
+                    const REAL th = K->fast_acos ? FN(o_fast_acos)(c) : ACOS_R(c);
+                    sep = (REAL)(th * (REAL)ORC_INV_PI_OVER_180);
+                }
+            } break;
+            default: continue;
+            }
+            K->npairs[slot]++;
+            if (K->need_avg) K->avg[slot] += (double)sep;
+            if (K->need_w) K->wavg[slot] += (double)(REAL)(w0[i] * w1[j]); /* weight_functions.h.src:71-73 */
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* theory entry point: DD / xi / wp / DDrppi / DDsmu                                            */
+/* Follows theory/DD/countpairs_impl.c.src:136-707 and its four siblings.                       */
+int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const REAL *Y1, const REAL *Z1,
+                      const REAL *W1, const int64_t ND2, const REAL *X2, const REAL *Y2, const REAL *Z2,
+                      const REAL *W2, int autocorr, const int nbin, const double *rupp, /* nbin edges */
+                      const double pimax_in, const double mu_max_in, const int nmu_bins, int periodic,
+                      const double boxsize_x, const double boxsize_y_in, const double boxsize_z_in,
+                      const int *refine_in, const int binning_cust, int max_cells, const int enable_min_sep,
+                      const int need_avg, const int need_w, uint64_t *npairs_out, double *avg_out,
+                      double *wavg_out, double *cf_out, int *lattice_out /* nmesh[3], refine[3] */)
+{
+    int rf[3] = {refine_in[0], refine_in[1], refine_in[2]};
+    if (max_cells == 0) max_cells = 100;
+    for (int i = 0; i < 3; i++)
+        if (rf[i] < 1) {
+            rf[0] = 2;
+            rf[1] = 2;
+            rf[2] = 1;
+            break;
+        }
+    const double rmin = rupp[0], rmax = rupp[nbin - 1];
+    if (!(rmin >= 0.0 && rmax > 0.0 && rmin < rmax && nbin > 0)) return EXIT_FAILURE;
+    REAL *esq = malloc(sizeof(REAL) * nbin);
+    for (int i = 0; i < nbin; i++) esq[i] = rupp[i] * rupp[i]; /* double product rounded to REAL (DD impl:435-438) */
+
+    const int is_box = (mode == ORC_XI || mode == ORC_WP);
+    REAL xmin, xmax, ymin, ymax, zmin, zmax, xwrap, ywrap, zwrap;
+    int px, py, pz;
+    REAL max_x, max_y, max_z; /* gridlink cell sizes */
+    REAL max3 = -1, max2 = -1, max1 = -1;
+    REAL pimax = 0;
+    int npibin = 0;
+    REAL mu_max = 0;
+    if (is_box) { /* xi impl:176-231, wp impl:191-260 */
+        periodic = 1;
+        autocorr = 1;
+        xmin = ymin = zmin = 0.0;
+        xmax = ymax = zmax = boxsize_x;
+        xwrap = ywrap = zwrap = boxsize_x;
+        px = py = pz = 1;
+        if (mode == ORC_XI) {
+            if (!binning_cust && rmax < 0.05 * boxsize_x) rf[0] = rf[1] = rf[2] = 1;
+            max_x = max_y = max_z = rmax;
+            max3 = rmax;
+        } else {
+            pimax = pimax_in;
+            if (!binning_cust) {
+                if (rmax < 0.05 * boxsize_x) rf[0] = rf[1] = 1;
+                if (pimax_in < 0.05 * boxsize_x) rf[2] = 1;
+            }
+            max_x = max_y = rmax;
+            max_z = pimax_in;
+            max2 = rmax;
+            max1 = pimax_in;
+        }
+    } else {
+        xmin = ymin = zmin = MAXPOS_R;
+        xmax = ymax = zmax = -MAXPOS_R;
+        for (int s = 0; s < (autocorr ? 1 : 2); s++) { /* gridlink_utils.c.src:52-70 */
+            const int64_t n = s ? ND2 : ND1;
+            const REAL *x = s ? X2 : X1, *y = s ? Y2 : Y1, *z = s ? Z2 : Z1;
+            for (int64_t i = 0; i < n; i++) {
+                if (x[i] < xmin) xmin = x[i];
+                if (y[i] < ymin) ymin = y[i];
+                if (z[i] < zmin) zmin = z[i];
+                if (x[i] > xmax) xmax = x[i];
+                if (y[i] > ymax) ymax = y[i];
+                if (z[i] > zmax) zmax = z[i];
+            }
+        }
+        if (periodic && boxsize_x == -2.) return EXIT_FAILURE;
+        const double bsy = boxsize_y_in == -2. ? boxsize_x : boxsize_y_in;
+        const double bsz = boxsize_z_in == -2. ? boxsize_x : boxsize_z_in;
+        px = periodic && boxsize_x >= 0;
+        py = periodic && bsy >= 0;
+        pz = periodic && bsz >= 0;
+        xwrap = px ? (boxsize_x > 0 ? boxsize_x : (xmax - xmin)) : 0.;
+        ywrap = py ? (bsy > 0 ? bsy : (ymax - ymin)) : 0.;
+        zwrap = pz ? (bsz > 0 ? bsz : (zmax - zmin)) : 0.;
+        if (mode == ORC_DD) { /* DD impl:252-282 */
+            pimax = (REAL)rmax;
+            if (!binning_cust) {
+                if (rmax < 0.05 * xwrap) rf[0] = 1;
+                if (rmax < 0.05 * ywrap) rf[1] = 1;
+                if (pimax < 0.05 * zwrap) rf[2] = 1;
+            }
+            max_x = max_y = max_z = rmax;
+            max3 = rmax;
+        } else if (mode == ORC_RPPI) { /* rp_pi impl:188-290 */
+            pimax = pimax_in;
+            npibin = (int)pimax_in;
+            if (!binning_cust) {
+                if (rmax < 0.05 * xwrap) rf[0] = 1;
+                if (rmax < 0.05 * ywrap) rf[1] = 1;
+                if (pimax_in < 0.05 * zwrap) rf[2] = 1;
+            }
+            max_x = max_y = rmax;
+            max_z = pimax_in;
+            max2 = rmax;
+            max1 = pimax_in;
+        } else { /* ORC_SMU: s_mu impl:212-234, 305-345 */
+            if (mu_max_in <= 0.0 || mu_max_in > 1.0 || nmu_bins < 1) return EXIT_FAILURE;
+            mu_max = (REAL)mu_max_in;
+            pimax = rmax * mu_max;
+            max_x = max_y = rmax;
+            max_z = pimax;
+            max3 = rmax;
+            max1 = pimax;
+        }
+    }
+
+    FN(olattice) *L1 = FN(o_gridlink)(ND1, X1, Y1, Z1, need_w ? W1 : NULL, xmin, xmax, ymin, ymax, zmin, zmax, max_x,
+                                      max_y, max_z, xwrap, ywrap, zwrap, rf[0], rf[1], rf[2], max_cells);
+    if (!L1) return EXIT_FAILURE;
+    if (mode != ORC_SMU) { /* boost: DD impl:298-332 (smu's boost multiplies by BOOST_BIN_REF=1: no-op) */
+        const double avg_np = ((double)ND1) / ((double)L1->nmesh[0] * L1->nmesh[1] * L1->nmesh[2]);
+        const int max_nmesh = (int)fmax(L1->nmesh[0], fmax(L1->nmesh[1], L1->nmesh[2]));
+        if ((max_nmesh <= 10 || avg_np >= 250) && max_nmesh < max_cells && !binning_cust) {
+            FN(o_free_lattice)(L1);
+            rf[0] += 1;
+            rf[1] += 1;
+            L1 = FN(o_gridlink)(ND1, X1, Y1, Z1, need_w ? W1 : NULL, xmin, xmax, ymin, ymax, zmin, zmax, max_x, max_y,
+                                max_z, xwrap, ywrap, zwrap, rf[0], rf[1], rf[2], max_cells);
+            if (!L1) return EXIT_FAILURE;
+        }
+    }
+    FN(olattice) *L2 = L1;
+    if (!autocorr) {
+        L2 = FN(o_gridlink)(ND2, X2, Y2, Z2, need_w ? W2 : NULL, xmin, xmax, ymin, ymax, zmin, zmax, max_x, max_y,
+                            max_z, xwrap, ywrap, zwrap, rf[0], rf[1], rf[2], max_cells);
+        if (!L2) return EXIT_FAILURE;
+    }
+    if (lattice_out) {
+        for (int i = 0; i < 3; i++) {
+            lattice_out[i] = L1->nmesh[i];
+            lattice_out[3 + i] = rf[i];
+        }
+    }
+    int64_t ncp = 0;
+    FN(opair) *CP = FN(o_cell_pairs)(L1, L2, &ncp, rf[0], rf[1], rf[2], xwrap, ywrap, zwrap, max3, max2, max1,
+                                     enable_min_sep, autocorr, px, py, pz);
+
+    int64_t nslots = nbin;
+    FN(okern) K;
+    memset(&K, 0, sizeof(K));
+    K.mode = mode;
+    K.nbin = nbin;
+    K.edges = esq;
+    K.need_avg = need_avg;
+    K.need_w = need_w;
+    K.pimax = pimax;
+    if (mode == ORC_RPPI) { /* rp_pi_kernels:65-66 */
+        K.npibin = npibin;
+        const REAL dpi = pimax / npibin;
+        K.inv_dpi = 1.0 / dpi;
+        nslots = (int64_t)(npibin + 1) * (nbin + 1);
+    } else if (mode == ORC_SMU) { /* s_mu_kernels:65-68 */
+        K.nmu = nmu_bins;
+        K.sqr_mumax = mu_max * mu_max;
+        const REAL dmu = mu_max / (REAL)nmu_bins;
+        K.inv_dmu = 1.0 / dmu;
+        nslots = (int64_t)(nmu_bins + 1) * (nbin + 1);
+    }
+
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    uint64_t *tn = calloc((size_t)nthreads * nslots, sizeof(uint64_t));
+    double *ta = calloc((size_t)nthreads * nslots, sizeof(double));
+    double *tw = calloc((size_t)nthreads * nslots, sizeof(double));
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        FN(okern) k = K;
+        k.npairs = tn + (size_t)tid * nslots;
+        k.avg = ta + (size_t)tid * nslots;
+        k.wavg = tw + (size_t)tid * nslots;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic)
+#endif
+        for (int64_t p = 0; p < ncp; p++) {
+            const FN(ocell) *a = &L1->cells[CP[p].c1], *b = &L2->cells[CP[p].c2];
+            FN(o_count_cellpair)(&k, a->n, L1->x + a->start, L1->y + a->start, L1->z + a->start,
+                                 need_w ? L1->w + a->start : NULL, b->n, L2->x + b->start, L2->y + b->start,
+                                 L2->z + b->start, need_w ? L2->w + b->start : NULL, CP[p].same, CP[p].xw, CP[p].yw,
+                                 CP[p].zw);
+        }
+    }
+    uint64_t *npairs = calloc(nslots, sizeof(uint64_t));
+    double *avg = calloc(nslots, sizeof(double)), *wavg = calloc(nslots, sizeof(double));
+    for (int t = 0; t < nthreads; t++)
+        for (int64_t s = 0; s < nslots; s++) {
+            npairs[s] += tn[(size_t)t * nslots + s];
+            avg[s] += ta[(size_t)t * nslots + s];
+            wavg[s] += tw[(size_t)t * nslots + s];
+        }
+    free(tn);
+    free(ta);
+    free(tw);
+    free(CP);
+
+    /* epilogue: DD impl:609-664 and siblings */
+    if (autocorr) {
+        for (int64_t s = 0; s < nslots; s++) {
+            npairs[s] *= 2;
+            avg[s] *= 2.0;
+            wavg[s] *= 2.0;
+        }
+        if (rupp[0] <= 0.0) {
+            const int64_t first = (mode == ORC_RPPI) ? (npibin + 1) : (mode == ORC_SMU ? (nmu_bins + 1) : 1);
+            npairs[first] += ND1;
+            if (need_w)
+                for (int64_t j = 0; j < ND1; j++) wavg[1] += (double)(REAL)(W1[j] * W1[j]); /* always slot 1 */
+        }
+    }
+    for (int64_t s = 0; s < nslots; s++)
+        if (npairs[s] > 0) {
+            avg[s] /= (double)npairs[s];
+            wavg[s] /= (double)npairs[s];
+        }
+    for (int64_t s = 0; s < nslots; s++) {
+        npairs_out[s] = npairs[s];
+        avg_out[s] = need_avg ? avg[s] : 0.0;
+        wavg_out[s] = need_w ? wavg[s] : 0.0;
+    }
+    if (is_box && cf_out) { /* xi impl:581-625, wp impl:619-664 -- arithmetic in REAL like the reference */
+        REAL weightsum = (REAL)ND1, weight_sqr_sum = (REAL)ND1;
+        if (need_w) {
+            weightsum = 0;
+            for (int64_t j = 0; j < ND1; j++) {
+                weightsum += W1[j];
+                weight_sqr_sum += W1[j] * W1[j];
+            }
+        }
+        const REAL prefac = weightsum * (weightsum - weightsum / ND1) / (boxsize_x * boxsize_x * boxsize_x);
+        REAL rlow = 0.0;
+        const REAL twice_pimax = 2.0 * pimax_in;
+        for (int i = 0; i < nbin; i++) {
+            REAL weight0 = (REAL)npairs_out[i];
+            if (need_w) weight0 *= wavg_out[i];
+            const REAL vol = (mode == ORC_XI)
+                                 ? (REAL)(4.0 / 3.0 * M_PI * (rupp[i] * rupp[i] * rupp[i] - rlow * rlow * rlow))
+                                 : (REAL)(M_PI * (rupp[i] * rupp[i] - rlow * rlow) * twice_pimax);
+            if (vol > 0.0) {
+                REAL weightrandom = prefac * vol;
+                if (rlow <= 0.) weightrandom += weight_sqr_sum;
+                cf_out[i] = (mode == ORC_XI) ? (REAL)(weight0 / weightrandom - 1.0)
+                                             : (REAL)((weight0 / weightrandom - 1) * twice_pimax);
+            } else {
+                cf_out[i] = (mode == ORC_XI) ? -2.0 : (REAL)(-2.0 * twice_pimax);
+            }
+            rlow = rupp[i];
+        }
+    }
+    free(npairs);
+    free(avg);
+    free(wavg);
+    free(esq);
+    if (L2 != L1) FN(o_free_lattice)(L2);
+    FN(o_free_lattice)(L1);
+    return EXIT_SUCCESS;
+}
+
+#undef FMA_R
+#undef SQRT_R
+#undef FABS_R
+#undef ACOS_R
+#undef ASIN_R
+#undef COSD_R
+#undef SIND_R
+#undef MAXPOS_R
+#undef CAT_
+#undef CAT
+#undef FN

@@ -1,0 +1,103 @@
+"""Test-side loaders for the checkers: the CPU oracle (oracle/libpairs_oracle.so) and the unmodified
+reference built into oracle/_ref by oracle/build_ref.sh.  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+MODES = dict(DD=0, xi=1, DDrppi=2, wp=3, DDsmu=4, DDtheta=5)
+
+
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def ref_variant():
+    return "v4" if "avx512f" in _cpu_flags() else "v3"
+
+
+def load_ref():
+    """The unmodified reference (AVX-512 kernels when the host has them).  None if not built."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libcorrfunc_ref_%s.so" % ref_variant())
+    if not os.path.exists(path):
+        return None
+    return C.CDLL(path, mode=os.RTLD_LOCAL)
+
+
+def ref_isa():
+    # -1 would hit the reference's NULL-kernel static-cache quirk (countpairs_impl.c.src:42-46)
+    return 9 if ref_variant() == "v4" else 7
+
+
+def load_oracle():
+    path = os.path.join(ORACLE_DIR, "libpairs_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "libpairs_oracle.so"])
+    lib = C.CDLL(path, mode=os.RTLD_LOCAL)
+    return lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(None)
+
+
+def oracle_theory(stat, X1, Y1, Z1, bins, *, w1=None, X2=None, Y2=None, Z2=None, w2=None, autocorr=True,
+                  pimax=0.0, mu_max=0.0, nmu_bins=0, periodic=True, boxsize=None, refine=(2, 2, 1),
+                  custom_refine=False, max_cells=100, enable_min_sep=True, need_avg=False, weight_type=None,
+                  nthreads=None):
+    lib = load_oracle()
+    if nthreads:
+        lib.oracle_set_num_threads(int(nthreads))
+    dtype = np.asarray(X1).dtype
+    fn = lib.oracle_theory_double if dtype == np.float64 else lib.oracle_theory_float
+    fn.restype = C.c_int
+    arrs = [None if a is None else np.ascontiguousarray(a, dtype=dtype) for a in (X1, Y1, Z1, w1, X2, Y2, Z2, w2)]
+    X1, Y1, Z1, w1, X2, Y2, Z2, w2 = arrs
+    edges = np.sort(np.asarray(bins, dtype=np.float64))
+    nbin = edges.size  # reference's nbin = nlines+1 = number of edges
+    mode = MODES[stat]
+    if stat == "DDrppi":
+        nslots = (nbin + 1) * (int(pimax) + 1)
+    elif stat == "DDsmu":
+        nslots = (nbin + 1) * (nmu_bins + 1)
+    else:
+        nslots = nbin
+    npairs = np.zeros(nslots, dtype=np.uint64)
+    avg = np.zeros(nslots)
+    wavg = np.zeros(nslots)
+    cf = np.zeros(nbin)
+    lat = np.zeros(6, dtype=np.int32)
+    if boxsize is None:
+        bx = (-2.0, -2.0, -2.0)
+    else:
+        b = np.atleast_1d(np.asarray(boxsize, dtype=np.float64))
+        bx = (float(b[0]),) * 3 if b.size == 1 else tuple(float(v) for v in b[:3])
+    rf = np.asarray(refine, dtype=np.int32)
+    need_w = weight_type is not None
+    st = fn(C.c_int(mode), C.c_int64(X1.size), _p(X1), _p(Y1), _p(Z1), _p(w1),
+            C.c_int64(0 if X2 is None else X2.size), _p(X2), _p(Y2), _p(Z2), _p(w2), C.c_int(int(autocorr)),
+            C.c_int(nbin), _p(edges), C.c_double(pimax), C.c_double(mu_max), C.c_int(nmu_bins),
+            C.c_int(int(periodic)), C.c_double(bx[0]), C.c_double(bx[1]), C.c_double(bx[2]), _p(rf),
+            C.c_int(int(custom_refine)), C.c_int(max_cells), C.c_int(int(enable_min_sep)), C.c_int(int(need_avg)),
+            C.c_int(int(need_w)), _p(npairs), _p(avg), _p(wavg), _p(cf), _p(lat))
+    if st != 0:
+        raise RuntimeError("oracle failed")
+    if stat == "DDrppi":
+        npi = int(pimax)
+        g = lambda a: a.reshape(nbin + 1, npi + 1)[1:nbin, :npi].copy()
+        return dict(npairs=g(npairs), ravg=g(avg), weightavg=g(wavg), lattice=lat)
+    if stat == "DDsmu":
+        g = lambda a: a.reshape(nbin + 1, nmu_bins + 1)[1:nbin, :nmu_bins].copy()
+        return dict(npairs=g(npairs), ravg=g(avg), weightavg=g(wavg), lattice=lat)
+    return dict(npairs=npairs[1:], ravg=avg[1:], weightavg=wavg[1:], cf=cf[1:], lattice=lat)
