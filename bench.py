@@ -1,0 +1,455 @@
+#!/usr/bin/env python
+"""bench.py -- pair-counting throughput on B200 (one JSON line on stdout, rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c5|c1|c2|c3|c4] [--impl ours|reference]
+
+A "step" is one complete pair count of the workload (gridlink + cell-pair enumeration + pair kernel +
+histogram read-back).  Workloads are the BASELINE.json configs with the synthetic generators of
+SURVEY.md section 8(d); the default (headline) is c5: xi on 100M uniform points in a 2 Gpc/h periodic
+box, 30 log bins 0.1-150 Mpc/h, float32.
+
+  value  = reference-equivalent candidate pair evaluations per second with inputs resident in HBM:
+           N_cand = sum over the REFERENCE's cell pairs of N1*N2 (same cell: N(N-1)/2) -- a property
+           of the workload, identical for both arms, so the ratio of the arms is a wall-time ratio.
+  e2e    = the same with HOST (pinned) buffers through the C ABI: H2D + gridlink + pairs + D2H timed.
+  roofline = the pair kernel alone: separations actually computed by the kernel (n_eval, counted on
+           the device) x 8 FLOP / kernel time, against the FP32 (or FP64) ALU peak.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, OpenMP, all host cores)
+on a bounded random subsample of the same workload (same box, same bins).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (stat, N, L, bins, dtype, extra)
+    "c1": dict(stat="DD", N=1_200_000, L=420.0, bins=("log", 0.1, 25.0, 15), dtype="f64", seed=1001),
+    "c2": dict(stat="wp", N=1_200_000, L=420.0, bins=("log", 0.1, 25.0, 15), dtype="f64", seed=1001, pimax=40.0),
+    "c3": dict(stat="DDsmu", N=10_000_000, L=1000.0, bins=("log", 0.1, 50.0, 21), dtype="f64", seed=1003,
+               mu_max=1.0, nmu=20, weights=True, avg=True),
+    "c4": dict(stat="DDtheta", N=2_000_000, L=0.0, bins=("log", 0.01, 10.0, 21), dtype="f64", seed=1004),
+    "c5": dict(stat="xi", N=100_000_000, L=2000.0, bins=("log", 0.1, 150.0, 31), dtype="f32", seed=1006),
+}
+FLOP_PER_EVAL = {"DD": 8, "xi": 8, "wp": 6, "DDrppi": 7, "DDsmu": 9, "DDtheta": 10}
+INSTR_PER_EVAL = {"DD": 6, "xi": 6, "wp": 5, "DDrppi": 6, "DDsmu": 7, "DDtheta": 8}
+
+
+def make_bins(spec):
+    kind, lo, hi, n = spec
+    return np.logspace(np.log10(lo), np.log10(hi), n)
+
+
+def gen_points(cfg, n, dtype):
+    rng = np.random.default_rng(cfg["seed"])
+    if cfg["stat"] == "DDtheta":
+        ra = (360.0 * rng.random(n)).astype(dtype)
+        dec = np.degrees(np.arcsin(2.0 * rng.random(n) - 1.0)).astype(dtype)
+        rng2 = np.random.default_rng(cfg["seed"] + 1)
+        ra2 = (360.0 * rng2.random(n)).astype(dtype)
+        dec2 = np.degrees(np.arcsin(2.0 * rng2.random(n) - 1.0)).astype(dtype)
+        return dict(ra=ra, dec=dec, ra2=ra2, dec2=dec2)
+    out = {}
+    for k in "xyz":  # one axis at a time keeps the peak host memory at ~2 arrays
+        out[k] = (rng.random(n) * cfg["L"]).astype(dtype)
+    if cfg.get("weights"):
+        out["w"] = (1.0 - rng.random(n)).astype(dtype)
+    return out
+
+
+def n_cand_box(counts, refine, periodic=True):
+    """Candidate pairs of the reference's cell-pair set (generate_cell_pairs, no min-sep pruning):
+    unordered pairs of particles whose reference cells are within +-refine of each other."""
+    c = counts.astype(np.float64)
+    s = np.zeros_like(c)
+    rx, ry, rz = refine
+    seen = set()
+    for dx in range(-rx, rx + 1):
+        for dy in range(-ry, ry + 1):
+            for dz in range(-rz, rz + 1):
+                key = (dx % c.shape[0], dy % c.shape[1], dz % c.shape[2])
+                if key in seen:  # tiny lattices: the same neighbour reached twice
+                    continue
+                seen.add(key)
+                s += np.roll(c, shift=(dx, dy, dz), axis=(0, 1, 2))
+    return float((c * s).sum() - c.sum()) / 2.0
+
+
+def ref_cell_counts(pts, L, nmesh, dtype):
+    """Reference cell occupancies for [0,L]^3 lattices (xi/wp): ix=(int)(x*xinv), clamp."""
+    idx = []
+    for k, n in zip("xyz", nmesh):
+        inv = dtype(1.0 / (dtype(L) / dtype(n)))
+        i = (pts[k] * inv).astype(np.int64)
+        np.minimum(i, n - 1, out=i)
+        idx.append(i)
+    lin = (idx[0] * nmesh[1] + idx[1]) * nmesh[2] + idx[2]
+    return np.bincount(lin, minlength=nmesh[0] * nmesh[1] * nmesh[2]).reshape(nmesh)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from corrfunc_b200 import _capi, _lib, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["CORRFUNC_B200_DEVICE"] = str(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    if world > 1:
+        parallel.enable_distributed(dist, dev)
+
+    stat = cfg["stat"]
+    dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
+    tdtype = torch.float32 if dtype == np.float32 else torch.float64
+    N = args.npart or cfg["N"]
+    bins = make_bins(cfg["bins"])
+    pts = gen_points(cfg, N, dtype)
+    keys = list(pts.keys())
+    # host copies in pinned memory (e2e) and device-resident copies (value)
+    pinned = {k: torch.from_numpy(pts[k]).pin_memory() for k in keys}
+    resident = {k: pinned[k].to(dev) for k in keys}
+    opt_kw = dict(periodic=True, need_avg_sep=bool(cfg.get("avg")), boxsize=cfg["L"] if cfg["L"] > 0 else None)
+    wtype = "pair_product" if cfg.get("weights") else None
+    _capi._declare(lib)
+
+    def one_call(bufs, bf):
+        """One pass through the C ABI; bufs: dict of torch tensors (host pinned or device)."""
+        o = _capi.default_options(dtype, **opt_kw)
+        P = {k: C.c_void_p(v.data_ptr()) for k, v in bufs.items()}
+        if wtype:
+            # the epilogue needs the weights on the host (self-pair term) -> always the pinned copy
+            e, keep = _capi.make_extra(pinned["w"].numpy(), pinned["w"].numpy(), wtype, dtype)
+        else:
+            e, keep = _capi.make_extra(None, None, None, dtype)
+        if stat == "xi":
+            r = _capi.ResultsXi()
+            st = lib.countpairs_xi(N, P["x"], P["y"], P["z"], cfg["L"], 1, bf, C.byref(r), C.byref(o), C.byref(e))
+            free = lib.free_results_xi
+        elif stat == "DD":
+            r = _capi.ResultsDD()
+            st = lib.countpairs(N, P["x"], P["y"], P["z"], N, P["x"], P["y"], P["z"], 1, 1, bf, C.byref(r), C.byref(o), C.byref(e))
+            free = lib.free_results
+        elif stat == "wp":
+            r = _capi.ResultsWp()
+            st = lib.countpairs_wp(N, P["x"], P["y"], P["z"], cfg["L"], 1, bf, cfg["pimax"], C.byref(r), C.byref(o), C.byref(e))
+            free = lib.free_results_wp
+        elif stat == "DDsmu":
+            r = _capi.ResultsSMu()
+            st = lib.countpairs_s_mu(N, P["x"], P["y"], P["z"], N, P["x"], P["y"], P["z"], 1, 1, bf, cfg["mu_max"],
+                                     cfg["nmu"], C.byref(r), C.byref(o), C.byref(e))
+            free = lib.free_results_s_mu
+        elif stat == "DDtheta":
+            # RA/DEC -> unit vectors happens on the host (glibc trig, for bit parity): host buffers only
+            r = _capi.ResultsTheta()
+            st = lib.countpairs_theta_mocks(N, C.c_void_p(pinned["ra"].data_ptr()), C.c_void_p(pinned["dec"].data_ptr()),
+                                            N, C.c_void_p(pinned["ra2"].data_ptr()), C.c_void_p(pinned["dec2"].data_ptr()),
+                                            1, 0, bf, C.byref(r), C.byref(o), C.byref(e))
+            free = lib.free_results_countpairs_theta
+        else:
+            raise ValueError(stat)
+        if st != 0:
+            raise RuntimeError("C call failed: %s" % lib.cfb_last_error())
+        nb = r.nbin if hasattr(r, "nbin") else r.nsbin
+        tot = int(np.ctypeslib.as_array(r.npairs, shape=(nb,)).astype(np.uint64)[1:].sum()) if stat not in ("DDsmu",) else -1
+        free(C.byref(r))
+        return tot
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    input_bytes = sum(v.numel() * v.element_size() for v in resident.values())
+    need_flush = input_bytes < 256 * 1024 * 1024
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    with _capi.binfile_for(bins) as bf:
+        # ---- warm-up ----
+        for _ in range(max(args.warmup, 3)):
+            if need_flush:
+                flush.zero_()
+            tot = one_call(resident, bf)
+        st0 = _lib.last_stats()
+        # ---- timed: inputs resident in HBM ----
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        kern_ms, grid_ms, n_eval, launches = [], [], 0, 0
+        barrier()
+        t_acc = 0.0
+        for _ in range(args.steps):
+            if need_flush:
+                flush.zero_()
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            one_call(resident, bf)  # synchronous: returns after the histogram has been read back
+            t_acc += time.perf_counter() - t0
+            s = _lib.last_stats()
+            kern_ms.append(s["ms_pairs"])
+            grid_ms.append(s["ms_gridlink"])
+            n_eval = s["n_eval"]
+            launches += s["kernel_launches"]
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        t_res = t_acc / args.steps
+        # ---- timed: end to end from pinned host buffers ----
+        barrier()
+        t_acc = 0.0
+        for _ in range(args.steps):
+            if need_flush:
+                flush.zero_()
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            one_call(pinned, bf)
+            t_acc += time.perf_counter() - t0
+        barrier()
+        t_e2e = t_acc / args.steps
+        st1 = _lib.last_stats()
+
+    # max over ranks (device-synchronised host clock around synchronous calls)
+    if world > 1:
+        tt = torch.tensor([t_res, t_e2e, float(np.mean(kern_ms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_res, t_e2e, kmean = (float(v) for v in tt.cpu())
+        ne = torch.tensor([n_eval], dtype=torch.int64, device=dev)
+        dist.all_reduce(ne, op=dist.ReduceOp.SUM)
+        n_eval_total = int(ne.item())
+    else:
+        kmean = float(np.mean(kern_ms))
+        n_eval_total = n_eval
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+
+    # ---- workload constants ----
+    if stat in ("xi", "wp", "DD"):
+        counts = ref_cell_counts(pts, cfg["L"], st0["nmesh"], dtype)
+        n_cand = n_cand_box(counts, st0["refine"])
+    else:
+        n_cand = float(n_eval_total)  # no cheap closed form: use the device's own evaluation count
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    lanes = 128 if dtype == np.float32 else 64
+    peak_tflops = 148 * lanes * 2 * sm_max * 1e6 / 1e12
+    flop = FLOP_PER_EVAL[stat]
+    ach_tflops = n_eval_total * flop / (kmean * 1e-3) / 1e12 / max(world, 1)  # per GPU
+    peak_evals = 148 * lanes * sm_max * 1e6 / INSTR_PER_EVAL[stat]
+    line = {
+        "metric": "pair evaluations/sec (reference-equivalent candidate pairs, N_cand/t) and DD wall-time",
+        "value": n_cand / t_res,
+        "unit": "pair_evals/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(args.warmup, 3),
+        "ms_per_step": t_res * 1e3,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": cfg["dtype"],
+        "data": "synthetic",
+        "config": {"workload": "%s %s: N=%d L=%g bins=%s%s" % (args.config, stat, N, cfg["L"], cfg["bins"],
+                                                              "" if not args.npart else " (REDUCED N, not the headline size)"),
+                   "l2": "inputs larger than L2" if not need_flush else "256 MiB L2 flush between iterations",
+                   "reference_lattice": list(st0["nmesh"]), "refine": list(st0["refine"]), "device_lattice": list(st0["fine"]),
+                   "timing": "host clock around synchronous C-ABI calls (device-synchronised on both sides), max over ranks; kernel time by CUDA events on the launch stream"},
+        "e2e": {"value": n_cand / t_e2e, "unit": "pair_evals/s", "ms_per_step": t_e2e * 1e3,
+                "h2d_bytes_per_step": int(input_bytes), "d2h_bytes_per_step": int(len(bins) * 24 + 64)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "fp32_alu" if dtype == np.float32 else "fp64_alu", "achieved": ach_tflops, "peak": peak_tflops,
+                     "unit": "TFLOP/s", "frac": ach_tflops / peak_tflops, "traffic": None,
+                     "peak_source": "nominal: 148 SMs x %d lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no FP32/FP64 ALU figure)" % (lanes, sm_max),
+                     "kernel_ms": kmean, "gridlink_ms": float(np.mean(grid_ms)), "n_eval": n_eval_total,
+                     "evals_per_s": n_eval_total / (kmean * 1e-3), "peak_evals_per_s_per_gpu": peak_evals,
+                     "kernel_share_of_step": kmean * 1e-3 / t_res},
+        "n_cand": n_cand,
+        "n_pairs_total": tot,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg, args, budget_s=15.0)
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
+def ref_call(ref, cfg, pts, n, bins, nthreads):
+    """One pass of the unmodified reference on the first n points; returns (seconds, nmesh-free n_cand)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
+    from corrfunc_b200 import _capi
+
+    dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
+    stat = cfg["stat"]
+    o = _capi.default_options(dtype, periodic=True, need_avg_sep=bool(cfg.get("avg")), isa=H.ref_isa(),
+                              boxsize=cfg["L"] if cfg["L"] > 0 else None)
+    w = pts.get("w")
+    wt = "pair_product" if cfg.get("weights") else None
+    t0 = time.perf_counter()
+    if stat == "xi":
+        _capi.call_xi(ref, cfg["L"], nthreads, bins, pts["x"][:n], pts["y"][:n], pts["z"][:n], options=o)
+    elif stat == "DD":
+        _capi.call_DD(ref, 1, nthreads, bins, pts["x"][:n], pts["y"][:n], pts["z"][:n], options=o)
+    elif stat == "wp":
+        _capi.call_wp(ref, cfg["L"], nthreads, cfg["pimax"], bins, pts["x"][:n], pts["y"][:n], pts["z"][:n], options=o)
+    elif stat == "DDsmu":
+        _capi.call_DDsmu(ref, 1, nthreads, bins, cfg["mu_max"], cfg["nmu"], pts["x"][:n], pts["y"][:n], pts["z"][:n],
+                         w1=None if w is None else w[:n], weight_type=wt, options=o)
+    elif stat == "DDtheta":
+        _capi.call_DDtheta(ref, 0, nthreads, bins, pts["ra"][:n], pts["dec"][:n], RA2=pts["ra2"][:n], DEC2=pts["dec2"][:n], options=o)
+    return time.perf_counter() - t0
+
+
+def ref_lattice_for(cfg, n, bins):
+    """nmesh/refine the reference picks for a [0,L]^3 periodic box (xi/wp/DD on uniform data)."""
+    rmax = bins[-1]
+    L = cfg["L"]
+    rf = [2, 2, 1]
+    if cfg["stat"] == "xi" and rmax < 0.05 * L:
+        rf = [1, 1, 1]
+    zmax = cfg.get("pimax", rmax)
+
+    def mesh(rf):
+        return [max(2, min(100, int(rf[0] * L / rmax))), max(2, min(100, int(rf[1] * L / rmax))),
+                max(2, min(100, int(rf[2] * L / zmax)))]
+
+    nm = mesh(rf)
+    if (max(nm) <= 10 or n / (nm[0] * nm[1] * nm[2]) >= 250) and max(nm) < 100:
+        rf = [rf[0] + 1, rf[1] + 1, rf[2]]
+        nm = mesh(rf)
+    return nm, rf
+
+
+def cpu_baseline(cfg, args, budget_s=15.0, steps=1):
+    """The reference's OpenMP AVX-512 path on this host's cores, on a bounded subsample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
+
+    ref = H.load_ref()
+    if ref is None:
+        return {"value": None, "unit": "pair_evals/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
+    cores = os.cpu_count() or 1
+    bins = make_bins(cfg["bins"])
+    stat = cfg["stat"]
+    n_full = args.npart or cfg["N"]
+    # calibrate on a small subsample, then size the sample for ~budget_s (cost ~ n^2)
+    n0 = min(n_full, 1_000_000 if stat != "DDtheta" else 300_000)
+    pts = gen_points(cfg, min(n_full, 12_000_000), dtype)
+    t_cal = ref_call(ref, cfg, pts, n0, bins, cores)
+    n_s = int(min(len(next(iter(pts.values()))), n0 * max(1.0, (budget_s / max(t_cal, 1e-3)) ** 0.5)))
+    ts = [ref_call(ref, cfg, pts, n_s, bins, cores) for _ in range(steps)]
+    t = float(np.mean(ts))
+    if stat in ("xi", "wp", "DD"):
+        nm, rf = ref_lattice_for(cfg, n_s, bins)
+        counts = ref_cell_counts({k: pts[k][:n_s] for k in "xyz"}, cfg["L"], nm, dtype)
+        n_cand = n_cand_box(counts, rf)
+    else:
+        n_cand = float("nan")
+    return {"value": n_cand / t, "unit": "pair_evals/s", "cores": cores, "kind": "reference",
+            "isa": "avx512f" if H.ref_variant() == "v4" else "avx", "seconds": t, "n_cand": n_cand,
+            "sample": "first %d of the %d points (same box, same bins): reference %s, %d OpenMP threads" % (n_s, n_full, stat, cores)}
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cb = cpu_baseline(cfg, args, budget_s=12.0, steps=max(1, args.steps))
+    N = args.npart or cfg["N"]
+    return {"impl": "reference", "metric": "pair evaluations/sec (reference-equivalent candidate pairs, N_cand/t) and DD wall-time",
+            "value": cb["value"], "unit": "pair_evals/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb.get("seconds", 0) * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": {"workload": "%s %s: N=%d L=%g bins=%s" % (args.config, cfg["stat"], N, cfg["L"], cfg["bins"])},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "pair_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default=os.environ.get("CORRFUNC_BENCH_CONFIG", "c5"))
+    ap.add_argument("--npart", type=int, default=0, help="override N (marks the line as reduced)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    line = run_reference(args, cfg) if args.impl == "reference" else run_ours(args, cfg)
+    if line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

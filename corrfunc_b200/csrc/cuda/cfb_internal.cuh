@@ -1,0 +1,113 @@
+// cfb_internal.cuh -- shared declarations of the CUDA layer (context, particle sets, launch params).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "corrfunc_b200_device.h"
+
+#define CFB_PAD 4            // every fine cell's run in the sorted SoA starts at a multiple of this (16 B for float)
+#define CFB_TILE 128         // primaries per tile in the generic kernel (one per thread)
+#define CFB_SHARD_GROUP 8    // tiles per shard group
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+// One particle set, raw (as uploaded) and cell-sorted.
+struct ParticleSet {
+    int prec = 0;
+    int64_t n = 0;
+    DevBuf rawbuf[6];            // owned copies of x,y,z,w,ra,dec when the caller passed host memory
+    const void *raw[6] = {0};    // pointers actually used (may alias caller's device memory)
+    DevBuf sorted[4];            // x,y,z,w cell-sorted, cells padded to CFB_PAD with NaN
+    DevBuf cidx, rank;           // int32 per particle: fine cell index, arrival rank within the cell
+    DevBuf count, start, tstart; // int32 per fine cell: particles, padded offset, first tile id
+    DevBuf bounds;               // per fine cell: 6 reals {xlo,xhi,ylo,yhi,zlo,zhi} (+ {ralo,rahi} for theta)
+    DevBuf tile_cell, tile_off;  // int32 per tile
+    int64_t ncells = 0, npad = 0, ntiles = 0;
+    bool gridded = false;
+};
+
+struct Ctx {
+    bool ready = false;
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8];
+    ParticleSet set[2];
+    DevBuf scratch;  // reductions, scalars
+    DevBuf hist;     // npairs | sum_sep | sum_w | n_eval, n_tilepairs
+    DevBuf edges;
+    DevBuf list_off, list_cells, ngrid_ra, ra_off;
+    void *pinned = nullptr;  // small pinned host staging area
+    size_t pinned_cap = 0;
+    int shard_rank = 0, shard_n = 1;
+    int target_occ = 0;
+    int force_kernel = -1;
+    int launches = 0;
+    char err[512];
+};
+
+Ctx &cfb_ctx();
+int cfb_fail(const char *fmt, ...);
+int cfb_ensure(DevBuf &b, size_t bytes);
+
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return cfb_fail("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                            cudaGetErrorString(e__));                                               \
+    } while (0)
+
+// Device view of a gridded particle set.
+template <typename T>
+struct SetView {
+    const T *x, *y, *z, *w;
+    const int *count, *start;
+    const T *bounds;  // stride CFB_NB
+};
+#define CFB_NB 8  // bounds stride (reals per cell)
+
+// Fine lattice = reference lattice with every cell split sub[] ways.
+struct FineGeom {
+    int n[3];    // reference nmesh
+    int s[3];    // subdivision
+    int ng[3];   // n*s
+    int refine[3]; // neighbour reach in reference cells
+    int reach[3];  // neighbour reach in fine cells: (refine+1)*s-1, whole reference cells on both sides
+    int periodic[3];
+};
+
+struct PairParams {
+    // binning
+    int mode, nedges, npibin, nmu_bins, autocorr, cross;
+    int64_t nslots;
+    double pimax, inv_dpi, sqr_mumax, inv_dmu;
+    int fast_acos;
+    const void *edges;  // device, T[nedges]
+    // lattice
+    FineGeom g;
+    double wrap[3];
+    double max_sep[3];
+    // neighbour list (theta)
+    const int64_t *list_off;
+    const int32_t *list_cells;
+    // tiles of the primary set
+    const int *tile_cell, *tile_off;
+    int64_t ntiles;
+    int shard_rank, shard_n;
+    // outputs
+    unsigned long long *npairs;
+    double *sum_sep, *sum_w;
+    unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs
+    int hist_in_smem;
+};
+
+// gridlink entry points (gridlink.cu)
+int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3]);
+int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t ncells);
+// pair kernels (pairs_generic.cu)
+int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode);

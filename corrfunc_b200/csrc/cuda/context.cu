@@ -1,0 +1,459 @@
+// context.cu -- process-wide device context, buffer pool, uploads, extents and the count_* drivers.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "cfb_internal.cuh"
+
+static Ctx g_ctx;
+Ctx &cfb_ctx() { return g_ctx; }
+
+int cfb_fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_ctx.err, sizeof(g_ctx.err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "corrfunc_b200> %s\n", g_ctx.err);
+    return 1;
+}
+
+extern "C" const char *cfb_last_error(void) { return g_ctx.err; }
+
+int cfb_ensure(DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap && b.p) return 0;
+    if (b.p) {
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;  // a little slack so slightly larger repeat calls do not realloc
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) return cfb_fail("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    b.cap = want;
+    return 0;
+}
+
+extern "C" int cfb_init(void)
+{
+    Ctx &c = g_ctx;
+    if (c.ready) return 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return cfb_fail("no CUDA device available (%s); corrfunc_b200 has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    int dev = 0;
+    const char *env = getenv("CORRFUNC_B200_DEVICE");
+    if (env && *env)
+        dev = atoi(env);
+    else
+        cudaGetDevice(&dev);
+    if (dev < 0 || dev >= ndev) return cfb_fail("CORRFUNC_B200_DEVICE=%d out of range (have %d devices)", dev, ndev);
+    CK(cudaSetDevice(dev));
+    c.dev = dev;
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c.ev[i]));
+    c.pinned_cap = 1 << 20;
+    CK(cudaMallocHost(&c.pinned, c.pinned_cap));
+    c.ready = true;
+    return 0;
+}
+
+extern "C" void cfb_shutdown(void)
+{
+    Ctx &c = g_ctx;
+    if (!c.ready) return;
+    cudaSetDevice(c.dev);
+    cudaStreamSynchronize(c.stream);
+    auto rel = [](DevBuf &b) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    };
+    for (int s = 0; s < 2; s++) {
+        ParticleSet &S = c.set[s];
+        for (int i = 0; i < 6; i++) rel(S.rawbuf[i]);
+        for (int i = 0; i < 4; i++) rel(S.sorted[i]);
+        rel(S.cidx); rel(S.rank); rel(S.count); rel(S.start); rel(S.tstart); rel(S.bounds);
+        rel(S.tile_cell); rel(S.tile_off);
+        S = ParticleSet();
+    }
+    rel(c.scratch); rel(c.hist); rel(c.edges); rel(c.list_off); rel(c.list_cells); rel(c.ngrid_ra); rel(c.ra_off);
+    if (c.pinned) cudaFreeHost(c.pinned);
+    c.pinned = nullptr;
+    for (int i = 0; i < 8; i++) cudaEventDestroy(c.ev[i]);
+    cudaStreamDestroy(c.stream);
+    c.ready = false;
+}
+
+extern "C" void cfb_set_shard(int rank, int nranks)
+{
+    if (nranks < 1) nranks = 1;
+    if (rank < 0 || rank >= nranks) rank = 0;
+    g_ctx.shard_rank = rank;
+    g_ctx.shard_n = nranks;
+}
+extern "C" void cfb_get_shard(int *rank, int *nranks)
+{
+    if (rank) *rank = g_ctx.shard_rank;
+    if (nranks) *nranks = g_ctx.shard_n;
+}
+extern "C" void cfb_set_target_occupancy(int n) { g_ctx.target_occ = n; }
+extern "C" void cfb_force_kernel(int kind) { g_ctx.force_kernel = kind; }
+
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int cfb_upload(int slot, int prec, int64_t n, const void *x, const void *y, const void *z, const void *w,
+                          const void *ra, const void *dec)
+{
+    if (cfb_init()) return 1;
+    Ctx &c = g_ctx;
+    CK(cudaSetDevice(c.dev));
+    if (slot < 0 || slot > 1) return cfb_fail("bad particle slot %d", slot);
+    if (prec != 4 && prec != 8) return cfb_fail("element size must be 4 or 8 (got %d)", prec);
+    if (n < 0 || n >= (int64_t)2000000000) return cfb_fail("particle count %lld not supported", (long long)n);
+    ParticleSet &S = c.set[slot];
+    S.prec = prec;
+    S.n = n;
+    S.gridded = false;
+    const void *src[6] = {x, y, z, w, ra, dec};
+    const size_t bytes = (size_t)n * prec;
+    for (int i = 0; i < 6; i++) {
+        S.raw[i] = nullptr;
+        if (!src[i] || n == 0) continue;
+        if (is_device_ptr(src[i])) {
+            S.raw[i] = src[i];  // borrowed for the duration of the call
+        } else {
+            if (cfb_ensure(S.rawbuf[i], bytes)) return 1;
+            CK(cudaMemcpyAsync(S.rawbuf[i].p, src[i], bytes, cudaMemcpyHostToDevice, c.stream));
+            S.raw[i] = S.rawbuf[i].p;
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// extents: per-block partial min/max, finished on the host (a few KB)
+template <typename T>
+__global__ void k_minmax(int64_t n, const T *a, const T *b, const T *cc, T *out)
+{
+    T lo[3], hi[3];
+    const T big = sizeof(T) == 4 ? (T)3.402823466e+38F : (T)1.7976931348623157e+308;
+    for (int k = 0; k < 3; k++) {
+        lo[k] = big;
+        hi[k] = -big;
+    }
+    const T *arr[3] = {a, b, cc};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        for (int k = 0; k < 3; k++) {
+            if (!arr[k]) continue;
+            const T v = arr[k][i];
+            if (v < lo[k]) lo[k] = v;
+            if (v > hi[k]) hi[k] = v;
+        }
+    }
+    __shared__ T s[6][256];
+    for (int k = 0; k < 3; k++) {
+        s[k][threadIdx.x] = lo[k];
+        s[3 + k][threadIdx.x] = hi[k];
+    }
+    __syncthreads();
+    for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            for (int k = 0; k < 3; k++) {
+                const T l2 = s[k][threadIdx.x + st], h2 = s[3 + k][threadIdx.x + st];
+                if (l2 < s[k][threadIdx.x]) s[k][threadIdx.x] = l2;
+                if (h2 > s[3 + k][threadIdx.x]) s[3 + k][threadIdx.x] = h2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 6; k++) out[(size_t)blockIdx.x * 6 + k] = s[k][0];
+}
+
+template <typename T>
+static int extent_T(Ctx &c, ParticleSet &S, int which, double lohi[6])
+{
+    const int nb = 512;
+    if (cfb_ensure(c.scratch, (size_t)nb * 6 * sizeof(T) + 4096)) return 1;
+    const T *a = (const T *)S.raw[which ? 4 : 0], *b = (const T *)S.raw[which ? 5 : 1],
+            *cc = which ? nullptr : (const T *)S.raw[2];
+    k_minmax<T><<<nb, 256, 0, c.stream>>>(S.n, a, b, cc, (T *)c.scratch.p);
+    c.launches++;
+    CK(cudaGetLastError());
+    T *h = (T *)c.pinned;
+    CK(cudaMemcpyAsync(h, c.scratch.p, (size_t)nb * 6 * sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    for (int blk = 0; blk < nb; blk++)
+        for (int k = 0; k < 3; k++) {
+            const double l = (double)h[blk * 6 + k], u = (double)h[blk * 6 + 3 + k];
+            if (l < lohi[k]) lohi[k] = l;
+            if (u > lohi[3 + k]) lohi[3 + k] = u;
+        }
+    return 0;
+}
+
+extern "C" int cfb_extent(int slot, int which, double lohi[6])
+{
+    Ctx &c = g_ctx;
+    if (!c.ready) return cfb_fail("cfb_extent before cfb_upload");
+    ParticleSet &S = c.set[slot];
+    if (S.n == 0) return 0;
+    return S.prec == 4 ? extent_T<float>(c, S, which, lohi) : extent_T<double>(c, S, which, lohi);
+}
+
+// ---------------------------------------------------------------------------------------------
+static void choose_subdivision(const Ctx &c, const cfb_box_lattice *lat, int64_t nmax, int sub[3])
+{
+    sub[0] = sub[1] = sub[2] = 1;
+    const int target = c.target_occ > 0 ? c.target_occ : 96;
+    const double ncell = (double)lat->nmesh[0] * lat->nmesh[1] * lat->nmesh[2];
+    const double occ = (double)nmax / ncell;
+    if (occ <= 1.5 * target) return;
+    double d[3];
+    for (int k = 0; k < 3; k++) d[k] = lat->inv[k] > 0 ? 1.0 / lat->inv[k] : 0.0;
+    if (!(d[0] > 0 && d[1] > 0 && d[2] > 0)) return;
+    const double K = occ / target;
+    const double f = cbrt(d[0] * d[1] * d[2] / K);
+    double tot = ncell;
+    for (int k = 0; k < 3; k++) {
+        int s = (int)floor(d[k] / f + 0.5);
+        if (s < 1) s = 1;
+        if (s > 16) s = 16;
+        sub[k] = s;
+        tot *= s;
+    }
+    // keep the fine lattice below ~48M cells
+    while (tot > 48e6) {
+        int k = 0;
+        for (int q = 1; q < 3; q++)
+            if (sub[q] > sub[k]) k = q;
+        if (sub[k] == 1) break;
+        tot = tot / sub[k] * (sub[k] - 1);
+        sub[k]--;
+    }
+}
+
+static int alloc_hist(Ctx &c, int64_t nslots)
+{
+    const size_t bytes = (size_t)nslots * 8 * 3 + 64;
+    if (cfb_ensure(c.hist, bytes)) return 1;
+    CK(cudaMemsetAsync(c.hist.p, 0, bytes, c.stream));
+    return 0;
+}
+
+static int fetch_hist(Ctx &c, int64_t nslots, const cfb_binning *bin, cfb_hist *out, cfb_stats *stats)
+{
+    const size_t bytes = (size_t)nslots * 8 * 3 + 64;
+    void *h = c.pinned;
+    bool tmp = false;
+    if (bytes > c.pinned_cap) {
+        h = malloc(bytes);
+        tmp = true;
+        if (!h) return cfb_fail("out of host memory");
+    }
+    CK(cudaMemcpyAsync(h, c.hist.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    const unsigned long long *n = (const unsigned long long *)h;
+    const double *s = (const double *)((char *)h + (size_t)nslots * 8);
+    const double *w = (const double *)((char *)h + (size_t)nslots * 16);
+    const unsigned long long *cnt = (const unsigned long long *)((char *)h + (size_t)nslots * 24);
+    for (int64_t i = 0; i < nslots; i++) {
+        out->npairs[i] = n[i];
+        if (out->sum_sep) out->sum_sep[i] = bin->need_avg ? s[i] : 0.0;
+        if (out->sum_w) out->sum_w[i] = bin->need_weights ? w[i] : 0.0;
+    }
+    if (stats) {
+        stats->n_eval = cnt[0];
+        stats->n_tilepairs = cnt[1];
+    }
+    if (tmp) free(h);
+    return 0;
+}
+
+static int upload_edges(Ctx &c, const cfb_binning *bin)
+{
+    if (bin->nedges < 2 || bin->nedges > CFB_MAX_EDGES) return cfb_fail("number of bin edges %d not in [2,%d]", bin->nedges, CFB_MAX_EDGES);
+    if (cfb_ensure(c.edges, (size_t)bin->nedges * 8)) return 1;
+    // convert on the host into the run precision (values are already REAL-representable)
+    if (bin->prec == 4) {
+        float *h = (float *)c.pinned;
+        for (int i = 0; i < bin->nedges; i++) h[i] = (float)bin->edges[i];
+        CK(cudaMemcpyAsync(c.edges.p, h, (size_t)bin->nedges * 4, cudaMemcpyHostToDevice, c.stream));
+    } else {
+        double *h = (double *)c.pinned;
+        for (int i = 0; i < bin->nedges; i++) h[i] = bin->edges[i];
+        CK(cudaMemcpyAsync(c.edges.p, h, (size_t)bin->nedges * 8, cudaMemcpyHostToDevice, c.stream));
+    }
+    CK(cudaStreamSynchronize(c.stream));  // pinned staging area is reused below
+    return 0;
+}
+
+static void fill_common(PairParams &P, Ctx &c, const cfb_binning *bin, int64_t nslots)
+{
+    memset(&P, 0, sizeof(P));
+    P.mode = bin->mode;
+    P.nedges = bin->nedges;
+    P.npibin = bin->npibin;
+    P.nmu_bins = bin->nmu_bins;
+    P.autocorr = bin->autocorr;
+    P.cross = bin->autocorr ? 0 : 1;
+    P.nslots = nslots;
+    P.pimax = bin->pimax;
+    P.inv_dpi = bin->inv_dpi;
+    P.sqr_mumax = bin->sqr_mumax;
+    P.inv_dmu = bin->inv_dmu;
+    P.fast_acos = bin->fast_acos;
+    P.edges = c.edges.p;
+    P.npairs = (unsigned long long *)c.hist.p;
+    P.sum_sep = (double *)((char *)c.hist.p + (size_t)nslots * 8);
+    P.sum_w = (double *)((char *)c.hist.p + (size_t)nslots * 16);
+    P.counters = (unsigned long long *)((char *)c.hist.p + (size_t)nslots * 24);
+    P.shard_rank = c.shard_rank;
+    P.shard_n = c.shard_n;
+}
+
+extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *out, cfb_stats *stats)
+{
+    Ctx &c = g_ctx;
+    if (!c.ready) return cfb_fail("cfb_count_box before cfb_upload");
+    CK(cudaSetDevice(c.dev));
+    const int nsets = bin->autocorr ? 1 : 2;
+    for (int s = 0; s < nsets; s++)
+        if (c.set[s].prec != bin->prec) return cfb_fail("particle set %d precision mismatch", s);
+    if (bin->need_weights)
+        for (int s = 0; s < nsets; s++)
+            if (c.set[s].n > 0 && !c.set[s].raw[3]) return cfb_fail("weights requested but set %d has none", s);
+    c.launches = 0;
+    cfb_stats st;
+    memset(&st, 0, sizeof(st));
+    CK(cudaEventRecord(c.ev[0], c.stream));
+
+    int sub[3];
+    int64_t nmax = c.set[0].n;
+    if (nsets == 2 && c.set[1].n > nmax) nmax = c.set[1].n;
+    choose_subdivision(c, lat, nmax, sub);
+    for (int s = 0; s < nsets; s++)
+        if (cfb_gridlink_box_set(c.set[s], lat, sub)) return 1;
+    CK(cudaEventRecord(c.ev[1], c.stream));
+
+    const int64_t nslots = bin->nslots;
+    if (alloc_hist(c, nslots)) return 1;
+    if (upload_edges(c, bin)) return 1;
+    PairParams P;
+    fill_common(P, c, bin, nslots);
+    for (int k = 0; k < 3; k++) {
+        P.g.n[k] = lat->nmesh[k];
+        P.g.s[k] = sub[k];
+        P.g.ng[k] = lat->nmesh[k] * sub[k];
+        P.g.refine[k] = lat->refine[k];
+        P.g.reach[k] = sub[k] > 1 ? (lat->refine[k] + 1) * sub[k] - 1 : lat->refine[k];
+        P.g.periodic[k] = lat->periodic[k];
+        P.wrap[k] = lat->wrap[k];
+        P.max_sep[k] = lat->max_sep[k];
+    }
+    P.tile_cell = (const int *)c.set[0].tile_cell.p;
+    P.tile_off = (const int *)c.set[0].tile_off.p;
+    P.ntiles = c.set[0].ntiles;
+    if (c.set[0].n > 0 && c.set[nsets - 1].n > 0 && P.ntiles > 0)
+        if (cfb_launch_pairs_generic(bin, P, bin->prec, false)) return 1;
+    CK(cudaEventRecord(c.ev[2], c.stream));
+    if (fetch_hist(c, nslots, bin, out, &st)) return 1;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]);
+    st.ms_gridlink = ms;
+    cudaEventElapsedTime(&ms, c.ev[1], c.ev[2]);
+    st.ms_pairs = ms;
+    cudaEventElapsedTime(&ms, c.ev[0], c.ev[2]);
+    st.ms_total_device = ms;
+    st.n_cells = c.set[0].ncells;
+    st.n_tiles = c.set[0].ntiles;
+    for (int k = 0; k < 3; k++) st.fine[k] = lat->nmesh[k] * sub[k];
+    st.kernel_launches = c.launches;
+    if (stats) *stats = st;
+    return 0;
+}
+
+extern "C" int cfb_theta_gridlink(int slot, int prec, const cfb_theta_lattice *lat, int64_t ncells, int64_t *counts,
+                                  double *ra_bounds, double *xyz_bounds)
+{
+    Ctx &c = g_ctx;
+    if (!c.ready) return cfb_fail("cfb_theta_gridlink before cfb_upload");
+    CK(cudaSetDevice(c.dev));
+    ParticleSet &S = c.set[slot];
+    if (S.prec != prec) return cfb_fail("particle set %d precision mismatch", slot);
+    if (cfb_gridlink_theta_set(S, lat, ncells)) return 1;
+    // bring per-cell counts and bounds back for the host-side neighbour search
+    int *hc = (int *)malloc((size_t)ncells * sizeof(int));
+    void *hb = malloc((size_t)ncells * CFB_NB * prec);
+    if (!hc || !hb) return cfb_fail("out of host memory");
+    CK(cudaMemcpyAsync(hc, S.count.p, (size_t)ncells * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(hb, S.bounds.p, (size_t)ncells * CFB_NB * prec, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    for (int64_t i = 0; i < ncells; i++) {
+        counts[i] = hc[i];
+        for (int k = 0; k < 6; k++)
+            xyz_bounds[i * 6 + k] = prec == 4 ? (double)((float *)hb)[i * CFB_NB + k] : ((double *)hb)[i * CFB_NB + k];
+        for (int k = 0; k < 2; k++)
+            ra_bounds[i * 2 + k] = prec == 4 ? (double)((float *)hb)[i * CFB_NB + 6 + k] : ((double *)hb)[i * CFB_NB + 6 + k];
+    }
+    free(hc);
+    free(hb);
+    return 0;
+}
+
+extern "C" int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int64_t *ngb_offsets,
+                               const int32_t *ngb_cells, cfb_hist *out, cfb_stats *stats)
+{
+    Ctx &c = g_ctx;
+    if (!c.ready) return cfb_fail("cfb_count_theta before cfb_upload");
+    CK(cudaSetDevice(c.dev));
+    c.launches = 0;
+    cfb_stats st;
+    memset(&st, 0, sizeof(st));
+    CK(cudaEventRecord(c.ev[0], c.stream));
+    const int64_t nslots = bin->nslots;
+    if (alloc_hist(c, nslots)) return 1;
+    if (upload_edges(c, bin)) return 1;
+    const int64_t nlist = ngb_offsets[ncells];
+    if (cfb_ensure(c.list_off, (size_t)(ncells + 1) * 8)) return 1;
+    if (cfb_ensure(c.list_cells, (size_t)(nlist > 0 ? nlist : 1) * 4)) return 1;
+    CK(cudaMemcpyAsync(c.list_off.p, ngb_offsets, (size_t)(ncells + 1) * 8, cudaMemcpyHostToDevice, c.stream));
+    if (nlist > 0) CK(cudaMemcpyAsync(c.list_cells.p, ngb_cells, (size_t)nlist * 4, cudaMemcpyHostToDevice, c.stream));
+    PairParams P;
+    fill_common(P, c, bin, nslots);
+    P.list_off = (const int64_t *)c.list_off.p;
+    P.list_cells = (const int32_t *)c.list_cells.p;
+    P.tile_cell = (const int *)c.set[0].tile_cell.p;
+    P.tile_off = (const int *)c.set[0].tile_off.p;
+    P.ntiles = c.set[0].ntiles;
+    if (P.ntiles > 0 && nlist > 0)
+        if (cfb_launch_pairs_generic(bin, P, bin->prec, true)) return 1;
+    CK(cudaEventRecord(c.ev[2], c.stream));
+    if (fetch_hist(c, nslots, bin, out, &st)) return 1;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev[0], c.ev[2]);
+    st.ms_pairs = ms;
+    st.ms_total_device = ms;
+    st.n_cells = ncells;
+    st.n_tiles = c.set[0].ntiles;
+    st.kernel_launches = c.launches;
+    if (stats) *stats = st;
+    return 0;
+}

@@ -1,0 +1,409 @@
+// gridlink.cu -- GPU counting sort of particles into lattice cells.
+//
+// Replaces gridlink_DOUBLE (utils/gridlink_impl.c.src:65-436) and the particle-assignment part of
+// gridlink_mocks_theta_ra_dec_DOUBLE (utils/gridlink_mocks_impl.c.src:1246-1350):
+//   k_cellindex_*  cell index per particle (the reference's truncating formula, bit-for-bit)
+//                  + per-cell histogram; the atomic's return value is the particle's rank in its cell
+//   k_scan_cells   exclusive scan of the (padded) cell counts -> cell start offsets, and of the
+//                  per-cell tile counts -> tile ids
+//   k_scatter      SoA scatter x|y|z|w into cell order
+//   k_bounds_pad   per-cell min/max bounds (the reference's xbounds/ybounds/zbounds/ra_bounds)
+//                  and NaN fill of the padding slots
+//   k_fill_tiles   (cell, offset) table of primary tiles
+// All of it is HBM-bound byte shuffling: coalesced streaming reads, one scattered write per value.
+#include "cfb_internal.cuh"
+
+template <typename T>
+struct BoxGeomT {
+    T lo[3], inv[3];
+    int n[3], s[3], ng[3];
+};
+
+// Reference cell index: ix=(int)((X-xmin)*xinv); if(ix>nmesh-1) ix--  (gridlink_impl.c.src:165-181).
+// The fine index subdivides the reference cell by the fractional position; it only steers pruning
+// (cell bounds are measured from the particles), never the results.
+template <typename T>
+__device__ __forceinline__ bool fine_coord(const T v, const T lo, const T inv, const int n, const int s, int &g)
+{
+    const T u = (v - lo) * inv;  // compiled with -fmad=false: one rounded subtract, one rounded multiply
+    if (!(u == u)) return false;
+    int i = (int)u;  // truncation toward zero, like the C cast
+    if (i > n - 1) i--;
+    if (i < 0 || i >= n) return false;
+    int sub = 0;
+    if (s > 1) {
+        sub = (int)((u - (T)i) * (T)s);
+        sub = sub < 0 ? 0 : (sub > s - 1 ? s - 1 : sub);
+    }
+    g = i * s + sub;
+    return true;
+}
+
+template <typename T>
+__global__ void k_cellindex_box(const int64_t n, const T *__restrict__ x, const T *__restrict__ y,
+                                const T *__restrict__ z, const BoxGeomT<T> G, int *__restrict__ cidx,
+                                int *__restrict__ rank, int *__restrict__ count, unsigned long long *oob)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int gx, gy, gz;
+    const bool ok = fine_coord(x[i], G.lo[0], G.inv[0], G.n[0], G.s[0], gx) &
+                    fine_coord(y[i], G.lo[1], G.inv[1], G.n[1], G.s[1], gy) &
+                    fine_coord(z[i], G.lo[2], G.inv[2], G.n[2], G.s[2], gz);
+    if (!ok) {
+        atomicAdd(oob, 1ULL);
+        cidx[i] = -1;
+        return;
+    }
+    const int c = (gx * G.ng[1] + gy) * G.ng[2] + gz;
+    cidx[i] = c;
+    rank[i] = atomicAdd(&count[c], 1);
+}
+
+// DDtheta lattice: idec=(int)(ngrid_dec*(DEC-dec_min)*inv_dec_diff); if(idec>=ngrid_dec) idec--;
+// ira=(int)(ngrid_ra[idec]*(RA-ra_min)*inv_ra_diff); if(ira>=ngrid_ra[idec]) ira--
+// (gridlink_mocks_impl.c.src:1249-1263)
+template <typename T>
+__global__ void k_cellindex_theta(const int64_t n, const T *__restrict__ ra, const T *__restrict__ dec,
+                                  const int ngrid_dec, const int *__restrict__ ngrid_ra,
+                                  const int *__restrict__ ra_off, const T dec_min, const T inv_dec_diff,
+                                  const T ra_min, const T inv_ra_diff, int *__restrict__ cidx,
+                                  int *__restrict__ rank, int *__restrict__ count, unsigned long long *oob)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T ud = (T)ngrid_dec * (dec[i] - dec_min) * inv_dec_diff;
+    int idec = (int)ud;
+    if (idec >= ngrid_dec) idec--;
+    bool ok = (ud == ud) && idec >= 0 && idec < ngrid_dec;
+    int ira = 0, nra = 1;
+    if (ok) {
+        nra = ngrid_ra[idec];
+        const T ur = (T)nra * (ra[i] - ra_min) * inv_ra_diff;
+        ira = (int)ur;
+        if (ira >= nra) ira--;
+        ok = (ur == ur) && ira >= 0 && ira < nra;
+    }
+    if (!ok) {
+        atomicAdd(oob, 1ULL);
+        cidx[i] = -1;
+        return;
+    }
+    const int c = ra_off[idec] + ira;
+    cidx[i] = c;
+    rank[i] = atomicAdd(&count[c], 1);
+}
+
+// Single-block exclusive scan of padded counts (-> start) and tile counts (-> tstart).
+// totals[0] = padded particle total, totals[1] = tile total.
+__global__ void k_scan_cells(const int64_t ncells, const int *__restrict__ count, int *__restrict__ start,
+                             int *__restrict__ tstart, long long *totals)
+{
+    __shared__ long long s_a[1024], s_b[1024];
+    __shared__ long long carry_a, carry_b;
+    if (threadIdx.x == 0) {
+        carry_a = 0;
+        carry_b = 0;
+    }
+    __syncthreads();
+    const int ITEMS = 8;
+    for (int64_t base = 0; base < ncells; base += 1024 * ITEMS) {
+        long long va[ITEMS], vb[ITEMS], sa = 0, sb = 0;
+        const int64_t i0 = base + (int64_t)threadIdx.x * ITEMS;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            const int64_t i = i0 + k;
+            const int cnt = i < ncells ? count[i] : 0;
+            va[k] = (cnt + CFB_PAD - 1) / CFB_PAD * CFB_PAD;
+            vb[k] = (cnt + CFB_TILE - 1) / CFB_TILE;
+            sa += va[k];
+            sb += vb[k];
+        }
+        s_a[threadIdx.x] = sa;
+        s_b[threadIdx.x] = sb;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of the thread sums
+            long long ta = 0, tb = 0;
+            if ((int)threadIdx.x >= off) {
+                ta = s_a[threadIdx.x - off];
+                tb = s_b[threadIdx.x - off];
+            }
+            __syncthreads();
+            s_a[threadIdx.x] += ta;
+            s_b[threadIdx.x] += tb;
+            __syncthreads();
+        }
+        long long ea = carry_a + s_a[threadIdx.x] - sa, eb = carry_b + s_b[threadIdx.x] - sb;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            const int64_t i = i0 + k;
+            if (i < ncells) {
+                start[i] = (int)ea;
+                tstart[i] = (int)eb;
+            }
+            ea += va[k];
+            eb += vb[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            carry_a += s_a[1023];
+            carry_b += s_b[1023];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        totals[0] = carry_a;
+        totals[1] = carry_b;
+    }
+}
+
+template <typename T>
+__global__ void k_scatter(const int64_t n, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
+                          const T *__restrict__ w, const int *__restrict__ cidx, const int *__restrict__ rank,
+                          const int *__restrict__ start, T *__restrict__ xs, T *__restrict__ ys, T *__restrict__ zs,
+                          T *__restrict__ ws)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cidx[i];
+    if (c < 0) return;
+    const int p = start[c] + rank[i];
+    xs[p] = x[i];
+    ys[p] = y[i];
+    zs[p] = z[i];
+    if (w) ws[p] = w[i];
+}
+
+// One warp per cell: min/max bounds of x,y,z (and of a fourth, unsorted-by-value array `ra` given
+// through the particle permutation) + NaN padding.
+template <typename T>
+__global__ void k_bounds_pad(const int64_t ncells, const int *__restrict__ count, const int *__restrict__ start,
+                             T *__restrict__ xs, T *__restrict__ ys, T *__restrict__ zs, T *__restrict__ ws,
+                             T *__restrict__ bounds)
+{
+    const int64_t cell = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cell >= ncells) return;
+    const int n = count[cell], s = start[cell];
+    const T big = sizeof(T) == 4 ? (T)3.402823466e+38F : (T)1.7976931348623157e+308;
+    T lo[3] = {big, big, big}, hi[3] = {-big, -big, -big};
+    for (int k = lane; k < n; k += 32) {
+        const T v[3] = {xs[s + k], ys[s + k], zs[s + k]};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            lo[a] = v[a] < lo[a] ? v[a] : lo[a];
+            hi[a] = v[a] > hi[a] ? v[a] : hi[a];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+        for (int off = 16; off > 0; off >>= 1) {
+            const T l2 = __shfl_xor_sync(0xffffffffu, lo[a], off), h2 = __shfl_xor_sync(0xffffffffu, hi[a], off);
+            lo[a] = l2 < lo[a] ? l2 : lo[a];
+            hi[a] = h2 > hi[a] ? h2 : hi[a];
+        }
+    if (lane == 0) {
+        T *b = bounds + cell * CFB_NB;
+        for (int a = 0; a < 3; a++) {
+            b[2 * a] = lo[a];
+            b[2 * a + 1] = hi[a];
+        }
+    }
+    const int npad = (n + CFB_PAD - 1) / CFB_PAD * CFB_PAD;
+    const T nanv = sizeof(T) == 4 ? (T)__int_as_float(0x7fc00000) : (T)__longlong_as_double(0x7ff8000000000000LL);
+    if (lane < npad - n) {
+        xs[s + n + lane] = nanv;
+        ys[s + n + lane] = nanv;
+        zs[s + n + lane] = nanv;
+        if (ws) ws[s + n + lane] = (T)0;
+    }
+}
+
+// RA bounds per theta cell (the reference keeps ra_bounds of each cell's particles,
+// gridlink_mocks_impl.c.src:1336-1350); RA is not carried into the sorted SoA, so use atomics on an
+// order-preserving integer image of the value.
+template <typename T>
+__global__ void k_ra_bounds_init(const int64_t ncells, T *bounds)
+{
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const T big = sizeof(T) == 4 ? (T)3.402823466e+38F : (T)1.7976931348623157e+308;
+    bounds[c * CFB_NB + 6] = big;
+    bounds[c * CFB_NB + 7] = -big;
+}
+__device__ __forceinline__ void atomic_min_real(float *a, float v)
+{  // valid for any sign: compare as signed ints when >=0, as unsigned reversed when negative
+    if (v >= 0) atomicMin((int *)a, __float_as_int(v));
+    else atomicMax((unsigned int *)a, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_real(float *a, float v)
+{
+    if (v >= 0) atomicMax((int *)a, __float_as_int(v));
+    else atomicMin((unsigned int *)a, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_real(double *a, double v)
+{
+    if (v >= 0) atomicMin((long long *)a, __double_as_longlong(v));
+    else atomicMax((unsigned long long *)a, (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ void atomic_max_real(double *a, double v)
+{
+    if (v >= 0) atomicMax((long long *)a, __double_as_longlong(v));
+    else atomicMin((unsigned long long *)a, (unsigned long long)__double_as_longlong(v));
+}
+template <typename T>
+__global__ void k_ra_bounds(const int64_t n, const T *__restrict__ ra, const int *__restrict__ cidx, T *bounds)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cidx[i];
+    if (c < 0) return;
+    atomic_min_real(&bounds[(int64_t)c * CFB_NB + 6], ra[i]);
+    atomic_max_real(&bounds[(int64_t)c * CFB_NB + 7], ra[i]);
+}
+
+__global__ void k_fill_tiles(const int64_t ncells, const int *__restrict__ count, const int *__restrict__ tstart,
+                             int *__restrict__ tile_cell, int *__restrict__ tile_off)
+{
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int n = count[c];
+    const int nt = (n + CFB_TILE - 1) / CFB_TILE;
+    const int t0 = tstart[c];
+    for (int t = 0; t < nt; t++) {
+        tile_cell[t0 + t] = (int)c;
+        tile_off[t0 + t] = t * CFB_TILE;
+    }
+}
+
+static inline unsigned int nblocks(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
+
+template <typename T>
+static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells)
+{
+    // scan -> starts / tile ids
+    if (cfb_ensure(S.start, (size_t)ncells * 4)) return 1;
+    if (cfb_ensure(S.tstart, (size_t)ncells * 4)) return 1;
+    unsigned long long *oob = (unsigned long long *)c.scratch.p;
+    long long *totals = (long long *)((char *)c.scratch.p + 64);
+    k_scan_cells<<<1, 1024, 0, c.stream>>>(ncells, (const int *)S.count.p, (int *)S.start.p, (int *)S.tstart.p, totals);
+    c.launches++;
+    CK(cudaGetLastError());
+    long long *h = (long long *)c.pinned;
+    CK(cudaMemcpyAsync(h, c.scratch.p, 64 + 16, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    const unsigned long long n_oob = *(unsigned long long *)h;
+    if (n_oob != 0)
+        return cfb_fail("%llu particles are out of bounds. Check periodic wrapping?", n_oob);  // gridlink_impl.c.src:183
+    S.npad = h[8];
+    S.ntiles = h[9];
+    if (S.npad >= 2147483647LL) return cfb_fail("padded particle count %lld exceeds 2^31", (long long)S.npad);
+    const size_t sb = (size_t)(S.npad > 0 ? S.npad : 1) * sizeof(T);
+    const bool hasw = S.raw[3] != nullptr;
+    for (int a = 0; a < (hasw ? 4 : 3); a++)
+        if (cfb_ensure(S.sorted[a], sb)) return 1;
+    if (S.n > 0) {
+        k_scatter<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(
+            S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2], (const T *)S.raw[3],
+            (const int *)S.cidx.p, (const int *)S.rank.p, (const int *)S.start.p, (T *)S.sorted[0].p,
+            (T *)S.sorted[1].p, (T *)S.sorted[2].p, hasw ? (T *)S.sorted[3].p : nullptr);
+        c.launches++;
+        CK(cudaGetLastError());
+    }
+    k_bounds_pad<T><<<nblocks(ncells * 32, 256), 256, 0, c.stream>>>(
+        ncells, (const int *)S.count.p, (const int *)S.start.p, (T *)S.sorted[0].p, (T *)S.sorted[1].p,
+        (T *)S.sorted[2].p, hasw ? (T *)S.sorted[3].p : nullptr, (T *)S.bounds.p);
+    c.launches++;
+    CK(cudaGetLastError());
+    if (cfb_ensure(S.tile_cell, (size_t)(S.ntiles > 0 ? S.ntiles : 1) * 4)) return 1;
+    if (cfb_ensure(S.tile_off, (size_t)(S.ntiles > 0 ? S.ntiles : 1) * 4)) return 1;
+    k_fill_tiles<<<nblocks(ncells, 256), 256, 0, c.stream>>>(ncells, (const int *)S.count.p, (const int *)S.tstart.p,
+                                                            (int *)S.tile_cell.p, (int *)S.tile_off.p);
+    c.launches++;
+    CK(cudaGetLastError());
+    S.ncells = ncells;
+    S.gridded = true;
+    return 0;
+}
+
+template <typename T>
+static int gridlink_box_T(Ctx &c, ParticleSet &S, const cfb_box_lattice *lat, const int sub[3])
+{
+    BoxGeomT<T> G;
+    int64_t ncells = 1;
+    for (int k = 0; k < 3; k++) {
+        G.lo[k] = (T)lat->lo[k];
+        G.inv[k] = (T)lat->inv[k];
+        G.n[k] = lat->nmesh[k];
+        G.s[k] = sub[k];
+        G.ng[k] = lat->nmesh[k] * sub[k];
+        ncells *= G.ng[k];
+    }
+    if (ncells >= 2147483647LL) return cfb_fail("fine lattice too large (%lld cells)", (long long)ncells);
+    if (cfb_ensure(c.scratch, 4096)) return 1;
+    if (cfb_ensure(S.count, (size_t)ncells * 4)) return 1;
+    if (cfb_ensure(S.bounds, (size_t)ncells * CFB_NB * sizeof(T))) return 1;
+    if (cfb_ensure(S.cidx, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
+    if (cfb_ensure(S.rank, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
+    CK(cudaMemsetAsync(S.count.p, 0, (size_t)ncells * 4, c.stream));
+    CK(cudaMemsetAsync(c.scratch.p, 0, 256, c.stream));
+    if (S.n > 0) {
+        k_cellindex_box<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(
+            S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2], G, (int *)S.cidx.p, (int *)S.rank.p,
+            (int *)S.count.p, (unsigned long long *)c.scratch.p);
+        c.launches++;
+        CK(cudaGetLastError());
+    }
+    return finish_sort<T>(c, S, ncells);
+}
+
+int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3])
+{
+    Ctx &c = cfb_ctx();
+    return S.prec == 4 ? gridlink_box_T<float>(c, S, lat, sub) : gridlink_box_T<double>(c, S, lat, sub);
+}
+
+template <typename T>
+static int gridlink_theta_T(Ctx &c, ParticleSet &S, const cfb_theta_lattice *lat, int64_t ncells)
+{
+    if (!S.raw[4] || !S.raw[5]) return cfb_fail("theta gridlink needs RA and DEC on the device");
+    if (cfb_ensure(c.scratch, 4096)) return 1;
+    if (cfb_ensure(c.ngrid_ra, (size_t)lat->ngrid_dec * 4)) return 1;
+    if (cfb_ensure(c.ra_off, (size_t)lat->ngrid_dec * 4)) return 1;
+    int *h = (int *)c.pinned;
+    int off = 0;
+    for (int i = 0; i < lat->ngrid_dec; i++) {
+        h[i] = lat->ngrid_ra[i];
+        h[lat->ngrid_dec + i] = off;
+        off += lat->ngrid_ra[i];
+    }
+    if (off != ncells) return cfb_fail("theta lattice: cell count mismatch (%d vs %lld)", off, (long long)ncells);
+    CK(cudaMemcpyAsync(c.ngrid_ra.p, h, (size_t)lat->ngrid_dec * 4, cudaMemcpyHostToDevice, c.stream));
+    CK(cudaMemcpyAsync(c.ra_off.p, h + lat->ngrid_dec, (size_t)lat->ngrid_dec * 4, cudaMemcpyHostToDevice, c.stream));
+    if (cfb_ensure(S.count, (size_t)ncells * 4)) return 1;
+    if (cfb_ensure(S.bounds, (size_t)ncells * CFB_NB * sizeof(T))) return 1;
+    if (cfb_ensure(S.cidx, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
+    if (cfb_ensure(S.rank, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
+    CK(cudaMemsetAsync(S.count.p, 0, (size_t)ncells * 4, c.stream));
+    CK(cudaMemsetAsync(c.scratch.p, 0, 256, c.stream));
+    k_cellindex_theta<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(
+        S.n, (const T *)S.raw[4], (const T *)S.raw[5], lat->ngrid_dec, (const int *)c.ngrid_ra.p,
+        (const int *)c.ra_off.p, (T)lat->dec_min, (T)lat->inv_dec_diff, (T)lat->ra_min, (T)lat->inv_ra_diff,
+        (int *)S.cidx.p, (int *)S.rank.p, (int *)S.count.p, (unsigned long long *)c.scratch.p);
+    c.launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c.stream));  // pinned staging reused by finish_sort
+    if (finish_sort<T>(c, S, ncells)) return 1;
+    k_ra_bounds_init<T><<<nblocks(ncells, 256), 256, 0, c.stream>>>(ncells, (T *)S.bounds.p);
+    k_ra_bounds<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(S.n, (const T *)S.raw[4], (const int *)S.cidx.p,
+                                                           (T *)S.bounds.p);
+    c.launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t ncells)
+{
+    Ctx &c = cfb_ctx();
+    return S.prec == 4 ? gridlink_theta_T<float>(c, S, lat, ncells) : gridlink_theta_T<double>(c, S, lat, ncells);
+}

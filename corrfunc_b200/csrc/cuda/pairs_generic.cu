@@ -1,0 +1,435 @@
+// pairs_generic.cu -- the general pair-counting kernel: every statistic, weights and averages.
+//
+// Replaces the per-cell-pair CPU kernels (theory/DD/countpairs_kernels.c.src:25-279 and siblings)
+// together with the cell-pair enumeration of generate_cell_pairs_DOUBLE
+// (utils/gridlink_impl.c.src:439-625), which is done on the fly from lattice coordinates:
+//
+//   block  = one primary tile: up to 128 particles of one fine cell, one per thread, in registers
+//   phase 1: the 128 threads test 128 candidate neighbour cells in parallel (periodic wrap, the
+//            reference's first/second role filter, bounds-based pruning) and queue survivors
+//   phase 2: per queued neighbour, its particles are staged through shared memory (coalesced SoA
+//            loads) and every thread runs its primary against them with the reference's arithmetic:
+//            same subtraction order (second - (first + wrap)), same FMA association per statistic,
+//            comparisons against the squared bin edges, 2-D bin index evaluated in floating point.
+//   histograms are privatised per block in shared memory and merged with 64-bit global atomics.
+//
+// Compiled with -fmad=false: an FMA appears exactly where the reference's AVX-512 kernels have one.
+#include <math_constants.h>
+
+#include "cfb_internal.cuh"
+
+#define GEN_CH 256  // secondaries staged per chunk
+
+template <typename T>
+__device__ __forceinline__ T fma_t(T a, T b, T c);
+template <>
+__device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <>
+__device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+template <typename T>
+__device__ __forceinline__ T sqrt_t(T a);
+template <>
+__device__ __forceinline__ float sqrt_t<float>(float a) { return __fsqrt_rn(a); }
+template <>
+__device__ __forceinline__ double sqrt_t<double>(double a) { return __dsqrt_rn(a); }
+template <typename T>
+__device__ __forceinline__ T divi_t(T a, T b);
+template <>
+__device__ __forceinline__ float divi_t<float>(float a, float b) { return __fdiv_rn(a, b); }
+template <>
+__device__ __forceinline__ double divi_t<double>(double a, double b) { return __ddiv_rn(a, b); }
+
+// utils/fast_acos.h:57-101 (degree-8 estimate, |err| < 3.7e-9)
+template <typename T>
+__device__ __forceinline__ T fast_acos_t(const T x)
+{
+    const T xa = x < 0 ? -x : x;
+    T poly = (T) + 7.1796493341480527e-04;
+    poly = (T)-4.1160981058965262e-03 + poly * xa;
+    poly = (T) + 1.1272900916992512e-02 + poly * xa;
+    poly = (T)-2.0949278766238422e-02 + poly * xa;
+    poly = (T) + 3.2683762943179318e-02 + poly * xa;
+    poly = (T)-5.0625279962389413e-02 + poly * xa;
+    poly = (T) + 8.9034700107934128e-02 + poly * xa;
+    poly = (T)-2.1460143648688035e-01 + poly * xa;
+    poly = (T) + 1.5707963267948966 + poly * xa;
+    poly = poly * sqrt_t<T>((T)1.0 - xa);
+    return (x < 0) ? (T)(3.14159265358979323846 - (double)poly) : poly;
+}
+
+template <typename T>
+struct GenShared {
+    T sx[GEN_CH], sy[GEN_CH], sz[GEN_CH], sw[GEN_CH];
+    int q_cell[CFB_TILE];
+    int q_code[CFB_TILE];
+    int q_n;
+};
+
+template <typename T, int MODE, bool AVG, bool WGT, bool LIST>
+__global__ void __launch_bounds__(CFB_TILE)
+k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // dynamic smem layout: edges | npairs(u64) | sum_sep(double) | sum_w(double)
+    T *s_edges = (T *)smem_raw;
+    const int nedges = P.nedges;
+    size_t off = ((size_t)nedges * sizeof(T) + 15) & ~(size_t)15;
+    unsigned long long *s_np = (unsigned long long *)(smem_raw + off);
+    double *s_sep = nullptr, *s_w = nullptr;
+    if (P.hist_in_smem) {
+        off += (size_t)P.nslots * 8;
+        if (AVG) {
+            s_sep = (double *)(smem_raw + off);
+            off += (size_t)P.nslots * 8;
+        }
+        if (WGT) s_w = (double *)(smem_raw + off);
+    }
+    __shared__ GenShared<T> S;
+
+    // which tile is mine (work sharding across ranks in groups of CFB_SHARD_GROUP tiles)
+    const int64_t grp = (int64_t)blockIdx.x / CFB_SHARD_GROUP;
+    const int64_t tile = (grp * P.shard_n + P.shard_rank) * CFB_SHARD_GROUP + (blockIdx.x % CFB_SHARD_GROUP);
+    if (tile >= P.ntiles) return;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < nedges; i += CFB_TILE) s_edges[i] = ((const T *)P.edges)[i];
+    if (P.hist_in_smem)
+        for (int64_t i = tid; i < P.nslots; i += CFB_TILE) {
+            s_np[i] = 0ULL;
+            if (AVG) s_sep[i] = 0.0;
+            if (WGT) s_w[i] = 0.0;
+        }
+
+    const int cellP = P.tile_cell[tile];
+    const int toff = P.tile_off[tile];
+    const int nP = A.count[cellP];
+    const int startP = A.start[cellP];
+    const int iloc = toff + tid;
+    const bool valid = iloc < nP;
+    const T nanv = sizeof(T) == 4 ? (T)CUDART_NAN_F : (T)CUDART_NAN;
+    T xp = nanv, yp = nanv, zp = nanv, wp = 0;
+    if (valid) {
+        xp = A.x[startP + iloc];
+        yp = A.y[startP + iloc];
+        zp = A.z[startP + iloc];
+        if (WGT) wp = A.w[startP + iloc];
+    }
+    // primary cell bounds (whole fine cell: conservative for the tile)
+    double pb[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) pb[k] = (double)A.bounds[(int64_t)cellP * CFB_NB + k];
+
+    // lattice coordinates of the primary fine cell and its reference cell
+    int gx = 0, gy = 0, gz = 0;
+    long long refA = 0;
+    int ncand;
+    int64_t list0 = 0;
+    if (LIST) {
+        list0 = P.list_off[cellP];
+        ncand = (int)(P.list_off[cellP + 1] - list0);
+    } else {
+        gz = cellP % P.g.ng[2];
+        gy = (cellP / P.g.ng[2]) % P.g.ng[1];
+        gx = cellP / (P.g.ng[2] * P.g.ng[1]);
+        refA = ((long long)(gx / P.g.s[0]) * P.g.n[1] + gy / P.g.s[1]) * P.g.n[2] + gz / P.g.s[2];
+        ncand = (2 * P.g.reach[0] + 1) * (2 * P.g.reach[1] + 1) * (2 * P.g.reach[2] + 1);
+    }
+    const int wy = 2 * P.g.reach[1] + 1, wz = 2 * P.g.reach[2] + 1;
+
+    const T pimax = (T)P.pimax;
+    const T inv_dpi = (T)P.inv_dpi, inv_dmu = (T)P.inv_dmu, sqr_mumax = (T)P.sqr_mumax;
+    const T npi_p1 = (T)(P.npibin + 1), nmu_p1 = (T)(P.nmu_bins + 1);
+    unsigned long long my_eval = 0, my_tp = 0;
+    __syncthreads();
+    const T e_lo = s_edges[0], e_hi = s_edges[nedges - 1];
+
+    for (int base = 0; base < ncand; base += CFB_TILE) {
+        if (tid == 0) S.q_n = 0;
+        __syncthreads();
+        // ---------------- phase 1: candidate test, one candidate per thread ----------------
+        const int cand = base + tid;
+        if (cand < ncand) {
+            int cellQ = -1, code = 0;
+            bool keep = true;
+            double offd[3] = {0.0, 0.0, 0.0};
+            if (LIST) {
+                cellQ = P.list_cells[list0 + cand];
+            } else {
+                const int dz = cand % wz - P.g.reach[2];
+                const int dy = (cand / wz) % wy - P.g.reach[1];
+                const int dx = cand / (wz * wy) - P.g.reach[0];
+                const int t[3] = {gx + dx, gy + dy, gz + dz};
+                int q[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const int ng = P.g.ng[a];
+                    {
+                        // the neighbour must sit in a reference cell within +-refine of the primary's
+                        // (gridlink_impl.c.src:499-518); the fine reach is padded to whole reference cells
+                        const int sa = P.g.s[a];
+                        const int rt = t[a] >= 0 ? t[a] / sa : -((-t[a] + sa - 1) / sa);
+                        const int dref = rt - (a == 0 ? gx : (a == 1 ? gy : gz)) / sa;
+                        if (dref > P.g.refine[a] || dref < -P.g.refine[a]) keep = false;
+                    }
+                    if (P.g.periodic[a]) {
+                        // one image per side at most; further images are exact duplicates the
+                        // reference suppresses (gridlink_utils.h.src:46-72), or fall outside its
+                        // single-wrap index map (gridlink_impl.c.src:500-504)
+                        if (t[a] < -ng || t[a] >= 2 * ng) keep = false;
+                        if (t[a] < 0) {
+                            q[a] = t[a] + ng;
+                            code |= 1 << (2 * a);  // +wrap on the first particle
+                            offd[a] = P.wrap[a];
+                        } else if (t[a] >= ng) {
+                            q[a] = t[a] - ng;
+                            code |= 2 << (2 * a);  // -wrap
+                            offd[a] = -P.wrap[a];
+                        } else
+                            q[a] = t[a];
+                    } else {
+                        if (t[a] < 0 || t[a] >= ng) keep = false;
+                        q[a] = t[a];
+                    }
+                }
+                if (keep) {
+                    cellQ = (q[0] * P.g.ng[1] + q[1]) * P.g.ng[2] + q[2];
+                    if (P.autocorr) {
+                        // reference: skip icell2 > icell (gridlink_impl.c.src:525); inside one reference
+                        // cell the pair (i<j) has i first, so only secondaries at or after the primary
+                        const long long refB =
+                            ((long long)(q[0] / P.g.s[0]) * P.g.n[1] + q[1] / P.g.s[1]) * P.g.n[2] + q[2] / P.g.s[2];
+                        if (refB > refA || (refB == refA && cellQ < cellP)) keep = false;
+                    }
+                }
+            }
+            if (keep && B.count[cellQ] == 0) keep = false;
+            if (keep && !LIST) {
+                // bounds-based pruning (pure optimisation; margins keep it conservative)
+                double qb[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) qb[k] = (double)B.bounds[(int64_t)cellQ * CFB_NB + k];
+                double md[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const double plo = pb[2 * a] + offd[a], phi = pb[2 * a + 1] + offd[a];
+                    double d = 0.0;
+                    if (qb[2 * a] > phi) d = qb[2 * a] - phi;
+                    else if (plo > qb[2 * a + 1]) d = plo - qb[2 * a + 1];
+                    md[a] = d;
+                }
+                const double slack = sizeof(T) == 4 ? 1.0e-5 : 1.0e-12;
+                if (P.max_sep[0] > 0) {
+                    const double s = md[0] * md[0] + md[1] * md[1] + md[2] * md[2];
+                    if (s > P.max_sep[0] * P.max_sep[0] * (1.0 + slack)) keep = false;
+                }
+                if (P.max_sep[1] > 0) {
+                    const double s = md[0] * md[0] + md[1] * md[1];
+                    if (s > P.max_sep[1] * P.max_sep[1] * (1.0 + slack)) keep = false;
+                }
+                if (P.max_sep[2] > 0) {
+                    if (md[2] > P.max_sep[2] * (1.0 + slack)) keep = false;
+                }
+            }
+            if (keep) {
+                const int slot = atomicAdd(&S.q_n, 1);
+                S.q_cell[slot] = cellQ;
+                S.q_code[slot] = code;
+            }
+        }
+        __syncthreads();
+        const int nq_cells = S.q_n;
+        if (tid == 0) my_tp += nq_cells;
+        // ---------------- phase 2: run the tile against each queued neighbour ----------------
+        for (int e = 0; e < nq_cells; e++) {
+            const int cellQ = S.q_cell[e];
+            const int code = S.q_code[e];
+            T xpos = xp, ypos = yp, zpos = zp;
+            if (!LIST) {
+                // first particle gets the wrap: xpos = x0 + off_xwrap (countpairs_kernels.c.src:79-81)
+                const int cx = code & 3, cy = (code >> 2) & 3, cz = (code >> 4) & 3;
+                if (cx) xpos = xp + (cx == 1 ? (T)P.wrap[0] : -(T)P.wrap[0]);
+                if (cy) ypos = yp + (cy == 1 ? (T)P.wrap[1] : -(T)P.wrap[1]);
+                if (cz) zpos = zp + (cz == 1 ? (T)P.wrap[2] : -(T)P.wrap[2]);
+            }
+            const bool tri = P.autocorr && (cellQ == cellP);  // same cell: only j > i
+            const int nQ = B.count[cellQ];
+            const int startQ = B.start[cellQ];
+            if (valid) my_eval += tri ? (unsigned long long)(nQ - 1 - iloc > 0 ? nQ - 1 - iloc : 0) : (unsigned long long)nQ;
+            for (int c0 = 0; c0 < nQ; c0 += GEN_CH) {
+                const int m = min(GEN_CH, nQ - c0);
+                __syncthreads();
+                for (int k = tid; k < m; k += CFB_TILE) {
+                    S.sx[k] = B.x[startQ + c0 + k];
+                    S.sy[k] = B.y[startQ + c0 + k];
+                    S.sz[k] = B.z[startQ + c0 + k];
+                    if (WGT) S.sw[k] = B.w[startQ + c0 + k];
+                }
+                __syncthreads();
+                if (!valid) continue;
+                int k0 = 0;
+                if (tri) {
+                    k0 = iloc + 1 - c0;
+                    if (k0 < 0) k0 = 0;
+                }
+                for (int k = k0; k < m; k++) {
+                    const T dx = S.sx[k] - xpos, dy = S.sy[k] - ypos, dz = S.sz[k] - zpos;
+                    int64_t slot;
+                    T sep = 0;
+                    if (MODE == CFB_DD || MODE == CFB_XI) {
+                        const T r2 = fma_t<T>(dz, dz, fma_t<T>(dy, dy, dx * dx));
+                        if (!(r2 < e_hi && r2 >= e_lo)) continue;
+                        int kb;
+                        for (kb = nedges - 1; kb >= 1; kb--)
+                            if (r2 >= s_edges[kb - 1]) break;
+                        slot = kb;
+                        if (AVG) sep = sqrt_t<T>(r2);
+                    } else if (MODE == CFB_WP) {
+                        const T r2 = fma_t<T>(dy, dy, dx * dx);
+                        if (!(dz > -pimax && dz < pimax)) continue;
+                        if (!(r2 < e_hi && r2 >= e_lo)) continue;
+                        int kb;
+                        for (kb = nedges - 1; kb >= 1; kb--)
+                            if (r2 >= s_edges[kb - 1]) break;
+                        slot = kb;
+                        if (AVG) sep = sqrt_t<T>(r2);
+                    } else if (MODE == CFB_RPPI) {
+                        const T r2 = fma_t<T>(dy, dy, dx * dx);
+                        if (!(dz > -pimax)) continue;
+                        const T adz = dz < 0 ? -dz : dz;
+                        if (!(adz < pimax)) continue;
+                        if (!(r2 < e_hi && r2 >= e_lo)) continue;
+                        int kb;
+                        for (kb = nedges - 1; kb >= 1; kb--)
+                            if (r2 >= s_edges[kb - 1]) break;
+                        // rpbin*(npibin+1) + |dz|*inv_dpi evaluated in T, then truncated
+                        // (countpairs_rp_pi_kernels.c.src:249-256)
+                        const T fin = (T)kb * npi_p1 + adz * inv_dpi;
+                        slot = (int64_t)(int)fin;
+                        if (AVG) sep = sqrt_t<T>(r2);
+                    } else if (MODE == CFB_SMU) {
+                        const T sqr_dz = dz * dz;
+                        const T s2 = fma_t<T>(dx, dx, fma_t<T>(dy, dy, sqr_dz));
+                        if (!(sqr_dz < s2 * sqr_mumax)) continue;
+                        if (!(s2 < e_hi && s2 >= e_lo)) continue;
+                        const T mu = sqrt_t<T>(divi_t<T>(sqr_dz, s2));
+                        int kb;
+                        for (kb = nedges - 1; kb >= 1; kb--)
+                            if (s2 >= s_edges[kb - 1]) break;
+                        const T fin = (T)kb * nmu_p1 + mu * inv_dmu;
+                        slot = (int64_t)(int)fin;
+                        if (AVG) sep = sqrt_t<T>(s2);
+                    } else {  // CFB_THETA: cos(theta) = 1 - chord^2/2, edges are cos(theta_upp) (decreasing)
+                        const T chord2 = fma_t<T>(dz, dz, fma_t<T>(dy, dy, dx * dx));
+                        const T ct = (T)1.0 - (T)0.5 * chord2;
+                        if (!(ct > e_hi && ct <= e_lo)) continue;
+                        int kb;
+                        for (kb = nedges - 1; kb >= 1; kb--)
+                            if (ct <= s_edges[kb - 1]) break;
+                        slot = kb;
+                        if (AVG) {
+                            const T cc = ct >= (T)1.0 ? (T)1.0 : ct;
+                            const T th = P.fast_acos ? fast_acos_t<T>(cc) : (T)acos(cc);
+                            sep = (T)(th * (T)57.29577951308232087679815481410517);
+                        }
+                    }
+                    if (P.hist_in_smem) {
+                        atomicAdd(&s_np[slot], 1ULL);
+                        if (AVG) atomicAdd(&s_sep[slot], (double)sep);
+                        if (WGT) atomicAdd(&s_w[slot], (double)(T)(wp * S.sw[k]));
+                    } else {
+                        atomicAdd(&P.npairs[slot], 1ULL);
+                        if (AVG) atomicAdd(&P.sum_sep[slot], (double)sep);
+                        if (WGT) atomicAdd(&P.sum_w[slot], (double)(T)(wp * S.sw[k]));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---------------- merge ----------------
+    __syncthreads();
+    if (P.hist_in_smem) {
+        for (int64_t i = tid; i < P.nslots; i += CFB_TILE) {
+            const unsigned long long v = s_np[i];
+            if (v) {
+                atomicAdd(&P.npairs[i], v);
+                if (AVG) atomicAdd(&P.sum_sep[i], s_sep[i]);
+                if (WGT) atomicAdd(&P.sum_w[i], s_w[i]);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) my_eval += __shfl_xor_sync(0xffffffffu, my_eval, o);
+    if ((tid & 31) == 0 && my_eval) atomicAdd(&P.counters[0], my_eval);
+    if (tid == 0 && my_tp) atomicAdd(&P.counters[1], my_tp);
+}
+
+template <typename T>
+static SetView<T> view_of(const ParticleSet &S)
+{
+    SetView<T> v;
+    v.x = (const T *)S.sorted[0].p;
+    v.y = (const T *)S.sorted[1].p;
+    v.z = (const T *)S.sorted[2].p;
+    v.w = (const T *)S.sorted[3].p;
+    v.count = (const int *)S.count.p;
+    v.start = (const int *)S.start.p;
+    v.bounds = (const T *)S.bounds.p;
+    return v;
+}
+
+template <typename T, int MODE, bool AVG, bool WGT, bool LIST>
+static int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cudaStream_t st)
+{
+    auto kern = k_pairs_generic<T, MODE, AVG, WGT, LIST>;
+    size_t sm = ((size_t)P.nedges * sizeof(T) + 15) & ~(size_t)15;
+    const size_t hist = (size_t)P.nslots * 8 * (1 + (AVG ? 1 : 0) + (WGT ? 1 : 0));
+    const size_t budget = 160 * 1024;
+    P.hist_in_smem = (sm + hist <= budget) ? 1 : 0;
+    sm += P.hist_in_smem ? hist : 8;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 16384));
+    const int64_t ngroups = (P.ntiles + CFB_SHARD_GROUP - 1) / CFB_SHARD_GROUP;
+    const int64_t mygroups = ngroups > P.shard_rank ? (ngroups - P.shard_rank + P.shard_n - 1) / P.shard_n : 0;
+    const int64_t nblk = mygroups * CFB_SHARD_GROUP;
+    if (nblk <= 0) return 0;
+    if (nblk >= 2147483647LL) return cfb_fail("too many tiles (%lld)", (long long)nblk);
+    kern<<<(unsigned int)nblk, CFB_TILE, sm, st>>>(P, view_of<T>(SA), view_of<T>(SB));
+    cfb_ctx().launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int MODE, bool LIST>
+static int launch_mode(const cfb_binning *bin, const PairParams &P, const ParticleSet &SA, const ParticleSet &SB,
+                       cudaStream_t st)
+{
+    const bool a = bin->need_avg != 0, w = bin->need_weights != 0;
+    if (a && w) return launch_inst<T, MODE, true, true, LIST>(P, SA, SB, st);
+    if (a) return launch_inst<T, MODE, true, false, LIST>(P, SA, SB, st);
+    if (w) return launch_inst<T, MODE, false, true, LIST>(P, SA, SB, st);
+    return launch_inst<T, MODE, false, false, LIST>(P, SA, SB, st);
+}
+
+template <typename T>
+static int launch_T(const cfb_binning *bin, const PairParams &P, bool list_mode)
+{
+    Ctx &c = cfb_ctx();
+    const ParticleSet &SA = c.set[0];
+    const ParticleSet &SB = bin->autocorr ? c.set[0] : c.set[1];
+    if (list_mode) {
+        if (bin->mode != CFB_THETA) return cfb_fail("neighbour-list mode is only used by DDtheta");
+        return launch_mode<T, CFB_THETA, true>(bin, P, SA, SB, c.stream);
+    }
+    switch (bin->mode) {
+    case CFB_DD:
+    case CFB_XI: return launch_mode<T, CFB_DD, false>(bin, P, SA, SB, c.stream);
+    case CFB_WP: return launch_mode<T, CFB_WP, false>(bin, P, SA, SB, c.stream);
+    case CFB_RPPI: return launch_mode<T, CFB_RPPI, false>(bin, P, SA, SB, c.stream);
+    case CFB_SMU: return launch_mode<T, CFB_SMU, false>(bin, P, SA, SB, c.stream);
+    default: return cfb_fail("unknown mode %d", bin->mode);
+    }
+}
+
+int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode)
+{
+    return prec == 4 ? launch_T<float>(bin, P, list_mode) : launch_T<double>(bin, P, list_mode);
+}

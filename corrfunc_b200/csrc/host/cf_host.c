@@ -1,0 +1,370 @@
+/* cf_host.c -- C host layer of libcorrfunc_b200: the reference's public C API, with everything the
+ * reference decides on the host (bins, extents, wrap, refine heuristics, lattice sizes, epilogues)
+ * kept on the host and everything it does per particle / per pair handed to the CUDA layer through
+ * include/corrfunc_b200_device.h.  Precision-specific code lives in cf_host_impl.h, included twice.
+ */
+#define _GNU_SOURCE
+#include <float.h>
+#include <inttypes.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <ctype.h>
+
+#include "corrfunc_b200.h"
+#include "corrfunc_b200_defs.h"
+#include "corrfunc_b200_device.h"
+#include "countpairs.h"
+#include "countpairs_rp_pi.h"
+#include "countpairs_s_mu.h"
+#include "countpairs_theta_mocks.h"
+#include "countpairs_wp.h"
+#include "countpairs_xi.h"
+
+#define CF_PI_OVER_180 0.017453292519943295769236907684886127134428718885417254560971
+#define CF_INV_PI_OVER_180 57.29577951308232087679815481410517033240547246656432154916024
+
+static corrfunc_b200_stats g_stats;
+static corrfunc_b200_reduce_fn g_reduce = NULL;
+static void *g_reduce_user = NULL;
+
+const corrfunc_b200_stats *corrfunc_b200_last_stats(void) { return &g_stats; }
+const char *corrfunc_b200_version(void) { return "corrfunc_b200 0.1.0 (API " CORRFUNC_API_VERSION ")"; }
+void corrfunc_b200_set_shard(int rank, int nranks) { cfb_set_shard(rank, nranks); }
+void corrfunc_b200_set_reduce_hook(corrfunc_b200_reduce_fn fn, void *user)
+{
+    g_reduce = fn;
+    g_reduce_user = user;
+}
+
+static double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+/* The reference stringifies a quoted macro, so its own version string is `"2.5.3"` including the
+ * quote characters (utils/defs.h:27 + common.mk:175); accept both spellings. */
+static int version_ok(const struct config_options *o)
+{
+    const char *v = o->version;
+    if (v[0] == '"') v++;
+    return strncmp(v, CORRFUNC_API_VERSION, strlen(CORRFUNC_API_VERSION)) == 0;
+}
+
+/* Bin file parser: "lo hi" per line, '#' comments; nbin = lines+1, rupp[0] = first low edge
+ * (utils/utils.c:62-106 and :715-745). Returns malloc'ed rupp[nbin+1]. */
+static int64_t count_data_lines(const char *fname)
+{
+    FILE *fp = fopen(fname, "rt");
+    if (!fp) {
+        fprintf(stderr, "Error: could not open bin file `%s'\n", fname);
+        return -1;
+    }
+    char line[10000];
+    int64_t n = 0;
+    while (fgets(line, sizeof(line), fp)) {
+        const char *c = line;
+        while (*c != '\0' && isspace((unsigned char)*c)) c++;
+        if (*c != '\0' && *c != '#') n++;
+    }
+    fclose(fp);
+    return n;
+}
+
+static int cf_setup_bins(const char *fname, double *rmin, double *rmax, int *nbin, double **rupp, const int as_float)
+{
+    const int64_t nl = count_data_lines(fname);
+    if (nl < 0) return EXIT_FAILURE;
+    *nbin = (int)nl + 1;
+    *rupp = calloc((size_t)*nbin + 1, sizeof(double));
+    if (!*rupp) return EXIT_FAILURE;
+    FILE *fp = fopen(fname, "r");
+    if (!fp) {
+        free(*rupp);
+        *rupp = NULL;
+        return EXIT_FAILURE;
+    }
+    char buf[1000];
+    int index = 1;
+    *rmin = 0.0;
+    while (fgets(buf, sizeof(buf), fp)) {
+        double lo, hi;
+        int nread;
+        if (as_float) { /* setup_bins_float parses with %f (utils/utils.c:154-196) */
+            float flo, fhi;
+            nread = sscanf(buf, "%f %f", &flo, &fhi);
+            lo = flo;
+            hi = fhi;
+        } else {
+            nread = sscanf(buf, "%lf %lf", &lo, &hi);
+        }
+        if (nread == 2 && index <= *nbin) {
+            if (index == 1) {
+                *rmin = lo;
+                (*rupp)[0] = lo;
+            }
+            (*rupp)[index++] = hi;
+        }
+    }
+    fclose(fp);
+    *rmax = (*rupp)[index - 1];
+    (*rupp)[*nbin] = *rmax;
+    (*rupp)[*nbin - 1] = *rmax;
+    return EXIT_SUCCESS;
+}
+
+/* raw device histograms -> optional cross-rank sum */
+static int reduce_across_ranks(uint64_t *np, double *ss, double *sw, int64_t nslots)
+{
+    int rank = 0, nranks = 1;
+    cfb_get_shard(&rank, &nranks);
+    if (nranks <= 1) return 0;
+    if (!g_reduce) {
+        fprintf(stderr, "corrfunc_b200> work is sharded over %d ranks but no reduce hook is set; "
+                        "results would be partial\n", nranks);
+        return 1;
+    }
+    return g_reduce(np, ss, sw, nslots, g_reduce_user);
+}
+
+/* what every statistic hands back to its public wrapper (arrays are malloc'ed, caller owns them) */
+typedef struct {
+    int nbin;         /* number of edges = reference's nbin */
+    int n2;           /* npibin / nmu_bins for the 2-D statistics */
+    uint64_t *npairs; /* [nslots] */
+    double *rupp;     /* [nbin] */
+    double *avg;      /* [nslots] */
+    double *wavg;     /* [nslots] */
+    double *cf;       /* [nbin] xi or wp, NULL otherwise */
+} cf_box_out;
+
+#define REAL float
+#define SFX f32
+#define REAL_IS_DOUBLE 0
+#include "cf_host_impl.h"
+#undef REAL
+#undef SFX
+#undef REAL_IS_DOUBLE
+
+#define REAL double
+#define SFX f64
+#define REAL_IS_DOUBLE 1
+#include "cf_host_impl.h"
+#undef REAL
+#undef SFX
+#undef REAL_IS_DOUBLE
+
+/* ------------------------------------------------------------------------------------------ */
+/* public entry points: float/double dispatch like theory/DD/countpairs.c:34-77                 */
+
+static int check_common(const struct config_options *options, const char *fn)
+{
+    if (options == NULL) {
+        fprintf(stderr, "Error: In %s> options can not be NULL\n", fn);
+        return EXIT_FAILURE;
+    }
+    if (!(options->float_type == sizeof(float) || options->float_type == sizeof(double))) {
+        fprintf(stderr, "ERROR: In %s> Can only handle doubles or floats. Got an array of size = %zu\n", fn,
+                options->float_type);
+        return EXIT_FAILURE;
+    }
+    if (!version_ok(options)) {
+        fprintf(stderr, "Error: Do not know this API version = `%s'. Expected version = `%s'\n", options->version,
+                CORRFUNC_API_VERSION);
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}
+
+void free_results(results_countpairs *r)
+{
+    if (!r) return;
+    free(r->npairs); free(r->rupp); free(r->rpavg); free(r->weightavg);
+    r->npairs = NULL; r->rupp = NULL; r->rpavg = NULL; r->weightavg = NULL;
+}
+void free_results_rp_pi(results_countpairs_rp_pi *r)
+{
+    if (!r) return;
+    free(r->npairs); free(r->rupp); free(r->rpavg); free(r->weightavg);
+    r->npairs = NULL; r->rupp = NULL; r->rpavg = NULL; r->weightavg = NULL;
+}
+void free_results_s_mu(results_countpairs_s_mu *r)
+{
+    if (!r) return;
+    free(r->npairs); free(r->supp); free(r->savg); free(r->weightavg);
+    r->npairs = NULL; r->supp = NULL; r->savg = NULL; r->weightavg = NULL;
+}
+void free_results_wp(results_countpairs_wp *r)
+{
+    if (!r) return;
+    free(r->npairs); free(r->rupp); free(r->rpavg); free(r->weightavg); free(r->wp);
+    r->npairs = NULL; r->rupp = NULL; r->rpavg = NULL; r->weightavg = NULL; r->wp = NULL;
+}
+void free_results_xi(results_countpairs_xi *r)
+{
+    if (!r) return;
+    free(r->npairs); free(r->rupp); free(r->ravg); free(r->weightavg); free(r->xi);
+    r->npairs = NULL; r->rupp = NULL; r->ravg = NULL; r->weightavg = NULL; r->xi = NULL;
+}
+void free_results_countpairs_theta(results_countpairs_theta *r)
+{
+    if (!r) return;
+    free(r->npairs); free(r->theta_upp); free(r->theta_avg); free(r->weightavg);
+    r->npairs = NULL; r->theta_upp = NULL; r->theta_avg = NULL; r->weightavg = NULL;
+}
+
+int countpairs(const int64_t ND1, void *X1, void *Y1, void *Z1, const int64_t ND2, void *X2, void *Y2, void *Z2,
+               const int numthreads, const int autocorr, const char *binfile, results_countpairs *results,
+               struct config_options *options, struct extra_options *extra)
+{
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_box_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_box_f32(CFB_DD, ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, binfile, 0.0, 0.0,
+                                    0, 0.0, options, extra, &o)
+                       : cf_box_f64(CFB_DD, ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, binfile, 0.0, 0.0,
+                                    0, 0.0, options, extra, &o);
+    if (st != EXIT_SUCCESS) return st;
+    results->nbin = o.nbin;
+    results->npairs = o.npairs;
+    results->rupp = o.rupp;
+    results->rpavg = o.avg;
+    results->weightavg = o.wavg;
+    free(o.cf);
+    return EXIT_SUCCESS;
+}
+
+int countpairs_rp_pi(const int64_t ND1, void *X1, void *Y1, void *Z1, const int64_t ND2, void *X2, void *Y2, void *Z2,
+                     const int numthreads, const int autocorr, const char *binfile, const double pimax,
+                     results_countpairs_rp_pi *results, struct config_options *options, struct extra_options *extra)
+{
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_box_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_box_f32(CFB_RPPI, ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, binfile, pimax,
+                                    0.0, 0, 0.0, options, extra, &o)
+                       : cf_box_f64(CFB_RPPI, ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, binfile, pimax,
+                                    0.0, 0, 0.0, options, extra, &o);
+    if (st != EXIT_SUCCESS) return st;
+    results->nbin = o.nbin;
+    results->npibin = o.n2;
+    results->pimax = pimax;
+    results->npairs = o.npairs;
+    results->rupp = o.rupp;
+    results->rpavg = o.avg;
+    results->weightavg = o.wavg;
+    free(o.cf);
+    return EXIT_SUCCESS;
+}
+
+int countpairs_s_mu(const int64_t ND1, void *X1, void *Y1, void *Z1, const int64_t ND2, void *X2, void *Y2, void *Z2,
+                    const int numthreads, const int autocorr, const char *sbinfile, const double mu_max,
+                    const int nmu_bins, results_countpairs_s_mu *results, struct config_options *options,
+                    struct extra_options *extra)
+{
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_box_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_box_f32(CFB_SMU, ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, sbinfile, 0.0,
+                                    mu_max, nmu_bins, 0.0, options, extra, &o)
+                       : cf_box_f64(CFB_SMU, ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, sbinfile, 0.0,
+                                    mu_max, nmu_bins, 0.0, options, extra, &o);
+    if (st != EXIT_SUCCESS) return st;
+    results->nsbin = o.nbin;
+    results->nmu_bins = nmu_bins;
+    results->mu_max = mu_max; /* the double the caller passed (countpairs_s_mu_impl.c.src:670) */
+    results->mu_min = 0.0;
+    results->npairs = o.npairs;
+    results->supp = o.rupp;
+    results->savg = o.avg;
+    results->weightavg = o.wavg;
+    free(o.cf);
+    return EXIT_SUCCESS;
+}
+
+int countpairs_wp(const int64_t ND, void *X, void *Y, void *Z, const double boxsize, const int numthreads,
+                  const char *binfile, const double pimax, results_countpairs_wp *results,
+                  struct config_options *options, struct extra_options *extra)
+{
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_box_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_box_f32(CFB_WP, ND, X, Y, Z, 0, NULL, NULL, NULL, numthreads, 1, binfile, pimax, 0.0, 0,
+                                    boxsize, options, extra, &o)
+                       : cf_box_f64(CFB_WP, ND, X, Y, Z, 0, NULL, NULL, NULL, numthreads, 1, binfile, pimax, 0.0, 0,
+                                    boxsize, options, extra, &o);
+    if (st != EXIT_SUCCESS) return st;
+    results->nbin = o.nbin;
+    results->pimax = pimax;
+    results->npairs = o.npairs;
+    results->rupp = o.rupp;
+    results->rpavg = o.avg;
+    results->weightavg = o.wavg;
+    results->wp = o.cf;
+    return EXIT_SUCCESS;
+}
+
+int countpairs_xi(const int64_t ND, void *X, void *Y, void *Z, const double boxsize, const int numthreads,
+                  const char *binfile, results_countpairs_xi *results, struct config_options *options,
+                  struct extra_options *extra)
+{
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_box_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_box_f32(CFB_XI, ND, X, Y, Z, 0, NULL, NULL, NULL, numthreads, 1, binfile, 0.0, 0.0, 0,
+                                    boxsize, options, extra, &o)
+                       : cf_box_f64(CFB_XI, ND, X, Y, Z, 0, NULL, NULL, NULL, numthreads, 1, binfile, 0.0, 0.0, 0,
+                                    boxsize, options, extra, &o);
+    if (st != EXIT_SUCCESS) return st;
+    results->nbin = o.nbin;
+    results->npairs = o.npairs;
+    results->rupp = o.rupp;
+    results->ravg = o.avg;
+    results->weightavg = o.wavg;
+    results->xi = o.cf;
+    return EXIT_SUCCESS;
+}
+
+int countpairs_theta_mocks(const int64_t ND1, void *phi1, void *theta1, const int64_t ND2, void *phi2, void *theta2,
+                           const int numthreads, const int autocorr, const char *binfile,
+                           results_countpairs_theta *results, struct config_options *options,
+                           struct extra_options *extra)
+{
+    if (ND1 == 0 || ND2 == 0) { /* countpairs_theta_mocks_impl.c.src:463-476 */
+        fprintf(stderr, "Warning: Received 0 particles in at least one of the arrays. len(array1) = %" PRId64
+                        " len(array2) = %" PRId64 "\n", ND1, ND2);
+        if (results != NULL) {
+            results->npairs = NULL;
+            results->theta_avg = NULL;
+            results->weightavg = NULL;
+            results->theta_upp = NULL;
+        }
+        return EXIT_SUCCESS;
+    }
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_box_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_theta_f32(ND1, phi1, theta1, ND2, phi2, theta2, numthreads, autocorr, binfile, options,
+                                      extra, &o)
+                       : cf_theta_f64(ND1, phi1, theta1, ND2, phi2, theta2, numthreads, autocorr, binfile, options,
+                                      extra, &o);
+    if (st != EXIT_SUCCESS) return st;
+    results->nbin = o.nbin;
+    results->npairs = o.npairs;
+    results->theta_upp = o.rupp;
+    results->theta_avg = o.avg;
+    results->weightavg = o.wavg;
+    free(o.cf);
+    return EXIT_SUCCESS;
+}

@@ -1,0 +1,834 @@
+/* cf_host_impl.h -- precision-templated host logic (included by cf_host.c with REAL=float|double).
+ *
+ * cf_box_<sfx>   : countpairs / countpairs_rp_pi / countpairs_s_mu / countpairs_wp / countpairs_xi
+ * cf_theta_<sfx> : countpairs_theta_mocks
+ *
+ * All REAL-typed arithmetic below mirrors the type and operation order of the reference's drivers so
+ * that the lattice (nmesh, binsize, inverse), the squared edges and the 2-D bin scale factors come
+ * out bit-identical; file:line citations point at the statement being mirrored.
+ */
+#define HCAT_(a, b) a##_##b
+#define HCAT(a, b) HCAT_(a, b)
+#define HFN(name) HCAT(name, SFX)
+
+#if REAL_IS_DOUBLE
+#define H_COSD(X) cos((X) * CF_PI_OVER_180)
+#define H_SIND(X) sin((X) * CF_PI_OVER_180)
+#define H_ASIN(X) asin(X)
+#define H_FABS(X) fabs(X)
+#define H_MAXPOS DBL_MAX
+#else
+#define H_COSD(X) cosf((X) * CF_PI_OVER_180)
+#define H_SIND(X) sinf((X) * CF_PI_OVER_180)
+#define H_ASIN(X) asinf(X)
+#define H_FABS(X) fabsf(X)
+#define H_MAXPOS FLT_MAX
+#endif
+
+/* get_binsize_DOUBLE (utils/gridlink_utils.c.src:31-49) */
+static int HFN(cf_binsize)(const REAL xdiff, const REAL xwrap, const REAL rmax, const int refine_factor,
+                           const int max_ncells, REAL *xbinsize, int *nlattice)
+{
+    int nmesh = (int)(refine_factor * xdiff / rmax);
+    nmesh = nmesh < 1 ? 1 : nmesh;
+    if (xwrap > 0 && rmax >= xwrap / 2) {
+        fprintf(stderr, "%s> ERROR: rmax=%f must be less than half of periodic boxize=%f to avoid double-counting particles\n",
+                __FILE__, (double)rmax, (double)xwrap);
+        return EXIT_FAILURE;
+    }
+    if (nmesh > max_ncells) nmesh = max_ncells;
+    if (nmesh < 2) nmesh = 2;
+    *xbinsize = xdiff / nmesh;
+    *nlattice = nmesh;
+    return EXIT_SUCCESS;
+}
+
+typedef struct {
+    int nmesh[3];
+    REAL inv[3];
+} HFN(cf_mesh);
+
+/* the sizing part of gridlink_DOUBLE (utils/gridlink_impl.c.src:94-100,156-158) */
+static int HFN(cf_mesh_for)(const REAL lo[3], const REAL hi[3], const REAL maxsize[3], const REAL wrap[3],
+                            const int8_t refine[3], const int max_cells, HFN(cf_mesh) * M)
+{
+    int bad = 0;
+    for (int a = 0; a < 3; a++) {
+        REAL binsize = 0;
+        bad |= HFN(cf_binsize)(hi[a] - lo[a], wrap[a], maxsize[a], refine[a], max_cells, &binsize, &M->nmesh[a]);
+        M->inv[a] = binsize > 0 ? 1.0 / binsize : 0.;
+    }
+    if (bad) {
+        fprintf(stderr, "Received an error status while sizing the lattice. Error\n");
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}
+
+static const void *HFN(host_copy)(const void *p, const int64_t n)
+{ /* the epilogue reads the weights on the host: weight arrays must be host memory (positions may be
+     device memory) */
+    (void)n;
+    return p;
+}
+
+static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, void *Z1, const int64_t ND2, void *X2,
+                       void *Y2, void *Z2, const int numthreads, int autocorr, const char *binfile,
+                       const double pimax_in, const double max_mu, const int nmu_bins, const double boxsize,
+                       struct config_options *options, struct extra_options *extra, cf_box_out *out)
+{
+    (void)numthreads; /* host helper threads are not needed: the per-particle work is on the GPU */
+    const double t_start = now_ms();
+    if (options->float_type != sizeof(REAL)) {
+        fprintf(stderr, "ERROR: In %s> Can only handle arrays of size=%zu. Got an array of size = %zu\n", __func__,
+                sizeof(REAL), options->float_type);
+        return EXIT_FAILURE;
+    }
+    struct extra_options dummy_extra;
+    if (extra == NULL) { /* countpairs_impl.c.src:154-159 */
+        dummy_extra = get_extra_options(NONE);
+        extra = &dummy_extra;
+    }
+    const int need_weightavg = extra->weight_method != NONE;
+    if (need_weightavg && extra->weight_method != PAIR_PRODUCT) {
+        fprintf(stderr, "Error: unknown weight method %d\n", (int)extra->weight_method);
+        return EXIT_FAILURE;
+    }
+    const int is_box = (mode == CFB_XI || mode == CFB_WP);
+    if (is_box) { /* countpairs_xi_impl.c.src:176-178, countpairs_wp_impl.c.src:191-193 */
+        options->periodic = 1;
+        options->autocorr = 1;
+        autocorr = 1;
+    }
+    options->sort_on_z = 1;
+    for (int i = 0; i < 3; i++) {
+        if (options->bin_refine_factors[i] < 1) {
+            fprintf(stderr, "Warning: bin refine factor along axis = %d *must* be >=1. Instead found bin refine factor =%d\n",
+                    i, options->bin_refine_factors[i]);
+            reset_bin_refine_factors(options);
+            break;
+        }
+    }
+    if (options->max_cells_per_dim == 0) {
+        fprintf(stderr, "Warning: Max. cells per dimension is set to 0 - resetting to `NLATMAX' = %d\n", NLATMAX);
+        options->max_cells_per_dim = NLATMAX;
+    }
+    if (mode == CFB_SMU && options->fast_divide_and_NR_steps >= MAX_FAST_DIVIDE_NR_STEPS) {
+        options->fast_divide_and_NR_steps = 0;
+    }
+    if (!(autocorr == 0 || autocorr == 1)) {
+        fprintf(stderr, "Error: Strange value of autocorr = %d. Expected to receive either 1 (auto-correlations) or 0 (cross-correlations)\n", autocorr);
+        return EXIT_FAILURE;
+    }
+
+    /* ---- bins ---- */
+    double *rupp = NULL, rpmin, rpmax;
+    int nrpbin;
+    if (cf_setup_bins(binfile, &rpmin, &rpmax, &nrpbin, &rupp, 0) != EXIT_SUCCESS) return EXIT_FAILURE;
+    if (!(rpmin >= 0.0 && rpmax > 0.0 && rpmin < rpmax && nrpbin > 0)) {
+        fprintf(stderr, "Error: Could not setup with R bins correctly. (rmin = %lf, rmax = %lf, with nbins = %d). "
+                        "Expected non-zero rmin/rmax with rmax > rmin and nbins >=1 \n", rpmin, rpmax, nrpbin);
+        free(rupp);
+        return EXIT_FAILURE;
+    }
+    if (mode == CFB_SMU) { /* countpairs_s_mu_impl.c.src:212-223 */
+        if (max_mu <= 0.0 || max_mu > 1.0) {
+            fprintf(stderr, "Error: max_mu (max. value for the cosine of the angle with line of sight) must be greater than 0 and at most 1).\n"
+                            "The passed value is max_mu = %lf. Please change it to be > 0 and <= 1.0\n", max_mu);
+            free(rupp);
+            return EXIT_FAILURE;
+        }
+        if (nmu_bins < 1) {
+            fprintf(stderr, "Error: Number of mu bins = %d must be at least 1\n", nmu_bins);
+            free(rupp);
+            return EXIT_FAILURE;
+        }
+    }
+    double *rupp_sqr = malloc(sizeof(double) * (size_t)nrpbin);
+    for (int i = 0; i < nrpbin; i++) {
+        const REAL sq = rupp[i] * rupp[i]; /* double product rounded to REAL (countpairs_impl.c.src:435-438) */
+        rupp_sqr[i] = (double)sq;
+    }
+
+    /* ---- particles to the device ---- */
+    const double t_up0 = now_ms();
+    const void *W1 = need_weightavg ? extra->weights0.weights[0] : NULL;
+    const void *W2 = need_weightavg ? extra->weights1.weights[0] : NULL;
+    if (need_weightavg && (W1 == NULL || (!autocorr && W2 == NULL))) {
+        fprintf(stderr, "Error: weight method needs one weight array per particle set\n");
+        free(rupp); free(rupp_sqr);
+        return EXIT_FAILURE;
+    }
+    int status = cfb_upload(0, (int)sizeof(REAL), ND1, X1, Y1, Z1, W1, NULL, NULL);
+    if (status == 0 && !autocorr) status = cfb_upload(1, (int)sizeof(REAL), ND2, X2, Y2, Z2, W2, NULL, NULL);
+    if (status) {
+        free(rupp); free(rupp_sqr);
+        return EXIT_FAILURE;
+    }
+    const double t_up1 = now_ms();
+
+    /* ---- extents, wrap, refine heuristics ---- */
+    REAL lo[3], hi[3], wrap[3], maxsize[3];
+    int periodic[3];
+    REAL pimax = 0, mu_max = 0;
+    int npibin = 0;
+    double max_sep[3] = {-1.0, -1.0, -1.0};
+    if (is_box) {
+        for (int a = 0; a < 3; a++) { /* countpairs_xi_impl.c.src:222-224 */
+            lo[a] = 0.0;
+            hi[a] = boxsize;
+            wrap[a] = boxsize;
+            periodic[a] = 1;
+        }
+        if (mode == CFB_XI) {
+            if (get_bin_refine_scheme(options) == BINNING_DFL && rpmax < 0.05 * boxsize)
+                for (int i = 0; i < 3; i++) options->bin_refine_factors[i] = 1; /* xi_impl:213-219 */
+            maxsize[0] = maxsize[1] = maxsize[2] = rpmax;
+            max_sep[0] = (double)(REAL)rpmax;
+        } else {
+            if (get_bin_refine_scheme(options) == BINNING_DFL) { /* wp_impl:238-247 */
+                if (rpmax < 0.05 * boxsize) options->bin_refine_factors[0] = options->bin_refine_factors[1] = 1;
+                if (pimax_in < 0.05 * boxsize) options->bin_refine_factors[2] = 1;
+            }
+            pimax = pimax_in;
+            maxsize[0] = maxsize[1] = rpmax;
+            maxsize[2] = pimax_in;
+            max_sep[1] = (double)(REAL)rpmax;
+            max_sep[2] = (double)(REAL)pimax_in;
+        }
+    } else {
+        double lohi[6] = {H_MAXPOS, H_MAXPOS, H_MAXPOS, -H_MAXPOS, -H_MAXPOS, -H_MAXPOS};
+        status = cfb_extent(0, 0, lohi); /* get_max_min_DOUBLE, countpairs_impl.c.src:210-224 */
+        if (status == 0 && !autocorr) status = cfb_extent(1, 0, lohi);
+        if (status) {
+            free(rupp); free(rupp_sqr);
+            return EXIT_FAILURE;
+        }
+        for (int a = 0; a < 3; a++) {
+            lo[a] = (REAL)lohi[a];
+            hi[a] = (REAL)lohi[3 + a];
+        }
+        if (options->periodic && options->boxsize == BOXSIZE_NOTGIVEN) { /* countpairs_impl.c.src:231-235 */
+            fprintf(stderr, "boxsize = %g must be specified with periodic wrap. Please specify a non-zero boxsize, or zero to detect the particle extent, or -1 to make a dimension non-periodic.\n",
+                    options->boxsize);
+            free(rupp); free(rupp_sqr);
+            return EXIT_FAILURE;
+        }
+        const double bs[3] = {options->boxsize_x,
+                              options->boxsize_y == BOXSIZE_NOTGIVEN ? options->boxsize : options->boxsize_y,
+                              options->boxsize_z == BOXSIZE_NOTGIVEN ? options->boxsize : options->boxsize_z};
+        for (int a = 0; a < 3; a++) { /* countpairs_impl.c.src:244-251 */
+            periodic[a] = options->periodic && bs[a] >= 0;
+            wrap[a] = periodic[a] ? (bs[a] > 0 ? bs[a] : (hi[a] - lo[a])) : 0.;
+        }
+        if (mode == CFB_DD) {
+            pimax = (REAL)rpmax;
+            if (get_bin_refine_scheme(options) == BINNING_DFL) { /* countpairs_impl.c.src:272-282 */
+                if (rpmax < 0.05 * wrap[0]) options->bin_refine_factors[0] = 1;
+                if (rpmax < 0.05 * wrap[1]) options->bin_refine_factors[1] = 1;
+                if (pimax < 0.05 * wrap[2]) options->bin_refine_factors[2] = 1;
+            }
+            maxsize[0] = maxsize[1] = maxsize[2] = rpmax;
+            max_sep[0] = (double)(REAL)rpmax;
+        } else if (mode == CFB_RPPI) {
+            pimax = pimax_in;
+            npibin = (int)pimax_in; /* countpairs_rp_pi_impl.c.src:188 */
+            if (npibin < 1) {
+                fprintf(stderr, "Error: pimax = %lf must be at least 1 (the pi bins are 1 unit wide)\n", pimax_in);
+                free(rupp); free(rupp_sqr);
+                return EXIT_FAILURE;
+            }
+            if (get_bin_refine_scheme(options) == BINNING_DFL) { /* rp_pi_impl:277-287 */
+                if (rpmax < 0.05 * wrap[0]) options->bin_refine_factors[0] = 1;
+                if (rpmax < 0.05 * wrap[1]) options->bin_refine_factors[1] = 1;
+                if (pimax_in < 0.05 * wrap[2]) options->bin_refine_factors[2] = 1;
+            }
+            maxsize[0] = maxsize[1] = rpmax;
+            maxsize[2] = pimax_in;
+            max_sep[1] = (double)(REAL)rpmax;
+            max_sep[2] = (double)(REAL)pimax_in;
+        } else { /* CFB_SMU: countpairs_s_mu_impl.c.src:231-234 */
+            mu_max = (REAL)max_mu;
+            pimax = rpmax * mu_max;
+            maxsize[0] = maxsize[1] = rpmax;
+            maxsize[2] = pimax;
+            max_sep[0] = (double)(REAL)rpmax;
+            max_sep[2] = (double)pimax;
+        }
+    }
+
+    /* ---- lattice sizes (gridlink's sizing) and the boost heuristic ---- */
+    HFN(cf_mesh) M;
+    if (HFN(cf_mesh_for)(lo, hi, maxsize, wrap, options->bin_refine_factors, options->max_cells_per_dim, &M)) {
+        free(rupp); free(rupp_sqr);
+        return EXIT_FAILURE;
+    }
+    if (mode != CFB_SMU) { /* countpairs_impl.c.src:298-332; DDsmu's boost multiplies by BOOST_BIN_REF=1 (no-op) */
+        const double avg_np = ((double)ND1) / ((double)M.nmesh[0] * M.nmesh[1] * M.nmesh[2]);
+        const int max_nmesh = (int)fmax(M.nmesh[0], fmax(M.nmesh[1], M.nmesh[2]));
+        if ((max_nmesh <= BOOST_CELL_THRESH || avg_np >= BOOST_NUMPART_THRESH) &&
+            max_nmesh < options->max_cells_per_dim && get_bin_refine_scheme(options) == BINNING_DFL) {
+            for (int i = 0; i < 2; i++) options->bin_refine_factors[i] += BOOST_BIN_REF;
+            if (HFN(cf_mesh_for)(lo, hi, maxsize, wrap, options->bin_refine_factors, options->max_cells_per_dim, &M)) {
+                free(rupp); free(rupp_sqr);
+                return EXIT_FAILURE;
+            }
+        }
+    }
+    if (options->verbose)
+        fprintf(stderr, "corrfunc_b200> reference lattice [nmesh_x, nmesh_y, nmesh_z] = %d,%d,%d refine = %d,%d,%d\n",
+                M.nmesh[0], M.nmesh[1], M.nmesh[2], options->bin_refine_factors[0], options->bin_refine_factors[1],
+                options->bin_refine_factors[2]);
+
+    /* ---- device job ---- */
+    cfb_binning B;
+    memset(&B, 0, sizeof(B));
+    B.mode = mode;
+    B.prec = (int)sizeof(REAL);
+    B.autocorr = autocorr;
+    B.nedges = nrpbin;
+    B.edges = rupp_sqr;
+    B.pimax = (double)pimax;
+    B.need_avg = options->need_avg_sep ? 1 : 0;
+    B.need_weights = need_weightavg;
+    int64_t nslots = nrpbin;
+    int n2 = 0;
+    if (mode == CFB_RPPI) { /* countpairs_rp_pi_kernels.c.src:65-66 */
+        const REAL dpi = pimax / npibin;
+        const REAL inv_dpi = 1.0 / dpi;
+        B.npibin = npibin;
+        B.inv_dpi = (double)inv_dpi;
+        n2 = npibin;
+        nslots = (int64_t)(npibin + 1) * (nrpbin + 1);
+    } else if (mode == CFB_SMU) { /* countpairs_s_mu_kernels.c.src:65-68 */
+        const REAL sqr_mumax = mu_max * mu_max;
+        const REAL dmu = mu_max / (REAL)nmu_bins;
+        const REAL inv_dmu = 1.0 / dmu;
+        B.nmu_bins = nmu_bins;
+        B.sqr_mumax = (double)sqr_mumax;
+        B.inv_dmu = (double)inv_dmu;
+        n2 = nmu_bins;
+        nslots = (int64_t)(nmu_bins + 1) * (nrpbin + 1);
+    }
+    B.nslots = nslots;
+    cfb_box_lattice L;
+    memset(&L, 0, sizeof(L));
+    for (int a = 0; a < 3; a++) {
+        L.nmesh[a] = M.nmesh[a];
+        L.refine[a] = options->bin_refine_factors[a];
+        L.periodic[a] = periodic[a];
+        L.lo[a] = (double)lo[a];
+        L.inv[a] = (double)M.inv[a];
+        L.wrap[a] = (double)wrap[a];
+        L.max_sep[a] = options->enable_min_sep_opt ? max_sep[a] : -1.0;
+    }
+    uint64_t *npairs = calloc((size_t)nslots, sizeof(uint64_t));
+    double *sum_sep = calloc((size_t)nslots, sizeof(double));
+    double *sum_w = calloc((size_t)nslots, sizeof(double));
+    if (!npairs || !sum_sep || !sum_w) {
+        free(npairs); free(sum_sep); free(sum_w); free(rupp); free(rupp_sqr);
+        return EXIT_FAILURE;
+    }
+    cfb_hist H = {npairs, sum_sep, sum_w};
+    cfb_stats dst;
+    memset(&dst, 0, sizeof(dst));
+    if (ND1 > 0 && (autocorr || ND2 > 0)) status = cfb_count_box(&B, &L, &H, &dst);
+    if (status == 0) status = reduce_across_ranks(npairs, sum_sep, sum_w, nslots);
+    if (status) {
+        free(npairs); free(sum_sep); free(sum_w); free(rupp); free(rupp_sqr);
+        return EXIT_FAILURE;
+    }
+
+    /* ---- epilogue (countpairs_impl.c.src:609-664 and siblings) ---- */
+    if (autocorr == 1) {
+        for (int64_t i = 0; i < nslots; i++) {
+            npairs[i] *= 2;
+            sum_sep[i] *= 2.0;
+            sum_w[i] *= 2.0;
+        }
+        if (rupp[0] <= 0.0) {
+            const int64_t first = (mode == CFB_RPPI) ? (npibin + 1) : (mode == CFB_SMU ? (nmu_bins + 1) : 1);
+            npairs[first] += (uint64_t)ND1;
+            if (need_weightavg) { /* always index 1, also in the 2-D layouts (rp_pi_impl:641, s_mu_impl:648) */
+                const REAL *w = (const REAL *)HFN(host_copy)(W1, ND1);
+                for (int64_t j = 0; j < ND1; j++) sum_w[1] += (double)(REAL)(w[j] * w[j]);
+            }
+        }
+    }
+    for (int64_t i = 0; i < nslots; i++) {
+        if (npairs[i] > 0) {
+            sum_sep[i] /= (double)npairs[i];
+            sum_w[i] /= (double)npairs[i];
+        }
+        if (!options->need_avg_sep) sum_sep[i] = 0.0;
+        if (!need_weightavg) sum_w[i] = 0.0;
+    }
+
+    out->nbin = nrpbin;
+    out->n2 = n2;
+    out->npairs = npairs;
+    out->avg = sum_sep;
+    out->wavg = sum_w;
+    out->rupp = malloc(sizeof(double) * (size_t)nrpbin);
+    for (int i = 0; i < nrpbin; i++) out->rupp[i] = rupp[i];
+    out->cf = NULL;
+
+    if (is_box) { /* xi: countpairs_xi_impl.c.src:581-625 ; wp: countpairs_wp_impl.c.src:619-664 */
+        out->cf = calloc((size_t)nrpbin, sizeof(double));
+        const int64_t ND = ND1;
+        REAL weightsum = (REAL)ND, weight_sqr_sum = (REAL)ND;
+        if (need_weightavg && extra->weight_method == PAIR_PRODUCT) {
+            const REAL *weights = (const REAL *)HFN(host_copy)(W1, ND1);
+            weightsum = 0;
+            for (int64_t j = 0; j < ND; j++) {
+                weightsum += weights[j];
+                weight_sqr_sum += weights[j] * weights[j];
+            }
+        }
+        const REAL prefac = weightsum * (weightsum - weightsum / ND) / (boxsize * boxsize * boxsize);
+        REAL rlow = 0.0;
+        const REAL twice_pimax = 2.0 * pimax_in;
+        for (int i = 0; i < nrpbin; i++) {
+            REAL weight0 = (REAL)npairs[i];
+            if (need_weightavg && extra->weight_method == PAIR_PRODUCT) weight0 *= out->wavg[i];
+            if (mode == CFB_XI) {
+                const REAL vol = 4.0 / 3.0 * M_PI * (rupp[i] * rupp[i] * rupp[i] - rlow * rlow * rlow);
+                if (vol > 0.0) {
+                    REAL weightrandom = prefac * vol;
+                    if (rlow <= 0.) weightrandom += weight_sqr_sum;
+                    out->cf[i] = (weight0 / weightrandom - 1.0);
+                } else
+                    out->cf[i] = -2.0;
+            } else {
+                const REAL vol = M_PI * (rupp[i] * rupp[i] - rlow * rlow) * twice_pimax;
+                if (vol > 0.0) {
+                    REAL weightrandom = prefac * vol;
+                    if (rlow <= 0.) weightrandom += weight_sqr_sum;
+                    out->cf[i] = (weight0 / weightrandom - 1) * twice_pimax;
+                } else
+                    out->cf[i] = -2.0 * twice_pimax;
+            }
+            rlow = rupp[i];
+        }
+    }
+    free(rupp);
+    free(rupp_sqr);
+
+    g_stats.dev = dst;
+    g_stats.ms_upload = t_up1 - t_up0;
+    for (int a = 0; a < 3; a++) {
+        g_stats.nmesh[a] = M.nmesh[a];
+        g_stats.refine[a] = options->bin_refine_factors[a];
+    }
+    reset_bin_refine_factors(options); /* countpairs_impl.c.src:697 */
+    const double t_end = now_ms();
+    g_stats.ms_host_total = t_end - t_start;
+    if (options->c_api_timer) {
+        /* seconds everywhere except wp, which reports nanoseconds (countpairs_wp_impl.c.src:672-676) */
+        options->c_api_time = (mode == CFB_WP) ? (t_end - t_start) * 1.0e6 : (t_end - t_start) * 1.0e-3;
+    }
+    return EXIT_SUCCESS;
+}
+
+/* ========================================================================================== */
+/* DDtheta                                                                                     */
+
+/* find_closest_pos_DOUBLE (utils/gridlink_utils.c.src:91-113): min 1-D separation of two intervals */
+static REAL HFN(cf_min_sep_1d)(const REAL a[2], const REAL b[2])
+{
+    if (a[0] <= b[1] && b[0] <= a[1]) return 0;
+    REAL m = H_FABS(a[0] - b[0]);
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) {
+            const REAL d = H_FABS(a[i] - b[j]);
+            if (d < m) m = d;
+        }
+    return m;
+}
+
+/* check_ra_dec_DOUBLE (countpairs_theta_mocks_impl.c.src:42-84): shifts the caller's arrays in place */
+static int HFN(cf_check_ra_dec)(const int64_t N, REAL *ra, REAL *dec)
+{
+    if (N == 0) return EXIT_SUCCESS;
+    if (ra == NULL || dec == NULL) {
+        fprintf(stderr, "Input arrays can not be NULL. Have RA = %p DEC = %p\n", (void *)ra, (void *)dec);
+        return EXIT_FAILURE;
+    }
+    int fix_ra = 0, fix_dec = 0;
+    for (int64_t i = 0; i < N; i++) {
+        if (ra[i] < 0.0) fix_ra = 1;
+        if (!(dec[i] <= 180.0)) {
+            fprintf(stderr, "Declination should not be more than 180. Did you swap ra and dec?\n");
+            return EXIT_FAILURE;
+        }
+        if (dec[i] > 90.0) fix_dec = 1;
+    }
+    if (fix_ra) fprintf(stderr, "DDtheta> Out of range values found for ra. Expected ra to be in the range [0.0,360.0]. Found ra values in [-180,180] -- fixing that\n");
+    if (fix_dec) fprintf(stderr, "DDtheta> Out of range values found for dec. Expected dec to be in the range [-90.0,90.0]. Found dec values in [0,180] -- fixing that\n");
+    if (fix_ra || fix_dec)
+        for (int64_t i = 0; i < N; i++) {
+            if (fix_ra) ra[i] += 180.0;
+            if (fix_dec) dec[i] -= 90.0;
+        }
+    return EXIT_SUCCESS;
+}
+
+static int HFN(cf_theta)(const int64_t ND1, void *vra1, void *vdec1, const int64_t ND2, void *vra2, void *vdec2,
+                         const int numthreads, const int autocorr, const char *binfile,
+                         struct config_options *options, struct extra_options *extra, cf_box_out *out)
+{
+    const double t_start = now_ms();
+    REAL *ra1 = vra1, *dec1 = vdec1, *ra2 = vra2, *dec2 = vdec2;
+    if (options->float_type != sizeof(REAL)) return EXIT_FAILURE;
+    struct extra_options dummy_extra;
+    if (extra == NULL) {
+        dummy_extra = get_extra_options(NONE);
+        extra = &dummy_extra;
+    }
+    const int need_weightavg = extra->weight_method != NONE;
+    options->sort_on_z = 1;
+    options->autocorr = autocorr;
+    if (HFN(cf_check_ra_dec)(ND1, ra1, dec1)) return EXIT_FAILURE;
+    if (autocorr == 0 && HFN(cf_check_ra_dec)(ND2, ra2, dec2)) return EXIT_FAILURE;
+
+    double *theta_upp = NULL, thetamin_d, thetamax_d;
+    int nthetabin;
+    /* setup_bins_DOUBLE: the float build parses the file with %f (utils/utils.c:154-196) */
+    if (cf_setup_bins(binfile, &thetamin_d, &thetamax_d, &nthetabin, &theta_upp, !REAL_IS_DOUBLE)) return EXIT_FAILURE;
+    const REAL thetamin = thetamin_d, thetamax = thetamax_d;
+    if (!(thetamin >= 0.0 && thetamax > 0.0 && thetamin < thetamax && thetamax <= 180.0 && nthetabin >= 1)) {
+        fprintf(stderr, "Error: Could not setup with theta bins correctly. (thetamin = %lf, thetamax = %lf, with nbins = %d). Expected non-zero rmin/rmax with thetamax > thetamin and nbins >=1 \n",
+                (double)thetamin, (double)thetamax, nthetabin);
+        free(theta_upp);
+        return EXIT_FAILURE;
+    }
+    /* with OpenMP and !link_in_ra the reference raises the DEC refine factor to numthreads
+       (countpairs_theta_mocks_impl.c.src:543-549); it only changes the lattice, never the result */
+    if (options->link_in_ra == 0 && options->bin_refine_factors[1] < numthreads &&
+        get_bin_refine_scheme(options) == BINNING_DFL)
+        options->bin_refine_factors[1] = numthreads > 127 ? 127 : (int8_t)numthreads;
+    if (options->link_in_ra && options->bin_refine_factors[0] < 1) reset_bin_refine_factors(options);
+    if (options->link_in_dec && options->bin_refine_factors[1] < 1) reset_bin_refine_factors(options);
+    if (options->max_cells_per_dim == 0) options->max_cells_per_dim = NLATMAX;
+
+    double *costheta_upp = malloc(sizeof(double) * (size_t)nthetabin);
+    for (int i = 0; i < nthetabin; i++) {
+        const REAL t = theta_upp[i];
+        const REAL c = H_COSD(t); /* countpairs_theta_mocks_impl.c.src:569-571 */
+        costheta_upp[i] = (double)c;
+    }
+
+    /* RA/DEC -> unit vectors with the host libm, exactly as the reference (impl:576-608);
+       CUDA's sin/cos are not bit-identical to glibc's, so this stays on the host */
+    const int nsets = autocorr ? 1 : 2;
+    REAL *XYZ[2][3] = {{NULL, NULL, NULL}, {NULL, NULL, NULL}};
+    REAL ra_min = H_MAXPOS, dec_min = H_MAXPOS, ra_max = -H_MAXPOS, dec_max = -H_MAXPOS;
+    int status = 0;
+    for (int s = 0; s < nsets && !status; s++) {
+        const int64_t N = s ? ND2 : ND1;
+        const REAL *ra = s ? ra2 : ra1, *dec = s ? dec2 : dec1;
+        for (int a = 0; a < 3; a++) {
+            XYZ[s][a] = malloc(sizeof(REAL) * (size_t)(N > 0 ? N : 1));
+            if (!XYZ[s][a]) status = 1;
+        }
+        if (status) break;
+        REAL *X = XYZ[s][0], *Y = XYZ[s][1], *Z = XYZ[s][2];
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static)
+#endif
+        for (int64_t i = 0; i < N; i++) {
+            X[i] = H_COSD(dec[i]) * H_COSD(ra[i]);
+            Y[i] = H_COSD(dec[i]) * H_SIND(ra[i]);
+            Z[i] = H_SIND(dec[i]);
+        }
+        for (int64_t i = 0; i < N; i++) { /* get_max_min_ra_dec_DOUBLE (gridlink_utils.c.src:74-89) */
+            if (ra[i] < ra_min) ra_min = ra[i];
+            if (dec[i] < dec_min) dec_min = dec[i];
+            if (ra[i] > ra_max) ra_max = ra[i];
+            if (dec[i] > dec_max) dec_max = dec[i];
+        }
+    }
+    int *ngrid_ra = NULL;
+    int64_t *counts[2] = {NULL, NULL};
+    double *rab[2] = {NULL, NULL}, *xyzb[2] = {NULL, NULL};
+    int64_t *ngb_off = NULL;
+    int32_t *ngb = NULL;
+    uint64_t *npairs = NULL;
+    double *sum_sep = NULL, *sum_w = NULL;
+    cfb_stats dst;
+    memset(&dst, 0, sizeof(dst));
+    double t_up = 0;
+    int ngrid_dec = 1;
+
+    if (!status) {
+        /* ---- lattice sizes: gridlink_mocks_theta_ra_dec_DOUBLE (gridlink_mocks_impl.c.src:1024-1148) ---- */
+        const int ra_refine = options->bin_refine_factors[0], dec_refine = options->bin_refine_factors[1];
+        const int max_size = options->max_cells_per_dim;
+        const REAL dec_diff = dec_max - dec_min, ra_diff = ra_max - ra_min;
+        if (options->link_in_dec || options->link_in_ra) {
+            if (!(dec_diff > 0.0)) {
+                fprintf(stderr, "All of the points can not be at the same declination. Declination difference = %lf must be non-zero\n", (double)dec_diff);
+                status = 1;
+            }
+            if (options->link_in_ra && !(ra_diff > 0.0)) {
+                fprintf(stderr, "All of the points can not be at the same RA. RA difference = %lf must be non-zero\n", (double)ra_diff);
+                status = 1;
+            }
+        }
+        if (!status) {
+            if (options->link_in_dec || options->link_in_ra) {
+                const REAL this_ngrid_dec = (dec_diff / thetamax < 1) ? 1 : dec_diff / thetamax;
+                const int this_ngrid_dec_int = ((int)this_ngrid_dec) * dec_refine;
+                ngrid_dec = this_ngrid_dec_int > max_size ? max_size : this_ngrid_dec_int;
+                ngrid_dec = ngrid_dec < 1 ? 1 : ngrid_dec;
+            }
+            ngrid_ra = malloc(sizeof(int) * (size_t)ngrid_dec);
+            const REAL dec_binsize = dec_diff / ngrid_dec;
+            const REAL sin_half_thetamax = H_SIND(0.5 * thetamax);
+            const REAL max_phi_cell = ra_diff;
+            for (int idec = 0; idec < ngrid_dec; idec++) {
+                int nmesh_ra = 1;
+                if (options->link_in_ra) { /* gridlink_mocks_impl.c.src:1081-1147 */
+                    REAL this_min_dec;
+                    const REAL dec_lower = dec_min + idec * dec_binsize;
+                    const REAL dec_upper = dec_lower + dec_binsize;
+                    const REAL cos_dec_upper = H_COSD(dec_upper);
+                    const REAL cos_dec_lower = H_COSD(dec_lower);
+                    REAL cos_min_dec;
+                    if (cos_dec_lower < cos_dec_upper) {
+                        this_min_dec = dec_lower;
+                        cos_min_dec = cos_dec_lower;
+                    } else {
+                        this_min_dec = dec_upper;
+                        cos_min_dec = cos_dec_upper;
+                    }
+                    REAL phi_cell = max_phi_cell;
+                    if ((90.0 - H_FABS(this_min_dec)) > 1.0) {
+                        const REAL _tmp = sin_half_thetamax / cos_min_dec;
+                        const REAL _tmp1 = _tmp < 0 ? 0 : (_tmp > 1.0 ? 1.0 : _tmp);
+                        phi_cell = 2.0 * H_ASIN(_tmp1) * CF_INV_PI_OVER_180;
+                        if (phi_cell <= 0) phi_cell = max_phi_cell;
+                    }
+                    if (!(phi_cell > 0)) {
+                        fprintf(stderr, "Error: Encountered invalid binsize for RA bins for declination bin = %d\n", idec);
+                        status = 1;
+                        break;
+                    }
+                    phi_cell = phi_cell > max_phi_cell ? max_phi_cell : phi_cell;
+                    const REAL this_nmesh_ra = (ra_diff / phi_cell < 1) ? 1 : ra_diff / phi_cell;
+                    const int this_nmesh_ra_int = ((int)this_nmesh_ra) * ra_refine;
+                    nmesh_ra = this_nmesh_ra_int > max_size ? max_size : this_nmesh_ra_int;
+                    if (nmesh_ra < 1) nmesh_ra = 1;
+                }
+                ngrid_ra[idec] = nmesh_ra;
+            }
+        }
+        int64_t ncells = 0;
+        if (!status)
+            for (int i = 0; i < ngrid_dec; i++) ncells += ngrid_ra[i];
+
+        /* ---- upload + GPU gridlink ---- */
+        cfb_theta_lattice TL;
+        memset(&TL, 0, sizeof(TL));
+        if (!status) {
+            TL.ngrid_dec = ngrid_dec;
+            TL.ngrid_ra = ngrid_ra;
+            TL.dec_min = (double)dec_min;
+            const REAL inv_dec_diff = (dec_diff > 0) ? (REAL)(1.0 / dec_diff) : (REAL)0;
+            const REAL inv_ra_diff = (ra_diff > 0) ? (REAL)(1.0 / ra_diff) : (REAL)0;
+            TL.inv_dec_diff = (double)inv_dec_diff;
+            TL.ra_min = (double)ra_min;
+            TL.ra_max = (double)ra_max;
+            TL.inv_ra_diff = (double)inv_ra_diff;
+            TL.ra_refine = ra_refine;
+            TL.dec_refine = dec_refine;
+            const double t0 = now_ms();
+            for (int s = 0; s < nsets && !status; s++) {
+                const int64_t N = s ? ND2 : ND1;
+                const void *W = need_weightavg ? (s ? extra->weights1.weights[0] : extra->weights0.weights[0]) : NULL;
+                if (need_weightavg && !W) {
+                    fprintf(stderr, "Error: weight method needs one weight array per particle set\n");
+                    status = 1;
+                    break;
+                }
+                status = cfb_upload(s, (int)sizeof(REAL), N, XYZ[s][0], XYZ[s][1], XYZ[s][2], W, s ? ra2 : ra1,
+                                    s ? dec2 : dec1);
+                if (status) break;
+                counts[s] = malloc(sizeof(int64_t) * (size_t)ncells);
+                rab[s] = malloc(sizeof(double) * 2 * (size_t)ncells);
+                xyzb[s] = malloc(sizeof(double) * 6 * (size_t)ncells);
+                status = cfb_theta_gridlink(s, (int)sizeof(REAL), &TL, ncells, counts[s], rab[s], xyzb[s]);
+            }
+            t_up = now_ms() - t0;
+        }
+
+        /* ---- neighbour list: generate_cell_pairs_mocks_theta_ra_dec_DOUBLE (gridlink_mocks_impl.c.src:1481-1650)
+                and, without RA linking, generate_cell_pairs_mocks_theta_dec_DOUBLE (:902-1003) ---- */
+        if (!status) {
+            const int s2 = autocorr ? 0 : 1;
+            const REAL sqr_max_chord_sep = 2.0 * (1.0 - H_COSD(thetamax));
+            const REAL inv_ra_diff = (ra_diff > 0) ? (REAL)(1.0 / ra_diff) : (REAL)0;
+            int64_t *ra_off = malloc(sizeof(int64_t) * (size_t)ngrid_dec);
+            int64_t o = 0;
+            for (int i = 0; i < ngrid_dec; i++) {
+                ra_off[i] = o;
+                o += ngrid_ra[i];
+            }
+            size_t cap = (size_t)ncells * 8 + 64, nn = 0;
+            ngb = malloc(sizeof(int32_t) * cap);
+            ngb_off = malloc(sizeof(int64_t) * (size_t)(ncells + 1));
+            for (int idec = 0; idec < ngrid_dec && !status; idec++) {
+                for (int ira = 0; ira < ngrid_ra[idec]; ira++) {
+                    const int64_t icell = ra_off[idec] + ira;
+                    ngb_off[icell] = (int64_t)nn;
+                    if (counts[0][icell] == 0) continue;
+                    const size_t first_nn = nn;
+                    for (int dr = -dec_refine; dr <= dec_refine; dr++) {
+                        const int this_dec = idec + dr;
+                        if (this_dec < 0 || this_dec >= ngrid_dec) continue;
+                        int lo_ra, hi_ra;
+                        if (options->link_in_ra) {
+                            const REAL rb0 = rab[0][2 * icell], rb1 = rab[0][2 * icell + 1];
+                            const int min_ra_this_dec = (int)(ngrid_ra[this_dec] * (rb0 - ra_min) * inv_ra_diff) - 1;
+                            const int max_ra_this_dec = (int)(ngrid_ra[this_dec] * (rb1 - ra_min) * inv_ra_diff) + 1;
+                            lo_ra = min_ra_this_dec - ra_refine;
+                            hi_ra = max_ra_this_dec + ra_refine;
+                        } else {
+                            lo_ra = hi_ra = 0;
+                        }
+                        for (int iira = lo_ra; iira <= hi_ra; iira++) {
+                            int this_ra = iira + ngrid_ra[this_dec];
+                            while (this_ra < 0) this_ra += ngrid_ra[this_dec];
+                            this_ra = this_ra % ngrid_ra[this_dec];
+                            const int64_t icell2 = ra_off[this_dec] + this_ra;
+                            if (counts[s2][icell2] == 0 || (autocorr == 1 && icell2 > icell)) continue;
+                            int dup = 0; /* CHECK_AND_CONTINUE_FOR_DUPLICATE_NGB_CELLS */
+                            for (size_t q = first_nn; q < nn; q++)
+                                if (ngb[q] == (int32_t)icell2) {
+                                    dup = 1;
+                                    break;
+                                }
+                            if (dup) continue;
+                            if (options->enable_min_sep_opt) {
+                                REAL fb[3][2], sb[3][2];
+                                for (int a = 0; a < 3; a++)
+                                    for (int e = 0; e < 2; e++) {
+                                        fb[a][e] = (REAL)xyzb[0][6 * icell + 2 * a + e];
+                                        sb[a][e] = (REAL)xyzb[s2][6 * icell2 + 2 * a + e];
+                                    }
+                                if (options->link_in_ra) {
+                                    const REAL min_dx = HFN(cf_min_sep_1d)(fb[0], sb[0]);
+                                    const REAL min_dy = HFN(cf_min_sep_1d)(fb[1], sb[1]);
+                                    const REAL min_dz = HFN(cf_min_sep_1d)(fb[2], sb[2]);
+                                    const REAL sqr_min_sep_cells = min_dx * min_dx + min_dy * min_dy + min_dz * min_dz;
+                                    if (sqr_min_sep_cells >= sqr_max_chord_sep) continue;
+                                } else if (dr != 0) { /* dec-only linking prunes on z alone (:951-965) */
+                                    const REAL first_z = dr < 0 ? fb[2][0] : fb[2][1];
+                                    const REAL second_z = dr < 0 ? sb[2][1] : sb[2][0];
+                                    const REAL min_dz = first_z - second_z;
+                                    if (min_dz * min_dz >= sqr_max_chord_sep) continue;
+                                }
+                            }
+                            if (nn + 1 > cap) {
+                                cap *= 2;
+                                int32_t *t = realloc(ngb, sizeof(int32_t) * cap);
+                                if (!t) {
+                                    status = 1;
+                                    break;
+                                }
+                                ngb = t;
+                            }
+                            ngb[nn++] = (int32_t)icell2;
+                        }
+                    }
+                }
+            }
+            ngb_off[ncells] = (int64_t)nn;
+            free(ra_off);
+        }
+
+        /* ---- count ---- */
+        if (!status) {
+            cfb_binning B;
+            memset(&B, 0, sizeof(B));
+            B.mode = CFB_THETA;
+            B.prec = (int)sizeof(REAL);
+            B.autocorr = autocorr;
+            B.nedges = nthetabin;
+            B.edges = costheta_upp;
+            B.need_avg = options->need_avg_sep ? 1 : 0;
+            B.need_weights = need_weightavg;
+            B.fast_acos = options->fast_acos;
+            B.nslots = nthetabin;
+            npairs = calloc((size_t)nthetabin, sizeof(uint64_t));
+            sum_sep = calloc((size_t)nthetabin, sizeof(double));
+            sum_w = calloc((size_t)nthetabin, sizeof(double));
+            cfb_hist H = {npairs, sum_sep, sum_w};
+            status = cfb_count_theta(&B, ncells, ngb_off, ngb, &H, &dst);
+            if (!status) status = reduce_across_ranks(npairs, sum_sep, sum_w, nthetabin);
+        }
+    }
+    for (int s = 0; s < 2; s++) {
+        for (int a = 0; a < 3; a++) free(XYZ[s][a]);
+        free(counts[s]); free(rab[s]); free(xyzb[s]);
+    }
+    free(ngrid_ra); free(ngb); free(ngb_off); free(costheta_upp);
+    if (status) {
+        free(npairs); free(sum_sep); free(sum_w); free(theta_upp);
+        return EXIT_FAILURE;
+    }
+
+    /* ---- epilogue (countpairs_theta_mocks_impl.c.src:1125-1203) ---- */
+    if (autocorr == 1) {
+        for (int i = 0; i < nthetabin; i++) {
+            npairs[i] *= 2;
+            sum_sep[i] *= 2.0;
+            sum_w[i] *= 2.0;
+        }
+        if (theta_upp[0] <= 0.0) {
+            npairs[1] += (uint64_t)ND1;
+            if (need_weightavg) {
+                const REAL *w = (const REAL *)extra->weights0.weights[0];
+                for (int64_t j = 0; j < ND1; j++) sum_w[1] += (double)(REAL)(w[j] * w[j]);
+            }
+        }
+    }
+    for (int i = 1; i < nthetabin; i++)
+        if (npairs[i] > 0) {
+            sum_sep[i] /= (double)npairs[i];
+            sum_w[i] /= (double)npairs[i];
+        }
+    for (int i = 0; i < nthetabin; i++) {
+        if (!options->need_avg_sep) sum_sep[i] = 0.0;
+        if (!need_weightavg) sum_w[i] = 0.0;
+    }
+    out->nbin = nthetabin;
+    out->n2 = 0;
+    out->npairs = npairs;
+    out->avg = sum_sep;
+    out->wavg = sum_w;
+    out->rupp = malloc(sizeof(double) * (size_t)nthetabin);
+    for (int i = 0; i < nthetabin; i++) out->rupp[i] = theta_upp[i];
+    out->cf = NULL;
+    free(theta_upp);
+
+    g_stats.dev = dst;
+    g_stats.ms_upload = t_up;
+    g_stats.nmesh[0] = ngrid_dec;
+    g_stats.nmesh[1] = g_stats.nmesh[2] = 0;
+    for (int a = 0; a < 3; a++) g_stats.refine[a] = options->bin_refine_factors[a];
+    reset_bin_refine_factors(options);
+    const double t_end = now_ms();
+    g_stats.ms_host_total = t_end - t_start;
+    if (options->c_api_timer) options->c_api_time = (t_end - t_start) * 1.0e-3;
+    return EXIT_SUCCESS;
+}
+
+#undef H_COSD
+#undef H_SIND
+#undef H_ASIN
+#undef H_FABS
+#undef H_MAXPOS
+#undef HCAT_
+#undef HCAT
+#undef HFN

@@ -652,6 +652,327 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
     return EXIT_SUCCESS;
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* DDtheta: mocks/DDtheta_mocks/countpairs_theta_mocks_impl.c.src:456-1203 with the RA/DEC lattice */
+/* of utils/gridlink_mocks_impl.c.src:1006-1650 (link_in_ra) / :552-1003 (DEC only) / one cell.   */
+static REAL FN(o_min_sep_1d)(const REAL a[2], const REAL b[2])
+{ /* find_closest_pos_DOUBLE, utils/gridlink_utils.c.src:91-113 */
+    if (a[0] <= b[1] && b[0] <= a[1]) return 0;
+    REAL m = FABS_R(a[0] - b[0]);
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) {
+            const REAL d = FABS_R(a[i] - b[j]);
+            if (d < m) m = d;
+        }
+    return m;
+}
+
+typedef struct {
+    int64_t ncells;
+    FN(ocell) * cells;
+    REAL *x, *y, *z, *w;
+} FN(othlat);
+
+static FN(othlat) * FN(o_theta_gridlink)(const int64_t N, const REAL *RA, const REAL *DEC, const REAL *W,
+                                          const int ngrid_dec, const int *ngrid_ra, const int64_t *ra_off,
+                                          const int64_t ncells, const REAL dec_min, const REAL inv_dec_diff,
+                                          const REAL ra_min, const REAL inv_ra_diff)
+{
+    FN(othlat) *L = calloc(1, sizeof(*L));
+    L->ncells = ncells;
+    L->cells = calloc(ncells, sizeof(*L->cells));
+    L->x = malloc(sizeof(REAL) * N);
+    L->y = malloc(sizeof(REAL) * N);
+    L->z = malloc(sizeof(REAL) * N);
+    L->w = W ? malloc(sizeof(REAL) * N) : NULL;
+    int64_t *idx = malloc(sizeof(int64_t) * N);
+    for (int64_t i = 0; i < N; i++) { /* gridlink_mocks_impl.c.src:1249-1263 */
+        int idec = (int)(ngrid_dec * (DEC[i] - dec_min) * inv_dec_diff);
+        if (idec >= ngrid_dec) idec--;
+        int ira = (int)(ngrid_ra[idec] * (RA[i] - ra_min) * inv_ra_diff);
+        if (ira >= ngrid_ra[idec]) ira--;
+        if (idec < 0 || idec >= ngrid_dec || ira < 0 || ira >= ngrid_ra[idec]) {
+            fprintf(stderr, "oracle> theta cell index out of range\n");
+            return NULL;
+        }
+        idx[i] = ra_off[idec] + ira;
+        L->cells[idx[i]].n++;
+    }
+    int64_t off = 0;
+    for (int64_t c = 0; c < ncells; c++) {
+        FN(ocell) *q = &L->cells[c];
+        q->start = off;
+        off += q->n;
+        q->n = 0;
+        q->xb[0] = q->yb[0] = q->zb[0] = q->rab[0] = q->decb[0] = MAXPOS_R;
+        q->xb[1] = q->yb[1] = q->zb[1] = q->rab[1] = q->decb[1] = -MAXPOS_R;
+    }
+    for (int64_t i = 0; i < N; i++) {
+        FN(ocell) *q = &L->cells[idx[i]];
+        const int64_t p = q->start + q->n++;
+        /* unit vectors with the host libm (countpairs_theta_mocks_impl.c.src:587-591) */
+        const REAL X = COSD_R(DEC[i]) * COSD_R(RA[i]);
+        const REAL Y = COSD_R(DEC[i]) * SIND_R(RA[i]);
+        const REAL Z = SIND_R(DEC[i]);
+        L->x[p] = X;
+        L->y[p] = Y;
+        L->z[p] = Z;
+        if (W) L->w[p] = W[i];
+        if (X < q->xb[0]) q->xb[0] = X;
+        if (Y < q->yb[0]) q->yb[0] = Y;
+        if (Z < q->zb[0]) q->zb[0] = Z;
+        if (X > q->xb[1]) q->xb[1] = X;
+        if (Y > q->yb[1]) q->yb[1] = Y;
+        if (Z > q->zb[1]) q->zb[1] = Z;
+        if (RA[i] < q->rab[0]) q->rab[0] = RA[i];
+        if (RA[i] > q->rab[1]) q->rab[1] = RA[i];
+    }
+    free(idx);
+    return L;
+}
+
+static void FN(o_free_thlat)(FN(othlat) * L)
+{
+    if (!L) return;
+    free(L->cells);
+    free(L->x);
+    free(L->y);
+    free(L->z);
+    free(L->w);
+    free(L);
+}
+
+/* RA1/DEC1 (and RA2/DEC2) must already be in [0,360] / [-90,90]; theta_upp[] are the nbin edges in
+ * degrees (for REAL=float they must be float-representable, as setup_bins_float would produce). */
+int FN(oracle_theta)(const int64_t ND1, const REAL *RA1, const REAL *DEC1, const REAL *W1, const int64_t ND2,
+                     const REAL *RA2, const REAL *DEC2, const REAL *W2, const int autocorr, const int nbin,
+                     const double *theta_upp, const int link_in_dec, const int link_in_ra, const int ra_refine,
+                     const int dec_refine, int max_cells, const int enable_min_sep, const int need_avg,
+                     const int need_w, const int fast_acos, uint64_t *npairs_out, double *avg_out,
+                     double *wavg_out, int *lattice_out /* ngrid_dec, ncells, ncellpairs */)
+{
+    if (max_cells == 0) max_cells = 100;
+    const REAL thetamax = theta_upp[nbin - 1];
+    REAL *cosup = malloc(sizeof(REAL) * nbin);
+    for (int i = 0; i < nbin; i++) {
+        const REAL t = theta_upp[i];
+        cosup[i] = COSD_R(t);
+    }
+    REAL ra_min = MAXPOS_R, dec_min = MAXPOS_R, ra_max = -MAXPOS_R, dec_max = -MAXPOS_R;
+    for (int s = 0; s < (autocorr ? 1 : 2); s++) {
+        const int64_t n = s ? ND2 : ND1;
+        const REAL *ra = s ? RA2 : RA1, *dec = s ? DEC2 : DEC1;
+        for (int64_t i = 0; i < n; i++) {
+            if (ra[i] < ra_min) ra_min = ra[i];
+            if (dec[i] < dec_min) dec_min = dec[i];
+            if (ra[i] > ra_max) ra_max = ra[i];
+            if (dec[i] > dec_max) dec_max = dec[i];
+        }
+    }
+    const REAL dec_diff = dec_max - dec_min, ra_diff = ra_max - ra_min;
+    int ngrid_dec = 1;
+    if (link_in_dec || link_in_ra) { /* gridlink_mocks_impl.c.src:1061-1066 */
+        const REAL this_ngrid_dec = (dec_diff / thetamax < 1) ? 1 : dec_diff / thetamax;
+        const int this_ngrid_dec_int = ((int)this_ngrid_dec) * dec_refine;
+        ngrid_dec = this_ngrid_dec_int > max_cells ? max_cells : this_ngrid_dec_int;
+        ngrid_dec = ngrid_dec < 1 ? 1 : ngrid_dec;
+    }
+    int *ngrid_ra = malloc(sizeof(int) * ngrid_dec);
+    int64_t *ra_off = malloc(sizeof(int64_t) * ngrid_dec);
+    const REAL dec_binsize = dec_diff / ngrid_dec;
+    const REAL sin_half_thetamax = SIND_R(0.5 * thetamax);
+    const REAL max_phi_cell = ra_diff;
+    int64_t ncells = 0;
+    for (int idec = 0; idec < ngrid_dec; idec++) { /* gridlink_mocks_impl.c.src:1081-1147 */
+        int nmesh_ra = 1;
+        if (link_in_ra) {
+            REAL this_min_dec, cos_min_dec;
+            const REAL dec_lower = dec_min + idec * dec_binsize;
+            const REAL dec_upper = dec_lower + dec_binsize;
+            const REAL cos_dec_upper = COSD_R(dec_upper);
+            const REAL cos_dec_lower = COSD_R(dec_lower);
+            if (cos_dec_lower < cos_dec_upper) {
+                this_min_dec = dec_lower;
+                cos_min_dec = cos_dec_lower;
+            } else {
+                this_min_dec = dec_upper;
+                cos_min_dec = cos_dec_upper;
+            }
+            REAL phi_cell = max_phi_cell;
+            if ((90.0 - FABS_R(this_min_dec)) > 1.0) {
+                const REAL _tmp = sin_half_thetamax / cos_min_dec;
+                const REAL _tmp1 = _tmp < 0 ? 0 : (_tmp > 1.0 ? 1.0 : _tmp);
+                phi_cell = 2.0 * ASIN_R(_tmp1) * ORC_INV_PI_OVER_180;
+                if (phi_cell <= 0) phi_cell = max_phi_cell;
+            }
+            phi_cell = phi_cell > max_phi_cell ? max_phi_cell : phi_cell;
+            const REAL this_nmesh_ra = (ra_diff / phi_cell < 1) ? 1 : ra_diff / phi_cell;
+            const int this_nmesh_ra_int = ((int)this_nmesh_ra) * ra_refine;
+            nmesh_ra = this_nmesh_ra_int > max_cells ? max_cells : this_nmesh_ra_int;
+            if (nmesh_ra < 1) nmesh_ra = 1;
+        }
+        ngrid_ra[idec] = nmesh_ra;
+        ra_off[idec] = ncells;
+        ncells += nmesh_ra;
+    }
+    const REAL inv_dec_diff = dec_diff > 0 ? (REAL)(1.0 / dec_diff) : (REAL)0;
+    const REAL inv_ra_diff = ra_diff > 0 ? (REAL)(1.0 / ra_diff) : (REAL)0;
+    FN(othlat) *L1 = FN(o_theta_gridlink)(ND1, RA1, DEC1, need_w ? W1 : NULL, ngrid_dec, ngrid_ra, ra_off, ncells,
+                                          dec_min, inv_dec_diff, ra_min, inv_ra_diff);
+    FN(othlat) *L2 = L1;
+    if (!autocorr)
+        L2 = FN(o_theta_gridlink)(ND2, RA2, DEC2, need_w ? W2 : NULL, ngrid_dec, ngrid_ra, ra_off, ncells, dec_min,
+                                  inv_dec_diff, ra_min, inv_ra_diff);
+    if (!L1 || !L2) return EXIT_FAILURE;
+
+    /* cell pairs: gridlink_mocks_impl.c.src:1481-1650 (RA+DEC) and :902-1003 (DEC only) */
+    const REAL sqr_max_chord_sep = 2.0 * (1.0 - COSD_R(thetamax));
+    size_t cap = (size_t)ncells * 8 + 64, np = 0;
+    int64_t *pc1 = malloc(sizeof(int64_t) * cap), *pc2 = malloc(sizeof(int64_t) * cap);
+    for (int idec = 0; idec < ngrid_dec; idec++) {
+        for (int ira = 0; ira < ngrid_ra[idec]; ira++) {
+            const int64_t icell = ra_off[idec] + ira;
+            const FN(ocell) *first = &L1->cells[icell];
+            if (first->n == 0) continue;
+            const size_t first_np = np;
+            for (int dr = -dec_refine; dr <= dec_refine; dr++) {
+                const int this_dec = idec + dr;
+                if (this_dec < 0 || this_dec >= ngrid_dec) continue;
+                int lo_ra = 0, hi_ra = 0;
+                if (link_in_ra) {
+                    const int min_ra = (int)(ngrid_ra[this_dec] * (first->rab[0] - ra_min) * inv_ra_diff) - 1;
+                    const int max_ra = (int)(ngrid_ra[this_dec] * (first->rab[1] - ra_min) * inv_ra_diff) + 1;
+                    lo_ra = min_ra - ra_refine;
+                    hi_ra = max_ra + ra_refine;
+                }
+                for (int iira = lo_ra; iira <= hi_ra; iira++) {
+                    int this_ra = iira + ngrid_ra[this_dec];
+                    while (this_ra < 0) this_ra += ngrid_ra[this_dec];
+                    this_ra = this_ra % ngrid_ra[this_dec];
+                    const int64_t icell2 = ra_off[this_dec] + this_ra;
+                    const FN(ocell) *second = &L2->cells[icell2];
+                    if (second->n == 0 || (autocorr == 1 && icell2 > icell)) continue;
+                    int dup = 0;
+                    for (size_t q = first_np; q < np; q++)
+                        if (pc2[q] == icell2) {
+                            dup = 1;
+                            break;
+                        }
+                    if (dup) continue;
+                    if (enable_min_sep) {
+                        if (link_in_ra) {
+                            const REAL mx = FN(o_min_sep_1d)(first->xb, second->xb);
+                            const REAL my = FN(o_min_sep_1d)(first->yb, second->yb);
+                            const REAL mz = FN(o_min_sep_1d)(first->zb, second->zb);
+                            if (mx * mx + my * my + mz * mz >= sqr_max_chord_sep) continue;
+                        } else if (dr != 0) {
+                            const REAL fz = dr < 0 ? first->zb[0] : first->zb[1];
+                            const REAL sz = dr < 0 ? second->zb[1] : second->zb[0];
+                            const REAL mz = fz - sz;
+                            if (mz * mz >= sqr_max_chord_sep) continue;
+                        }
+                    }
+                    if (np + 1 > cap) {
+                        cap *= 2;
+                        pc1 = realloc(pc1, sizeof(int64_t) * cap);
+                        pc2 = realloc(pc2, sizeof(int64_t) * cap);
+                    }
+                    pc1[np] = icell;
+                    pc2[np] = icell2;
+                    np++;
+                }
+            }
+        }
+    }
+    if (lattice_out) {
+        lattice_out[0] = ngrid_dec;
+        lattice_out[1] = (int)ncells;
+        lattice_out[2] = (int)np;
+    }
+    FN(okern) K;
+    memset(&K, 0, sizeof(K));
+    K.mode = ORC_THETA;
+    K.nbin = nbin;
+    K.edges = cosup;
+    K.need_avg = need_avg;
+    K.need_w = need_w;
+    K.fast_acos = fast_acos;
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    uint64_t *tn = calloc((size_t)nthreads * nbin, sizeof(uint64_t));
+    double *ta = calloc((size_t)nthreads * nbin, sizeof(double));
+    double *tw = calloc((size_t)nthreads * nbin, sizeof(double));
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        FN(okern) k = K;
+        k.npairs = tn + (size_t)tid * nbin;
+        k.avg = ta + (size_t)tid * nbin;
+        k.wavg = tw + (size_t)tid * nbin;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic)
+#endif
+        for (int64_t p = 0; p < (int64_t)np; p++) {
+            const FN(ocell) *a = &L1->cells[pc1[p]], *b = &L2->cells[pc2[p]];
+            FN(o_count_cellpair)(&k, a->n, L1->x + a->start, L1->y + a->start, L1->z + a->start,
+                                 need_w ? L1->w + a->start : NULL, b->n, L2->x + b->start, L2->y + b->start,
+                                 L2->z + b->start, need_w ? L2->w + b->start : NULL,
+                                 (autocorr && pc1[p] == pc2[p]) ? 1 : 0, 0, 0, 0);
+        }
+    }
+    for (int i = 0; i < nbin; i++) {
+        npairs_out[i] = 0;
+        avg_out[i] = 0;
+        wavg_out[i] = 0;
+        for (int t = 0; t < nthreads; t++) {
+            npairs_out[i] += tn[(size_t)t * nbin + i];
+            avg_out[i] += ta[(size_t)t * nbin + i];
+            wavg_out[i] += tw[(size_t)t * nbin + i];
+        }
+    }
+    free(tn);
+    free(ta);
+    free(tw);
+    free(pc1);
+    free(pc2);
+    /* epilogue: countpairs_theta_mocks_impl.c.src:1125-1180 */
+    if (autocorr) {
+        for (int i = 0; i < nbin; i++) {
+            npairs_out[i] *= 2;
+            avg_out[i] *= 2.0;
+            wavg_out[i] *= 2.0;
+        }
+        if (theta_upp[0] <= 0.0) {
+            npairs_out[1] += ND1;
+            if (need_w)
+                for (int64_t j = 0; j < ND1; j++) wavg_out[1] += (double)(REAL)(W1[j] * W1[j]);
+        }
+    }
+    for (int i = 1; i < nbin; i++)
+        if (npairs_out[i] > 0) {
+            avg_out[i] /= (double)npairs_out[i];
+            wavg_out[i] /= (double)npairs_out[i];
+        }
+    if (!need_avg)
+        for (int i = 0; i < nbin; i++) avg_out[i] = 0;
+    if (!need_w)
+        for (int i = 0; i < nbin; i++) wavg_out[i] = 0;
+    if (L2 != L1) FN(o_free_thlat)(L2);
+    FN(o_free_thlat)(L1);
+    free(ngrid_ra);
+    free(ra_off);
+    free(cosup);
+    return EXIT_SUCCESS;
+}
+
 #undef FMA_R
 #undef SQRT_R
 #undef FABS_R

@@ -101,3 +101,66 @@ def oracle_theory(stat, X1, Y1, Z1, bins, *, w1=None, X2=None, Y2=None, Z2=None,
         g = lambda a: a.reshape(nbin + 1, nmu_bins + 1)[1:nbin, :nmu_bins].copy()
         return dict(npairs=g(npairs), ravg=g(avg), weightavg=g(wavg), lattice=lat)
     return dict(npairs=npairs[1:], ravg=avg[1:], weightavg=wavg[1:], cf=cf[1:], lattice=lat)
+
+
+def oracle_theta(RA1, DEC1, bins, *, w1=None, RA2=None, DEC2=None, w2=None, autocorr=True, link_in_dec=True,
+                 link_in_ra=True, ra_refine=2, dec_refine=2, max_cells=100, enable_min_sep=True, need_avg=False,
+                 weight_type=None, fast_acos=False, nthreads=None):
+    """DDtheta oracle.  RA in [0,360], DEC in [-90,90] expected (the wrappers' fix_ra_dec does that)."""
+    lib = load_oracle()
+    if nthreads:
+        lib.oracle_set_num_threads(int(nthreads))
+    dtype = np.asarray(RA1).dtype
+    fn = lib.oracle_theta_double if dtype == np.float64 else lib.oracle_theta_float
+    fn.restype = C.c_int
+    RA1, DEC1, w1, RA2, DEC2, w2 = [None if a is None else np.ascontiguousarray(a, dtype=dtype)
+                                    for a in (RA1, DEC1, w1, RA2, DEC2, w2)]
+    edges = np.sort(np.asarray(bins, dtype=np.float64))
+    if dtype == np.float32:  # setup_bins_float parses the file with %f
+        edges = edges.astype(np.float32).astype(np.float64)
+    nbin = edges.size
+    npairs = np.zeros(nbin, dtype=np.uint64)
+    avg = np.zeros(nbin)
+    wavg = np.zeros(nbin)
+    lat = np.zeros(3, dtype=np.int32)
+    need_w = weight_type is not None
+    st = fn(C.c_int64(RA1.size), _p(RA1), _p(DEC1), _p(w1), C.c_int64(0 if RA2 is None else RA2.size), _p(RA2),
+            _p(DEC2), _p(w2), C.c_int(int(autocorr)), C.c_int(nbin), _p(edges), C.c_int(int(link_in_dec)),
+            C.c_int(int(link_in_ra)), C.c_int(ra_refine), C.c_int(dec_refine), C.c_int(max_cells),
+            C.c_int(int(enable_min_sep)), C.c_int(int(need_avg)), C.c_int(int(need_w)), C.c_int(int(fast_acos)),
+            _p(npairs), _p(avg), _p(wavg), _p(lat))
+    if st != 0:
+        raise RuntimeError("oracle_theta failed")
+    return dict(npairs=npairs[1:], ravg=avg[1:], weightavg=wavg[1:], lattice=lat)
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def load_bins_file(name):
+    b = np.loadtxt(os.path.join(GOLDEN, name))
+    return np.concatenate([b[:1, 0], b[:, 1]])
+
+
+def load_mr19_mock():
+    d = np.load(os.path.join(GOLDEN, "Mr19_mock_northonly_radecw.npz"))
+    return d["ra"], d["dec"], d["w"]
+
+
+def load_wtheta_golden():
+    g = np.loadtxt(os.path.join(GOLDEN, "Mr19_mock_wtheta_DD.txt"))
+    return dict(npairs=g[:, 0].astype(np.uint64), ravg=g[:, 1], weightavg=g[:, 4])
+
+
+def sphere_points(seed, n, dtype):
+    rng = np.random.default_rng(seed)
+    ra = (360.0 * rng.random(n)).astype(dtype)
+    dec = np.degrees(np.arcsin(2.0 * rng.random(n) - 1.0)).astype(dtype)
+    return ra, dec
+
+
+def box_points(seed, n, boxsize, dtype):
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((3, n)) * boxsize).astype(dtype)
+    w = (1.0 - rng.random(n)).astype(dtype)
+    return pos[0], pos[1], pos[2], w

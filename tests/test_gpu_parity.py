@@ -1,0 +1,349 @@
+"""GPU parity tests: the CUDA path, called through the C ABI / the Python drop-in wrappers, against
+  (1) the CPU oracle (oracle/libpairs_oracle.so) on the same seeded inputs,
+  (2) committed golden outputs of the unmodified reference (tests/golden/ref_synthetic_*.npz, the
+      reference's own Mr19 DDtheta golden file),
+  (3) the unmodified reference itself (oracle/_ref) when the prebuilt library travelled to the box,
+  (4) the reference's data-free known-answer tests (Corrfunc/tests/test_theory.py:115-286).
+Bar: npairs bit-exact (double AND float on these inputs); averages within 1e-10 (double) / 1e-5 (float)
+relative -- the tolerances BASELINE.json's north_star states.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-10, np.float32: 1e-5}
+
+
+def _theory():
+    import corrfunc_b200.theory as T
+
+    return T
+
+
+def _close(a, b, tol, what):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(b), 1e-300)
+    rel = np.abs(a - b) / scale
+    # bins with no pairs hold 0 in both
+    rel[(a == 0) & (b == 0)] = 0
+    assert rel.max() <= tol, "%s: max rel diff %.3e > %.1e" % (what, rel.max(), tol)
+
+
+@pytest.fixture(scope="module")
+def edges():
+    return H.load_bins_file("theory_bins.txt")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("autocorr", [1, 0])
+@pytest.mark.parametrize("weights", [False, True])
+def test_DD_vs_oracle(dtype, periodic, autocorr, weights, edges):
+    T = _theory()
+    L, N = 420.0, 30000
+    x, y, z, w = H.box_points(11, N, L, dtype)
+    x2, y2, z2, w2 = H.box_points(12, N // 2, L, dtype)
+    kw = dict(periodic=periodic, boxsize=L, output_ravg=True)
+    okw = dict(periodic=periodic, boxsize=L, need_avg=True, autocorr=bool(autocorr))
+    if weights:
+        kw.update(weights1=w, weight_type="pair_product")
+        okw.update(w1=w, weight_type="pair_product")
+    if not autocorr:
+        kw.update(X2=x2, Y2=y2, Z2=z2)
+        okw.update(X2=x2, Y2=y2, Z2=z2)
+        if weights:
+            kw.update(weights2=w2)
+            okw.update(w2=w2)
+    got = T.DD(autocorr, 4, edges, x, y, z, **kw)
+    ref = H.oracle_theory("DD", x, y, z, edges, **okw)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+    _close(got["ravg"], ref["ravg"], TOL[dtype], "ravg")
+    if weights:
+        _close(got["weightavg"], ref["weightavg"], TOL[dtype], "weightavg")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("autocorr", [1, 0])
+def test_DDrppi_vs_oracle(dtype, periodic, autocorr, edges):
+    T = _theory()
+    L, N, pimax = 420.0, 30000, 40.0
+    x, y, z, w = H.box_points(21, N, L, dtype)
+    x2, y2, z2, w2 = H.box_points(22, N // 2, L, dtype)
+    kw = dict(periodic=periodic, boxsize=L, output_rpavg=True, weights1=w, weight_type="pair_product")
+    okw = dict(periodic=periodic, boxsize=L, need_avg=True, autocorr=bool(autocorr), w1=w,
+               weight_type="pair_product", pimax=pimax)
+    if not autocorr:
+        kw.update(X2=x2, Y2=y2, Z2=z2, weights2=w2)
+        okw.update(X2=x2, Y2=y2, Z2=z2, w2=w2)
+    got = T.DDrppi(autocorr, 4, pimax, edges, x, y, z, **kw)
+    ref = H.oracle_theory("DDrppi", x, y, z, edges, **okw)
+    assert np.array_equal(got["npairs"], ref["npairs"].ravel())
+    _close(got["rpavg"], ref["ravg"].ravel(), TOL[dtype], "rpavg")
+    _close(got["weightavg"], ref["weightavg"].ravel(), TOL[dtype], "weightavg")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("autocorr", [1, 0])
+def test_DDsmu_vs_oracle(dtype, periodic, autocorr, edges):
+    T = _theory()
+    L, N, mu_max, nmu = 420.0, 30000, 0.5, 10
+    x, y, z, w = H.box_points(31, N, L, dtype)
+    x2, y2, z2, w2 = H.box_points(32, N // 2, L, dtype)
+    kw = dict(periodic=periodic, boxsize=L, output_savg=True, weights1=w, weight_type="pair_product")
+    okw = dict(periodic=periodic, boxsize=L, need_avg=True, autocorr=bool(autocorr), w1=w,
+               weight_type="pair_product", mu_max=mu_max, nmu_bins=nmu)
+    if not autocorr:
+        kw.update(X2=x2, Y2=y2, Z2=z2, weights2=w2)
+        okw.update(X2=x2, Y2=y2, Z2=z2, w2=w2)
+    got = T.DDsmu(autocorr, 4, edges, mu_max, nmu, x, y, z, **kw)
+    ref = H.oracle_theory("DDsmu", x, y, z, edges, **okw)
+    assert np.array_equal(got["npairs"], ref["npairs"].ravel())
+    _close(got["savg"], ref["ravg"].ravel(), TOL[dtype], "savg")
+    _close(got["weightavg"], ref["weightavg"].ravel(), TOL[dtype], "weightavg")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("weights", [False, True])
+def test_xi_wp_vs_oracle(dtype, weights, edges):
+    T = _theory()
+    L, N, pimax = 420.0, 40000, 40.0
+    x, y, z, w = H.box_points(41, N, L, dtype)
+    kw = dict(weights=w, weight_type="pair_product") if weights else {}
+    okw = dict(w1=w, weight_type="pair_product") if weights else {}
+    got = T.xi(L, 4, edges, x, y, z, output_ravg=True, **kw)
+    ref = H.oracle_theory("xi", x, y, z, edges, boxsize=L, need_avg=True, **okw)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+    _close(got["ravg"], ref["ravg"], TOL[dtype], "ravg")
+    assert np.allclose(got["xi"], ref["cf"], rtol=1e-6 if dtype == np.float64 else 1e-2, atol=1e-9 if dtype == np.float64 else 1e-3)
+    got = T.wp(L, pimax, 4, edges, x, y, z, output_rpavg=True, **kw)
+    ref = H.oracle_theory("wp", x, y, z, edges, boxsize=L, pimax=pimax, need_avg=True, **okw)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+    _close(got["rpavg"], ref["ravg"], TOL[dtype], "rpavg")
+    assert np.allclose(got["wp"], ref["cf"], rtol=1e-6 if dtype == np.float64 else 1e-2, atol=1e-7 if dtype == np.float64 else 1e-1)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_subdivided_lattice_matches(dtype, edges):
+    """Dense cells force the GPU's fine (sub-divided) lattice; results must not change."""
+    from corrfunc_b200 import _lib
+
+    T = _theory()
+    L, N = 100.0, 60000
+    x, y, z, w = H.box_points(51, N, L, dtype)
+    bins = np.logspace(-1, np.log10(20.0), 12)
+    ref = H.oracle_theory("DD", x, y, z, bins, periodic=True, boxsize=L, need_avg=True, w1=w, weight_type="pair_product")
+    lib = _lib.load()
+    for occ in (16, 48, 0):
+        lib.cfb_set_target_occupancy(occ)
+        got = T.DD(1, 4, bins, x, y, z, periodic=True, boxsize=L, output_ravg=True, weights1=w, weight_type="pair_product")
+        st = _lib.last_stats()
+        assert np.array_equal(got["npairs"], ref["npairs"]), (occ, st)
+        _close(got["ravg"], ref["ravg"], TOL[dtype], "ravg")
+    lib.cfb_set_target_occupancy(0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_against_reference_golden_outputs(dtype):
+    """Committed outputs of the UNMODIFIED reference (AVX-512 kernels) on seeded synthetic inputs."""
+    T = _theory()
+    g = np.load(os.path.join(H.GOLDEN, "ref_synthetic_%s.npz" % np.dtype(dtype).name))
+    seed, N, L, edges = int(g["seed"]), int(g["N"]), float(g["L"]), g["edges"]
+    x, y, z, w = H.box_points(seed, N, L, dtype)
+    x2, y2, z2, w2 = H.box_points(seed + 1, N // 2, L, dtype)
+    tol = TOL[dtype] if dtype == np.float64 else 1e-4  # the reference's float path sums in float
+    for periodic in (True, False):
+        p = "per" if periodic else "nonper"
+        r = T.DD(1, 4, edges, x, y, z, weights1=w, weight_type="pair_product", periodic=periodic, boxsize=L, output_ravg=True)
+        assert np.array_equal(r["npairs"], g["DD_auto_%s__npairs" % p])
+        _close(r["ravg"], g["DD_auto_%s__ravg" % p], tol, "ravg")
+        _close(r["weightavg"], g["DD_auto_%s__weightavg" % p], tol, "weightavg")
+        r = T.DD(0, 4, edges, x, y, z, weights1=w, weight_type="pair_product", periodic=periodic, boxsize=L,
+                 output_ravg=True, X2=x2, Y2=y2, Z2=z2, weights2=w2)
+        assert np.array_equal(r["npairs"], g["DD_cross_%s__npairs" % p])
+        r = T.DDrppi(1, 4, 40.0, edges, x, y, z, weights1=w, weight_type="pair_product", periodic=periodic, boxsize=L, output_rpavg=True)
+        assert np.array_equal(r["npairs"], g["DDrppi_auto_%s__npairs" % p].ravel())
+        _close(r["rpavg"], g["DDrppi_auto_%s__ravg" % p].ravel(), tol, "rpavg")
+        r = T.DDsmu(1, 4, edges, 0.5, 10, x, y, z, weights1=w, weight_type="pair_product", periodic=periodic, boxsize=L, output_savg=True)
+        assert np.array_equal(r["npairs"], g["DDsmu_auto_%s__npairs" % p].ravel())
+        _close(r["savg"], g["DDsmu_auto_%s__ravg" % p].ravel(), tol, "savg")
+    r = T.xi(L, 4, edges, x, y, z, weights=w, weight_type="pair_product", output_ravg=True)
+    assert np.array_equal(r["npairs"], g["xi__npairs"])
+    r = T.wp(L, 40.0, 4, edges, x, y, z, weights=w, weight_type="pair_product", output_rpavg=True)
+    assert np.array_equal(r["npairs"], g["wp__npairs"])
+
+
+def test_DDtheta_reference_golden_file():
+    """The reference's own known-answer test (Corrfunc/tests/test_mocks.py:61-80): DDtheta autocorr of
+    the Mr19 mock vs mocks/tests/Mr19_mock_wtheta.DD, atol 1e-9 / rtol 1e-6 as in common.py:83-105."""
+    from corrfunc_b200.mocks import DDtheta_mocks
+
+    ra, dec, w = H.load_mr19_mock()
+    bins = H.load_bins_file("angular_bins.txt")
+    gold = H.load_wtheta_golden()
+    r = DDtheta_mocks(1, 4, bins, ra, dec, weights1=w, weight_type="pair_product", output_thetaavg=True)
+    assert np.array_equal(r["npairs"], gold["npairs"])
+    assert np.allclose(r["thetaavg"], gold["ravg"], atol=1e-9, rtol=1e-6)
+    assert np.allclose(r["weightavg"], gold["weightavg"], atol=1e-9, rtol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("autocorr", [1, 0])
+@pytest.mark.parametrize("link", [(1, 1), (1, 0), (0, 0)])
+def test_DDtheta_vs_oracle(dtype, autocorr, link):
+    from corrfunc_b200.mocks import DDtheta_mocks
+
+    ra1, dec1 = H.sphere_points(5, 30000, dtype)
+    ra2, dec2 = H.sphere_points(6, 20000, dtype)
+    w1 = (1.0 - np.random.default_rng(7).random(ra1.size)).astype(dtype)
+    w2 = (1.0 - np.random.default_rng(8).random(ra2.size)).astype(dtype)
+    # theta_min large enough that cos(theta_min) < 1 in float (the reference warns below 0.2 deg)
+    tb = np.logspace(np.log10(0.05), 1, 16)
+    kw = dict(weights1=w1, weight_type="pair_product", output_thetaavg=True, link_in_dec=bool(link[0]), link_in_ra=bool(link[1]))
+    okw = dict(w1=w1, weight_type="pair_product", need_avg=True, link_in_dec=link[0], link_in_ra=link[1], autocorr=bool(autocorr))
+    if not autocorr:
+        kw.update(RA2=ra2, DEC2=dec2, weights2=w2)
+        okw.update(RA2=ra2, DEC2=dec2, w2=w2)
+    got = DDtheta_mocks(autocorr, 4, tb, ra1, dec1, **kw)
+    ref = H.oracle_theta(ra1, dec1, tb, **okw)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+    _close(got["thetaavg"], ref["ravg"], 1e-9 if dtype == np.float64 else 1e-4, "thetaavg")
+    _close(got["weightavg"], ref["weightavg"], TOL[dtype], "weightavg")
+
+
+# ---- the reference's data-free known-answer tests -------------------------------------------------
+
+@pytest.mark.parametrize("N", [1, 2])
+def test_narrow_extent(N):
+    T = _theory()
+    boxsize = (3.0, 3.0, 3.0)
+    r_bins = [0.2, 0.6, 1.0]
+    pos = np.array([[0.0, 0.0], [0.0, 0.0], [0.0, 0.5]]) if N == 2 else np.array([[0.1], [0.2], [0.3]])
+    res = T.DD(1, 1, r_bins, pos[0], pos[1], pos[2], boxsize=boxsize, periodic=True)
+    assert np.all(res["npairs"] == ([2, 0] if N == 2 else [0, 0]))
+
+
+@pytest.mark.parametrize("autocorr", [0, 1])
+@pytest.mark.parametrize("binref", [1, 2, 3])
+@pytest.mark.parametrize("min_sep_opt", [False, True])
+@pytest.mark.parametrize("maxcells", [1, 2, 3])
+def test_duplicate_cellpairs(autocorr, binref, min_sep_opt, maxcells):
+    T = _theory()
+    boxsize = 432.0
+    kw = dict(boxsize=boxsize, periodic=True, max_cells_per_dim=maxcells, xbin_refine_factor=binref,
+              ybin_refine_factor=binref, zbin_refine_factor=binref, enable_min_sep_opt=min_sep_opt)
+    r_bins = np.array([0.01, 0.4]) * boxsize
+    pos = np.array([[0.02, 0.98], [0.0, 0.0], [0.0, 0.0]]) * boxsize
+    res = T.DD(autocorr, 1, r_bins, pos[0], pos[1], pos[2], X2=pos[0], Y2=pos[1], Z2=pos[2], **kw)
+    assert np.all(res["npairs"] == [2])
+    r_bins = np.array([0.2, 0.3, 0.49]) * boxsize
+    pos = np.array([[0.0, 0.0], [0.0, 0.0], [0.0, 0.48]]) * boxsize
+    res = T.DD(autocorr, 1, r_bins, pos[0], pos[1], pos[2], X2=pos[0], Y2=pos[1], Z2=pos[2], **kw)
+    assert np.all(res["npairs"] == [0, 2])
+
+
+@pytest.mark.parametrize("autocorr", [0, 1], ids=["cross", "auto"])
+@pytest.mark.parametrize("binref", [1, 2, 3], ids=["ref1", "ref2", "ref3"])
+@pytest.mark.parametrize("maxcells", [1, 2, 3], ids=["max1", "max2", "max3"])
+@pytest.mark.parametrize("boxsize", [123.0, (51.0, 75.0, 123.0)], ids=["iso", "aniso"])
+@pytest.mark.parametrize("funcname", ["DD", "DDrppi", "DDsmu"])
+@pytest.mark.parametrize("periodic", [False, True], ids=["nowrap", "wrap"])
+def test_brute(autocorr, binref, maxcells, boxsize, funcname, periodic):
+    """Corrfunc/tests/test_theory.py:197-286: two small clouds, numpy brute-force histogram."""
+    T = _theory()
+    np.random.seed(1234)
+    npts, eps = 100, 0.2
+    boxsize = np.array(boxsize)
+    bins = np.linspace(0.01, 0.49 * boxsize.min(), 20) if periodic else np.linspace(0.01, 2 * boxsize.max(), 20)
+    pimax = np.floor(0.49 * boxsize.min())
+    mu_max, nmu_bins = 0.5, 10
+    func = getattr(T, funcname)
+    pos = np.random.uniform(low=-eps, high=eps, size=(npts, 3)) * boxsize
+    pos[npts // 2:] += boxsize / 2.0
+    pos %= boxsize
+    pdiff = np.abs(pos[:, np.newaxis] - pos)
+    if periodic:
+        mask = pdiff >= boxsize / 2
+        pdiff -= mask * boxsize
+    args = [autocorr, 1, bins, pos[:, 0], pos[:, 1], pos[:, 2]]
+    kwargs = dict(periodic=periodic, boxsize=boxsize, X2=pos[:, 0], Y2=pos[:, 1], Z2=pos[:, 2],
+                  max_cells_per_dim=maxcells, xbin_refine_factor=binref, ybin_refine_factor=binref,
+                  zbin_refine_factor=binref)
+    if funcname == "DDrppi":
+        args.insert(2, pimax)
+        sqr_rp = (pdiff[:, :, :2] ** 2).sum(axis=-1).reshape(-1)
+        pidiff = np.abs(pdiff[:, :, 2]).reshape(-1)
+        pibins = np.linspace(0.0, pimax, int(pimax) + 1)
+        brute, _, _ = np.histogram2d(sqr_rp, pidiff, bins=(bins ** 2, pibins))
+        brute = brute.reshape(-1)
+    elif funcname == "DDsmu":
+        args[3:3] = (mu_max, nmu_bins)
+        sdiff = np.sqrt((pdiff ** 2).sum(axis=-1).reshape(-1))
+        sdiff[sdiff == 0.0] = np.inf
+        mu = np.abs(pdiff[:, :, 2]).reshape(-1) / sdiff
+        mubins = np.linspace(0, mu_max, nmu_bins + 1)
+        brute, _, _ = np.histogram2d(sdiff, mu, bins=(bins, mubins))
+        brute = brute.reshape(-1)
+    else:
+        brute, _ = np.histogram((pdiff ** 2).sum(axis=-1).reshape(-1), bins=bins ** 2)
+    assert np.any(brute > 0)
+    res = func(*args, **kwargs)
+    assert np.all(res["npairs"] == brute)
+
+
+def test_errors_are_loud():
+    T = _theory()
+    x = np.random.default_rng(0).random(1000) * 10.0
+    with pytest.raises(RuntimeError):  # rmax >= L/2 under periodic wrap (gridlink_utils.c.src:37-41)
+        T.DD(1, 1, np.linspace(0.1, 6.0, 5), x, x, x, boxsize=10.0, periodic=True)
+    with pytest.raises(RuntimeError):  # particles outside [0, L] for xi (gridlink_impl.c.src:183)
+        T.xi(5.0, 1, np.linspace(0.1, 1.0, 5), x, x, x)
+
+
+def test_full_size_config1_properties():
+    """BASELINE config 1 at full size (1.2M points, L=420, 14 log bins 0.1-25, double, autocorr):
+    size-independent checks -- DD == xi counts (different lattice extents, same pairs), cross(D,D)
+    equals auto(D) (no self pairs since rmin>0), and the total is invariant under the device lattice."""
+    from corrfunc_b200 import _lib
+
+    T = _theory()
+    N, L = 1200000, 420.0
+    x, y, z, _ = H.box_points(1001, N, L, np.float64)
+    bins = np.logspace(np.log10(0.1), np.log10(25.0), 15)
+    a = T.DD(1, 4, bins, x, y, z, periodic=True, boxsize=L)
+    b = T.xi(L, 4, bins, x, y, z)
+    assert np.array_equal(a["npairs"], b["npairs"])
+    c = T.DD(0, 4, bins, x, y, z, X2=x, Y2=y, Z2=z, periodic=True, boxsize=L)
+    assert np.array_equal(a["npairs"], c["npairs"])
+    _lib.load().cfb_set_target_occupancy(24)
+    d = T.DD(1, 4, bins, x, y, z, periodic=True, boxsize=L)
+    _lib.load().cfb_set_target_occupancy(0)
+    assert np.array_equal(a["npairs"], d["npairs"])
+    # expected pair count for a uniform periodic box: N(N-1) * V_shell / L^3 within a few sigma
+    vol = 4.0 / 3.0 * np.pi * (bins[1:] ** 3 - bins[:-1] ** 3)
+    expect = N * (N - 1.0) * vol / L ** 3
+    assert np.all(np.abs(a["npairs"] - expect) < 6 * np.sqrt(expect) + 10)
+
+
+@pytest.mark.skipif(H.load_ref() is None, reason="oracle/_ref was not prebuilt")
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_live_reference(dtype, edges):
+    """The unmodified reference, run on this box's CPU, vs the GPU on a 200k-point box."""
+    from corrfunc_b200 import _capi as capi
+
+    T = _theory()
+    ref = H.load_ref()
+    L, N = 420.0, 200000
+    x, y, z, w = H.box_points(77, N, L, dtype)
+    o = capi.default_options(dtype, need_avg_sep=True, isa=H.ref_isa(), periodic=True, boxsize=L)
+    r = capi.call_DD(ref, 1, os.cpu_count() or 4, edges, x, y, z, w1=w, weight_type="pair_product", options=o)
+    g = T.DD(1, 4, edges, x, y, z, weights1=w, weight_type="pair_product", periodic=True, boxsize=L, output_ravg=True)
+    assert np.array_equal(g["npairs"], r["npairs"])
+    _close(g["ravg"], r["ravg"], 1e-10 if dtype == np.float64 else 1e-4, "ravg")
