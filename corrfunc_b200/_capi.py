@@ -4,7 +4,7 @@ The layouts mirror ``include/corrfunc_b200_defs.h`` / ``include/countpairs*.h`` 
 the binary layout of the reference's ``utils/defs.h:53-156,353-402`` and result structs).  The
 callers in this module work on *any* library exporting that ABI: the product library
 ``libcorrfunc_b200.so`` (see :mod:`corrfunc_b200._lib`) and -- in the tests only -- the unmodified
-reference compiled into ``oracle/_ref``.
+reference built by the test harness.
 """
 from __future__ import annotations
 

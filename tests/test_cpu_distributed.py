@@ -1,0 +1,68 @@
+"""World-size-2 gloo test of the multi-rank plumbing (no GPU): the tile sharding map covers every
+primary tile exactly once, and the reduce hook sums partial histograms exactly."""
+import os
+
+import numpy as np
+import torch.multiprocessing as mp
+
+SHARD_GROUP = 8  # CFB_SHARD_GROUP in corrfunc_b200/csrc/cuda/cfb_internal.cuh
+
+
+def tiles_of_rank(ntiles, rank, nranks):
+    """Python restatement of the block -> tile map in k_pairs_generic / launch_inst."""
+    ngroups = (ntiles + SHARD_GROUP - 1) // SHARD_GROUP
+    mygroups = (ngroups - rank + nranks - 1) // nranks if ngroups > rank else 0
+    out = []
+    for b in range(mygroups * SHARD_GROUP):
+        grp = b // SHARD_GROUP
+        t = (grp * nranks + rank) * SHARD_GROUP + b % SHARD_GROUP
+        if t < ntiles:
+            out.append(t)
+    return out
+
+
+def test_shard_map_is_a_partition():
+    for ntiles in (0, 1, 7, 8, 9, 63, 64, 65, 1000, 17424):
+        for nranks in (1, 2, 3, 4, 8):
+            allt = sorted(t for r in range(nranks) for t in tiles_of_rank(ntiles, r, nranks))
+            assert allt == list(range(ntiles)), (ntiles, nranks)
+            sizes = [len(tiles_of_rank(ntiles, r, nranks)) for r in range(nranks)]
+            assert max(sizes) - min(sizes) <= SHARD_GROUP
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from corrfunc_b200 import parallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    npairs = rng.integers(0, 2 ** 40, size=31, dtype=np.uint64)
+    ssep = rng.random(31)
+    sw = rng.random(31)
+    mine = (npairs.copy(), ssep.copy(), sw.copy())
+    parallel.make_allreduce(dist)(npairs, ssep, sw)
+    q.put((rank, mine, (npairs, ssep, sw)))
+    dist.destroy_process_group()
+
+
+def test_histogram_allreduce_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tot_n = sum(r[1][0].astype(np.uint64) for r in res)
+    tot_s = sum(r[1][1] for r in res)
+    tot_w = sum(r[1][2] for r in res)
+    for _, _, (n, s, w) in res:
+        assert np.array_equal(n, tot_n)  # integer sums exact -> npairs independent of the rank count
+        assert np.allclose(s, tot_s, rtol=1e-15) and np.allclose(w, tot_w, rtol=1e-15)

@@ -1,0 +1,139 @@
+"""CPU tests of the checker itself: the oracle restatement vs (a) the reference's golden file,
+(b) committed outputs of the unmodified reference on seeded inputs, (c) the reference's data-free
+known-answer tests, (d) the live unmodified reference when oracle/_ref is present."""
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+
+
+def test_oracle_matches_reference_golden_wtheta():
+    """mocks/tests/Mr19_mock_wtheta.DD: all 20 npairs exact, averages to the file's print precision."""
+    ra, dec, w = H.load_mr19_mock()
+    bins = H.load_bins_file("angular_bins.txt")
+    gold = H.load_wtheta_golden()
+    a = H.oracle_theta(ra, dec, bins, w1=w, weight_type="pair_product", need_avg=True)
+    assert np.array_equal(a["npairs"], gold["npairs"])
+    assert np.allclose(a["ravg"], gold["ravg"], atol=1e-8, rtol=1e-6)
+    assert np.allclose(a["weightavg"], gold["weightavg"], atol=1e-8, rtol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_matches_committed_reference_outputs(dtype):
+    g = np.load(os.path.join(H.GOLDEN, "ref_synthetic_%s.npz" % np.dtype(dtype).name))
+    seed, N, L, edges = int(g["seed"]), int(g["N"]), float(g["L"]), g["edges"]
+    x, y, z, w = H.box_points(seed, N, L, dtype)
+    x2, y2, z2, w2 = H.box_points(seed + 1, N // 2, L, dtype)
+    tol = 1e-10 if dtype == np.float64 else 1e-4
+    kw = dict(w1=w, weight_type="pair_product", need_avg=True, boxsize=L)
+    for periodic in (True, False):
+        p = "per" if periodic else "nonper"
+        a = H.oracle_theory("DD", x, y, z, edges, periodic=periodic, **kw)
+        assert np.array_equal(a["npairs"], g["DD_auto_%s__npairs" % p])
+        assert np.allclose(a["ravg"], g["DD_auto_%s__ravg" % p], rtol=tol)
+        assert np.allclose(a["weightavg"], g["DD_auto_%s__weightavg" % p], rtol=tol)
+        a = H.oracle_theory("DD", x, y, z, edges, periodic=periodic, autocorr=False, X2=x2, Y2=y2, Z2=z2, w2=w2, **kw)
+        assert np.array_equal(a["npairs"], g["DD_cross_%s__npairs" % p])
+        a = H.oracle_theory("DDrppi", x, y, z, edges, periodic=periodic, pimax=40.0, **kw)
+        assert np.array_equal(a["npairs"], g["DDrppi_auto_%s__npairs" % p])
+        assert np.allclose(a["ravg"], g["DDrppi_auto_%s__ravg" % p], rtol=tol)
+        a = H.oracle_theory("DDsmu", x, y, z, edges, periodic=periodic, mu_max=0.5, nmu_bins=10, **kw)
+        assert np.array_equal(a["npairs"], g["DDsmu_auto_%s__npairs" % p])
+        assert np.allclose(a["ravg"], g["DDsmu_auto_%s__ravg" % p], rtol=tol)
+    a = H.oracle_theory("xi", x, y, z, edges, **kw)
+    assert np.array_equal(a["npairs"], g["xi__npairs"])
+    assert np.allclose(a["cf"], g["xi__cf"], rtol=1e-6 if dtype == np.float64 else 2e-2, atol=1e-9 if dtype == np.float64 else 1e-3)
+    a = H.oracle_theory("wp", x, y, z, edges, pimax=40.0, **kw)
+    assert np.array_equal(a["npairs"], g["wp__npairs"])
+
+
+@pytest.mark.parametrize("N", [1, 2])
+def test_oracle_narrow_extent(N):  # Corrfunc/tests/test_theory.py:115-147
+    pos = np.array([[0.0, 0.0], [0.0, 0.0], [0.0, 0.5]]) if N == 2 else np.array([[0.1], [0.2], [0.3]])
+    a = H.oracle_theory("DD", pos[0], pos[1], pos[2], [0.2, 0.6, 1.0], periodic=True, boxsize=(3.0, 3.0, 3.0))
+    assert np.all(a["npairs"] == ([2, 0] if N == 2 else [0, 0]))
+
+
+@pytest.mark.parametrize("autocorr", [0, 1])
+@pytest.mark.parametrize("binref", [1, 2, 3])
+@pytest.mark.parametrize("maxcells", [1, 2, 3])
+def test_oracle_duplicate_cellpairs(autocorr, binref, maxcells):  # test_theory.py:150-194
+    boxsize = 432.0
+    kw = dict(periodic=True, boxsize=boxsize, refine=(binref,) * 3, custom_refine=binref != 2 or True, max_cells=maxcells,
+              autocorr=bool(autocorr))
+    pos = np.array([[0.02, 0.98], [0.0, 0.0], [0.0, 0.0]]) * boxsize
+    x2 = {} if autocorr else dict(X2=pos[0], Y2=pos[1], Z2=pos[2])
+    a = H.oracle_theory("DD", pos[0], pos[1], pos[2], np.array([0.01, 0.4]) * boxsize, **kw, **x2)
+    assert np.all(a["npairs"] == [2])
+    pos = np.array([[0.0, 0.0], [0.0, 0.0], [0.0, 0.48]]) * boxsize
+    x2 = {} if autocorr else dict(X2=pos[0], Y2=pos[1], Z2=pos[2])
+    a = H.oracle_theory("DD", pos[0], pos[1], pos[2], np.array([0.2, 0.3, 0.49]) * boxsize, **kw, **x2)
+    assert np.all(a["npairs"] == [0, 2])
+
+
+@pytest.mark.parametrize("autocorr", [0, 1], ids=["cross", "auto"])
+@pytest.mark.parametrize("binref", [1, 3], ids=["ref1", "ref3"])
+@pytest.mark.parametrize("maxcells", [1, 3], ids=["max1", "max3"])
+@pytest.mark.parametrize("boxsize", [123.0, (51.0, 75.0, 123.0)], ids=["iso", "aniso"])
+@pytest.mark.parametrize("funcname", ["DD", "DDrppi", "DDsmu"])
+@pytest.mark.parametrize("periodic", [False, True], ids=["nowrap", "wrap"])
+def test_oracle_brute(autocorr, binref, maxcells, boxsize, funcname, periodic):  # test_theory.py:197-286
+    np.random.seed(1234)
+    npts, eps = 100, 0.2
+    boxsize = np.array(boxsize)
+    bins = np.linspace(0.01, 0.49 * boxsize.min(), 20) if periodic else np.linspace(0.01, 2 * boxsize.max(), 20)
+    pimax = np.floor(0.49 * boxsize.min())
+    mu_max, nmu_bins = 0.5, 10
+    pos = np.random.uniform(low=-eps, high=eps, size=(npts, 3)) * boxsize
+    pos[npts // 2:] += boxsize / 2.0
+    pos %= boxsize
+    pdiff = np.abs(pos[:, np.newaxis] - pos)
+    if periodic:
+        pdiff -= (pdiff >= boxsize / 2) * boxsize
+    kw = dict(periodic=periodic, boxsize=boxsize, refine=(binref,) * 3, custom_refine=True, max_cells=maxcells,
+              autocorr=bool(autocorr))
+    if not autocorr:
+        kw.update(X2=pos[:, 0], Y2=pos[:, 1], Z2=pos[:, 2])
+    if funcname == "DDrppi":
+        kw["pimax"] = pimax
+        brute, _, _ = np.histogram2d((pdiff[:, :, :2] ** 2).sum(axis=-1).reshape(-1), np.abs(pdiff[:, :, 2]).reshape(-1),
+                                     bins=(bins ** 2, np.linspace(0.0, pimax, int(pimax) + 1)))
+    elif funcname == "DDsmu":
+        kw.update(mu_max=mu_max, nmu_bins=nmu_bins)
+        sdiff = np.sqrt((pdiff ** 2).sum(axis=-1).reshape(-1))
+        sdiff[sdiff == 0.0] = np.inf
+        brute, _, _ = np.histogram2d(sdiff, np.abs(pdiff[:, :, 2]).reshape(-1) / sdiff,
+                                     bins=(bins, np.linspace(0, mu_max, nmu_bins + 1)))
+    else:
+        brute, _ = np.histogram((pdiff ** 2).sum(axis=-1).reshape(-1), bins=bins ** 2)
+    a = H.oracle_theory(funcname, pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), bins, **kw)
+    assert np.all(a["npairs"].reshape(brute.shape) == brute)
+
+
+@pytest.mark.skipif(H.load_ref() is None, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_vs_live_reference(dtype):
+    from corrfunc_b200 import _capi as capi
+
+    ref, isa = H.load_ref(), H.ref_isa()
+    L, N = 300.0, 30000
+    x, y, z, w = H.box_points(99, N, L, dtype)
+    edges = H.load_bins_file("theory_bins.txt")
+    for periodic in (True, False):
+        o = capi.default_options(dtype, periodic=periodic, need_avg_sep=True, boxsize=L, isa=isa)
+        r = capi.call_DD(ref, 1, 4, edges, x, y, z, w1=w, weight_type="pair_product", options=o)
+        a = H.oracle_theory("DD", x, y, z, edges, periodic=periodic, boxsize=L, w1=w, weight_type="pair_product", need_avg=True)
+        assert np.array_equal(a["npairs"], r["npairs"])
+        o = capi.default_options(dtype, periodic=periodic, need_avg_sep=True, boxsize=L, isa=isa)
+        r = capi.call_DDsmu(ref, 1, 4, edges, 1.0, 20, x, y, z, w1=w, weight_type="pair_product", options=o)
+        a = H.oracle_theory("DDsmu", x, y, z, edges, periodic=periodic, boxsize=L, w1=w, weight_type="pair_product",
+                            need_avg=True, mu_max=1.0, nmu_bins=20)
+        assert np.array_equal(a["npairs"], r["npairs"])
+    ra, dec = H.sphere_points(3, 20000, dtype)
+    tb = np.logspace(-1.3, 1, 12)
+    o = capi.default_options(dtype, need_avg_sep=True, isa=isa)
+    r = capi.call_DDtheta(ref, 1, 4, tb, ra, dec, options=o)
+    a = H.oracle_theta(ra, dec, tb, need_avg=True)
+    assert np.array_equal(a["npairs"], r["npairs"])
