@@ -161,6 +161,8 @@ def run_ours(args, cfg):
     lib = _lib.load()
     if world > 1:
         parallel.enable_distributed(dist, dev)
+    if args.occ:
+        lib.cfb_set_target_occupancy(args.occ)
 
     stat = cfg["stat"]
     dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
@@ -331,7 +333,9 @@ def run_ours(args, cfg):
                      "peak_source": "nominal: 148 SMs x %d lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no FP32/FP64 ALU figure)" % (lanes, sm_max),
                      "kernel_ms": kmean, "gridlink_ms": float(np.mean(grid_ms)), "n_eval": n_eval_total,
                      "evals_per_s": n_eval_total / (kmean * 1e-3), "peak_evals_per_s_per_gpu": peak_evals,
-                     "kernel_share_of_step": kmean * 1e-3 / t_res},
+                     "kernel_share_of_step": kmean * 1e-3 / t_res,
+                     "levels_per_eval": st0["n_levelpairs"] / max(st0["n_eval"], 1), "n_analytic": st0["n_analytic"],
+                     "n_jobs": st0["n_tilepairs"], "n_tiles": st0["n_tiles"], "kernel_kind": st0["kernel_kind"]},
         "n_cand": n_cand,
         "n_pairs_total": tot,
     }
@@ -442,10 +446,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default=os.environ.get("CORRFUNC_BENCH_CONFIG", "c5"))
     ap.add_argument("--npart", type=int, default=0, help="override N (marks the line as reduced)")
+    ap.add_argument("--same-density", action="store_true", help="with --npart: shrink the box to keep the number density")
+    ap.add_argument("--occ", type=int, default=0, help="target particles per device cell (0 = default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.npart and args.same_density and cfg["L"] > 0:
+        cfg["L"] = float(cfg["L"] * (args.npart / cfg["N"]) ** (1.0 / 3.0))
     line = run_reference(args, cfg) if args.impl == "reference" else run_ours(args, cfg)
     if line is not None:
         print(json.dumps(line))

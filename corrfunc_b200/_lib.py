@@ -18,7 +18,7 @@ class CfbStats(C.Structure):
     _fields_ = [("ms_h2d", C.c_double), ("ms_gridlink", C.c_double), ("ms_pairs", C.c_double),
                 ("ms_total_device", C.c_double), ("n_eval", C.c_uint64), ("n_tilepairs", C.c_uint64),
                 ("n_cells", C.c_int64), ("n_tiles", C.c_int64), ("fine", C.c_int * 3),
-                ("kernel_launches", C.c_int), ("kernel_kind", C.c_int)]
+                ("kernel_launches", C.c_int), ("kernel_kind", C.c_int), ("n_analytic", C.c_uint64), ("n_levelpairs", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -59,7 +59,7 @@ def last_stats() -> dict:
     return dict(ms_gridlink=d.ms_gridlink, ms_pairs=d.ms_pairs, ms_total_device=d.ms_total_device,
                 n_eval=int(d.n_eval), n_tilepairs=int(d.n_tilepairs), n_cells=int(d.n_cells),
                 n_tiles=int(d.n_tiles), fine=tuple(d.fine), kernel_launches=int(d.kernel_launches),
-                kernel_kind=int(d.kernel_kind), ms_host_total=s.ms_host_total, ms_upload=s.ms_upload,
+                kernel_kind=int(d.kernel_kind), n_analytic=int(d.n_analytic), n_levelpairs=int(d.n_levelpairs), ms_host_total=s.ms_host_total, ms_upload=s.ms_upload,
                 nmesh=tuple(s.nmesh), refine=tuple(s.refine))
 
 

@@ -10,6 +10,7 @@
 #define CFB_PAD 4            // every fine cell's run in the sorted SoA starts at a multiple of this (16 B for float)
 #define CFB_TILE 128         // primaries per tile in the generic kernel (one per thread)
 #define CFB_SHARD_GROUP 8    // tiles per shard group
+#define CFB_FAST_MAX_EDGES 64 // the fast kernel keeps edges and the block histogram in static shared memory
 
 struct DevBuf {
     void *p = nullptr;
@@ -82,6 +83,8 @@ struct FineGeom {
 };
 
 struct PairParams {
+    // exact-division magics for the fast kernel's candidate decode: ceil(2^32/d), 0 for d == 1
+    unsigned m_wz, m_s[3];
     // binning
     int mode, nedges, npibin, nmu_bins, autocorr, cross;
     int64_t nslots;
@@ -102,12 +105,15 @@ struct PairParams {
     // outputs
     unsigned long long *npairs;
     double *sum_sep, *sum_w;
-    unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs
+    unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs [2]=pairs binned without evaluation [3]=sum of evaluated pairs x levels
     int hist_in_smem;
 };
 
 // gridlink entry points (gridlink.cu)
-int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3]);
+// scale: power of two applied to the sorted copy of the positions (1 unless the fast float kernel runs)
+int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3], double scale);
 int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t ncells);
 // pair kernels (pairs_generic.cu)
 int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode);
+// fast 1-D kernel (pairs_fast.cu); P.edges / P.wrap / P.pimax are in the kernel's scaled units
+int cfb_launch_pairs_fast(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode);

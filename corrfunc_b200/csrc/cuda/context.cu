@@ -219,36 +219,39 @@ extern "C" int cfb_extent(int slot, int which, double lohi[6])
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fine lattice: every reference cell is split sub[] ways so that a fine cell holds about `target`
+// particles (one warp tile = up to 128) and is as close to a cube as the integer splits allow.
 static void choose_subdivision(const Ctx &c, const cfb_box_lattice *lat, int64_t nmax, int sub[3])
 {
     sub[0] = sub[1] = sub[2] = 1;
-    const int target = c.target_occ > 0 ? c.target_occ : 96;
+    const int target = c.target_occ > 0 ? c.target_occ : 100;
     const double ncell = (double)lat->nmesh[0] * lat->nmesh[1] * lat->nmesh[2];
     const double occ = (double)nmax / ncell;
-    if (occ <= 1.5 * target) return;
+    if (occ <= 1.3 * target) return;
     double d[3];
     for (int k = 0; k < 3; k++) d[k] = lat->inv[k] > 0 ? 1.0 / lat->inv[k] : 0.0;
     if (!(d[0] > 0 && d[1] > 0 && d[2] > 0)) return;
-    const double K = occ / target;
-    const double f = cbrt(d[0] * d[1] * d[2] / K);
-    double tot = ncell;
-    for (int k = 0; k < 3; k++) {
-        int s = (int)floor(d[k] / f + 0.5);
-        if (s < 1) s = 1;
-        if (s > 16) s = 16;
-        sub[k] = s;
-        tot *= s;
-    }
-    // keep the fine lattice below ~48M cells
-    while (tot > 48e6) {
-        int k = 0;
-        for (int q = 1; q < 3; q++)
-            if (sub[q] > sub[k]) k = q;
-        if (sub[k] == 1) break;
-        tot = tot / sub[k] * (sub[k] - 1);
-        sub[k]--;
-    }
+    double best = 1e300;
+    for (int a = 1; a <= 16; a++)
+        for (int b = 1; b <= 16; b++)
+            for (int e = 1; e <= 16; e++) {
+                const double tot = ncell * a * b * e;
+                if (tot > 48e6) continue;  // keep the fine lattice below ~48M cells
+                const double o = occ / ((double)a * b * e);
+                const double x = d[0] / a, y = d[1] / b, z = d[2] / e;
+                const double mx = fmax(x, fmax(y, z)), mn = fmin(x, fmin(y, z));
+                // over-full cells (second, nearly empty tile) cost more than slightly emptier ones
+                const double score = (o > target ? 3.0 : 1.5) * fabs(log(o / target)) + log(mx / mn);
+                if (score < best) {
+                    best = score;
+                    sub[0] = a;
+                    sub[1] = b;
+                    sub[2] = e;
+                }
+            }
 }
+
+static unsigned div_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)((0x100000000ULL + d - 1) / d); }
 
 static int alloc_hist(Ctx &c, int64_t nslots)
 {
@@ -282,23 +285,25 @@ static int fetch_hist(Ctx &c, int64_t nslots, const cfb_binning *bin, cfb_hist *
     if (stats) {
         stats->n_eval = cnt[0];
         stats->n_tilepairs = cnt[1];
+        stats->n_analytic = cnt[2];
+        stats->n_levelpairs = cnt[3];
     }
     if (tmp) free(h);
     return 0;
 }
 
-static int upload_edges(Ctx &c, const cfb_binning *bin)
+static int upload_edges(Ctx &c, const cfb_binning *bin, const double *edges)
 {
     if (bin->nedges < 2 || bin->nedges > CFB_MAX_EDGES) return cfb_fail("number of bin edges %d not in [2,%d]", bin->nedges, CFB_MAX_EDGES);
     if (cfb_ensure(c.edges, (size_t)bin->nedges * 8)) return 1;
     // convert on the host into the run precision (values are already REAL-representable)
     if (bin->prec == 4) {
         float *h = (float *)c.pinned;
-        for (int i = 0; i < bin->nedges; i++) h[i] = (float)bin->edges[i];
+        for (int i = 0; i < bin->nedges; i++) h[i] = (float)edges[i];
         CK(cudaMemcpyAsync(c.edges.p, h, (size_t)bin->nedges * 4, cudaMemcpyHostToDevice, c.stream));
     } else {
         double *h = (double *)c.pinned;
-        for (int i = 0; i < bin->nedges; i++) h[i] = bin->edges[i];
+        for (int i = 0; i < bin->nedges; i++) h[i] = edges[i];
         CK(cudaMemcpyAsync(c.edges.p, h, (size_t)bin->nedges * 8, cudaMemcpyHostToDevice, c.stream));
     }
     CK(cudaStreamSynchronize(c.stream));  // pinned staging area is reused below
@@ -329,6 +334,46 @@ static void fill_common(PairParams &P, Ctx &c, const cfb_binning *bin, int64_t n
     P.shard_n = c.shard_n;
 }
 
+// The fast kernel (pairs_fast.cu) handles the 1-D statistics without per-pair sums.  In float it
+// needs the positions multiplied by 2^k such that the smallest positive (squared) edge is >= 2^24:
+// then two distinct floats at or above that edge differ by >= 1 and one saturating subtract is an
+// exact [v < edge] indicator.  Power-of-two scaling commutes with every rounding the reference does.
+static bool fast_box_plan(const Ctx &c, const cfb_binning *bin, const cfb_box_lattice *lat, double *scale)
+{
+    *scale = 1.0;
+    if (c.force_kernel == 0) return false;
+    if (!(bin->mode == CFB_DD || bin->mode == CFB_XI || bin->mode == CFB_WP)) return false;
+    if (bin->need_avg || bin->need_weights) return false;
+    if (bin->nedges < 2 || bin->nedges > CFB_FAST_MAX_EDGES) return false;
+    for (int i = 0; i < bin->nedges; i++) {
+        if (!(bin->edges[i] >= 0.0) || !isfinite(bin->edges[i])) return false;
+        if (i > 0 && !(bin->edges[i] > bin->edges[i - 1])) return false;
+    }
+    if (bin->prec == 8) return true;
+    double emin = 0.0;
+    for (int i = 0; i < bin->nedges; i++)
+        if (bin->edges[i] > 0.0) {
+            emin = bin->edges[i];
+            break;
+        }
+    if (!(emin > 0.0)) return false;
+    int e = 0;
+    frexp(emin, &e);  // emin = m * 2^e, m in [0.5, 1)  ->  emin >= 2^(e-1)
+    int k = (25 - e + 1) / 2;  // ceil((25 - e) / 2) for positive numerators
+    if (25 - e <= 0) k = 0;
+    double cmax = 1.0;
+    for (int a = 0; a < 3; a++) {
+        const double ext = lat->inv[a] > 0 ? lat->nmesh[a] / lat->inv[a] : 0.0;
+        const double m = fabs(lat->lo[a]) + ext + fabs(lat->wrap[a]);
+        if (m > cmax) cmax = m;
+    }
+    int ce = 0;
+    frexp(cmax, &ce);
+    if (ce + k > 55) return false;  // keep 3 * (2 cmax 2^k)^2 far below FLT_MAX
+    *scale = ldexp(1.0, k);
+    return true;
+}
+
 extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *out, cfb_stats *stats)
 {
     Ctx &c = g_ctx;
@@ -349,30 +394,57 @@ extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat,
     int64_t nmax = c.set[0].n;
     if (nsets == 2 && c.set[1].n > nmax) nmax = c.set[1].n;
     choose_subdivision(c, lat, nmax, sub);
+    double scale = 1.0;
+    const bool fast = fast_box_plan(c, bin, lat, &scale);
     for (int s = 0; s < nsets; s++)
-        if (cfb_gridlink_box_set(c.set[s], lat, sub)) return 1;
+        if (cfb_gridlink_box_set(c.set[s], lat, sub, scale)) return 1;
     CK(cudaEventRecord(c.ev[1], c.stream));
 
     const int64_t nslots = bin->nslots;
     if (alloc_hist(c, nslots)) return 1;
-    if (upload_edges(c, bin)) return 1;
+    double edges_v[CFB_FAST_MAX_EDGES];
+    if (fast) {
+        for (int i = 0; i < bin->nedges; i++) edges_v[i] = bin->edges[i] * scale * scale;
+        if (upload_edges(c, bin, edges_v)) return 1;
+    } else if (upload_edges(c, bin, bin->edges))
+        return 1;
     PairParams P;
     fill_common(P, c, bin, nslots);
+    P.pimax *= scale;
     for (int k = 0; k < 3; k++) {
         P.g.n[k] = lat->nmesh[k];
         P.g.s[k] = sub[k];
         P.g.ng[k] = lat->nmesh[k] * sub[k];
         P.g.refine[k] = lat->refine[k];
         P.g.reach[k] = sub[k] > 1 ? (lat->refine[k] + 1) * sub[k] - 1 : lat->refine[k];
+        if (sub[k] > 1 && lat->inv[k] > 0) {
+            // fine cells more than ceil(maxsep / fine size) + 1 away (two cells of slack) cannot hold a pair in range
+            const double rmax = sqrt(bin->edges[bin->nedges - 1]);
+            const double sep = (k == 2 && (bin->mode == CFB_WP || bin->mode == CFB_RPPI)) ? bin->pimax : rmax;
+            const double cells = ceil(sep * lat->inv[k] * sub[k] * (1.0 + 1e-6)) + 1.0;
+            if (cells < P.g.reach[k]) P.g.reach[k] = (int)cells;
+        }
+        P.m_s[k] = div_magic((unsigned)sub[k]);
         P.g.periodic[k] = lat->periodic[k];
-        P.wrap[k] = lat->wrap[k];
+        P.wrap[k] = lat->wrap[k] * scale;
         P.max_sep[k] = lat->max_sep[k];
     }
     P.tile_cell = (const int *)c.set[0].tile_cell.p;
     P.tile_off = (const int *)c.set[0].tile_off.p;
     P.ntiles = c.set[0].ntiles;
-    if (c.set[0].n > 0 && c.set[nsets - 1].n > 0 && P.ntiles > 0)
-        if (cfb_launch_pairs_generic(bin, P, bin->prec, false)) return 1;
+    {
+        const unsigned wy = 2 * P.g.reach[1] + 1, wz = 2 * P.g.reach[2] + 1;
+        P.m_wz = div_magic(wz);
+        // the magic-number divisions are exact while n * d < 2^32
+        bool ok = (double)wy * wz * wz < 4.0e9;
+        for (int k = 0; k < 3; k++) ok = ok && 3.0 * P.g.ng[k] * sub[k] < 4.0e9;
+        if (fast && !ok) return cfb_fail("lattice too large for the fast kernel's index arithmetic");
+    }
+    if (c.set[0].n > 0 && c.set[nsets - 1].n > 0 && P.ntiles > 0) {
+        if (fast ? cfb_launch_pairs_fast(bin, P, bin->prec, false) : cfb_launch_pairs_generic(bin, P, bin->prec, false))
+            return 1;
+    }
+    st.kernel_kind = fast ? 1 : 0;
     CK(cudaEventRecord(c.ev[2], c.stream));
     if (fetch_hist(c, nslots, bin, out, &st)) return 1;
     float ms = 0;
@@ -430,7 +502,18 @@ extern "C" int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int
     CK(cudaEventRecord(c.ev[0], c.stream));
     const int64_t nslots = bin->nslots;
     if (alloc_hist(c, nslots)) return 1;
-    if (upload_edges(c, bin)) return 1;
+    // fast kernel: works on v = -cos(theta) (increasing edges); in float on v * 2^24, where every
+    // value the kernel can produce is an integer, so edges are rounded up to the next integer
+    bool fast = c.force_kernel != 0 && !bin->need_avg && !bin->need_weights && bin->nedges >= 2 &&
+                bin->nedges <= CFB_FAST_MAX_EDGES;
+    double edges_v[CFB_FAST_MAX_EDGES];
+    if (fast) {
+        for (int i = 0; i < bin->nedges; i++) {
+            edges_v[i] = bin->prec == 4 ? ceil(-bin->edges[i] * 16777216.0) : -bin->edges[i];
+            if (!isfinite(edges_v[i]) || (i > 0 && !(edges_v[i] >= edges_v[i - 1]))) fast = false;
+        }
+    }
+    if (upload_edges(c, bin, fast ? edges_v : bin->edges)) return 1;
     const int64_t nlist = ngb_offsets[ncells];
     if (cfb_ensure(c.list_off, (size_t)(ncells + 1) * 8)) return 1;
     if (cfb_ensure(c.list_cells, (size_t)(nlist > 0 ? nlist : 1) * 4)) return 1;
@@ -443,8 +526,11 @@ extern "C" int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int
     P.tile_cell = (const int *)c.set[0].tile_cell.p;
     P.tile_off = (const int *)c.set[0].tile_off.p;
     P.ntiles = c.set[0].ntiles;
-    if (P.ntiles > 0 && nlist > 0)
-        if (cfb_launch_pairs_generic(bin, P, bin->prec, true)) return 1;
+    if (P.ntiles > 0 && nlist > 0) {
+        if (fast ? cfb_launch_pairs_fast(bin, P, bin->prec, true) : cfb_launch_pairs_generic(bin, P, bin->prec, true))
+            return 1;
+    }
+    st.kernel_kind = fast ? 1 : 0;
     CK(cudaEventRecord(c.ev[2], c.stream));
     if (fetch_hist(c, nslots, bin, out, &st)) return 1;
     float ms = 0;

@@ -161,16 +161,17 @@ template <typename T>
 __global__ void k_scatter(const int64_t n, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
                           const T *__restrict__ w, const int *__restrict__ cidx, const int *__restrict__ rank,
                           const int *__restrict__ start, T *__restrict__ xs, T *__restrict__ ys, T *__restrict__ zs,
-                          T *__restrict__ ws)
+                          T *__restrict__ ws, const T scale)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = cidx[i];
     if (c < 0) return;
     const int p = start[c] + rank[i];
-    xs[p] = x[i];
-    ys[p] = y[i];
-    zs[p] = z[i];
+    // scale is a power of two (exact): the fast float kernel works on pre-scaled positions
+    xs[p] = x[i] * scale;
+    ys[p] = y[i] * scale;
+    zs[p] = z[i] * scale;
     if (w) ws[p] = w[i];
 }
 
@@ -279,7 +280,7 @@ __global__ void k_fill_tiles(const int64_t ncells, const int *__restrict__ count
 static inline unsigned int nblocks(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
 
 template <typename T>
-static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells)
+static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells, double scale)
 {
     // scan -> starts / tile ids
     if (cfb_ensure(S.start, (size_t)ncells * 4)) return 1;
@@ -306,7 +307,7 @@ static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells)
         k_scatter<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(
             S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2], (const T *)S.raw[3],
             (const int *)S.cidx.p, (const int *)S.rank.p, (const int *)S.start.p, (T *)S.sorted[0].p,
-            (T *)S.sorted[1].p, (T *)S.sorted[2].p, hasw ? (T *)S.sorted[3].p : nullptr);
+            (T *)S.sorted[1].p, (T *)S.sorted[2].p, hasw ? (T *)S.sorted[3].p : nullptr, (T)scale);
         c.launches++;
         CK(cudaGetLastError());
     }
@@ -327,7 +328,7 @@ static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells)
 }
 
 template <typename T>
-static int gridlink_box_T(Ctx &c, ParticleSet &S, const cfb_box_lattice *lat, const int sub[3])
+static int gridlink_box_T(Ctx &c, ParticleSet &S, const cfb_box_lattice *lat, const int sub[3], double scale)
 {
     BoxGeomT<T> G;
     int64_t ncells = 1;
@@ -354,13 +355,13 @@ static int gridlink_box_T(Ctx &c, ParticleSet &S, const cfb_box_lattice *lat, co
         c.launches++;
         CK(cudaGetLastError());
     }
-    return finish_sort<T>(c, S, ncells);
+    return finish_sort<T>(c, S, ncells, scale);
 }
 
-int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3])
+int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3], double scale)
 {
     Ctx &c = cfb_ctx();
-    return S.prec == 4 ? gridlink_box_T<float>(c, S, lat, sub) : gridlink_box_T<double>(c, S, lat, sub);
+    return S.prec == 4 ? gridlink_box_T<float>(c, S, lat, sub, scale) : gridlink_box_T<double>(c, S, lat, sub, scale);
 }
 
 template <typename T>
@@ -393,7 +394,7 @@ static int gridlink_theta_T(Ctx &c, ParticleSet &S, const cfb_theta_lattice *lat
     c.launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c.stream));  // pinned staging reused by finish_sort
-    if (finish_sort<T>(c, S, ncells)) return 1;
+    if (finish_sort<T>(c, S, ncells, 1.0)) return 1;
     k_ra_bounds_init<T><<<nblocks(ncells, 256), 256, 0, c.stream>>>(ncells, (T *)S.bounds.p);
     k_ra_bounds<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(S.n, (const T *)S.raw[4], (const int *)S.cidx.p,
                                                            (T *)S.bounds.p);

@@ -1,0 +1,748 @@
+// pairs_fast.cu -- the hot kernel: pair counts for the 1-D statistics (DD, xi, wp, DDtheta) when no
+// per-pair averages or weights are requested (the BASELINE configs c1, c2-wp, c4, c5).
+//
+// Replaces the per-cell-pair CPU kernels (theory/DD/countpairs_kernels.c.src:25-279,
+// theory/xi/xi_kernels.c.src:23-270, theory/wp/wp_kernels.c.src:23-305,
+// mocks/DDtheta_mocks/countpairs_theta_mocks_kernels.c.src:872-1141) and the cell-pair enumeration
+// of generate_cell_pairs_DOUBLE (utils/gridlink_impl.c.src:439-625).
+//
+// Design:
+//   * one WARP owns one primary tile: up to 128 particles of one fine cell, 4 per lane in registers;
+//   * phase 1: the 32 lanes test 32 candidate neighbour cells at a time.  From the two cells' particle
+//     bounding boxes a lane derives a conservative interval [vlo, vhi] of every separation the pair
+//     of cells can produce and, from it, the few bin edges that can actually split those pairs
+//     ("levels").  No level -> the whole N1 x N2 block goes to one bin without touching a particle;
+//   * phase 2: the neighbour's particles are staged in shared memory with 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier, double buffered, per warp) and every lane runs its 4 primaries
+//     against them with the reference's arithmetic: same subtraction order (second - (first + wrap)),
+//     same FMA association.  Instead of searching a bin per pair, the warp keeps one cumulative
+//     counter per level, #{v < edge}, in registers; bin counts are differences of those counters.
+//     float : two pairs per instruction (sub/mul/fma.f32x2); the indicator [v < edge] is ONE
+//             saturating subtract, exact because positions are pre-scaled by a power of two so that
+//             distinct values at or above the smallest edge differ by at least 1;
+//     double: plain compare-and-count.
+//   * per-block histogram in shared memory (64-bit), merged with global atomics at the end.
+//
+// Compiled with -fmad=false: an FMA appears exactly where the reference's AVX-512 kernels have one.
+#include <math_constants.h>
+#include <stdlib.h>
+
+#include "cfb_internal.cuh"
+
+#define FAST_CH 128     // secondaries per staged chunk
+#define FAST_WARPS 4    // warps (= primary tiles) per block
+#define FAST_QCAP 128   // job queue entries per warp
+#define FAST_LMAX 8     // levels per pass over a chunk
+#define FAST_PRIM 4     // primaries per lane  (32 * 4 = CFB_TILE)
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy, packed f32x2 arithmetic
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, u64 *b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *b, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ u64 pk(float a, float b)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk(u64 v, float &a, float &b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b)
+{
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// sat(a - b): 1.0f when a - b >= 1, 0.0f when a <= b (also for b = NaN or a - b = NaN)
+__device__ __forceinline__ float subsat(float a, float b)
+{
+    float d;
+    asm("sub.rn.sat.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// exact n / d for n * d < 2^32, magic = ceil(2^32 / d) (0 stands for d == 1)
+__device__ __forceinline__ unsigned fdiv(unsigned n, unsigned magic) { return magic ? __umulhi(n, magic) : n; }
+
+// ------------------------------------------------------------------------------------------------
+struct FastJob {
+    int start;  // first secondary (index into the sorted arrays, multiple of CFB_PAD)
+    int n;      // secondaries
+    int meta;   // bits 0-5 wrap code | 6-12 kbase | 13-19 L | 20 tri | 21 zcut | 22 top level measured
+};
+#define JOB_TRI (1 << 20)
+#define JOB_ZCUT (1 << 21)
+#define JOB_TOPM (1 << 22)
+
+template <typename T>
+struct FastWarp {
+    alignas(16) T buf[2][3][FAST_CH];
+    u64 mbar[2];
+    FastJob q[FAST_QCAP];
+};
+
+template <typename T>
+struct FastShared {
+    FastWarp<T> w[FAST_WARPS];
+    u64 hist[CFB_FAST_MAX_EDGES + 1];
+    double edges_d[CFB_FAST_MAX_EDGES];
+    T edges[CFB_FAST_MAX_EDGES];
+};
+
+// ------------------------------------------------------------------------------------------------
+// One chunk of secondaries against the lane's 4 primaries; cnt[l] += #{pairs with v < E[l]}.
+template <int MODE, int NL, int PA, bool ZCUT>
+__device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, const float *sz, const int m4,
+                                          const float (&xq)[FAST_PRIM], const float (&yq)[FAST_PRIM],
+                                          const float (&zq)[FAST_PRIM], const float (&E)[FAST_LMAX], const float pimax,
+                                          int (&cnt)[FAST_LMAX])
+{
+    u64 xp[PA], yp[PA], zp[PA], acc[NL];
+#pragma unroll
+    for (int p = 0; p < PA; p++) {
+        xp[p] = pk(xq[p], xq[p]);
+        yp[p] = pk(yq[p], yq[p]);
+        zp[p] = pk(zq[p], zq[p]);
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) acc[l] = 0ULL;
+    const u64 th_a = pk(8388608.0f, 8388608.0f), th_b = pk(-16777216.0f, -16777216.0f);
+    // The loop is deliberately NOT unrolled: the kernel holds one loop per (levels, primaries) variant
+    // and warps on an SM run different ones; unrolled copies overflow the instruction cache (measured:
+    // 26 "no instruction" stall cycles per issue).  The next step's loads are issued before the math.
+    float4 Xn = *reinterpret_cast<const float4 *>(sx);
+    float4 Yn = *reinterpret_cast<const float4 *>(sy);
+    float4 Zn = *reinterpret_cast<const float4 *>(sz);
+#pragma unroll 1
+    for (int j = 0; j < m4; j += 4) {
+        const float4 X = Xn, Y = Yn, Z = Zn;
+        const int jn = min(j + 4, FAST_CH - 4);
+        Xn = *reinterpret_cast<const float4 *>(sx + jn);
+        Yn = *reinterpret_cast<const float4 *>(sy + jn);
+        Zn = *reinterpret_cast<const float4 *>(sz + jn);
+        const u64 xs[2] = {pk(X.x, X.y), pk(X.z, X.w)};
+        const u64 ys[2] = {pk(Y.x, Y.y), pk(Y.z, Y.w)};
+        const u64 zs[2] = {pk(Z.x, Z.y), pk(Z.z, Z.w)};
+#pragma unroll
+        for (int p = 0; p < PA; p++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const u64 dx = sub2(xs[h], xp[p]), dy = sub2(ys[h], yp[p]), dz = sub2(zs[h], zp[p]);
+                u64 v2;
+                if (MODE == CFB_WP) {
+                    v2 = fma2(dy, dy, mul2(dx, dx));  // wp_kernels.c.src:197-198
+                } else {
+                    v2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));  // countpairs_kernels.c.src:188-190
+                    // -cos(theta) * 2^24 = chord^2 * 2^23 - 2^24 (countpairs_theta_mocks_kernels.c.src:1062-1066)
+                    if (MODE == CFB_THETA) v2 = fma2(v2, th_a, th_b);
+                }
+                float v0, v1;
+                upk(v2, v0, v1);
+                if (ZCUT) {  // -pimax < dz < pimax (wp_kernels.c.src:207-221)
+                    float z0, z1;
+                    upk(dz, z0, z1);
+                    v0 = fabsf(z0) < pimax ? v0 : CUDART_INF_F;
+                    v1 = fabsf(z1) < pimax ? v1 : CUDART_INF_F;
+                }
+#pragma unroll
+                for (int l = 0; l < NL; l++) acc[l] = add2(acc[l], pk(subsat(E[l], v0), subsat(E[l], v1)));
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+        float a, b;
+        upk(acc[l], a, b);
+        cnt[l] += (int)a + (int)b;  // exact: at most 256 increments per half
+    }
+}
+
+template <int MODE, int NL, int PA, bool ZCUT>
+__device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, const double *sz, const int m4,
+                                          const double (&xq)[FAST_PRIM], const double (&yq)[FAST_PRIM],
+                                          const double (&zq)[FAST_PRIM], const double (&E)[FAST_LMAX],
+                                          const double pimax, int (&cnt)[FAST_LMAX])
+{
+#pragma unroll 1
+    for (int j = 0; j < m4; j += 2) {
+        const double2 X = *reinterpret_cast<const double2 *>(sx + j);
+        const double2 Y = *reinterpret_cast<const double2 *>(sy + j);
+        const double2 Z = *reinterpret_cast<const double2 *>(sz + j);
+        const double xs[2] = {X.x, X.y}, ys[2] = {Y.x, Y.y}, zs[2] = {Z.x, Z.y};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int p = 0; p < PA; p++) {
+                const double dx = xs[h] - xq[p], dy = ys[h] - yq[p], dz = zs[h] - zq[p];
+                double v;
+                if (MODE == CFB_WP) {
+                    v = __fma_rn(dy, dy, dx * dx);
+                } else {
+                    v = __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
+                    if (MODE == CFB_THETA) v = __fma_rn(v, 0.5, -1.0);  // -(1 - chord^2/2), exactly
+                }
+                if (ZCUT) v = fabs(dz) < pimax ? v : CUDART_INF;
+#pragma unroll
+                for (int l = 0; l < NL; l++) cnt[l] += (v < E[l]) ? 1 : 0;
+            }
+        }
+    }
+}
+
+template <typename T, int MODE, int NL, int PA, bool ZCUT>
+__device__ __forceinline__ void chunk_T(const T *sx, const T *sy, const T *sz, const int m4, const T (&xq)[FAST_PRIM],
+                                        const T (&yq)[FAST_PRIM], const T (&zq)[FAST_PRIM], const T (&E)[FAST_LMAX],
+                                        const T pimax, int (&cnt)[FAST_LMAX])
+{
+    if constexpr (sizeof(T) == 4)
+        chunk_f32<MODE, NL, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
+    else
+        chunk_f64<MODE, NL, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
+}
+
+template <typename T, int MODE, int PA, bool ZCUT>
+__device__ __forceinline__ void chunk_dispatch_nl(const int nl, const T *sx, const T *sy, const T *sz, const int m4,
+                                                  const T (&xq)[FAST_PRIM], const T (&yq)[FAST_PRIM],
+                                                  const T (&zq)[FAST_PRIM], const T (&E)[FAST_LMAX], const T pimax,
+                                                  int (&cnt)[FAST_LMAX])
+{
+    switch (nl) {
+    case 1: chunk_T<T, MODE, 1, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 2: chunk_T<T, MODE, 2, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 3: chunk_T<T, MODE, 3, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 4: chunk_T<T, MODE, 4, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 5: chunk_T<T, MODE, 5, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 6: chunk_T<T, MODE, 6, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    default: chunk_T<T, MODE, 8, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;  // 7 runs as 8 (E[7] = +inf)
+    }
+}
+
+// pa = primaries per lane actually in use in this tile (1..4): empty register slots are not evaluated
+template <typename T, int MODE, bool ZCUT>
+__device__ __forceinline__ void chunk_dispatch(const int nl, const int pa, const T *sx, const T *sy, const T *sz,
+                                               const int m4, const T (&xq)[FAST_PRIM], const T (&yq)[FAST_PRIM],
+                                               const T (&zq)[FAST_PRIM], const T (&E)[FAST_LMAX], const T pimax,
+                                               int (&cnt)[FAST_LMAX])
+{
+    switch (pa) {
+    case 1: chunk_dispatch_nl<T, MODE, 1, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 2: chunk_dispatch_nl<T, MODE, 2, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 3: chunk_dispatch_nl<T, MODE, 3, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    default: chunk_dispatch_nl<T, MODE, 4, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staging of one chunk of secondaries (x, y, z runs of m4 elements) into the warp's buffer `bsel`.
+//   TMA = true : three 1-D bulk copies issued by lane 0, completion on the buffer's mbarrier
+//   TMA = false: 16-byte cp.async per lane, completion through cp.async groups
+template <typename T, bool TMA>
+__device__ __forceinline__ void stage_chunk(FastWarp<T> &W, const int bsel, const SetView<T> &B, const int first,
+                                            const int m4, const int lane)
+{
+    if (TMA) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)m4 * sizeof(T);
+            mbar_expect_tx(&W.mbar[bsel], 3 * bytes);
+            tma_load_1d(W.buf[bsel][0], B.x + first, bytes, &W.mbar[bsel]);
+            tma_load_1d(W.buf[bsel][1], B.y + first, bytes, &W.mbar[bsel]);
+            tma_load_1d(W.buf[bsel][2], B.z + first, bytes, &W.mbar[bsel]);
+        }
+    } else {
+        constexpr int EPV = 16 / (int)sizeof(T);
+        for (int v = lane * EPV; v < m4; v += 32 * EPV) {
+            cp_async16(&W.buf[bsel][0][v], B.x + first + v);
+            cp_async16(&W.buf[bsel][1][v], B.y + first + v);
+            cp_async16(&W.buf[bsel][2][v], B.z + first + v);
+        }
+        cp_async_commit();
+    }
+}
+
+template <typename T, int MODE, bool LIST, bool TMA>
+__global__ void __launch_bounds__(FAST_WARPS * 32, sizeof(T) == 4 ? 4 : 3)
+k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
+{
+    __shared__ __align__(16) FastShared<T> S;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nedges = P.nedges;
+    for (int i = tid; i <= nedges; i += blockDim.x) S.hist[i] = 0ULL;
+    for (int i = tid; i < nedges; i += blockDim.x) {
+        const T e = ((const T *)P.edges)[i];
+        S.edges[i] = e;
+        S.edges_d[i] = (double)e;
+    }
+    FastWarp<T> &W = S.w[wid];
+    if (TMA && lane == 0) {
+        mbar_init(&W.mbar[0], 1);
+        mbar_init(&W.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    // which tile is mine (sharded across ranks in groups of CFB_SHARD_GROUP tiles)
+    const int64_t gw = (int64_t)blockIdx.x * FAST_WARPS + wid;
+    const int64_t grp = gw / CFB_SHARD_GROUP;
+    const int64_t tile = (grp * P.shard_n + P.shard_rank) * CFB_SHARD_GROUP + (gw % CFB_SHARD_GROUP);
+    u64 my_eval = 0, my_jobs = 0, my_analytic = 0, my_levels = 0;
+
+    if (tile < P.ntiles) {
+        const int cellP = P.tile_cell[tile];
+        const int toff = P.tile_off[tile];
+        const int nP = A.count[cellP];
+        const int startP = A.start[cellP];
+        const int nv = min(CFB_TILE, nP - toff);  // valid primaries of this tile
+        const int pa = (nv + 31) >> 5;            // primaries per lane in use
+        const T nanv = sizeof(T) == 4 ? (T)CUDART_NAN_F : (T)CUDART_NAN;
+        T xr[FAST_PRIM], yr[FAST_PRIM], zr[FAST_PRIM];
+#pragma unroll
+        for (int p = 0; p < FAST_PRIM; p++) {
+            const int i = lane + 32 * p;
+            const bool ok = i < nv;
+            xr[p] = ok ? A.x[startP + toff + i] : nanv;
+            yr[p] = ok ? A.y[startP + toff + i] : nanv;
+            zr[p] = ok ? A.z[startP + toff + i] : nanv;
+        }
+
+        int gx = 0, gy = 0, gz = 0, rax = 0, ray = 0, raz = 0;
+        long long refA = 0;
+        int nrow = 1, rowlen, wz = 1, rx = 0, ry = 0, rz = 0;
+        int64_t list0 = 0;
+        if (LIST) {
+            list0 = P.list_off[cellP];
+            rowlen = (int)(P.list_off[cellP + 1] - list0);
+        } else {
+            gz = cellP % P.g.ng[2];
+            gy = (cellP / P.g.ng[2]) % P.g.ng[1];
+            gx = cellP / (P.g.ng[2] * P.g.ng[1]);
+            rax = gx / P.g.s[0];
+            ray = gy / P.g.s[1];
+            raz = gz / P.g.s[2];
+            refA = ((long long)rax * P.g.n[1] + ray) * P.g.n[2] + raz;
+            rx = P.g.reach[0];
+            ry = P.g.reach[1];
+            rz = P.g.reach[2];
+            wz = 2 * rz + 1;
+            nrow = 2 * rx + 1;             // one "row" of candidates per x offset
+            rowlen = (2 * ry + 1) * wz;    // (y, z) offsets, 32 at a time across the lanes
+        }
+        // relative error bound of one rounded operation (with slack), in double
+        const double eps = sizeof(T) == 4 ? 2.384185791015625e-07 /* 2^-22 */ : 4.440892098500626e-16 /* 2^-51 */;
+        const T pimax = (T)P.pimax;
+        const double v_self = MODE == CFB_THETA ? (sizeof(T) == 4 ? -16777216.0 : -1.0) : 0.0;
+
+        int qn = 0;       // queued jobs (warp-uniform)
+        uint32_t it = 0;  // chunks staged so far by this warp (buffer = it & 1, TMA parity = (it >> 1) & 1)
+
+        for (int row = 0; row < nrow; row++) {
+            for (int base = 0; base < rowlen; base += 32) {
+                // ---------------- phase 1: one candidate per lane ----------------
+                const int cand = base + lane;
+                bool keep = cand < rowlen;
+                int cellQ = -1, code = 0, kbase = 0, nl = 0, flags = 0;
+                int j_start = 0, j_n = 0, j2_start = 0, j2_n = 0;  // same cell: diagonal + rectangle jobs
+                if (keep) {
+                    double offd[3] = {0.0, 0.0, 0.0};
+                    if (LIST) {
+                        cellQ = P.list_cells[list0 + cand];
+                    } else {
+                        const unsigned iy = fdiv((unsigned)cand, P.m_wz);
+                        const int t[3] = {gx + row - rx, gy + (int)iy - ry, gz + (cand - (int)iy * wz) - rz};
+                        const int ra[3] = {rax, ray, raz};
+                        int q[3], rb[3];
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const int ng = P.g.ng[a];
+                            if (P.g.periodic[a]) {
+                                if (t[a] < -ng || t[a] >= 2 * ng) keep = false;
+                            } else if (t[a] < 0 || t[a] >= ng)
+                                keep = false;
+                            if (!keep) break;
+                            // neighbour reference cell within +-refine of the primary's (gridlink_impl.c.src:499-518)
+                            const int rt = (int)fdiv((unsigned)(t[a] + ng), P.m_s[a]) - P.g.n[a];
+                            const int dref = rt - ra[a];
+                            if (dref > P.g.refine[a] || dref < -P.g.refine[a]) keep = false;
+                            if (t[a] < 0) {
+                                q[a] = t[a] + ng;
+                                rb[a] = rt + P.g.n[a];
+                                code |= 1 << (2 * a);  // +wrap on the first particle (gridlink_impl.c.src:504)
+                                offd[a] = P.wrap[a];
+                            } else if (t[a] >= ng) {
+                                q[a] = t[a] - ng;
+                                rb[a] = rt - P.g.n[a];
+                                code |= 2 << (2 * a);
+                                offd[a] = -P.wrap[a];
+                            } else {
+                                q[a] = t[a];
+                                rb[a] = rt;
+                            }
+                        }
+                        if (keep) {
+                            cellQ = (q[0] * P.g.ng[1] + q[1]) * P.g.ng[2] + q[2];
+                            if (P.autocorr) {
+                                // reference keeps icell2 <= icell (gridlink_impl.c.src:525); within one reference
+                                // cell every unordered pair of fine cells is taken once
+                                const long long refB = ((long long)rb[0] * P.g.n[1] + rb[1]) * P.g.n[2] + rb[2];
+                                if (refB > refA || (refB == refA && cellQ < cellP)) keep = false;
+                                // a cell against its own periodic image: |d| >= L/2 > rmax, nothing to count
+                                if (cellQ == cellP && code != 0) keep = false;
+                            }
+                        }
+                    }
+                    int nQ = 0;
+                    if (keep) {
+                        nQ = B.count[cellQ];
+                        if (nQ == 0) keep = false;
+                    }
+                    if (keep) {
+                        // ---- conservative interval of v over all pairs of the two cells ----
+                        double dmin[3], dmax[3];
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const double plo = (double)A.bounds[(int64_t)cellP * CFB_NB + 2 * a] + offd[a];
+                            const double phi = (double)A.bounds[(int64_t)cellP * CFB_NB + 2 * a + 1] + offd[a];
+                            const double qlo = (double)B.bounds[(int64_t)cellQ * CFB_NB + 2 * a];
+                            const double qhi = (double)B.bounds[(int64_t)cellQ * CFB_NB + 2 * a + 1];
+                            double lo = 0.0;
+                            if (qlo > phi) lo = qlo - phi;
+                            else if (plo > qhi) lo = plo - qhi;
+                            const double hi = fmax(qhi - plo, phi - qlo);
+                            // rounding of (first + wrap) and of the subtraction
+                            const double del = eps * (fmax(fabs(plo), fabs(phi)) + hi);
+                            dmin[a] = fmax(0.0, lo - del);
+                            dmax[a] = hi + del;
+                        }
+                        double vlo, vhi;
+                        if (MODE == CFB_WP) {
+                            vlo = dmin[0] * dmin[0] + dmin[1] * dmin[1];
+                            vhi = dmax[0] * dmax[0] + dmax[1] * dmax[1];
+                        } else {
+                            vlo = dmin[0] * dmin[0] + dmin[1] * dmin[1] + dmin[2] * dmin[2];
+                            vhi = dmax[0] * dmax[0] + dmax[1] * dmax[1] + dmax[2] * dmax[2];
+                        }
+                        vlo *= (1.0 - 2.0 * eps);
+                        vhi *= (1.0 + 2.0 * eps);
+                        if (MODE == CFB_THETA) {
+                            if (sizeof(T) == 4) {
+                                vlo = 16777216.0 * (0.5 * vlo - 1.0) - 4.0;
+                                vhi = 16777216.0 * (0.5 * vhi - 1.0) + 4.0;
+                            } else {
+                                vlo = (0.5 * vlo - 1.0) - 4.0 * eps;
+                                vhi = (0.5 * vhi - 1.0) + 4.0 * eps;
+                            }
+                        }
+                        bool zpartial = false;
+                        if (MODE == CFB_WP) {
+                            const double pm = P.pimax;
+                            if (dmin[2] >= pm) keep = false;           // every |dz| >= pimax
+                            else if (!(dmax[2] < pm)) zpartial = true;  // some pairs may fail the cut
+                        }
+                        if (vlo >= S.edges_d[nedges - 1] || vhi < S.edges_d[0]) keep = false;
+                        if (keep) {
+                            // klo = largest k with E[k] <= vlo, khi = smallest k with E[k] > vhi
+                            int a = 0, b = nedges;  // first k with E[k] > vlo
+                            while (a < b) {
+                                const int m = (a + b) >> 1;
+                                if (S.edges_d[m] <= vlo) a = m + 1; else b = m;
+                            }
+                            const int klo = a - 1;
+                            b = nedges;  // first k with E[k] > vhi (>= the previous answer)
+                            while (a < b) {
+                                const int m = (a + b) >> 1;
+                                if (S.edges_d[m] <= vhi) a = m + 1; else b = m;
+                            }
+                            const int khi = a;
+                            kbase = klo + 1;
+                            nl = khi - klo - 1;
+                            const bool tri = P.autocorr && cellQ == cellP;
+                            const int startQ = B.start[cellQ];
+                            u64 npairs_an;  // pairs this candidate contributes if none is cut
+                            if (tri) {
+                                // same cell: the tile against itself + the secondaries after this tile
+                                const int after = nP - (toff + CFB_TILE);
+                                j_start = startQ + toff;
+                                j_n = nv;
+                                flags |= JOB_TRI;
+                                if (after > 0) {
+                                    j2_start = startQ + toff + CFB_TILE;
+                                    j2_n = after;
+                                }
+                                npairs_an = (u64)nv * (u64)(nv - 1) / 2 + (u64)nv * (u64)(after > 0 ? after : 0);
+                            } else {
+                                j_start = startQ;
+                                j_n = nQ;
+                                npairs_an = (u64)nv * (u64)nQ;
+                            }
+                            if (zpartial) {
+                                flags |= JOB_ZCUT;
+                                if (khi < nedges) {  // the count below the top edge must be measured too
+                                    nl += 1;
+                                    flags |= JOB_TOPM;
+                                }
+                            } else {
+                                atomicAdd(&S.hist[khi], npairs_an);  // everything is below E[khi]
+                            }
+                            if (nl == 0) {
+                                keep = false;  // one bin for the whole block of pairs: nothing to evaluate
+                                my_analytic += npairs_an;
+                            } else {
+                                my_eval += npairs_an;
+                                my_levels += npairs_an * (u64)nl;
+                            }
+                        }
+                    }
+                }
+                // ---------------- push the survivors ----------------
+                {
+                    const unsigned m1 = __ballot_sync(0xffffffffu, keep);
+                    const unsigned m2 = __ballot_sync(0xffffffffu, keep && j2_n > 0);
+                    const unsigned lt = (1u << lane) - 1u;
+                    const int meta = code | (kbase << 6) | (nl << 13) | flags;
+                    if (keep) {
+                        FastJob jb;
+                        jb.start = j_start;
+                        jb.n = j_n;
+                        jb.meta = meta;
+                        W.q[qn + __popc(m1 & lt)] = jb;
+                        if (j2_n > 0) {
+                            jb.start = j2_start;
+                            jb.n = j2_n;
+                            jb.meta = meta & ~JOB_TRI;
+                            W.q[qn + __popc(m1) + __popc(m2 & lt)] = jb;
+                        }
+                    }
+                    qn += __popc(m1) + __popc(m2);
+                    __syncwarp();
+                }
+                // at most 2 * 32 new jobs per round: drain before another round could overflow the queue
+                const bool last = (row == nrow - 1) && (base + 32 >= rowlen);
+                if (qn <= FAST_QCAP - 64 && !last) continue;
+
+                // ---------------- phase 2: drain the queue ----------------
+                my_jobs += qn;
+                int e = 0, c0 = 0;  // job being computed, its chunk offset
+                if (qn > 0) {
+                    const FastJob jb = W.q[0];
+                    stage_chunk<T, TMA>(W, it & 1, B, jb.start, (min(FAST_CH, jb.n) + 3) & ~3, lane);
+                }
+                while (e < qn) {
+                    const FastJob jb = W.q[e];
+                    const int m4 = (min(FAST_CH, jb.n - c0) + 3) & ~3;
+                    // next chunk: same job or the next one
+                    int e2 = e, c2 = c0 + FAST_CH;
+                    if (c2 >= jb.n) {
+                        e2 = e + 1;
+                        c2 = 0;
+                    }
+                    const int bsel = it & 1;
+                    if (e2 < qn) {
+                        const FastJob jn = W.q[e2];
+                        stage_chunk<T, TMA>(W, bsel ^ 1, B, jn.start + c2, (min(FAST_CH, jn.n - c2) + 3) & ~3, lane);
+                        if (!TMA) cp_async_wait<1>();
+                    } else if (!TMA)
+                        cp_async_wait<0>();
+                    if (TMA) mbar_wait(&W.mbar[bsel], (it >> 1) & 1);
+                    else __syncwarp();
+                    const T *sx = W.buf[bsel][0], *sy = W.buf[bsel][1], *sz = W.buf[bsel][2];
+
+                    // first particle gets the wrap: xpos = x0 + off_xwrap (countpairs_kernels.c.src:79-81)
+                    const int jcode = jb.meta & 63;
+                    T xq[FAST_PRIM], yq[FAST_PRIM], zq[FAST_PRIM];
+                    {
+                        const int cx = jcode & 3, cy = (jcode >> 2) & 3, cz = (jcode >> 4) & 3;
+                        const T ox = cx == 0 ? (T)0 : (cx == 1 ? (T)P.wrap[0] : -(T)P.wrap[0]);
+                        const T oy = cy == 0 ? (T)0 : (cy == 1 ? (T)P.wrap[1] : -(T)P.wrap[1]);
+                        const T oz = cz == 0 ? (T)0 : (cz == 1 ? (T)P.wrap[2] : -(T)P.wrap[2]);
+#pragma unroll
+                        for (int p = 0; p < FAST_PRIM; p++) {
+                            xq[p] = cx ? xr[p] + ox : xr[p];
+                            yq[p] = cy ? yr[p] + oy : yr[p];
+                            zq[p] = cz ? zr[p] + oz : zr[p];
+                        }
+                    }
+                    const int jk = (jb.meta >> 6) & 127, jl = (jb.meta >> 13) & 127;
+                    const bool tri = jb.meta & JOB_TRI, zcut = jb.meta & JOB_ZCUT, topm = jb.meta & JOB_TOPM;
+                    for (int l0 = 0; l0 < jl; l0 += FAST_LMAX) {
+                        const int nlp = min(FAST_LMAX, jl - l0);
+                        T E[FAST_LMAX];
+                        int cnt[FAST_LMAX];
+#pragma unroll
+                        for (int l = 0; l < FAST_LMAX; l++) {
+                            cnt[l] = 0;
+                            const int k = jk + l0 + l;
+                            const bool top = topm && (l0 + l == jl - 1);
+                            E[l] = (l < nlp && !top) ? S.edges[k < nedges ? k : nedges - 1]
+                                                     : (sizeof(T) == 4 ? (T)CUDART_INF_F : (T)CUDART_INF);
+                        }
+                        if (MODE == CFB_WP && zcut)
+                            chunk_dispatch<T, MODE, true>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
+                        else
+                            chunk_dispatch<T, MODE, false>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
+                        // ---- warp totals -> block histogram: +C at the level's slot, -C one above ----
+                        int mine = 0;
+#pragma unroll
+                        for (int l = 0; l < FAST_LMAX; l++) {
+                            if (l < nlp) {
+                                const int tot = __reduce_add_sync(0xffffffffu, cnt[l]);
+                                if (lane == l) mine = tot;
+                            }
+                        }
+                        if (lane < nlp) {
+                            const int k = jk + l0 + lane;
+                            const bool top = topm && (l0 + lane == jl - 1);
+                            long long C = mine;
+                            if (tri) {  // full square of the tile against itself: drop self pairs, halve
+                                const double Ed = top ? CUDART_INF : S.edges_d[k];
+                                C = (C - (v_self < Ed ? nv : 0)) / 2;
+                            }
+                            if (C != 0) {
+                                atomicAdd(&S.hist[k], (u64)C);
+                                if (!top) atomicAdd(&S.hist[k + 1], (u64)(-C));
+                            }
+                        }
+                    }
+                    __syncwarp();  // everyone is done with buf[bsel] before it is staged again
+                    it++;
+                    e = e2;
+                    c0 = c2;
+                }
+                qn = 0;
+            }
+        }
+    }
+    // ---------------- merge ----------------
+    __syncthreads();
+    for (int i = 1 + tid; i < nedges; i += blockDim.x) {
+        const u64 v = S.hist[i];
+        if (v) atomicAdd(&P.npairs[i], v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        my_eval += __shfl_xor_sync(0xffffffffu, my_eval, o);
+        my_jobs += __shfl_xor_sync(0xffffffffu, my_jobs, o);
+        my_analytic += __shfl_xor_sync(0xffffffffu, my_analytic, o);
+        my_levels += __shfl_xor_sync(0xffffffffu, my_levels, o);
+    }
+    if (lane == 0) {
+        if (my_eval) atomicAdd(&P.counters[0], my_eval);
+        if (my_jobs) atomicAdd(&P.counters[1], my_jobs / 32);  // my_jobs is warp-uniform: the shuffle sum counted it 32x
+        if (my_analytic) atomicAdd(&P.counters[2], my_analytic);
+        if (my_levels) atomicAdd(&P.counters[3], my_levels);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static SetView<T> view_of(const ParticleSet &S)
+{
+    SetView<T> v;
+    v.x = (const T *)S.sorted[0].p;
+    v.y = (const T *)S.sorted[1].p;
+    v.z = (const T *)S.sorted[2].p;
+    v.w = (const T *)S.sorted[3].p;
+    v.count = (const int *)S.count.p;
+    v.start = (const int *)S.start.p;
+    v.bounds = (const T *)S.bounds.p;
+    return v;
+}
+
+template <typename T, int MODE, bool LIST>
+static int launch_fast(const PairParams &P, const ParticleSet &SA, const ParticleSet &SB, cudaStream_t st)
+{
+    static int use_tma = -1;  // CORRFUNC_B200_STAGE=tma selects the bulk-copy staging (default: cp.async)
+    if (use_tma < 0) {
+        const char *e = getenv("CORRFUNC_B200_STAGE");
+        use_tma = (e && strcmp(e, "tma") == 0) ? 1 : 0;
+    }
+    const int64_t ngroups = (P.ntiles + CFB_SHARD_GROUP - 1) / CFB_SHARD_GROUP;
+    const int64_t mygroups = ngroups > P.shard_rank ? (ngroups - P.shard_rank + P.shard_n - 1) / P.shard_n : 0;
+    const int64_t nblk = mygroups * CFB_SHARD_GROUP / FAST_WARPS;
+    if (nblk <= 0) return 0;
+    if (nblk >= 2147483647LL) return cfb_fail("too many tiles (%lld)", (long long)nblk);
+    if (use_tma)
+        k_pairs_fast<T, MODE, LIST, true><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(P, view_of<T>(SA), view_of<T>(SB));
+    else
+        k_pairs_fast<T, MODE, LIST, false><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(P, view_of<T>(SA), view_of<T>(SB));
+    cfb_ctx().launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int launch_fast_T(const cfb_binning *bin, const PairParams &P, bool list_mode)
+{
+    Ctx &c = cfb_ctx();
+    const ParticleSet &SA = c.set[0];
+    const ParticleSet &SB = bin->autocorr ? c.set[0] : c.set[1];
+    if (list_mode) return launch_fast<T, CFB_THETA, true>(P, SA, SB, c.stream);
+    switch (bin->mode) {
+    case CFB_DD:
+    case CFB_XI: return launch_fast<T, CFB_DD, false>(P, SA, SB, c.stream);
+    case CFB_WP: return launch_fast<T, CFB_WP, false>(P, SA, SB, c.stream);
+    default: return cfb_fail("fast kernel: unsupported mode %d", bin->mode);
+    }
+}
+
+int cfb_launch_pairs_fast(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode)
+{
+    static_assert(CFB_SHARD_GROUP % FAST_WARPS == 0, "shard groups must hold whole blocks");
+    static_assert(FAST_PRIM * 32 == CFB_TILE, "a warp owns one tile");
+    return prec == 4 ? launch_fast_T<float>(bin, P, list_mode) : launch_fast_T<double>(bin, P, list_mode);
+}

@@ -80,6 +80,8 @@ typedef struct {
     int fine[3];          /* fine lattice used on the device */
     int kernel_launches;  /* CUDA kernels launched by this call */
     int kernel_kind;      /* 0 = generic, 1 = fast 1-D */
+    uint64_t n_analytic;  /* pairs binned from cell bounding boxes alone, without evaluating a separation */
+    uint64_t n_levelpairs; /* sum over evaluated pairs of the number of edge compares (levels) each one took */
 } cfb_stats;
 
 /* Lifetime: a lazily created per-process context on the current CUDA device (or CORRFUNC_B200_DEVICE). */

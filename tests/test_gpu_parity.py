@@ -347,3 +347,142 @@ def test_live_reference(dtype, edges):
     g = T.DD(1, 4, edges, x, y, z, weights1=w, weight_type="pair_product", periodic=True, boxsize=L, output_ravg=True)
     assert np.array_equal(g["npairs"], r["npairs"])
     _close(g["ravg"], r["ravg"], 1e-10 if dtype == np.float64 else 1e-4, "ravg")
+
+
+# ---- the fast kernel (pairs_fast.cu): 1-D statistics without per-pair sums --------------------------
+
+def _force(kind):
+    from corrfunc_b200 import _lib
+
+    _lib.load().cfb_force_kernel(kind)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("autocorr", [1, 0])
+def test_fast_DD_vs_oracle(dtype, periodic, autocorr, edges):
+    """No ravg / weights -> the level-counting kernel; bit-exact npairs vs the oracle, and the generic
+    per-pair kernel must agree with it."""
+    from corrfunc_b200 import _lib
+
+    T = _theory()
+    L, N = 420.0, 40000
+    x, y, z, _ = H.box_points(61, N, L, dtype)
+    x2, y2, z2, _ = H.box_points(62, N // 2, L, dtype)
+    kw = dict(periodic=periodic, boxsize=L)
+    okw = dict(periodic=periodic, boxsize=L, autocorr=bool(autocorr))
+    if not autocorr:
+        kw.update(X2=x2, Y2=y2, Z2=z2)
+        okw.update(X2=x2, Y2=y2, Z2=z2)
+    got = T.DD(autocorr, 4, edges, x, y, z, **kw)
+    assert _lib.last_stats()["kernel_kind"] == 1
+    ref = H.oracle_theory("DD", x, y, z, edges, **okw)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+    _force(0)
+    try:
+        gen = T.DD(autocorr, 4, edges, x, y, z, **kw)
+        assert _lib.last_stats()["kernel_kind"] == 0
+    finally:
+        _force(-1)
+    assert np.array_equal(got["npairs"], gen["npairs"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("occ", [0, 12, 40, 300])
+def test_fast_dense_cells_and_subdivision(dtype, occ):
+    """Dense boxes: many tiles per cell (same-cell rectangle + diagonal jobs), chunked secondaries,
+    analytic (no-level) cell pairs on fine lattices; rmin = 0 bins included."""
+    from corrfunc_b200 import _lib
+
+    T = _theory()
+    L, N = 60.0, 50000
+    x, y, z, _ = H.box_points(63, N, L, dtype)
+    lib = _lib.load()
+    for bins in (np.logspace(-1, np.log10(14.0), 13), np.linspace(0.0, 12.0, 25), np.array([2.0, 9.0])):
+        ref = H.oracle_theory("DD", x, y, z, bins, periodic=True, boxsize=L)
+        lib.cfb_set_target_occupancy(occ)
+        try:
+            got = T.DD(1, 4, bins, x, y, z, periodic=True, boxsize=L)
+            st = _lib.last_stats()
+        finally:
+            lib.cfb_set_target_occupancy(0)
+        assert st["kernel_kind"] == 1
+        assert np.array_equal(got["npairs"], ref["npairs"]), st
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fast_xi_wp_vs_oracle(dtype, edges):
+    from corrfunc_b200 import _lib
+
+    T = _theory()
+    L, N, pimax = 420.0, 60000, 40.0
+    x, y, z, _ = H.box_points(64, N, L, dtype)
+    got = T.xi(L, 4, edges, x, y, z)
+    assert _lib.last_stats()["kernel_kind"] == 1
+    ref = H.oracle_theory("xi", x, y, z, edges, boxsize=L)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+    assert np.allclose(got["xi"], ref["cf"], rtol=1e-6 if dtype == np.float64 else 1e-2, atol=1e-9 if dtype == np.float64 else 1e-3)
+    for pm in (pimax, 7.5):
+        got = T.wp(L, pm, 4, edges, x, y, z)
+        assert _lib.last_stats()["kernel_kind"] == 1
+        ref = H.oracle_theory("wp", x, y, z, edges, boxsize=L, pimax=pm)
+        assert np.array_equal(got["npairs"], ref["npairs"])
+    # a dense small box: fine lattice + pi cut through the cells
+    L2 = 50.0
+    x, y, z, _ = H.box_points(65, N, L2, dtype)
+    bins = np.logspace(-1, np.log10(10.0), 10)
+    got = T.wp(L2, 6.0, 4, bins, x, y, z)
+    ref = H.oracle_theory("wp", x, y, z, bins, boxsize=L2, pimax=6.0)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("autocorr", [1, 0])
+@pytest.mark.parametrize("link", [(1, 1), (1, 0), (0, 0)])
+def test_fast_DDtheta_vs_oracle(dtype, autocorr, link):
+    from corrfunc_b200 import _lib
+    from corrfunc_b200.mocks import DDtheta_mocks
+
+    ra1, dec1 = H.sphere_points(15, 40000, dtype)
+    ra2, dec2 = H.sphere_points(16, 25000, dtype)
+    tb = np.logspace(np.log10(0.05), 1, 16)
+    kw = dict(link_in_dec=bool(link[0]), link_in_ra=bool(link[1]))
+    okw = dict(link_in_dec=link[0], link_in_ra=link[1], autocorr=bool(autocorr))
+    if not autocorr:
+        kw.update(RA2=ra2, DEC2=dec2)
+        okw.update(RA2=ra2, DEC2=dec2)
+    got = DDtheta_mocks(autocorr, 4, tb, ra1, dec1, **kw)
+    assert _lib.last_stats()["kernel_kind"] == 1
+    ref = H.oracle_theta(ra1, dec1, tb, **okw)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+
+
+def test_fast_DDtheta_reference_golden_counts():
+    """npairs of the reference's Mr19 DDtheta golden file through the fast kernel (no weights/thetaavg)."""
+    from corrfunc_b200.mocks import DDtheta_mocks
+
+    ra, dec, _ = H.load_mr19_mock()
+    bins = H.load_bins_file("angular_bins.txt")
+    gold = H.load_wtheta_golden()
+    r = DDtheta_mocks(1, 4, bins, ra, dec)
+    assert np.array_equal(r["npairs"], gold["npairs"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fast_against_reference_golden_counts(dtype):
+    """npairs of the committed reference outputs, through the fast kernel."""
+    T = _theory()
+    g = np.load(os.path.join(H.GOLDEN, "ref_synthetic_%s.npz" % np.dtype(dtype).name))
+    seed, N, L, edges = int(g["seed"]), int(g["N"]), float(g["L"]), g["edges"]
+    x, y, z, _ = H.box_points(seed, N, L, dtype)
+    x2, y2, z2, _ = H.box_points(seed + 1, N // 2, L, dtype)
+    for periodic in (True, False):
+        p = "per" if periodic else "nonper"
+        r = T.DD(1, 4, edges, x, y, z, periodic=periodic, boxsize=L)
+        assert np.array_equal(r["npairs"], g["DD_auto_%s__npairs" % p])
+        r = T.DD(0, 4, edges, x, y, z, periodic=periodic, boxsize=L, X2=x2, Y2=y2, Z2=z2)
+        assert np.array_equal(r["npairs"], g["DD_cross_%s__npairs" % p])
+    r = T.xi(L, 4, edges, x, y, z)
+    assert np.array_equal(r["npairs"], g["xi__npairs"])
+    r = T.wp(L, 40.0, 4, edges, x, y, z)
+    assert np.array_equal(r["npairs"], g["wp__npairs"])
