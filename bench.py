@@ -302,8 +302,11 @@ def run_ours(args, cfg):
         pass
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     lanes = 128 if dtype == np.float32 else 64
-    peak_tflops = 148 * lanes * 2 * sm_max * 1e6 / 1e12
     flop = FLOP_PER_EVAL[stat]
+    # ALU roofline of SURVEY.md 8(d): one evaluation costs INSTR_PER_EVAL lane-instructions of the FP32
+    # (FP64) pipe, so peak evals/s = SMs x lanes x clock / INSTR_PER_EVAL; in FLOP terms that mix carries
+    # FLOP_PER_EVAL per INSTR_PER_EVAL lane-cycles (sub and mul count 1, fma 2)
+    peak_tflops = 148 * lanes * sm_max * 1e6 * flop / INSTR_PER_EVAL[stat] / 1e12
     ach_tflops = n_eval_total * flop / (kmean * 1e-3) / 1e12 / max(world, 1)  # per GPU
     peak_evals = 148 * lanes * sm_max * 1e6 / INSTR_PER_EVAL[stat]
     line = {
@@ -330,7 +333,7 @@ def run_ours(args, cfg):
         "clocks": clocks,
         "roofline": {"bound": "fp32_alu" if dtype == np.float32 else "fp64_alu", "achieved": ach_tflops, "peak": peak_tflops,
                      "unit": "TFLOP/s", "frac": ach_tflops / peak_tflops, "traffic": None,
-                     "peak_source": "nominal: 148 SMs x %d lanes x 2 x %.0f MHz (MEASURED_PEAKS.json has no FP32/FP64 ALU figure)" % (lanes, sm_max),
+                     "peak_source": "nominal ALU issue rate: 148 SMs x %d lanes x %.0f MHz x %d FLOP / %d instr per evaluation (MEASURED_PEAKS.json has no FP32/FP64 ALU figure; clock = its sm_max_mhz)" % (lanes, sm_max, flop, INSTR_PER_EVAL[stat]),
                      "kernel_ms": kmean, "gridlink_ms": float(np.mean(grid_ms)), "n_eval": n_eval_total,
                      "evals_per_s": n_eval_total / (kmean * 1e-3), "peak_evals_per_s_per_gpu": peak_evals,
                      "kernel_share_of_step": kmean * 1e-3 / t_res,
