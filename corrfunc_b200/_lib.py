@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcorrfunc_b200.so")
+LIB_PATH = os.environ.get("CORRFUNC_B200_LIBPATH") or os.path.join(_HERE, "csrc", "libcorrfunc_b200.so")
 _lib = None
 _hook_keepalive = None
 

@@ -101,11 +101,12 @@ struct PairParams {
     // tiles of the primary set
     const int *tile_cell, *tile_off;
     int64_t ntiles;
+    int64_t my_ntiles;  // fast kernel: tiles this rank works through (whole shard groups)
     int shard_rank, shard_n;
     // outputs
     unsigned long long *npairs;
     double *sum_sep, *sum_w;
-    unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs [2]=pairs binned without evaluation [3]=sum of evaluated pairs x levels
+    unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs [2]=pairs binned without evaluation [3]=sum of evaluated pairs x levels [4]=next tile (persistent warps)
     int hist_in_smem;
 };
 

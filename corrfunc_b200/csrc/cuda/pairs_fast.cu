@@ -143,7 +143,7 @@ struct FastShared {
     FastWarp<T> w[FAST_WARPS];
     u64 hist[CFB_FAST_MAX_EDGES + 1];
     double edges_d[CFB_FAST_MAX_EDGES];
-    T edges[CFB_FAST_MAX_EDGES];
+    T edges[CFB_FAST_MAX_EDGES + FAST_LMAX];  // padded with +inf
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -326,10 +326,10 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nedges = P.nedges;
     for (int i = tid; i <= nedges; i += blockDim.x) S.hist[i] = 0ULL;
-    for (int i = tid; i < nedges; i += blockDim.x) {
-        const T e = ((const T *)P.edges)[i];
+    for (int i = tid; i < nedges + FAST_LMAX; i += blockDim.x) {
+        const T e = i < nedges ? ((const T *)P.edges)[i] : (sizeof(T) == 4 ? (T)CUDART_INF_F : (T)CUDART_INF);
         S.edges[i] = e;
-        S.edges_d[i] = (double)e;
+        if (i < nedges) S.edges_d[i] = (double)e;
     }
     FastWarp<T> &W = S.w[wid];
     if (TMA && lane == 0) {
@@ -392,6 +392,14 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         const double v_self = MODE == CFB_THETA ? (sizeof(T) == 4 ? -16777216.0 : -1.0) : 0.0;
 
         int qn = 0;       // queued jobs (warp-uniform)
+        int cur_code = 0;  // wrap code the shifted primaries xq/yq/zq currently hold
+        T xq[FAST_PRIM], yq[FAST_PRIM], zq[FAST_PRIM];
+#pragma unroll
+        for (int p = 0; p < FAST_PRIM; p++) {
+            xq[p] = xr[p];
+            yq[p] = yr[p];
+            zq[p] = zr[p];
+        }
         uint32_t it = 0;  // chunks staged so far by this warp (buffer = it & 1, TMA parity = (it >> 1) & 1)
 
         for (int row = 0; row < nrow; row++) {
@@ -605,14 +613,15 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                     else __syncwarp();
                     const T *sx = W.buf[bsel][0], *sy = W.buf[bsel][1], *sz = W.buf[bsel][2];
 
-                    // first particle gets the wrap: xpos = x0 + off_xwrap (countpairs_kernels.c.src:79-81)
+                    // first particle gets the wrap: xpos = x0 + off_xwrap (countpairs_kernels.c.src:79-81);
+                    // shifted copies are kept in registers until a job with another wrap code comes up
                     const int jcode = jb.meta & 63;
-                    T xq[FAST_PRIM], yq[FAST_PRIM], zq[FAST_PRIM];
-                    {
+                    if (jcode != cur_code) {
+                        cur_code = jcode;
                         const int cx = jcode & 3, cy = (jcode >> 2) & 3, cz = (jcode >> 4) & 3;
-                        const T ox = cx == 0 ? (T)0 : (cx == 1 ? (T)P.wrap[0] : -(T)P.wrap[0]);
-                        const T oy = cy == 0 ? (T)0 : (cy == 1 ? (T)P.wrap[1] : -(T)P.wrap[1]);
-                        const T oz = cz == 0 ? (T)0 : (cz == 1 ? (T)P.wrap[2] : -(T)P.wrap[2]);
+                        const T ox = cx == 1 ? (T)P.wrap[0] : -(T)P.wrap[0];
+                        const T oy = cy == 1 ? (T)P.wrap[1] : -(T)P.wrap[1];
+                        const T oz = cz == 1 ? (T)P.wrap[2] : -(T)P.wrap[2];
 #pragma unroll
                         for (int p = 0; p < FAST_PRIM; p++) {
                             xq[p] = cx ? xr[p] + ox : xr[p];
@@ -621,20 +630,18 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                         }
                     }
                     const int jk = (jb.meta >> 6) & 127, jl = (jb.meta >> 13) & 127;
-                    const bool tri = jb.meta & JOB_TRI, zcut = jb.meta & JOB_ZCUT, topm = jb.meta & JOB_TOPM;
                     for (int l0 = 0; l0 < jl; l0 += FAST_LMAX) {
                         const int nlp = min(FAST_LMAX, jl - l0);
+                        // the edge table is padded with +inf, and a measured top level (JOB_TOPM) may use
+                        // its real edge: every unmasked value of the job lies below it
                         T E[FAST_LMAX];
                         int cnt[FAST_LMAX];
 #pragma unroll
                         for (int l = 0; l < FAST_LMAX; l++) {
                             cnt[l] = 0;
-                            const int k = jk + l0 + l;
-                            const bool top = topm && (l0 + l == jl - 1);
-                            E[l] = (l < nlp && !top) ? S.edges[k < nedges ? k : nedges - 1]
-                                                     : (sizeof(T) == 4 ? (T)CUDART_INF_F : (T)CUDART_INF);
+                            E[l] = S.edges[jk + l0 + l];
                         }
-                        if (MODE == CFB_WP && zcut)
+                        if (MODE == CFB_WP && (jb.meta & JOB_ZCUT))
                             chunk_dispatch<T, MODE, true>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
                         else
                             chunk_dispatch<T, MODE, false>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
@@ -649,12 +656,10 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                         }
                         if (lane < nlp) {
                             const int k = jk + l0 + lane;
-                            const bool top = topm && (l0 + lane == jl - 1);
+                            const bool top = (jb.meta & JOB_TOPM) && (l0 + lane == jl - 1);
                             long long C = mine;
-                            if (tri) {  // full square of the tile against itself: drop self pairs, halve
-                                const double Ed = top ? CUDART_INF : S.edges_d[k];
-                                C = (C - (v_self < Ed ? nv : 0)) / 2;
-                            }
+                            if (jb.meta & JOB_TRI)  // full square of the tile against itself: drop self pairs, halve
+                                C = (C - (v_self < S.edges_d[k] ? nv : 0)) / 2;
                             if (C != 0) {
                                 atomicAdd(&S.hist[k], (u64)C);
                                 if (!top) atomicAdd(&S.hist[k + 1], (u64)(-C));
