@@ -224,7 +224,7 @@ extern "C" int cfb_extent(int slot, int which, double lohi[6])
 static void choose_subdivision(const Ctx &c, const cfb_box_lattice *lat, int64_t nmax, int sub[3])
 {
     sub[0] = sub[1] = sub[2] = 1;
-    const int target = c.target_occ > 0 ? c.target_occ : 86;  // mostly 3 primaries per lane (<= 96 per tile)
+    const int target = c.target_occ > 0 ? c.target_occ : 112;  // mostly 4 primaries per lane (97..128 per tile): measured best on config 5
     const double ncell = (double)lat->nmesh[0] * lat->nmesh[1] * lat->nmesh[2];
     const double occ = (double)nmax / ncell;
     if (occ <= 1.3 * target) return;

@@ -21,7 +21,8 @@
 //             saturating subtract, exact because positions are pre-scaled by a power of two so that
 //             distinct values at or above the smallest edge differ by at least 1;
 //     double: plain compare-and-count.
-//   * per-block histogram in shared memory (64-bit), merged with global atomics at the end.
+//   * per-warp histogram of signed 32-bit deltas in shared memory (no atomics on the per-job path), flushed into
+//     the block's 64-bit histogram before it can overflow; blocks merge with global atomics at the end.
 //
 // Compiled with -fmad=false: an FMA appears exactly where the reference's AVX-512 kernels have one.
 #include <math_constants.h>
@@ -32,7 +33,18 @@
 #define FAST_CH 128     // secondaries per staged chunk
 #define FAST_WARPS 4    // warps (= primary tiles) per block
 #define FAST_QCAP 128   // job queue entries per warp
-#define FAST_LMAX 8     // levels per pass over a chunk
+#ifndef FAST_LMAX
+#define FAST_LMAX 8     // levels per pass over a chunk (more levels -> more passes)
+#endif
+#ifndef FAST_UNROLL
+#define FAST_UNROLL 1   // unroll factor of the hottest inner-loop variants (2 measured 15 % slower: instruction cache)
+#endif
+#ifndef FAST_MINB_F32
+#define FAST_MINB_F32 4 // resident blocks per SM the float kernel is compiled for (register budget); 5 and 6 measured no faster
+#endif
+#ifndef FAST_MINB_F64
+#define FAST_MINB_F64 3
+#endif
 #define FAST_PRIM 4     // primaries per lane  (32 * 4 = CFB_TILE)
 
 typedef unsigned long long u64;
@@ -80,6 +92,13 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b)
 {
     u64 d;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// a - {b, b}: the scalar operand is broadcast by the instruction (SASS operand form R.F32), no register pair needed
+__device__ __forceinline__ u64 sub2s(u64 a, float b)
+{
+    u64 d;
+    asm("{\n.reg .b64 t;\nmov.b64 t, {%2,%2};\nsub.rn.f32x2 %0, %1, t;\n}" : "=l"(d) : "l"(a), "f"(b));
     return d;
 }
 __device__ __forceinline__ u64 add2(u64 a, u64 b)
@@ -136,6 +155,7 @@ struct FastWarp {
     alignas(16) T buf[2][3][FAST_CH];
     u64 mbar[2];
     FastJob q[FAST_QCAP];
+    int wh[CFB_FAST_MAX_EDGES + 2];  // the warp's private histogram of signed 32-bit deltas (flushed before it can overflow)
 };
 
 template <typename T>
@@ -151,27 +171,24 @@ struct FastShared {
 template <int MODE, int NL, int PA, bool ZCUT>
 __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, const float *sz, const int m4,
                                           const float (&xq)[FAST_PRIM], const float (&yq)[FAST_PRIM],
-                                          const float (&zq)[FAST_PRIM], const float (&E)[FAST_LMAX], const float pimax,
+                                          const float (&zq)[FAST_PRIM], const float *Es, const float pimax,
                                           int (&cnt)[FAST_LMAX])
 {
-    u64 xp[PA], yp[PA], zp[PA], E2[NL];
+    float E[NL];
     unsigned c[NL];
 #pragma unroll
-    for (int p = 0; p < PA; p++) {
-        xp[p] = pk(xq[p], xq[p]);
-        yp[p] = pk(yq[p], yq[p]);
-        zp[p] = pk(zq[p], zq[p]);
-    }
-#pragma unroll
     for (int l = 0; l < NL; l++) {
-        E2[l] = pk(E[l], E[l]);
+        E[l] = Es[l];
         c[l] = 0u;
     }
     const u64 th_a = pk(8388608.0f, 8388608.0f), th_b = pk(-16777216.0f, -16777216.0f);
-    // The loop is deliberately NOT unrolled: the kernel holds one loop per (levels, primaries) variant
-    // and the warps of an SM run different ones; unrolled copies overflow the instruction cache
-    // (measured: 26 "no instruction" stall cycles per issued instruction, 5x slower).
-#pragma unroll 1
+    // The kernel holds one loop per (levels, primaries) variant and the warps of an SM run different ones:
+    // unrolling them all 4x overflowed the instruction cache (measured: 26 "no instruction" stall cycles per
+    // issued instruction, 5x slower).  Only the variants that carry ~95 % of the iterations (3 primaries per
+    // lane, 1-3 levels) are unrolled, by 2: the sub-partition is issue bound and the 7 loop-control
+    // instructions are 5-7 % of such an iteration.
+    constexpr int UNR = (PA == 3 && NL <= 3) ? FAST_UNROLL : 1;
+#pragma unroll UNR
     for (int j = 0; j < m4; j += 4) {
         const float4 X = *reinterpret_cast<const float4 *>(sx + j);
         const float4 Y = *reinterpret_cast<const float4 *>(sy + j);
@@ -183,7 +200,7 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
         for (int p = 0; p < PA; p++) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const u64 dx = sub2(xs[h], xp[p]), dy = sub2(ys[h], yp[p]), dz = sub2(zs[h], zp[p]);
+                const u64 dx = sub2s(xs[h], xq[p]), dy = sub2s(ys[h], yq[p]), dz = sub2s(zs[h], zq[p]);
                 u64 v2;
                 if (MODE == CFB_WP) {
                     v2 = fma2(dy, dy, mul2(dx, dx));  // wp_kernels.c.src:197-198
@@ -205,7 +222,7 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
                 // sign bits are added to the level's counter on the integer pipe (LEA.HI)
 #pragma unroll
                 for (int l = 0; l < NL; l++) {
-                    const u64 d = sub2(v2, E2[l]);
+                    const u64 d = sub2s(v2, E[l]);
                     c[l] += (unsigned)d >> 31;
                     c[l] += (unsigned)(d >> 63);
                 }
@@ -219,9 +236,12 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
 template <int MODE, int NL, int PA, bool ZCUT>
 __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, const double *sz, const int m4,
                                           const double (&xq)[FAST_PRIM], const double (&yq)[FAST_PRIM],
-                                          const double (&zq)[FAST_PRIM], const double (&E)[FAST_LMAX],
+                                          const double (&zq)[FAST_PRIM], const double *Es,
                                           const double pimax, int (&cnt)[FAST_LMAX])
 {
+    double E[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) E[l] = Es[l];
 #pragma unroll 1
     for (int j = 0; j < m4; j += 2) {
         const double2 X = *reinterpret_cast<const double2 *>(sx + j);
@@ -250,7 +270,7 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
 
 template <typename T, int MODE, int NL, int PA, bool ZCUT>
 __device__ __forceinline__ void chunk_T(const T *sx, const T *sy, const T *sz, const int m4, const T (&xq)[FAST_PRIM],
-                                        const T (&yq)[FAST_PRIM], const T (&zq)[FAST_PRIM], const T (&E)[FAST_LMAX],
+                                        const T (&yq)[FAST_PRIM], const T (&zq)[FAST_PRIM], const T *E,
                                         const T pimax, int (&cnt)[FAST_LMAX])
 {
     if constexpr (sizeof(T) == 4)
@@ -262,17 +282,21 @@ __device__ __forceinline__ void chunk_T(const T *sx, const T *sy, const T *sz, c
 template <typename T, int MODE, int PA, bool ZCUT>
 __device__ __forceinline__ void chunk_dispatch_nl(const int nl, const T *sx, const T *sy, const T *sz, const int m4,
                                                   const T (&xq)[FAST_PRIM], const T (&yq)[FAST_PRIM],
-                                                  const T (&zq)[FAST_PRIM], const T (&E)[FAST_LMAX], const T pimax,
+                                                  const T (&zq)[FAST_PRIM], const T *E, const T pimax,
                                                   int (&cnt)[FAST_LMAX])
 {
     switch (nl) {
     case 1: chunk_T<T, MODE, 1, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
     case 2: chunk_T<T, MODE, 2, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
     case 3: chunk_T<T, MODE, 3, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+#if FAST_LMAX == 4
+    default: chunk_T<T, MODE, 4, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+#else
     case 4: chunk_T<T, MODE, 4, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
     case 5: chunk_T<T, MODE, 5, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
     case 6: chunk_T<T, MODE, 6, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
     default: chunk_T<T, MODE, 8, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;  // 7 runs as 8 (E[7] = +inf)
+#endif
     }
 }
 
@@ -280,7 +304,7 @@ __device__ __forceinline__ void chunk_dispatch_nl(const int nl, const T *sx, con
 template <typename T, int MODE, bool ZCUT>
 __device__ __forceinline__ void chunk_dispatch(const int nl, const int pa, const T *sx, const T *sy, const T *sz,
                                                const int m4, const T (&xq)[FAST_PRIM], const T (&yq)[FAST_PRIM],
-                                               const T (&zq)[FAST_PRIM], const T (&E)[FAST_LMAX], const T pimax,
+                                               const T (&zq)[FAST_PRIM], const T *E, const T pimax,
                                                int (&cnt)[FAST_LMAX])
 {
     switch (pa) {
@@ -318,8 +342,22 @@ __device__ __forceinline__ void stage_chunk(FastWarp<T> &W, const int bsel, cons
     }
 }
 
+// adds the warp's signed 32-bit deltas to the block's 64-bit histogram and clears them
+__device__ __forceinline__ void flush_warp_hist(int *wh, u64 *hist, const int nedges, const int lane)
+{
+    __syncwarp();
+    for (int i = lane; i <= nedges; i += 32) {
+        const int v = wh[i];
+        if (v != 0) {
+            atomicAdd(&hist[i], (u64)(long long)v);
+            wh[i] = 0;
+        }
+    }
+    __syncwarp();
+}
+
 template <typename T, int MODE, bool LIST, bool TMA>
-__global__ void __launch_bounds__(FAST_WARPS * 32, sizeof(T) == 4 ? 4 : 3)
+__global__ void __launch_bounds__(FAST_WARPS * 32, sizeof(T) == 4 ? FAST_MINB_F32 : FAST_MINB_F64)
 k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
 {
     __shared__ __align__(16) FastShared<T> S;
@@ -332,6 +370,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         if (i < nedges) S.edges_d[i] = (double)e;
     }
     FastWarp<T> &W = S.w[wid];
+    for (int i = lane; i < CFB_FAST_MAX_EDGES + 2; i += 32) W.wh[i] = 0;
     if (TMA && lane == 0) {
         mbar_init(&W.mbar[0], 1);
         mbar_init(&W.mbar[1], 1);
@@ -340,13 +379,21 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
     }
     __syncthreads();
 
-    // which tile is mine (sharded across ranks in groups of CFB_SHARD_GROUP tiles)
-    const int64_t gw = (int64_t)blockIdx.x * FAST_WARPS + wid;
-    const int64_t grp = gw / CFB_SHARD_GROUP;
-    const int64_t tile = (grp * P.shard_n + P.shard_rank) * CFB_SHARD_GROUP + (gw % CFB_SHARD_GROUP);
+    // Persistent warps: every warp pulls its next primary tile from a global counter (tiles differ in
+    // work by the cell occupancies; one tile per warp left 7 % of the warp time waiting at the block's
+    // final barrier).  Tiles are sharded across ranks in groups of CFB_SHARD_GROUP.
     u64 my_eval = 0, my_jobs = 0, my_analytic = 0, my_levels = 0;
+    unsigned wbound = 0;  // warp-uniform bound on the magnitude of any slot of W.wh
+    uint32_t it = 0;  // chunks staged so far by this warp (buffer = it & 1, TMA parity = (it >> 1) & 1)
 
-    if (tile < P.ntiles) {
+    for (;;) {
+        long long gw = 0;
+        if (lane == 0) gw = (long long)atomicAdd(&P.counters[4], 1ULL);
+        gw = __shfl_sync(0xffffffffu, gw, 0);
+        if (gw >= P.my_ntiles) break;
+        const int64_t grp = gw / CFB_SHARD_GROUP;
+        const int64_t tile = (grp * P.shard_n + P.shard_rank) * CFB_SHARD_GROUP + (gw % CFB_SHARD_GROUP);
+        if (tile >= P.ntiles) continue;
         const int cellP = P.tile_cell[tile];
         const int toff = P.tile_off[tile];
         const int nP = A.count[cellP];
@@ -354,15 +401,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         const int nv = min(CFB_TILE, nP - toff);  // valid primaries of this tile
         const int pa = (nv + 31) >> 5;            // primaries per lane in use
         const T nanv = sizeof(T) == 4 ? (T)CUDART_NAN_F : (T)CUDART_NAN;
-        T xr[FAST_PRIM], yr[FAST_PRIM], zr[FAST_PRIM];
-#pragma unroll
-        for (int p = 0; p < FAST_PRIM; p++) {
-            const int i = lane + 32 * p;
-            const bool ok = i < nv;
-            xr[p] = ok ? A.x[startP + toff + i] : nanv;
-            yr[p] = ok ? A.y[startP + toff + i] : nanv;
-            zr[p] = ok ? A.z[startP + toff + i] : nanv;
-        }
+        const T *pxg = A.x + startP + toff, *pyg = A.y + startP + toff, *pzg = A.z + startP + toff;
 
         int gx = 0, gy = 0, gz = 0, rax = 0, ray = 0, raz = 0;
         long long refA = 0;
@@ -396,11 +435,12 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         T xq[FAST_PRIM], yq[FAST_PRIM], zq[FAST_PRIM];
 #pragma unroll
         for (int p = 0; p < FAST_PRIM; p++) {
-            xq[p] = xr[p];
-            yq[p] = yr[p];
-            zq[p] = zr[p];
+            const int i = lane + 32 * p;
+            const bool ok = i < nv;
+            xq[p] = ok ? pxg[i] : nanv;
+            yq[p] = ok ? pyg[i] : nanv;
+            zq[p] = ok ? pzg[i] : nanv;
         }
-        uint32_t it = 0;  // chunks staged so far by this warp (buffer = it & 1, TMA parity = (it >> 1) & 1)
 
         for (int row = 0; row < nrow; row++) {
             for (int base = 0; base < rowlen; base += 32) {
@@ -409,6 +449,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                 bool keep = cand < rowlen;
                 int cellQ = -1, code = 0, kbase = 0, nl = 0, flags = 0;
                 int j_start = 0, j_n = 0, j2_start = 0, j2_n = 0;  // same cell: diagonal + rectangle jobs
+                unsigned npairs_w = 0;
                 if (keep) {
                     double offd[3] = {0.0, 0.0, 0.0};
                     if (LIST) {
@@ -547,9 +588,12 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                                     nl += 1;
                                     flags |= JOB_TOPM;
                                 }
+                            } else if (npairs_an < (1ULL << 24)) {
+                                atomicAdd(&W.wh[khi], (int)npairs_an);  // everything is below E[khi]
                             } else {
-                                atomicAdd(&S.hist[khi], npairs_an);  // everything is below E[khi]
+                                atomicAdd(&S.hist[khi], npairs_an);  // too big for the 32-bit warp histogram (huge theta cells)
                             }
+                            if (!zpartial && npairs_an < (1ULL << 24)) npairs_w = (unsigned)npairs_an;  // booked into W.wh
                             if (nl == 0) {
                                 keep = false;  // one bin for the whole block of pairs: nothing to evaluate
                                 my_analytic += npairs_an;
@@ -581,6 +625,13 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                     }
                     qn += __popc(m1) + __popc(m2);
                     __syncwarp();
+                }
+                // overflow guard of the warp's 32-bit histogram: |slot| <= wbound, the pairs booked since the
+                // last flush (<= 32 * 2^24 more per round here, <= 2^14 more per chunk pass below)
+                wbound += __reduce_add_sync(0xffffffffu, npairs_w);
+                if (wbound >= (1u << 30)) {
+                    flush_warp_hist(W.wh, S.hist, nedges, lane);
+                    wbound = 0;
                 }
                 // at most 2 * 32 new jobs per round: drain before another round could overflow the queue
                 const bool last = (row == nrow - 1) && (base + 32 >= rowlen);
@@ -615,6 +666,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
 
                     // first particle gets the wrap: xpos = x0 + off_xwrap (countpairs_kernels.c.src:79-81);
                     // shifted copies are kept in registers until a job with another wrap code comes up
+                    // (then the primaries are read again: only tiles at the box faces ever do)
                     const int jcode = jb.meta & 63;
                     if (jcode != cur_code) {
                         cur_code = jcode;
@@ -624,9 +676,13 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                         const T oz = cz == 1 ? (T)P.wrap[2] : -(T)P.wrap[2];
 #pragma unroll
                         for (int p = 0; p < FAST_PRIM; p++) {
-                            xq[p] = cx ? xr[p] + ox : xr[p];
-                            yq[p] = cy ? yr[p] + oy : yr[p];
-                            zq[p] = cz ? zr[p] + oz : zr[p];
+                            const int i = lane + 32 * p;
+                            if (i < nv) {
+                                const T xr = pxg[i], yr = pyg[i], zr = pzg[i];
+                                xq[p] = cx ? xr + ox : xr;
+                                yq[p] = cy ? yr + oy : yr;
+                                zq[p] = cz ? zr + oz : zr;
+                            }
                         }
                     }
                     const int jk = (jb.meta >> 6) & 127, jl = (jb.meta >> 13) & 127;
@@ -634,37 +690,41 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                         const int nlp = min(FAST_LMAX, jl - l0);
                         // the edge table is padded with +inf, and a measured top level (JOB_TOPM) may use
                         // its real edge: every unmasked value of the job lies below it
-                        T E[FAST_LMAX];
+                        const T *Es = &S.edges[jk + l0];
                         int cnt[FAST_LMAX];
 #pragma unroll
-                        for (int l = 0; l < FAST_LMAX; l++) {
-                            cnt[l] = 0;
-                            E[l] = S.edges[jk + l0 + l];
-                        }
+                        for (int l = 0; l < FAST_LMAX; l++) cnt[l] = 0;
                         if (MODE == CFB_WP && (jb.meta & JOB_ZCUT))
-                            chunk_dispatch<T, MODE, true>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
+                            chunk_dispatch<T, MODE, true>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
                         else
-                            chunk_dispatch<T, MODE, false>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
-                        // ---- warp totals -> block histogram: +C at the level's slot, -C one above ----
-                        int mine = 0;
+                            chunk_dispatch<T, MODE, false>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                        // ---- warp totals -> warp histogram: +C at the level's slot, -C one above ----
+                        // a lane counts at most FAST_PRIM * FAST_CH = 512 pairs per level here and the warp 2^14:
+                        // two levels share one 32-bit warp reduction
+                        unsigned mine = 0;
 #pragma unroll
-                        for (int l = 0; l < FAST_LMAX; l++) {
-                            if (l < nlp) {
-                                const int tot = __reduce_add_sync(0xffffffffu, cnt[l]);
-                                if (lane == l) mine = tot;
+                        for (int m = 0; m < FAST_LMAX / 2; m++) {
+                            if (2 * m < nlp) {
+                                const unsigned tot = __reduce_add_sync(0xffffffffu, (unsigned)cnt[2 * m] | ((unsigned)cnt[2 * m + 1] << 16));
+                                if ((lane >> 1) == m) mine = (lane & 1) ? (tot >> 16) : (tot & 0xffffu);
                             }
                         }
+                        const int k = jk + l0 + lane;
+                        const bool top = (jb.meta & JOB_TOPM) && (l0 + lane == jl - 1);
+                        int C = (int)mine;
                         if (lane < nlp) {
-                            const int k = jk + l0 + lane;
-                            const bool top = (jb.meta & JOB_TOPM) && (l0 + lane == jl - 1);
-                            long long C = mine;
                             if (jb.meta & JOB_TRI)  // full square of the tile against itself: drop self pairs, halve
                                 C = (C - (v_self < S.edges_d[k] ? nv : 0)) / 2;
-                            if (C != 0) {
-                                atomicAdd(&S.hist[k], (u64)C);
-                                if (!top) atomicAdd(&S.hist[k + 1], (u64)(-C));
-                            }
+                            W.wh[k] += C;  // distinct slots across the lanes
                         }
+                        __syncwarp();
+                        if (lane < nlp && !top) W.wh[k + 1] -= C;
+                        __syncwarp();
+                        wbound += (unsigned)(nv * m4);
+                    }
+                    if (wbound >= (1u << 30)) {
+                        flush_warp_hist(W.wh, S.hist, nedges, lane);
+                        wbound = 0;
                     }
                     __syncwarp();  // everyone is done with buf[bsel] before it is staged again
                     it++;
@@ -676,6 +736,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         }
     }
     // ---------------- merge ----------------
+    flush_warp_hist(W.wh, S.hist, nedges, lane);
     __syncthreads();
     for (int i = 1 + tid; i < nedges; i += blockDim.x) {
         const u64 v = S.hist[i];
@@ -720,13 +781,28 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
     }
     const int64_t ngroups = (P.ntiles + CFB_SHARD_GROUP - 1) / CFB_SHARD_GROUP;
     const int64_t mygroups = ngroups > P.shard_rank ? (ngroups - P.shard_rank + P.shard_n - 1) / P.shard_n : 0;
-    const int64_t nblk = mygroups * CFB_SHARD_GROUP / FAST_WARPS;
-    if (nblk <= 0) return 0;
-    if (nblk >= 2147483647LL) return cfb_fail("too many tiles (%lld)", (long long)nblk);
+    PairParams Q = P;
+    Q.my_ntiles = mygroups * CFB_SHARD_GROUP;
+    if (Q.my_ntiles <= 0) return 0;
+    // persistent warps: as many blocks as the device keeps resident, never more than there are tiles
+    static int resident[2][2] = {{0, 0}, {0, 0}};
+    int &res = resident[sizeof(T) == 8][use_tma];
+    if (res == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (use_tma)
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_fast<T, MODE, LIST, true>, FAST_WARPS * 32, 0));
+        else
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_fast<T, MODE, LIST, false>, FAST_WARPS * 32, 0));
+        res = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    int64_t nblk = (Q.my_ntiles + FAST_WARPS - 1) / FAST_WARPS;
+    if (nblk > res) nblk = res;
     if (use_tma)
-        k_pairs_fast<T, MODE, LIST, true><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(P, view_of<T>(SA), view_of<T>(SB));
+        k_pairs_fast<T, MODE, LIST, true><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q, view_of<T>(SA), view_of<T>(SB));
     else
-        k_pairs_fast<T, MODE, LIST, false><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(P, view_of<T>(SA), view_of<T>(SB));
+        k_pairs_fast<T, MODE, LIST, false><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q, view_of<T>(SA), view_of<T>(SB));
     cfb_ctx().launches++;
     CK(cudaGetLastError());
     return 0;
