@@ -39,6 +39,12 @@
 #ifndef FAST_UNROLL
 #define FAST_UNROLL 1   // unroll factor of the hottest inner-loop variants (2 measured 15 % slower: instruction cache)
 #endif
+#ifndef FAST_SPI2_PA
+#define FAST_SPI2_PA 4  // inner-loop bodies with >= this many primaries per lane and >= FAST_SPI2_NL levels
+#endif                  // take 2 instead of 4 secondaries per iteration (instruction-cache footprint)
+#ifndef FAST_SPI2_NL
+#define FAST_SPI2_NL 2
+#endif
 #ifndef FAST_MINB_F32
 #define FAST_MINB_F32 4 // resident blocks per SM the float kernel is compiled for (register budget); 5 and 6 measured no faster
 #endif
@@ -188,18 +194,34 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
     // lane, 1-3 levels) are unrolled, by 2: the sub-partition is issue bound and the 7 loop-control
     // instructions are 5-7 % of such an iteration.
     constexpr int UNR = (PA == 3 && NL <= 3) ? FAST_UNROLL : 1;
+    // Secondaries per iteration: 4 (three LDS.128), or 2 for the long bodies (many primaries x levels) -- a body
+    // must stay small enough that the loops of the four warps of a sub-partition fit its instruction cache
+    // together (measured with ncu: 24 % of all warp samples were instruction-fetch stalls at every 128-byte
+    // line of the 100+ instruction bodies)
+    constexpr int SPI = (PA >= FAST_SPI2_PA && NL >= FAST_SPI2_NL) ? 2 : 4;
+    constexpr int H = SPI / 2;
 #pragma unroll UNR
-    for (int j = 0; j < m4; j += 4) {
-        const float4 X = *reinterpret_cast<const float4 *>(sx + j);
-        const float4 Y = *reinterpret_cast<const float4 *>(sy + j);
-        const float4 Z = *reinterpret_cast<const float4 *>(sz + j);
-        const u64 xs[2] = {pk(X.x, X.y), pk(X.z, X.w)};
-        const u64 ys[2] = {pk(Y.x, Y.y), pk(Y.z, Y.w)};
-        const u64 zs[2] = {pk(Z.x, Z.y), pk(Z.z, Z.w)};
+    for (int j = 0; j < m4; j += SPI) {
+        u64 xs[H], ys[H], zs[H];
+        if constexpr (SPI == 4) {
+            const float4 X = *reinterpret_cast<const float4 *>(sx + j);
+            const float4 Y = *reinterpret_cast<const float4 *>(sy + j);
+            const float4 Z = *reinterpret_cast<const float4 *>(sz + j);
+            xs[0] = pk(X.x, X.y), xs[1] = pk(X.z, X.w);
+            ys[0] = pk(Y.x, Y.y), ys[1] = pk(Y.z, Y.w);
+            zs[0] = pk(Z.x, Z.y), zs[1] = pk(Z.z, Z.w);
+        } else {
+            const float2 X = *reinterpret_cast<const float2 *>(sx + j);
+            const float2 Y = *reinterpret_cast<const float2 *>(sy + j);
+            const float2 Z = *reinterpret_cast<const float2 *>(sz + j);
+            xs[0] = pk(X.x, X.y);
+            ys[0] = pk(Y.x, Y.y);
+            zs[0] = pk(Z.x, Z.y);
+        }
 #pragma unroll
         for (int p = 0; p < PA; p++) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int h = 0; h < H; h++) {
                 const u64 dx = sub2s(xs[h], xq[p]), dy = sub2s(ys[h], yq[p]), dz = sub2s(zs[h], zq[p]);
                 u64 v2;
                 if (MODE == CFB_WP) {
