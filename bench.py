@@ -457,9 +457,19 @@ def main():
     cfg = dict(CONFIGS[args.config])
     if args.npart and args.same_density and cfg["L"] > 0:
         cfg["L"] = float(cfg["L"] * (args.npart / cfg["N"]) ** (1.0 / 3.0))
-    line = run_reference(args, cfg) if args.impl == "reference" else run_ours(args, cfg)
+    # stdout carries exactly one JSON line: anything a library prints there meanwhile (e.g. NCCL's version
+    # banner) is routed to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference(args, cfg) if args.impl == "reference" else run_ours(args, cfg)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
