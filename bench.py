@@ -36,6 +36,9 @@ CONFIGS = {
     # name: (stat, N, L, bins, dtype, extra)
     "c1": dict(stat="DD", N=1_200_000, L=420.0, bins=("log", 0.1, 25.0, 15), dtype="f64", seed=1001),
     "c2": dict(stat="wp", N=1_200_000, L=420.0, bins=("log", 0.1, 25.0, 15), dtype="f64", seed=1001, pimax=40.0),
+    "c2rppi": dict(stat="DDrppi", N=1_200_000, L=420.0, bins=("log", 0.1, 25.0, 15), dtype="f64", seed=1001, pimax=40.0),
+    "c2rppi32": dict(stat="DDrppi", N=1_200_000, L=420.0, bins=("log", 0.1, 25.0, 15), dtype="f32", seed=1001, pimax=40.0),
+    "c2wp32": dict(stat="wp", N=1_200_000, L=420.0, bins=("log", 0.1, 25.0, 15), dtype="f32", seed=1001, pimax=40.0),
     "c3": dict(stat="DDsmu", N=10_000_000, L=1000.0, bins=("log", 0.1, 50.0, 21), dtype="f64", seed=1003,
                mu_max=1.0, nmu=20, weights=True, avg=True),
     "c4": dict(stat="DDtheta", N=2_000_000, L=0.0, bins=("log", 0.01, 10.0, 21), dtype="f64", seed=1004),
@@ -199,6 +202,11 @@ def run_ours(args, cfg):
             r = _capi.ResultsWp()
             st = lib.countpairs_wp(N, P["x"], P["y"], P["z"], cfg["L"], 1, bf, cfg["pimax"], C.byref(r), C.byref(o), C.byref(e))
             free = lib.free_results_wp
+        elif stat == "DDrppi":
+            r = _capi.ResultsRpPi()
+            st = lib.countpairs_rp_pi(N, P["x"], P["y"], P["z"], N, P["x"], P["y"], P["z"], 1, 1, bf, cfg["pimax"],
+                                      C.byref(r), C.byref(o), C.byref(e))
+            free = lib.free_results_rp_pi
         elif stat == "DDsmu":
             r = _capi.ResultsSMu()
             st = lib.countpairs_s_mu(N, P["x"], P["y"], P["z"], N, P["x"], P["y"], P["z"], 1, 1, bf, cfg["mu_max"],
@@ -216,7 +224,7 @@ def run_ours(args, cfg):
         if st != 0:
             raise RuntimeError("C call failed: %s" % lib.cfb_last_error())
         nb = r.nbin if hasattr(r, "nbin") else r.nsbin
-        tot = int(np.ctypeslib.as_array(r.npairs, shape=(nb,)).astype(np.uint64)[1:].sum()) if stat not in ("DDsmu",) else -1
+        tot = int(np.ctypeslib.as_array(r.npairs, shape=(nb,)).astype(np.uint64)[1:].sum()) if stat not in ("DDsmu", "DDrppi") else -1
         free(C.byref(r))
         return tot
 
@@ -290,7 +298,7 @@ def run_ours(args, cfg):
         return None
 
     # ---- workload constants ----
-    if stat in ("xi", "wp", "DD"):
+    if stat in ("xi", "wp", "DD", "DDrppi"):
         counts = ref_cell_counts(pts, cfg["L"], st0["nmesh"], dtype)
         n_cand = n_cand_box(counts, st0["refine"])
     else:
@@ -368,6 +376,8 @@ def ref_call(ref, cfg, pts, n, bins, nthreads):
         _capi.call_DD(ref, 1, nthreads, bins, pts["x"][:n], pts["y"][:n], pts["z"][:n], options=o)
     elif stat == "wp":
         _capi.call_wp(ref, cfg["L"], nthreads, cfg["pimax"], bins, pts["x"][:n], pts["y"][:n], pts["z"][:n], options=o)
+    elif stat == "DDrppi":
+        _capi.call_DDrppi(ref, 1, nthreads, cfg["pimax"], bins, pts["x"][:n], pts["y"][:n], pts["z"][:n], options=o)
     elif stat == "DDsmu":
         _capi.call_DDsmu(ref, 1, nthreads, bins, cfg["mu_max"], cfg["nmu"], pts["x"][:n], pts["y"][:n], pts["z"][:n],
                          w1=None if w is None else w[:n], weight_type=wt, options=o)

@@ -106,6 +106,7 @@ struct PairParams {
     // outputs
     unsigned long long *npairs;
     double *sum_sep, *sum_w;
+    const double *wmax;  // device: max |weight| of the first and of the second set (generic kernel, weights on)
     unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs [2]=pairs binned without evaluation [3]=sum of evaluated pairs x levels [4]=next tile (persistent warps)
     int hist_in_smem;
 };

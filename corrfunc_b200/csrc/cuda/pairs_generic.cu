@@ -57,6 +57,42 @@ __device__ __forceinline__ T fast_acos_t(const T x)
     return (x < 0) ? (T)(3.14159265358979323846 - (double)poly) : poly;
 }
 
+// Shared-memory accumulation without compare-and-swap loops.  On sm_100a only the 32-bit integer add is a
+// native shared-memory atomic (64-bit, float and double adds compile to ATOMS.CAST.SPIN loops), so a
+// block keeps its counts as two and its sums as three 32-bit words per slot: sums are 96-bit fixed point,
+// value * 2^k rounded to an integer below 2^60 in magnitude (k from the bin's upper edge, or from the largest
+// weight product), added word by word with the carries of the returned old values.  Integer sums are
+// exact and order independent, so the averages are reproducible from run to run.
+__device__ __forceinline__ void add_count(unsigned *w0, unsigned *w1)
+{
+    if (atomicAdd(w0, 1u) == 0xffffffffu) atomicAdd(w1, 1u);
+}
+__device__ __forceinline__ void add_fixed96(unsigned *w0, unsigned *w1, unsigned *w2, const long long q)
+{
+    const unsigned lo = (unsigned)q, mid = (unsigned)((unsigned long long)q >> 32), hi = q < 0 ? 0xffffffffu : 0u;
+    const unsigned old0 = atomicAdd(w0, lo);
+    const unsigned long long t = (unsigned long long)mid + ((unsigned)(old0 + lo) < lo ? 1u : 0u);
+    const unsigned m = (unsigned)t;
+    unsigned h = hi + (unsigned)(t >> 32);
+    if (m) {
+        const unsigned old1 = atomicAdd(w1, m);
+        h += (unsigned)(old1 + m) < m ? 1u : 0u;
+    }
+    if (h) atomicAdd(w2, h);
+}
+// value of a signed 96-bit word triple
+__device__ __forceinline__ double fixed96_to_double(const unsigned w0, const unsigned w1, const unsigned w2)
+{
+    return (double)(int)w2 * 18446744073709551616.0 + (double)w1 * 4294967296.0 + (double)w0;
+}
+// 2^k such that |v| * 2^k < 2^59 for every |v| <= vmax
+__device__ __forceinline__ double fixed_scale(const double vmax)
+{
+    int e = 0;
+    if (vmax > 0.0 && vmax < 1.0e300) frexp(vmax, &e);  // vmax < 2^e
+    return ldexp(1.0, 59 - e);
+}
+
 template <typename T>
 struct GenShared {
     T sx[GEN_CH], sy[GEN_CH], sz[GEN_CH], sw[GEN_CH];
@@ -70,19 +106,22 @@ __global__ void __launch_bounds__(CFB_TILE)
 k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // dynamic smem layout: edges | npairs(u64) | sum_sep(double) | sum_w(double)
+    // dynamic smem layout: edges | sep scale per edge (double) | npairs (2 words) | sum_sep (3 words) | sum_w (3 words)
     T *s_edges = (T *)smem_raw;
     const int nedges = P.nedges;
     size_t off = ((size_t)nedges * sizeof(T) + 15) & ~(size_t)15;
-    unsigned long long *s_np = (unsigned long long *)(smem_raw + off);
-    double *s_sep = nullptr, *s_w = nullptr;
+    double *s_scale = (double *)(smem_raw + off);
+    off += (size_t)nedges * 8;
+    unsigned *s_np = (unsigned *)(smem_raw + off);
+    unsigned *s_sep = nullptr, *s_w = nullptr;
+    const int64_t ns = P.nslots;
     if (P.hist_in_smem) {
-        off += (size_t)P.nslots * 8;
+        off += (size_t)ns * 8;
         if (AVG) {
-            s_sep = (double *)(smem_raw + off);
-            off += (size_t)P.nslots * 8;
+            s_sep = (unsigned *)(smem_raw + off);
+            off += (size_t)ns * 12;
         }
-        if (WGT) s_w = (double *)(smem_raw + off);
+        if (WGT) s_w = (unsigned *)(smem_raw + off);
     }
     __shared__ GenShared<T> S;
 
@@ -92,12 +131,24 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
     if (tile >= P.ntiles) return;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < nedges; i += CFB_TILE) s_edges[i] = ((const T *)P.edges)[i];
+    for (int i = tid; i < nedges; i += CFB_TILE) {
+        const T e = ((const T *)P.edges)[i];
+        s_edges[i] = e;
+        // largest separation a pair of the bin below edge i can have: sqrt(edge) (edges are squared), or the
+        // angle in degrees whose cosine the edge is
+        double vmax;
+        if (MODE == CFB_THETA) vmax = acos(fmin(1.0, fmax(-1.0, (double)e))) * 57.29577951308232087679815481410517 + 1e-9;
+        else vmax = sqrt(fmax(0.0, (double)e));
+        s_scale[i] = fixed_scale(vmax);
+    }
+    double w_scale = 1.0;
+    if (WGT) w_scale = fixed_scale(P.wmax[0] * P.wmax[1]);
     if (P.hist_in_smem)
-        for (int64_t i = tid; i < P.nslots; i += CFB_TILE) {
-            s_np[i] = 0ULL;
-            if (AVG) s_sep[i] = 0.0;
-            if (WGT) s_w[i] = 0.0;
+        for (int64_t i = tid; i < ns; i += CFB_TILE) {
+            s_np[i] = 0u;
+            s_np[ns + i] = 0u;
+            if (AVG) s_sep[i] = s_sep[ns + i] = s_sep[2 * ns + i] = 0u;
+            if (WGT) s_w[i] = s_w[ns + i] = s_w[2 * ns + i] = 0u;
         }
 
     const int cellP = P.tile_cell[tile];
@@ -271,9 +322,13 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                     k0 = iloc + 1 - c0;
                     if (k0 < 0) k0 = 0;
                 }
+                // (Deferring the accepted pairs -- a lane parks the indices of up to 2 or 4 accepted secondaries and
+                // the warp retires one parked pair per lane when some lane is full, so that the bin search / sqrt /
+                // histogram code runs with most lanes active -- was measured 15-50 % SLOWER on configs 2 and 3.)
                 for (int k = k0; k < m; k++) {
                     const T dx = S.sx[k] - xpos, dy = S.sy[k] - ypos, dz = S.sz[k] - zpos;
                     int64_t slot;
+                    int kbin = 0;  // the separation bin (upper-edge index) of the pair
                     T sep = 0;
                     if (MODE == CFB_DD || MODE == CFB_XI) {
                         const T r2 = fma_t<T>(dz, dz, fma_t<T>(dy, dy, dx * dx));
@@ -282,6 +337,7 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         for (kb = nedges - 1; kb >= 1; kb--)
                             if (r2 >= s_edges[kb - 1]) break;
                         slot = kb;
+                        kbin = kb;
                         if (AVG) sep = sqrt_t<T>(r2);
                     } else if (MODE == CFB_WP) {
                         const T r2 = fma_t<T>(dy, dy, dx * dx);
@@ -291,6 +347,7 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         for (kb = nedges - 1; kb >= 1; kb--)
                             if (r2 >= s_edges[kb - 1]) break;
                         slot = kb;
+                        kbin = kb;
                         if (AVG) sep = sqrt_t<T>(r2);
                     } else if (MODE == CFB_RPPI) {
                         const T r2 = fma_t<T>(dy, dy, dx * dx);
@@ -305,6 +362,7 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         // (countpairs_rp_pi_kernels.c.src:249-256)
                         const T fin = (T)kb * npi_p1 + adz * inv_dpi;
                         slot = (int64_t)(int)fin;
+                        kbin = kb;
                         if (AVG) sep = sqrt_t<T>(r2);
                     } else if (MODE == CFB_SMU) {
                         const T sqr_dz = dz * dz;
@@ -317,6 +375,7 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                             if (s2 >= s_edges[kb - 1]) break;
                         const T fin = (T)kb * nmu_p1 + mu * inv_dmu;
                         slot = (int64_t)(int)fin;
+                        kbin = kb;
                         if (AVG) sep = sqrt_t<T>(s2);
                     } else {  // CFB_THETA: cos(theta) = 1 - chord^2/2, edges are cos(theta_upp) (decreasing)
                         const T chord2 = fma_t<T>(dz, dz, fma_t<T>(dy, dy, dx * dx));
@@ -326,6 +385,7 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         for (kb = nedges - 1; kb >= 1; kb--)
                             if (ct <= s_edges[kb - 1]) break;
                         slot = kb;
+                        kbin = kb;
                         if (AVG) {
                             const T cc = ct >= (T)1.0 ? (T)1.0 : ct;
                             const T th = P.fast_acos ? fast_acos_t<T>(cc) : (T)acos(cc);
@@ -333,9 +393,11 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         }
                     }
                     if (P.hist_in_smem) {
-                        atomicAdd(&s_np[slot], 1ULL);
-                        if (AVG) atomicAdd(&s_sep[slot], (double)sep);
-                        if (WGT) atomicAdd(&s_w[slot], (double)(T)(wp * S.sw[k]));
+                        add_count(&s_np[slot], &s_np[ns + slot]);
+                        if (AVG) add_fixed96(&s_sep[slot], &s_sep[ns + slot], &s_sep[2 * ns + slot], __double2ll_rn((double)sep * s_scale[kbin]));
+                        if (WGT)
+                            add_fixed96(&s_w[slot], &s_w[ns + slot], &s_w[2 * ns + slot],
+                                        __double2ll_rn((double)(T)(wp * S.sw[k]) * w_scale));
                     } else {
                         atomicAdd(&P.npairs[slot], 1ULL);
                         if (AVG) atomicAdd(&P.sum_sep[slot], (double)sep);
@@ -349,18 +411,35 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
     // ---------------- merge ----------------
     __syncthreads();
     if (P.hist_in_smem) {
-        for (int64_t i = tid; i < P.nslots; i += CFB_TILE) {
-            const unsigned long long v = s_np[i];
+        for (int64_t i = tid; i < ns; i += CFB_TILE) {
+            const unsigned long long v = (unsigned long long)s_np[i] | ((unsigned long long)s_np[ns + i] << 32);
             if (v) {
                 atomicAdd(&P.npairs[i], v);
-                if (AVG) atomicAdd(&P.sum_sep[i], s_sep[i]);
-                if (WGT) atomicAdd(&P.sum_w[i], s_w[i]);
+                if (AVG) {
+                    const int kb = MODE == CFB_RPPI ? (int)(i / (P.npibin + 1)) : (MODE == CFB_SMU ? (int)(i / (P.nmu_bins + 1)) : (int)i);
+                    atomicAdd(&P.sum_sep[i], fixed96_to_double(s_sep[i], s_sep[ns + i], s_sep[2 * ns + i]) / s_scale[kb < nedges ? kb : nedges - 1]);
+                }
+                if (WGT) atomicAdd(&P.sum_w[i], fixed96_to_double(s_w[i], s_w[ns + i], s_w[2 * ns + i]) / w_scale);
             }
         }
     }
     for (int o = 16; o > 0; o >>= 1) my_eval += __shfl_xor_sync(0xffffffffu, my_eval, o);
     if ((tid & 31) == 0 && my_eval) atomicAdd(&P.counters[0], my_eval);
     if (tid == 0 && my_tp) atomicAdd(&P.counters[1], my_tp);
+}
+
+// max |w| over the cell-sorted weights of one set (padding holds zeros), as the bit pattern of a non-negative
+// double (ordered like the value) so that one 64-bit atomicMax merges the blocks
+template <typename T>
+__global__ void k_absmax(const int64_t n, const T *__restrict__ w, unsigned long long *out)
+{
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = fabs((double)w[i]);
+        if (a > m && a < 1.0e300) m = a;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
 template <typename T>
@@ -381,8 +460,8 @@ template <typename T, int MODE, bool AVG, bool WGT, bool LIST>
 static int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cudaStream_t st)
 {
     auto kern = k_pairs_generic<T, MODE, AVG, WGT, LIST>;
-    size_t sm = ((size_t)P.nedges * sizeof(T) + 15) & ~(size_t)15;
-    const size_t hist = (size_t)P.nslots * 8 * (1 + (AVG ? 1 : 0) + (WGT ? 1 : 0));
+    size_t sm = (((size_t)P.nedges * sizeof(T) + 15) & ~(size_t)15) + (size_t)P.nedges * 8;
+    const size_t hist = (size_t)P.nslots * (8 + (AVG ? 12 : 0) + (WGT ? 12 : 0));
     const size_t budget = 160 * 1024;
     P.hist_in_smem = (sm + hist <= budget) ? 1 : 0;
     sm += P.hist_in_smem ? hist : 8;
@@ -429,7 +508,34 @@ static int launch_T(const cfb_binning *bin, const PairParams &P, bool list_mode)
     }
 }
 
-int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode)
+template <typename T>
+static int weight_maxima(Ctx &c, const cfb_binning *bin, PairParams &P)
 {
+    // two doubles at scratch + 2048 (the first 256 bytes belong to gridlink)
+    if (cfb_ensure(c.scratch, 4096)) return 1;
+    unsigned long long *out = (unsigned long long *)((char *)c.scratch.p + 2048);
+    CK(cudaMemsetAsync(out, 0, 16, c.stream));
+    const ParticleSet &SA = c.set[0];
+    const ParticleSet &SB = bin->autocorr ? c.set[0] : c.set[1];
+    const ParticleSet *sets[2] = {&SA, &SB};
+    for (int k = 0; k < 2; k++) {
+        const ParticleSet &S = *sets[k];
+        if (S.npad <= 0 || !S.sorted[3].p) continue;
+        int nb = (int)((S.npad + 1023) / 1024);
+        if (nb > 1184) nb = 1184;
+        k_absmax<T><<<nb, 256, 0, c.stream>>>(S.npad, (const T *)S.sorted[3].p, out + k);
+        c.launches++;
+    }
+    CK(cudaGetLastError());
+    P.wmax = (const double *)out;
+    return 0;
+}
+
+int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P0, int prec, bool list_mode)
+{
+    PairParams P = P0;
+    if (bin->need_weights) {
+        if (prec == 4 ? weight_maxima<float>(cfb_ctx(), bin, P) : weight_maxima<double>(cfb_ctx(), bin, P)) return 1;
+    }
     return prec == 4 ? launch_T<float>(bin, P, list_mode) : launch_T<double>(bin, P, list_mode);
 }

@@ -486,3 +486,40 @@ def test_fast_against_reference_golden_counts(dtype):
     assert np.array_equal(r["npairs"], g["xi__npairs"])
     r = T.wp(L, 40.0, 4, edges, x, y, z)
     assert np.array_equal(r["npairs"], g["wp__npairs"])
+
+
+# ------------------------------------------------------------------------------------------------
+# The generic kernel keeps its per-block sums as 96-bit fixed point (three native 32-bit shared-memory
+# atomics with carries, scaled by the bin's upper edge / the largest weight product): signed weights,
+# weights of very different magnitude and a first bin that starts at zero must still meet the tolerance.
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["signed", "wide", "large"])
+def test_weighted_sums_fixed_point(dtype, kind):
+    T = _theory()
+    L, N = 100.0, 20000
+    x, y, z, w = H.box_points(31, N, L, dtype)
+    rng = np.random.default_rng(32)
+    if kind == "signed":
+        w = (rng.random(N) - 0.5).astype(dtype)
+    elif kind == "wide":
+        w = (10.0 ** rng.uniform(-6, 3, N)).astype(dtype)
+    else:
+        w = (1.0e6 * (1.0 + rng.random(N))).astype(dtype)
+    edges = np.concatenate([[0.0], np.logspace(-1, np.log10(12.0), 9)])  # rmin = 0: self pairs enter the first bin
+    got = T.DD(1, 2, edges, x, y, z, weights1=w, weight_type="pair_product", periodic=True, boxsize=L, output_ravg=True)
+    ref = H.oracle_theory("DD", x, y, z, edges, w1=w, weight_type="pair_product", periodic=True, boxsize=L, need_avg=True)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+    _close(got["ravg"], ref["ravg"], TOL[dtype], "ravg")
+    # signed weights cancel in the sum: compare against the scale of the summed magnitudes
+    wsum_got = got["weightavg"] * got["npairs"]
+    wsum_ref = ref["weightavg"] * ref["npairs"]
+    scale = np.abs(w).astype(np.float64).max() ** 2 * np.maximum(ref["npairs"], 1)
+    assert np.max(np.abs(wsum_got - wsum_ref) / scale) <= TOL[dtype], kind
+    if kind != "signed":
+        _close(got["weightavg"], ref["weightavg"], TOL[dtype], "weightavg")
+    got = T.DDsmu(1, 2, edges[1:], 1.0, 7, x, y, z, weights1=w, weight_type="pair_product", periodic=True, boxsize=L,
+                  output_savg=True)
+    ref = H.oracle_theory("DDsmu", x, y, z, edges[1:], w1=w, weight_type="pair_product", periodic=True, boxsize=L,
+                          need_avg=True, mu_max=1.0, nmu_bins=7)
+    assert np.array_equal(got["npairs"], ref["npairs"].ravel())
+    _close(got["savg"], ref["ravg"].ravel(), TOL[dtype], "savg")
