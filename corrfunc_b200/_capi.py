@@ -262,7 +262,9 @@ def _declare(lib):
 
 EXPORTED_SYMBOLS = ("countpairs", "free_results", "countpairs_rp_pi", "free_results_rp_pi", "countpairs_s_mu",
                     "free_results_s_mu", "countpairs_wp", "free_results_wp", "countpairs_xi", "free_results_xi",
-                    "countpairs_theta_mocks", "free_results_countpairs_theta")
+                    "countpairs_theta_mocks", "free_results_countpairs_theta") + tuple(
+    "%s_%s" % (f, t) for f in ("countpairs", "countpairs_rp_pi", "countpairs_s_mu", "countpairs_wp", "countpairs_xi",
+                               "countpairs_theta_mocks") for t in ("float", "double"))
 
 
 def call_DD(lib, autocorr, nthreads, bins, X1, Y1, Z1, w1=None, X2=None, Y2=None, Z2=None, w2=None,

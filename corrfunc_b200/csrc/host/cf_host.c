@@ -368,3 +368,66 @@ int countpairs_theta_mocks(const int64_t ND1, void *phi1, void *theta1, const in
     free(o.cf);
     return EXIT_SUCCESS;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Precision-suffixed entry points (the reference's *_impl.h.src prototypes): typed pointers; the
+ * options' float_type is overridden for the call and restored afterwards. */
+#define CF_TYPED(call)                                                      \
+    do {                                                                    \
+        if (!options) {                                                     \
+            fprintf(stderr, "Error: In %s> options can not be NULL\n", __func__); \
+            return EXIT_FAILURE;                                            \
+        }                                                                   \
+        const size_t saved = options->float_type;                           \
+        options->float_type = sizeof(*X1);                                  \
+        const int st = (call);                                              \
+        options->float_type = saved;                                        \
+        return st;                                                          \
+    } while (0)
+
+#define CF_TYPED_FUNCS(SUF, REAL)                                                                                        \
+    int countpairs_##SUF(const int64_t ND1, REAL *X1, REAL *Y1, REAL *Z1, const int64_t ND2, REAL *X2, REAL *Y2,         \
+                         REAL *Z2, const int numthreads, const int autocorr, const char *binfile,                       \
+                         results_countpairs *results, struct config_options *options, struct extra_options *extra)      \
+    {                                                                                                                    \
+        CF_TYPED(countpairs(ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, binfile, results, options, extra));  \
+    }                                                                                                                    \
+    int countpairs_rp_pi_##SUF(const int64_t ND1, REAL *X1, REAL *Y1, REAL *Z1, const int64_t ND2, REAL *X2, REAL *Y2,   \
+                               REAL *Z2, const int numthreads, const int autocorr, const char *binfile,                 \
+                               const double pimax, results_countpairs_rp_pi *results, struct config_options *options,   \
+                               struct extra_options *extra)                                                              \
+    {                                                                                                                    \
+        CF_TYPED(countpairs_rp_pi(ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, binfile, pimax, results,       \
+                                  options, extra));                                                                      \
+    }                                                                                                                    \
+    int countpairs_s_mu_##SUF(const int64_t ND1, REAL *X1, REAL *Y1, REAL *Z1, const int64_t ND2, REAL *X2, REAL *Y2,    \
+                              REAL *Z2, const int numthreads, const int autocorr, const char *sbinfile,                 \
+                              const double mu_max, const int nmu_bins, results_countpairs_s_mu *results,                \
+                              struct config_options *options, struct extra_options *extra)                              \
+    {                                                                                                                    \
+        CF_TYPED(countpairs_s_mu(ND1, X1, Y1, Z1, ND2, X2, Y2, Z2, numthreads, autocorr, sbinfile, mu_max, nmu_bins,     \
+                                 results, options, extra));                                                              \
+    }                                                                                                                    \
+    int countpairs_wp_##SUF(const int64_t ND1, REAL *X1, REAL *Y1, REAL *Z1, const double boxsize, const int numthreads, \
+                            const char *binfile, const double pimax, results_countpairs_wp *result,                     \
+                            struct config_options *options, struct extra_options *extra)                                \
+    {                                                                                                                    \
+        CF_TYPED(countpairs_wp(ND1, X1, Y1, Z1, boxsize, numthreads, binfile, pimax, result, options, extra));           \
+    }                                                                                                                    \
+    int countpairs_xi_##SUF(const int64_t ND1, REAL *X1, REAL *Y1, REAL *Z1, const double boxsize, const int numthreads, \
+                            const char *binfile, results_countpairs_xi *results, struct config_options *options,       \
+                            struct extra_options *extra)                                                                 \
+    {                                                                                                                    \
+        CF_TYPED(countpairs_xi(ND1, X1, Y1, Z1, boxsize, numthreads, binfile, results, options, extra));                 \
+    }                                                                                                                    \
+    int countpairs_theta_mocks_##SUF(const int64_t ND1, REAL *X1, REAL *theta1, const int64_t ND2, REAL *phi2,           \
+                                     REAL *theta2, const int numthreads, const int autocorr, const char *binfile,       \
+                                     results_countpairs_theta *results, struct config_options *options,                 \
+                                     struct extra_options *extra)                                                        \
+    {                                                                                                                    \
+        CF_TYPED(countpairs_theta_mocks(ND1, X1, theta1, ND2, phi2, theta2, numthreads, autocorr, binfile, results,      \
+                                        options, extra));                                                                \
+    }
+
+CF_TYPED_FUNCS(float, float)
+CF_TYPED_FUNCS(double, double)

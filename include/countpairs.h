@@ -28,6 +28,15 @@ extern int countpairs(const int64_t ND1, void *X1, void *Y1, void *Z1, const int
                       results_countpairs *results, struct config_options *options,
                       struct extra_options *extra) __attribute__((warn_unused_result));
 extern void free_results(results_countpairs *results);
+/* Precision-suffixed entry points of the reference's static libraries (theory/DD/countpairs_impl.h.src:37-44):
+ * typed pointers, options->float_type is ignored (set to the suffix's width for the duration of the call). */
+extern int countpairs_float(const int64_t ND1, float *X1, float *Y1, float *Z1, const int64_t ND2, float *X2, float *Y2,
+                            float *Z2, const int numthreads, const int autocorr, const char *binfile,
+                            results_countpairs *results, struct config_options *options, struct extra_options *extra);
+extern int countpairs_double(const int64_t ND1, double *X1, double *Y1, double *Z1, const int64_t ND2, double *X2,
+                             double *Y2, double *Z2, const int numthreads, const int autocorr, const char *binfile,
+                             results_countpairs *results, struct config_options *options, struct extra_options *extra);
+
 
 #ifdef __cplusplus
 }

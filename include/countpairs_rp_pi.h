@@ -30,6 +30,16 @@ extern int countpairs_rp_pi(const int64_t ND1, void *X1, void *Y1, void *Z1, con
                             const double pimax, results_countpairs_rp_pi *results, struct config_options *options,
                             struct extra_options *extra);
 extern void free_results_rp_pi(results_countpairs_rp_pi *results);
+/* theory/DDrppi/countpairs_rp_pi_impl.h.src:37-45 */
+extern int countpairs_rp_pi_float(const int64_t ND1, float *X1, float *Y1, float *Z1, const int64_t ND2, float *X2,
+                                  float *Y2, float *Z2, const int numthreads, const int autocorr, const char *binfile,
+                                  const double pimax, results_countpairs_rp_pi *results,
+                                  struct config_options *options, struct extra_options *extra);
+extern int countpairs_rp_pi_double(const int64_t ND1, double *X1, double *Y1, double *Z1, const int64_t ND2, double *X2,
+                                   double *Y2, double *Z2, const int numthreads, const int autocorr,
+                                   const char *binfile, const double pimax, results_countpairs_rp_pi *results,
+                                   struct config_options *options, struct extra_options *extra);
+
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,17 @@ extern int countpairs_s_mu(const int64_t ND1, void *X1, void *Y1, void *Z1, cons
                            const double mu_max, const int nmu_bins, results_countpairs_s_mu *results,
                            struct config_options *options, struct extra_options *extra);
 extern void free_results_s_mu(results_countpairs_s_mu *results);
+/* theory/DDsmu/countpairs_s_mu_impl.h.src:39-48 */
+extern int countpairs_s_mu_float(const int64_t ND1, float *X1, float *Y1, float *Z1, const int64_t ND2, float *X2,
+                                 float *Y2, float *Z2, const int numthreads, const int autocorr, const char *sbinfile,
+                                 const double mu_max, const int nmu_bins, results_countpairs_s_mu *results,
+                                 struct config_options *options, struct extra_options *extra);
+extern int countpairs_s_mu_double(const int64_t ND1, double *X1, double *Y1, double *Z1, const int64_t ND2, double *X2,
+                                  double *Y2, double *Z2, const int numthreads, const int autocorr,
+                                  const char *sbinfile, const double mu_max, const int nmu_bins,
+                                  results_countpairs_s_mu *results, struct config_options *options,
+                                  struct extra_options *extra);
+
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,16 @@ extern int countpairs_theta_mocks(const int64_t ND1, void *phi1, void *theta1, c
                                   results_countpairs_theta *results, struct config_options *options,
                                   struct extra_options *extra);
 extern void free_results_countpairs_theta(results_countpairs_theta *results);
+/* mocks/DDtheta_mocks/countpairs_theta_mocks_impl.h.src:39-45 */
+extern int countpairs_theta_mocks_float(const int64_t ND1, float *phi1, float *theta1, const int64_t ND2, float *phi2,
+                                        float *theta2, const int numthreads, const int autocorr, const char *binfile,
+                                        results_countpairs_theta *results, struct config_options *options,
+                                        struct extra_options *extra);
+extern int countpairs_theta_mocks_double(const int64_t ND1, double *phi1, double *theta1, const int64_t ND2,
+                                         double *phi2, double *theta2, const int numthreads, const int autocorr,
+                                         const char *binfile, results_countpairs_theta *results,
+                                         struct config_options *options, struct extra_options *extra);
+
 
 #ifdef __cplusplus
 }

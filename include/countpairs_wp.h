@@ -28,6 +28,16 @@ extern int countpairs_wp(const int64_t ND1, void *X1, void *Y1, void *Z1, const 
                          struct config_options *options, struct extra_options *extra)
     __attribute__((warn_unused_result));
 extern void free_results_wp(results_countpairs_wp *results);
+/* theory/wp/countpairs_wp_impl.h.src:37-44 */
+extern int countpairs_wp_float(const int64_t ND1, float *X1, float *Y1, float *Z1, const double boxsize,
+                               const int numthreads, const char *binfile, const double pimax,
+                               results_countpairs_wp *result, struct config_options *options,
+                               struct extra_options *extra);
+extern int countpairs_wp_double(const int64_t ND1, double *X1, double *Y1, double *Z1, const double boxsize,
+                                const int numthreads, const char *binfile, const double pimax,
+                                results_countpairs_wp *result, struct config_options *options,
+                                struct extra_options *extra);
+
 
 #ifdef __cplusplus
 }

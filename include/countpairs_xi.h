@@ -26,6 +26,14 @@ extern int countpairs_xi(const int64_t ND1, void *X1, void *Y1, void *Z1, const 
                          const char *binfile, results_countpairs_xi *results, struct config_options *options,
                          struct extra_options *extra);
 extern void free_results_xi(results_countpairs_xi *results);
+/* theory/xi/countpairs_xi_impl.h.src:35-41 */
+extern int countpairs_xi_float(const int64_t ND1, float *X1, float *Y1, float *Z1, const double boxsize,
+                               const int numthreads, const char *binfile, results_countpairs_xi *results,
+                               struct config_options *options, struct extra_options *extra);
+extern int countpairs_xi_double(const int64_t ND1, double *X1, double *Y1, double *Z1, const double boxsize,
+                                const int numthreads, const char *binfile, results_countpairs_xi *results,
+                                struct config_options *options, struct extra_options *extra);
+
 
 #ifdef __cplusplus
 }

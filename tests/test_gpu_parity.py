@@ -523,3 +523,34 @@ def test_weighted_sums_fixed_point(dtype, kind):
                           need_avg=True, mu_max=1.0, nmu_bins=7)
     assert np.array_equal(got["npairs"], ref["npairs"].ravel())
     _close(got["savg"], ref["ravg"].ravel(), TOL[dtype], "savg")
+
+
+def test_precision_suffixed_entry_points():
+    """countpairs_float / countpairs_xi_double ... (the reference's *_impl.h.src prototypes) take typed pointers
+    and ignore options->float_type."""
+    import ctypes as C
+
+    from corrfunc_b200 import _capi, _lib
+
+    lib = _lib.load()
+    _capi._declare(lib)
+    L, N = 150.0, 20000
+    bins = np.logspace(-1, np.log10(10.0), 9)
+    for dtype, suf in ((np.float32, "float"), (np.float64, "double")):
+        x, y, z, _ = H.box_points(41, N, L, dtype)
+        want = _capi.call_DD(lib, 1, 1, bins, x, y, z, options=_capi.default_options(dtype, periodic=True, boxsize=L))
+        o = _capi.default_options(dtype, periodic=True, boxsize=L)
+        o.float_type = 12 - o.float_type  # deliberately the other width: the typed entry point must not look at it
+        e, keep = _capi.make_extra(None, None, None, dtype)
+        r = _capi.ResultsDD()
+        fn = getattr(lib, "countpairs_" + suf)
+        fn.restype = C.c_int
+        with _capi.binfile_for(bins) as bf:
+            p = [C.c_void_p(a.ctypes.data) for a in (x, y, z)]
+            st = fn(C.c_int64(N), p[0], p[1], p[2], C.c_int64(N), p[0], p[1], p[2], C.c_int(1), C.c_int(1), bf,
+                    C.byref(r), C.byref(o), C.byref(e))
+        assert st == 0
+        got = np.ctypeslib.as_array(r.npairs, shape=(r.nbin,)).astype(np.uint64)[1:].copy()
+        lib.free_results(C.byref(r))
+        assert np.array_equal(got, want["npairs"])
+        assert o.float_type == 12 - np.dtype(dtype).itemsize  # restored
