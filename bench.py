@@ -42,6 +42,7 @@ CONFIGS = {
     "c3": dict(stat="DDsmu", N=10_000_000, L=1000.0, bins=("log", 0.1, 50.0, 21), dtype="f64", seed=1003,
                mu_max=1.0, nmu=20, weights=True, avg=True),
     "c4": dict(stat="DDtheta", N=2_000_000, L=0.0, bins=("log", 0.01, 10.0, 21), dtype="f64", seed=1004),
+    "c5d": dict(stat="xi", N=100_000_000, L=2000.0, bins=("log", 0.1, 150.0, 31), dtype="f64", seed=1006),
     "c5": dict(stat="xi", N=100_000_000, L=2000.0, bins=("log", 0.1, 150.0, 31), dtype="f32", seed=1006),
 }
 FLOP_PER_EVAL = {"DD": 8, "xi": 8, "wp": 6, "DDrppi": 7, "DDsmu": 9, "DDtheta": 10}
@@ -274,7 +275,13 @@ def run_ours(args, cfg):
                 flush.zero_()
                 torch.cuda.synchronize()
             t0 = time.perf_counter()
-            one_call(pinned, bf)
+            if world > 1 and stat != "DDtheta":
+                # each rank uploads 1/world of the host arrays, one NVLink all-gather completes the replicas
+                dev_t = parallel.replicate_from_host([pinned[k] for k in keys], dev, dist)
+                torch.cuda.current_stream().synchronize()
+                one_call(dict(zip(keys, dev_t)), bf)
+            else:
+                one_call(pinned, bf)
             t_acc += time.perf_counter() - t0
         barrier()
         t_e2e = t_acc / args.steps

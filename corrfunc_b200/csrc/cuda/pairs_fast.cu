@@ -7,22 +7,24 @@
 // of generate_cell_pairs_DOUBLE (utils/gridlink_impl.c.src:439-625).
 //
 // Design:
-//   * one WARP owns one primary tile: up to 128 particles of one fine cell, 4 per lane in registers;
+//   * one WARP owns one primary tile: up to 128 particles of one fine cell, 4 per lane in registers; warps are
+//     persistent and pull their next tile from a global counter;
 //   * phase 1: the 32 lanes test 32 candidate neighbour cells at a time.  From the two cells' particle
 //     bounding boxes a lane derives a conservative interval [vlo, vhi] of every separation the pair
 //     of cells can produce and, from it, the few bin edges that can actually split those pairs
 //     ("levels").  No level -> the whole N1 x N2 block goes to one bin without touching a particle;
-//   * phase 2: the neighbour's particles are staged in shared memory with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier, double buffered, per warp) and every lane runs its 4 primaries
-//     against them with the reference's arithmetic: same subtraction order (second - (first + wrap)),
+//   * phase 2: the neighbour's particles are staged in shared memory per warp, double buffered, with 16-byte
+//     cp.async (default) or 1-D TMA bulk copies + mbarrier (CORRFUNC_B200_STAGE=tma), and every lane runs its
+//     primaries against them with the reference's arithmetic: same subtraction order (second - (first + wrap)),
 //     same FMA association.  Instead of searching a bin per pair, the warp keeps one cumulative
 //     counter per level, #{v < edge}, in registers; bin counts are differences of those counters.
-//     float : two pairs per instruction (sub/mul/fma.f32x2); the indicator [v < edge] is ONE
-//             saturating subtract, exact because positions are pre-scaled by a power of two so that
-//             distinct values at or above the smallest edge differ by at least 1;
+//     float : two pairs per instruction (sub/mul/fma.f32x2 with the primary broadcast by the instruction); the
+//             indicator [v < edge] is the sign bit of one more packed subtract, added to the counter by LEA.HI;
 //     double: plain compare-and-count.
 //   * per-warp histogram of signed 32-bit deltas in shared memory (no atomics on the per-job path), flushed into
 //     the block's 64-bit histogram before it can overflow; blocks merge with global atomics at the end.
+//   The kernel is bound by warp-instruction issue (a packed f32x2 instruction holds the issue port two cycles)
+//   and sensitive to the instruction-cache footprint of its inner-loop bodies: see DESIGN.md section 4.
 //
 // Compiled with -fmad=false: an FMA appears exactly where the reference's AVX-512 kernels have one.
 #include <math_constants.h>

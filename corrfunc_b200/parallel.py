@@ -46,3 +46,30 @@ def disable_distributed():
     from . import _lib
 
     _lib.set_shard(0, 1, None)
+
+
+def replicate_from_host(host_tensors, device, dist=None):
+    """Every rank needs the full particle arrays on its GPU.  Instead of N full host->device copies over a shared
+    PCIe / host-memory path, rank r uploads the r-th 1/world slice of each (pinned) host tensor and one all-gather
+    over NVLink completes the replica on every GPU.  Returns device tensors that can be
+    passed to the C ABI as device pointers.  All ranks must hold the same host data."""
+    import torch
+
+    if dist is None:
+        import torch.distributed as dist  # noqa: PLC0415
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    out = []
+    for t in host_tensors:
+        n = t.numel()
+        if world == 1:
+            out.append(t.to(device, non_blocking=True))
+            continue
+        per = (n + world - 1) // world
+        full = torch.empty(per * world, dtype=t.dtype, device=device)
+        lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+        mine = full[rank * per: rank * per + (hi - lo)]
+        mine.copy_(t[lo:hi], non_blocking=True)
+        dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per])
+        out.append(full[:n])
+    return out

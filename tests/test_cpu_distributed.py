@@ -66,3 +66,36 @@ def test_histogram_allreduce_gloo_world2():
     for _, _, (n, s, w) in res:
         assert np.array_equal(n, tot_n)  # integer sums exact -> npairs independent of the rank count
         assert np.allclose(s, tot_s, rtol=1e-15) and np.allclose(w, tot_w, rtol=1e-15)
+
+
+def _worker_replicate(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from corrfunc_b200 import parallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a = torch.arange(1001, dtype=torch.float32)  # not a multiple of the world size
+    b = torch.arange(7, dtype=torch.float64)
+    c = torch.zeros(0, dtype=torch.float32)
+    out = parallel.replicate_from_host([a, b, c], torch.device("cpu"), dist)
+    q.put((rank, bool(torch.equal(out[0], a) and torch.equal(out[1], b) and out[2].numel() == 0)))
+    dist.destroy_process_group()
+
+
+def test_sharded_upload_allgather_gloo_world2():
+    """replicate_from_host: every rank contributes 1/world of the host arrays, all ranks end with the full copy."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_replicate, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == [0, 1]
+    assert all(ok for _, ok in res)
