@@ -9,7 +9,7 @@
 
 #define CFB_PAD 4            // every fine cell's run in the sorted SoA starts at a multiple of this (16 B for float)
 #define CFB_TILE 128         // primaries per tile in the generic kernel (one per thread)
-#define CFB_SHARD_GROUP 8    // tiles per shard group
+#define CFB_SHARD_GROUP 8    // fine cells per shard group: rank r owns the cells c with (c / 8) % nranks == r
 #define CFB_FAST_MAX_EDGES 64 // the fast kernel keeps edges and the block histogram in static shared memory
 
 struct DevBuf {
@@ -101,7 +101,6 @@ struct PairParams {
     // tiles of the primary set
     const int *tile_cell, *tile_off;
     int64_t ntiles;
-    int64_t my_ntiles;  // fast kernel: tiles this rank works through (whole shard groups)
     int shard_rank, shard_n;
     // outputs
     unsigned long long *npairs;
@@ -110,6 +109,14 @@ struct PairParams {
     unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs [2]=pairs binned without evaluation [3]=sum of evaluated pairs x levels [4]=next tile (persistent warps)
     int hist_in_smem;
 };
+
+// Multi-rank sharding is by primary CELL, never by tile: every rank sorts its own replica and the order of the
+// particles inside a cell (atomic arrival ranks) differs from rank to rank, so the tiles of one cell only
+// partition its particles consistently when one rank handles all of them.
+__host__ __device__ __forceinline__ bool cfb_owns_cell(const int cell, const int rank, const int nranks)
+{
+    return nranks <= 1 || (cell / CFB_SHARD_GROUP) % nranks == rank;
+}
 
 // gridlink entry points (gridlink.cu)
 // scale: power of two applied to the sorted copy of the positions (1 unless the fast float kernel runs)

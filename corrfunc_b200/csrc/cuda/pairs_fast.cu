@@ -405,7 +405,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
 
     // Persistent warps: every warp pulls its next primary tile from a global counter (tiles differ in
     // work by the cell occupancies; one tile per warp left 7 % of the warp time waiting at the block's
-    // final barrier).  Tiles are sharded across ranks in groups of CFB_SHARD_GROUP.
+    // final barrier).  Across ranks the work is sharded by primary cell (cfb_owns_cell).
     u64 my_eval = 0, my_jobs = 0, my_analytic = 0, my_levels = 0;
     unsigned wbound = 0;  // warp-uniform bound on the magnitude of any slot of W.wh
     uint32_t it = 0;  // chunks staged so far by this warp (buffer = it & 1, TMA parity = (it >> 1) & 1)
@@ -414,11 +414,10 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         long long gw = 0;
         if (lane == 0) gw = (long long)atomicAdd(&P.counters[4], 1ULL);
         gw = __shfl_sync(0xffffffffu, gw, 0);
-        if (gw >= P.my_ntiles) break;
-        const int64_t grp = gw / CFB_SHARD_GROUP;
-        const int64_t tile = (grp * P.shard_n + P.shard_rank) * CFB_SHARD_GROUP + (gw % CFB_SHARD_GROUP);
-        if (tile >= P.ntiles) continue;
+        if (gw >= P.ntiles) break;
+        const int64_t tile = gw;
         const int cellP = P.tile_cell[tile];
+        if (!cfb_owns_cell(cellP, P.shard_rank, P.shard_n)) continue;  // another rank's cell (see cfb_owns_cell)
         const int toff = P.tile_off[tile];
         const int nP = A.count[cellP];
         const int startP = A.start[cellP];
@@ -803,11 +802,8 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
         const char *e = getenv("CORRFUNC_B200_STAGE");
         use_tma = (e && strcmp(e, "tma") == 0) ? 1 : 0;
     }
-    const int64_t ngroups = (P.ntiles + CFB_SHARD_GROUP - 1) / CFB_SHARD_GROUP;
-    const int64_t mygroups = ngroups > P.shard_rank ? (ngroups - P.shard_rank + P.shard_n - 1) / P.shard_n : 0;
-    PairParams Q = P;
-    Q.my_ntiles = mygroups * CFB_SHARD_GROUP;
-    if (Q.my_ntiles <= 0) return 0;
+    const PairParams &Q = P;
+    if (Q.ntiles <= 0) return 0;
     // persistent warps: as many blocks as the device keeps resident, never more than there are tiles
     static int resident[2][2] = {{0, 0}, {0, 0}};
     int &res = resident[sizeof(T) == 8][use_tma];
@@ -821,7 +817,7 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_fast<T, MODE, LIST, false>, FAST_WARPS * 32, 0));
         res = sms * (per_sm > 0 ? per_sm : 1);
     }
-    int64_t nblk = (Q.my_ntiles + FAST_WARPS - 1) / FAST_WARPS;
+    int64_t nblk = (Q.ntiles / (Q.shard_n > 1 ? Q.shard_n : 1) + FAST_WARPS - 1) / FAST_WARPS + 1;
     if (nblk > res) nblk = res;
     if (use_tma)
         k_pairs_fast<T, MODE, LIST, true><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q, view_of<T>(SA), view_of<T>(SB));
@@ -849,7 +845,6 @@ static int launch_fast_T(const cfb_binning *bin, const PairParams &P, bool list_
 
 int cfb_launch_pairs_fast(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode)
 {
-    static_assert(CFB_SHARD_GROUP % FAST_WARPS == 0, "shard groups must hold whole blocks");
     static_assert(FAST_PRIM * 32 == CFB_TILE, "a warp owns one tile");
     return prec == 4 ? launch_fast_T<float>(bin, P, list_mode) : launch_fast_T<double>(bin, P, list_mode);
 }

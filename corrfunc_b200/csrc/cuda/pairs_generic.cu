@@ -125,10 +125,10 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
     }
     __shared__ GenShared<T> S;
 
-    // which tile is mine (work sharding across ranks in groups of CFB_SHARD_GROUP tiles)
-    const int64_t grp = (int64_t)blockIdx.x / CFB_SHARD_GROUP;
-    const int64_t tile = (grp * P.shard_n + P.shard_rank) * CFB_SHARD_GROUP + (blockIdx.x % CFB_SHARD_GROUP);
+    // one block per primary tile; across ranks the work is sharded by primary cell (cfb_owns_cell)
+    const int64_t tile = blockIdx.x;
     if (tile >= P.ntiles) return;
+    if (!cfb_owns_cell(P.tile_cell[tile], P.shard_rank, P.shard_n)) return;
     const int tid = threadIdx.x;
 
     for (int i = tid; i < nedges; i += CFB_TILE) {
@@ -466,9 +466,7 @@ static int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &S
     P.hist_in_smem = (sm + hist <= budget) ? 1 : 0;
     sm += P.hist_in_smem ? hist : 8;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 16384));
-    const int64_t ngroups = (P.ntiles + CFB_SHARD_GROUP - 1) / CFB_SHARD_GROUP;
-    const int64_t mygroups = ngroups > P.shard_rank ? (ngroups - P.shard_rank + P.shard_n - 1) / P.shard_n : 0;
-    const int64_t nblk = mygroups * CFB_SHARD_GROUP;
+    const int64_t nblk = P.ntiles;
     if (nblk <= 0) return 0;
     if (nblk >= 2147483647LL) return cfb_fail("too many tiles (%lld)", (long long)nblk);
     kern<<<(unsigned int)nblk, CFB_TILE, sm, st>>>(P, view_of<T>(SA), view_of<T>(SB));

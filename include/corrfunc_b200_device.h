@@ -96,9 +96,9 @@ int cfb_upload(int slot, int prec, int64_t n, const void *x, const void *y, cons
 /* Folds the device-side min/max of slot's x,y,z (or ra,dec when which==1) into lohi[6]={min3,max3}. */
 int cfb_extent(int slot, int which, double lohi[6]);
 
-/* Work sharding across ranks (one process per GPU): this process handles primary tiles t with
- * (t / 8) % nranks == rank.  Histograms returned are then partial and must be summed by the caller
- * (see corrfunc_b200_set_reduce_hook in corrfunc_b200.h). */
+/* Work sharding across ranks (one process per GPU): this process handles the primary cells c with
+ * (c / 8) % nranks == rank -- by cell, not by tile, because the particle order inside a cell differs between
+ * the ranks' replicas; every rank holds all particles and the histograms are summed by the reduce hook. */
 void cfb_set_shard(int rank, int nranks);
 void cfb_get_shard(int *rank, int *nranks);
 

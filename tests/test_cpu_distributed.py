@@ -8,26 +8,28 @@ import torch.multiprocessing as mp
 SHARD_GROUP = 8  # CFB_SHARD_GROUP in corrfunc_b200/csrc/cuda/cfb_internal.cuh
 
 
-def tiles_of_rank(ntiles, rank, nranks):
-    """Python restatement of the block -> tile map in k_pairs_generic / launch_inst."""
-    ngroups = (ntiles + SHARD_GROUP - 1) // SHARD_GROUP
-    mygroups = (ngroups - rank + nranks - 1) // nranks if ngroups > rank else 0
-    out = []
-    for b in range(mygroups * SHARD_GROUP):
-        grp = b // SHARD_GROUP
-        t = (grp * nranks + rank) * SHARD_GROUP + b % SHARD_GROUP
-        if t < ntiles:
-            out.append(t)
-    return out
+def owner_of_cell(cell, nranks):
+    """Python restatement of cfb_owns_cell (cfb_internal.cuh): rank r owns the cells c with (c / 8) % nranks == r."""
+    return (cell // SHARD_GROUP) % nranks if nranks > 1 else 0
 
 
-def test_shard_map_is_a_partition():
-    for ntiles in (0, 1, 7, 8, 9, 63, 64, 65, 1000, 17424):
+def test_shard_map_is_a_partition_by_cell():
+    """Sharding is by primary cell: every tile of a cell goes to the same rank (the order of the particles inside
+    a cell differs between the ranks' replicas, so tiles of one cell must not be split across ranks), every tile is
+    owned by exactly one rank, and the ranks' shares are balanced."""
+    rng = np.random.default_rng(5)
+    for ncells in (1, 7, 8, 9, 64, 1000, 17424):
+        counts = rng.poisson(114, size=ncells)
+        ntile = (counts + 127) // 128
+        tile_cell = np.repeat(np.arange(ncells), ntile)
         for nranks in (1, 2, 3, 4, 8):
-            allt = sorted(t for r in range(nranks) for t in tiles_of_rank(ntiles, r, nranks))
-            assert allt == list(range(ntiles)), (ntiles, nranks)
-            sizes = [len(tiles_of_rank(ntiles, r, nranks)) for r in range(nranks)]
-            assert max(sizes) - min(sizes) <= SHARD_GROUP
+            owner = np.array([owner_of_cell(c, nranks) for c in tile_cell])
+            assert owner.min() >= 0 and owner.max() < nranks
+            for c in np.unique(tile_cell[:200]):
+                assert len(set(owner[tile_cell == c])) == 1
+            if ncells >= 1000:
+                share = np.bincount(owner, weights=counts[tile_cell] / np.maximum(ntile[tile_cell], 1), minlength=nranks)
+                assert share.max() / share.mean() < 1.05
 
 
 def _worker(rank, world, port, q):

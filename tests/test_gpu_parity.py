@@ -554,3 +554,45 @@ def test_precision_suffixed_entry_points():
         lib.free_results(C.byref(r))
         assert np.array_equal(got, want["npairs"])
         assert o.float_type == 12 - np.dtype(dtype).itemsize  # restored
+
+
+@pytest.mark.parametrize("stat", ["xi", "DDsmu"])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_rank_sharding_sums_to_the_full_count(stat, nranks):
+    """Multi-GPU sharding emulated in one process: the library is run once per rank (each run sorts the particles
+    again, in another order inside the cells, exactly like separate processes do) and the partial histograms are
+    summed through the reduce hook.  Cells hold ~140 particles here, i.e. two primary tiles each: npairs must not
+    depend on the number of ranks."""
+    from corrfunc_b200 import _lib
+
+    T = _theory()
+    L, N = 100.0, 560000
+    x, y, z, w = H.box_points(51, N, L, np.float32)
+    bins = np.logspace(-1, 1, 11)
+
+    def run():
+        if stat == "xi":
+            return T.xi(L, 1, bins, x, y, z)["npairs"]
+        return T.DDsmu(1, 1, bins, 1.0, 5, x, y, z, periodic=True, boxsize=L, weights1=w, weight_type="pair_product",
+                       output_savg=True)["npairs"]
+
+    full = run()
+    acc = {}
+
+    def hook(n, s, ww):
+        if acc:
+            n += acc["n"]
+            s += acc["s"]
+            ww += acc["w"]
+        acc["n"], acc["s"], acc["w"] = n.copy(), s.copy(), ww.copy()
+
+    try:
+        for r in range(nranks):
+            _lib.set_shard(r, nranks, hook)
+            got = run()  # complete after the last rank's hook
+    finally:
+        _lib.set_shard(0, 1, None)
+    assert np.array_equal(got, full)
+    if stat == "xi":
+        ref = H.oracle_theory("xi", x, y, z, bins, boxsize=L)
+        assert np.array_equal(full, ref["npairs"])
