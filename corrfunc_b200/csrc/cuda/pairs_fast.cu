@@ -815,6 +815,8 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_fast<T, MODE, LIST, true>, FAST_WARPS * 32, 0));
         else
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_fast<T, MODE, LIST, false>, FAST_WARPS * 32, 0));
+        const char *cap = getenv("CORRFUNC_B200_FAST_BLOCKS_PER_SM");  // tuning knob: fewer resident warps
+        if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
         res = sms * (per_sm > 0 ? per_sm : 1);
     }
     int64_t nblk = (Q.ntiles / (Q.shard_n > 1 ? Q.shard_n : 1) + FAST_WARPS - 1) / FAST_WARPS + 1;
