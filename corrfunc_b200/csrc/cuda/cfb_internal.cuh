@@ -46,6 +46,7 @@ struct Ctx {
     size_t pinned_cap = 0;
     int shard_rank = 0, shard_n = 1;
     int target_occ = 0;
+    int theta_sub = 1;  // sub x sub fine cells per reference RA/DEC cell of the last theta gridlink
     int force_kernel = -1;
     int launches = 0;
     char err[512];
@@ -95,9 +96,10 @@ struct PairParams {
     FineGeom g;
     double wrap[3];
     double max_sep[3];
-    // neighbour list (theta)
+    // neighbour list (theta): CSR over REFERENCE cells; a fine cell is reference cell * list_sub2 + sub-cell
     const int64_t *list_off;
     const int32_t *list_cells;
+    int list_sub2;
     // tiles of the primary set
     const int *tile_cell, *tile_off;
     int64_t ntiles;
@@ -121,7 +123,7 @@ __host__ __device__ __forceinline__ bool cfb_owns_cell(const int cell, const int
 // gridlink entry points (gridlink.cu)
 // scale: power of two applied to the sorted copy of the positions (1 unless the fast float kernel runs)
 int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3], double scale);
-int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t ncells);
+int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t ncells /* reference cells */);
 // pair kernels (pairs_generic.cu)
 int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode);
 // fast 1-D kernel (pairs_fast.cu); P.edges / P.wrap / P.pimax are in the kernel's scaled units

@@ -462,6 +462,20 @@ extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat,
     return 0;
 }
 
+extern "C" int cfb_theta_subdivision(int64_t nmax, int64_t ncells)
+{
+    // sub x sub fine cells per reference cell, about `target` particles each; the fine lattice stays below ~4M cells
+    const Ctx &c = g_ctx;
+    const int target = c.target_occ > 0 ? c.target_occ : 112;
+    if (ncells <= 0 || nmax <= 0) return 1;
+    const double occ = (double)nmax / (double)ncells;
+    if (occ <= 1.5 * target) return 1;
+    int s = (int)floor(sqrt(occ / target) + 0.5);
+    if (s < 1) s = 1;
+    while (s > 1 && (double)ncells * s * s > 4.0e6) s--;
+    return s;
+}
+
 extern "C" int cfb_theta_gridlink(int slot, int prec, const cfb_theta_lattice *lat, int64_t ncells, int64_t *counts,
                                   double *ra_bounds, double *xyz_bounds)
 {
@@ -471,19 +485,38 @@ extern "C" int cfb_theta_gridlink(int slot, int prec, const cfb_theta_lattice *l
     ParticleSet &S = c.set[slot];
     if (S.prec != prec) return cfb_fail("particle set %d precision mismatch", slot);
     if (cfb_gridlink_theta_set(S, lat, ncells)) return 1;
-    // bring per-cell counts and bounds back for the host-side neighbour search
-    int *hc = (int *)malloc((size_t)ncells * sizeof(int));
-    void *hb = malloc((size_t)ncells * CFB_NB * prec);
+    const int sub = lat->sub > 0 ? lat->sub : 1;
+    const int s2 = sub * sub;
+    c.theta_sub = sub;
+    const int64_t nfine = ncells * s2;
+    // bring the per-cell counts and bounds back for the host-side neighbour search, folded from the fine cells
+    // into the reference cells the search works on
+    int *hc = (int *)malloc((size_t)nfine * sizeof(int));
+    void *hb = malloc((size_t)nfine * CFB_NB * prec);
     if (!hc || !hb) return cfb_fail("out of host memory");
-    CK(cudaMemcpyAsync(hc, S.count.p, (size_t)ncells * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    CK(cudaMemcpyAsync(hb, S.bounds.p, (size_t)ncells * CFB_NB * prec, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(hc, S.count.p, (size_t)nfine * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(hb, S.bounds.p, (size_t)nfine * CFB_NB * prec, cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
+    auto bnd = [&](int64_t f, int k) -> double {
+        return prec == 4 ? (double)((float *)hb)[f * CFB_NB + k] : ((double *)hb)[f * CFB_NB + k];
+    };
     for (int64_t i = 0; i < ncells; i++) {
-        counts[i] = hc[i];
-        for (int k = 0; k < 6; k++)
-            xyz_bounds[i * 6 + k] = prec == 4 ? (double)((float *)hb)[i * CFB_NB + k] : ((double *)hb)[i * CFB_NB + k];
-        for (int k = 0; k < 2; k++)
-            ra_bounds[i * 2 + k] = prec == 4 ? (double)((float *)hb)[i * CFB_NB + 6 + k] : ((double *)hb)[i * CFB_NB + 6 + k];
+        int64_t n = 0;
+        bool first = true;
+        for (int q = 0; q < s2; q++) {
+            const int64_t f = i * s2 + q;
+            if (hc[f] == 0 && !(q == s2 - 1 && first)) continue;  // an empty reference cell reports its last sub-cell
+            n += hc[f];
+            for (int k = 0; k < 8; k++) {
+                const double v = bnd(f, k);
+                double *dst = k < 6 ? &xyz_bounds[i * 6 + k] : &ra_bounds[i * 2 + (k - 6)];
+                if (first) *dst = v;
+                else if (k & 1) *dst = v > *dst ? v : *dst;  // odd slots hold maxima
+                else *dst = v < *dst ? v : *dst;
+            }
+            first = false;
+        }
+        counts[i] = n;
     }
     free(hc);
     free(hb);
@@ -523,6 +556,12 @@ extern "C" int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int
     fill_common(P, c, bin, nslots);
     P.list_off = (const int64_t *)c.list_off.p;
     P.list_cells = (const int32_t *)c.list_cells.p;
+    P.list_sub2 = c.theta_sub * c.theta_sub;
+    {
+        // pruning radius of fine-cell pairs: the largest chord in range, from the last edge cos(thetamax)
+        const double cmax = bin->edges[bin->nedges - 1];
+        P.max_sep[0] = sqrt(fmax(0.0, 2.0 * (1.0 - cmax)));
+    }
     P.tile_cell = (const int *)c.set[0].tile_cell.p;
     P.tile_off = (const int *)c.set[0].tile_off.p;
     P.ntiles = c.set[0].ntiles;

@@ -67,19 +67,21 @@ template <typename T>
 __global__ void k_cellindex_theta(const int64_t n, const T *__restrict__ ra, const T *__restrict__ dec,
                                   const int ngrid_dec, const int *__restrict__ ngrid_ra,
                                   const int *__restrict__ ra_off, const T dec_min, const T inv_dec_diff,
-                                  const T ra_min, const T inv_ra_diff, int *__restrict__ cidx,
+                                  const T ra_min, const T inv_ra_diff, const int sub, int *__restrict__ cidx,
                                   int *__restrict__ rank, int *__restrict__ count, unsigned long long *oob)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // reference cell: gridlink_mocks_impl.c.src:1249-1263
     const T ud = (T)ngrid_dec * (dec[i] - dec_min) * inv_dec_diff;
     int idec = (int)ud;
     if (idec >= ngrid_dec) idec--;
     bool ok = (ud == ud) && idec >= 0 && idec < ngrid_dec;
     int ira = 0, nra = 1;
+    T ur = 0;
     if (ok) {
         nra = ngrid_ra[idec];
-        const T ur = (T)nra * (ra[i] - ra_min) * inv_ra_diff;
+        ur = (T)nra * (ra[i] - ra_min) * inv_ra_diff;
         ira = (int)ur;
         if (ira >= nra) ira--;
         ok = (ur == ur) && ira >= 0 && ira < nra;
@@ -89,7 +91,12 @@ __global__ void k_cellindex_theta(const int64_t n, const T *__restrict__ ra, con
         cidx[i] = -1;
         return;
     }
-    const int c = ra_off[idec] + ira;
+    // device-only refinement: position inside the reference cell -> one of sub x sub fine cells.  It only groups
+    // particles (tighter bounding boxes, smaller work units); which reference cells are paired is untouched.
+    int sd = (int)((ud - (T)idec) * (T)sub), sr = (int)((ur - (T)ira) * (T)sub);
+    sd = sd < 0 ? 0 : (sd >= sub ? sub - 1 : sd);
+    sr = sr < 0 ? 0 : (sr >= sub ? sub - 1 : sr);
+    const int c = ((ra_off[idec] + ira) * sub + sd) * sub + sr;
     cidx[i] = c;
     rank[i] = atomicAdd(&count[c], 1);
 }
@@ -379,23 +386,26 @@ static int gridlink_theta_T(Ctx &c, ParticleSet &S, const cfb_theta_lattice *lat
         off += lat->ngrid_ra[i];
     }
     if (off != ncells) return cfb_fail("theta lattice: cell count mismatch (%d vs %lld)", off, (long long)ncells);
+    const int sub = lat->sub > 0 ? lat->sub : 1;
+    const int64_t nfine = ncells * sub * sub;
+    if (nfine >= 2147483647LL / 2) return cfb_fail("theta lattice: too many fine cells (%lld)", (long long)nfine);
     CK(cudaMemcpyAsync(c.ngrid_ra.p, h, (size_t)lat->ngrid_dec * 4, cudaMemcpyHostToDevice, c.stream));
     CK(cudaMemcpyAsync(c.ra_off.p, h + lat->ngrid_dec, (size_t)lat->ngrid_dec * 4, cudaMemcpyHostToDevice, c.stream));
-    if (cfb_ensure(S.count, (size_t)ncells * 4)) return 1;
-    if (cfb_ensure(S.bounds, (size_t)ncells * CFB_NB * sizeof(T))) return 1;
+    if (cfb_ensure(S.count, (size_t)nfine * 4)) return 1;
+    if (cfb_ensure(S.bounds, (size_t)nfine * CFB_NB * sizeof(T))) return 1;
     if (cfb_ensure(S.cidx, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
     if (cfb_ensure(S.rank, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
-    CK(cudaMemsetAsync(S.count.p, 0, (size_t)ncells * 4, c.stream));
+    CK(cudaMemsetAsync(S.count.p, 0, (size_t)nfine * 4, c.stream));
     CK(cudaMemsetAsync(c.scratch.p, 0, 256, c.stream));
     k_cellindex_theta<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(
         S.n, (const T *)S.raw[4], (const T *)S.raw[5], lat->ngrid_dec, (const int *)c.ngrid_ra.p,
-        (const int *)c.ra_off.p, (T)lat->dec_min, (T)lat->inv_dec_diff, (T)lat->ra_min, (T)lat->inv_ra_diff,
+        (const int *)c.ra_off.p, (T)lat->dec_min, (T)lat->inv_dec_diff, (T)lat->ra_min, (T)lat->inv_ra_diff, sub,
         (int *)S.cidx.p, (int *)S.rank.p, (int *)S.count.p, (unsigned long long *)c.scratch.p);
     c.launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c.stream));  // pinned staging reused by finish_sort
-    if (finish_sort<T>(c, S, ncells, 1.0)) return 1;
-    k_ra_bounds_init<T><<<nblocks(ncells, 256), 256, 0, c.stream>>>(ncells, (T *)S.bounds.p);
+    if (finish_sort<T>(c, S, nfine, 1.0)) return 1;
+    k_ra_bounds_init<T><<<nblocks(nfine, 256), 256, 0, c.stream>>>(nfine, (T *)S.bounds.p);
     k_ra_bounds<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(S.n, (const T *)S.raw[4], (const int *)S.cidx.p,
                                                            (T *)S.bounds.p);
     c.launches += 2;

@@ -430,9 +430,11 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         long long refA = 0;
         int nrow = 1, rowlen, wz = 1, rx = 0, ry = 0, rz = 0;
         int64_t list0 = 0;
+        const int sub2 = LIST ? P.list_sub2 : 1;  // fine cells per reference cell of the RA/DEC lattice
+        const int refP = LIST ? cellP / sub2 : 0;
         if (LIST) {
-            list0 = P.list_off[cellP];
-            rowlen = (int)(P.list_off[cellP + 1] - list0);
+            list0 = P.list_off[refP];
+            rowlen = (int)(P.list_off[refP + 1] - list0) * sub2;  // every fine cell of every listed reference cell
         } else {
             gz = cellP % P.g.ng[2];
             gy = (cellP / P.g.ng[2]) % P.g.ng[1];
@@ -476,7 +478,12 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                 if (keep) {
                     double offd[3] = {0.0, 0.0, 0.0};
                     if (LIST) {
-                        cellQ = P.list_cells[list0 + cand];
+                        const int li = cand / sub2;
+                        const int refQ = P.list_cells[list0 + li];
+                        cellQ = refQ * sub2 + (cand - li * sub2);
+                        // the host lists every unordered pair of reference cells once (and a cell with itself):
+                        // inside one reference cell every unordered pair of fine cells is taken once
+                        if (P.autocorr && refQ == refP && cellQ > cellP) keep = false;
                     } else {
                         const unsigned iy = fdiv((unsigned)cand, P.m_wz);
                         const int t[3] = {gx + row - rx, gy + (int)iy - ry, gz + (cand - (int)iy * wz) - rz};

@@ -175,9 +175,11 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
     long long refA = 0;
     int ncand;
     int64_t list0 = 0;
+    const int sub2 = LIST ? P.list_sub2 : 1;  // fine cells per reference cell of the RA/DEC lattice
+    const int refP = LIST ? cellP / sub2 : 0;
     if (LIST) {
-        list0 = P.list_off[cellP];
-        ncand = (int)(P.list_off[cellP + 1] - list0);
+        list0 = P.list_off[refP];
+        ncand = (int)(P.list_off[refP + 1] - list0) * sub2;
     } else {
         gz = cellP % P.g.ng[2];
         gy = (cellP / P.g.ng[2]) % P.g.ng[1];
@@ -204,7 +206,10 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
             bool keep = true;
             double offd[3] = {0.0, 0.0, 0.0};
             if (LIST) {
-                cellQ = P.list_cells[list0 + cand];
+                const int li = cand / sub2;
+                const int refQ = P.list_cells[list0 + li];
+                cellQ = refQ * sub2 + (cand - li * sub2);
+                if (P.autocorr && refQ == refP && cellQ > cellP) keep = false;  // fine pairs of one reference cell: once
             } else {
                 const int dz = cand % wz - P.g.reach[2];
                 const int dy = (cand / wz) % wy - P.g.reach[1];
@@ -254,8 +259,8 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                 }
             }
             if (keep && B.count[cellQ] == 0) keep = false;
-            if (keep && !LIST) {
-                // bounds-based pruning (pure optimisation; margins keep it conservative)
+            if (keep) {
+                // bounds-based pruning (pure optimisation; margins keep it conservative); theta: chord vs max chord
                 double qb[6];
 #pragma unroll
                 for (int k = 0; k < 6; k++) qb[k] = (double)B.bounds[(int64_t)cellQ * CFB_NB + k];

@@ -642,6 +642,7 @@ static int HFN(cf_theta)(const int64_t ND1, void *vra1, void *vdec1, const int64
             TL.inv_ra_diff = (double)inv_ra_diff;
             TL.ra_refine = ra_refine;
             TL.dec_refine = dec_refine;
+            TL.sub = cfb_theta_subdivision(nsets == 2 && ND2 > ND1 ? ND2 : ND1, ncells);
             const double t0 = now_ms();
             for (int s = 0; s < nsets && !status; s++) {
                 const int64_t N = s ? ND2 : ND1;

@@ -63,6 +63,8 @@ typedef struct {
     int ra_refine, dec_refine;
     double sqr_max_chord; /* 2(1-cos(thetamax)) */
     int enable_min_sep;
+    int sub;             /* device-only refinement: every reference cell is split sub x sub ways (in DEC and RA);
+                          * from cfb_theta_subdivision, the same value for both particle sets */
 } cfb_theta_lattice;
 
 typedef struct {
@@ -108,6 +110,8 @@ int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *
  * cfb_theta_gridlink sorts slot(s) into the lattice and returns per-cell counts and bounds (host
  * arrays, caller-allocated, ncells entries; bounds are {lo,hi} pairs).  cfb_count_theta then takes
  * the CSR neighbour list built by the host. */
+/* sub x sub fine cells per reference cell such that a fine cell holds about the target occupancy. */
+int cfb_theta_subdivision(int64_t nmax, int64_t ncells);
 int cfb_theta_gridlink(int slot, int prec, const cfb_theta_lattice *lat, int64_t ncells, int64_t *counts,
                        double *ra_bounds, double *xyz_bounds /* [ncells][6] */);
 int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int64_t *ngb_offsets /* [ncells+1] */,
