@@ -6,6 +6,9 @@
 #include "cfb_internal.cuh"
 
 static Ctx g_ctx;
+// persistent pinned host buffers handed to the host layer (cfb_host_scratch)
+static void *g_host_scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+static size_t g_host_scratch_cap[6] = {0, 0, 0, 0, 0, 0};
 Ctx &cfb_ctx() { return g_ctx; }
 
 int cfb_fail(const char *fmt, ...)
@@ -87,6 +90,11 @@ extern "C" void cfb_shutdown(void)
     rel(c.scratch); rel(c.hist); rel(c.edges); rel(c.list_off); rel(c.list_cells); rel(c.ngrid_ra); rel(c.ra_off);
     if (c.pinned) cudaFreeHost(c.pinned);
     c.pinned = nullptr;
+    for (int i = 0; i < 6; i++) {
+        if (g_host_scratch[i]) cudaFreeHost(g_host_scratch[i]);
+        g_host_scratch[i] = nullptr;
+        g_host_scratch_cap[i] = 0;
+    }
     for (int i = 0; i < 8; i++) cudaEventDestroy(c.ev[i]);
     cudaStreamDestroy(c.stream);
     c.ready = false;
@@ -116,6 +124,26 @@ static bool is_device_ptr(const void *p)
         return false;
     }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Persistent pinned host buffers for arrays the host layer computes itself (DDtheta's unit vectors): written
+// without page faults on repeated calls and uploaded at full PCIe rate.  Grow-only; freed by cfb_shutdown.
+extern "C" void *cfb_host_scratch(int which, size_t bytes)
+{
+    if (which < 0 || which >= 6) return nullptr;
+    if (cfb_init()) return nullptr;
+    if (bytes <= g_host_scratch_cap[which]) return g_host_scratch[which];
+    if (g_host_scratch[which]) cudaFreeHost(g_host_scratch[which]);
+    g_host_scratch[which] = nullptr;
+    g_host_scratch_cap[which] = 0;
+    const size_t cap = bytes + bytes / 8 + 4096;
+    if (cudaMallocHost(&g_host_scratch[which], cap) != cudaSuccess) {
+        cudaGetLastError();
+        g_host_scratch[which] = nullptr;
+        return nullptr;
+    }
+    g_host_scratch_cap[which] = cap;
+    return g_host_scratch[which];
 }
 
 extern "C" int cfb_upload(int slot, int prec, int64_t n, const void *x, const void *y, const void *z, const void *w,

@@ -528,8 +528,12 @@ static int HFN(cf_theta)(const int64_t ND1, void *vra1, void *vdec1, const int64
         const int64_t N = s ? ND2 : ND1;
         const REAL *ra = s ? ra2 : ra1, *dec = s ? dec2 : dec1;
         for (int a = 0; a < 3; a++) {
-            XYZ[s][a] = malloc(sizeof(REAL) * (size_t)(N > 0 ? N : 1));
-            if (!XYZ[s][a]) status = 1;
+            /* pinned, persistent across calls (no page faults, full-rate upload) */
+            XYZ[s][a] = cfb_host_scratch(3 * s + a, sizeof(REAL) * (size_t)(N > 0 ? N : 1));
+            if (!XYZ[s][a]) {
+                fprintf(stderr, "Error: could not get host staging memory for %" PRId64 " unit vectors: %s\n", N, cfb_last_error());
+                status = 1;
+            }
         }
         if (status) break;
         REAL *X = XYZ[s][0], *Y = XYZ[s][1], *Z = XYZ[s][2];
@@ -541,7 +545,11 @@ static int HFN(cf_theta)(const int64_t ND1, void *vra1, void *vdec1, const int64
             Y[i] = H_COSD(dec[i]) * H_SIND(ra[i]);
             Z[i] = H_SIND(dec[i]);
         }
-        for (int64_t i = 0; i < N; i++) { /* get_max_min_ra_dec_DOUBLE (gridlink_utils.c.src:74-89) */
+        /* get_max_min_ra_dec_DOUBLE (gridlink_utils.c.src:74-89); min/max are order independent */
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static) reduction(min : ra_min, dec_min) reduction(max : ra_max, dec_max)
+#endif
+        for (int64_t i = 0; i < N; i++) {
             if (ra[i] < ra_min) ra_min = ra[i];
             if (dec[i] < dec_min) dec_min = dec[i];
             if (ra[i] > ra_max) ra_max = ra[i];
@@ -770,7 +778,7 @@ static int HFN(cf_theta)(const int64_t ND1, void *vra1, void *vdec1, const int64
         }
     }
     for (int s = 0; s < 2; s++) {
-        for (int a = 0; a < 3; a++) free(XYZ[s][a]);
+        for (int a = 0; a < 3; a++) XYZ[s][a] = NULL; /* context-owned staging buffers */
         free(counts[s]); free(rab[s]); free(xyzb[s]);
     }
     free(ngrid_ra); free(ngb); free(ngb_off); free(costheta_upp);

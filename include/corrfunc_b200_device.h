@@ -110,6 +110,8 @@ int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *
  * cfb_theta_gridlink sorts slot(s) into the lattice and returns per-cell counts and bounds (host
  * arrays, caller-allocated, ncells entries; bounds are {lo,hi} pairs).  cfb_count_theta then takes
  * the CSR neighbour list built by the host. */
+/* Persistent pinned host buffer number `which` (0..5) of at least `bytes` bytes, owned by the context (NULL on failure). */
+void *cfb_host_scratch(int which, size_t bytes);
 /* sub x sub fine cells per reference cell such that a fine cell holds about the target occupancy. */
 int cfb_theta_subdivision(int64_t nmax, int64_t ncells);
 int cfb_theta_gridlink(int slot, int prec, const cfb_theta_lattice *lat, int64_t ncells, int64_t *counts,
