@@ -596,3 +596,43 @@ def test_rank_sharding_sums_to_the_full_count(stat, nranks):
     if stat == "xi":
         ref = H.oracle_theory("xi", x, y, z, bins, boxsize=L)
         assert np.array_equal(full, ref["npairs"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("autocorr", [1, 0])
+@pytest.mark.parametrize("link", [(1, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("occ", [6, 25])
+def test_DDtheta_refined_lattice(dtype, autocorr, link, occ):
+    """The device-only sub x sub refinement of the reference RA/DEC cells (cfb_theta_subdivision) must not change a
+    single count: a small target occupancy forces sub > 1 at test sizes, for both kernels (the plain counts take the
+    fast kernel, weights + thetaavg the generic one), every linking mode, auto and cross."""
+    from corrfunc_b200 import _lib
+    from corrfunc_b200.mocks import DDtheta_mocks
+
+    ra1, dec1 = H.sphere_points(15, 40000, dtype)
+    ra2, dec2 = H.sphere_points(16, 25000, dtype)
+    w1 = (1.0 - np.random.default_rng(17).random(ra1.size)).astype(dtype)
+    w2 = (1.0 - np.random.default_rng(18).random(ra2.size)).astype(dtype)
+    tb = np.logspace(np.log10(0.05), 1, 16)
+    lk = dict(link_in_dec=bool(link[0]), link_in_ra=bool(link[1]))
+    kw_plain, kw_full = dict(lk), dict(lk, weights1=w1, weight_type="pair_product", output_thetaavg=True)
+    okw = dict(w1=w1, weight_type="pair_product", need_avg=True, link_in_dec=link[0], link_in_ra=link[1], autocorr=bool(autocorr))
+    if not autocorr:
+        kw_plain.update(RA2=ra2, DEC2=dec2)
+        kw_full.update(RA2=ra2, DEC2=dec2, weights2=w2)
+        okw.update(RA2=ra2, DEC2=dec2, w2=w2)
+    ref = H.oracle_theta(ra1, dec1, tb, **okw)
+    lib = _lib.load()
+    lib.cfb_set_target_occupancy(occ)
+    try:
+        got = DDtheta_mocks(autocorr, 2, tb, ra1, dec1, **kw_plain)
+        st = _lib.last_stats()
+        assert st["kernel_kind"] == 1 and st["n_cells"] >= 1
+        assert np.array_equal(got["npairs"], ref["npairs"])
+        got = DDtheta_mocks(autocorr, 2, tb, ra1, dec1, **kw_full)
+        assert _lib.last_stats()["kernel_kind"] == 0
+    finally:
+        lib.cfb_set_target_occupancy(0)
+    assert np.array_equal(got["npairs"], ref["npairs"])
+    _close(got["thetaavg"], ref["ravg"], 1e-9 if dtype == np.float64 else 1e-4, "thetaavg")
+    _close(got["weightavg"], ref["weightavg"], TOL[dtype], "weightavg")
