@@ -18,7 +18,8 @@
 
 #include "cfb_internal.cuh"
 
-#define GEN_CH 256  // secondaries staged per chunk
+#define GEN_CH 64   // secondaries staged per chunk, per warp (shared memory per block decides the occupancy)
+#define GEN_WARPS (CFB_TILE / 32)
 
 template <typename T>
 __device__ __forceinline__ T fma_t(T a, T b, T c);
@@ -95,12 +96,15 @@ __device__ __forceinline__ double fixed_scale(const double vmax)
 
 template <typename T>
 struct GenShared {
-    T sx[GEN_CH], sy[GEN_CH], sz[GEN_CH], sw[GEN_CH];
+    // staging buffers are per WARP: the warps of a tile walk the queue independently (block-wide barriers around a
+    // shared buffer cost 13 % of all warp samples, the warps' accepted-pair work differs too much)
+    T sx[GEN_WARPS][GEN_CH], sy[GEN_WARPS][GEN_CH], sz[GEN_WARPS][GEN_CH], sw[GEN_WARPS][GEN_CH];
     int q_cell[CFB_TILE];
     int q_code[CFB_TILE];
     int q_n;
 };
 
+// (explicit minimum-blocks launch bounds of 8, 6 or 5 were measured 15-35 % slower than leaving the choice to ptxas)
 template <typename T, int MODE, bool AVG, bool WGT, bool LIST>
 __global__ void __launch_bounds__(CFB_TILE)
 k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
@@ -195,6 +199,9 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
     unsigned long long my_eval = 0, my_tp = 0;
     __syncthreads();
     const T e_lo = s_edges[0], e_hi = s_edges[nedges - 1];
+    const int lane = tid & 31, wid = tid >> 5;
+    T *sx = S.sx[wid], *sy = S.sy[wid], *sz = S.sz[wid], *sw = S.sw[wid];
+    const bool warp_has_work = __any_sync(0xffffffffu, valid);
 
     for (int base = 0; base < ncand; base += CFB_TILE) {
         if (tid == 0) S.q_n = 0;
@@ -311,16 +318,17 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
             const int nQ = B.count[cellQ];
             const int startQ = B.start[cellQ];
             if (valid) my_eval += tri ? (unsigned long long)(nQ - 1 - iloc > 0 ? nQ - 1 - iloc : 0) : (unsigned long long)nQ;
+            if (!warp_has_work) continue;  // warp-uniform: no primary in this warp
             for (int c0 = 0; c0 < nQ; c0 += GEN_CH) {
                 const int m = min(GEN_CH, nQ - c0);
-                __syncthreads();
-                for (int k = tid; k < m; k += CFB_TILE) {
-                    S.sx[k] = B.x[startQ + c0 + k];
-                    S.sy[k] = B.y[startQ + c0 + k];
-                    S.sz[k] = B.z[startQ + c0 + k];
-                    if (WGT) S.sw[k] = B.w[startQ + c0 + k];
+                __syncwarp();  // everyone is done with the previous chunk
+                for (int k = lane; k < m; k += 32) {
+                    sx[k] = B.x[startQ + c0 + k];
+                    sy[k] = B.y[startQ + c0 + k];
+                    sz[k] = B.z[startQ + c0 + k];
+                    if (WGT) sw[k] = B.w[startQ + c0 + k];
                 }
-                __syncthreads();
+                __syncwarp();
                 if (!valid) continue;
                 int k0 = 0;
                 if (tri) {
@@ -331,7 +339,7 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                 // the warp retires one parked pair per lane when some lane is full, so that the bin search / sqrt /
                 // histogram code runs with most lanes active -- was measured 15-50 % SLOWER on configs 2 and 3.)
                 for (int k = k0; k < m; k++) {
-                    const T dx = S.sx[k] - xpos, dy = S.sy[k] - ypos, dz = S.sz[k] - zpos;
+                    const T dx = sx[k] - xpos, dy = sy[k] - ypos, dz = sz[k] - zpos;
                     int64_t slot;
                     int kbin = 0;  // the separation bin (upper-edge index) of the pair
                     T sep = 0;
@@ -402,11 +410,11 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         if (AVG) add_fixed96(&s_sep[slot], &s_sep[ns + slot], &s_sep[2 * ns + slot], __double2ll_rn((double)sep * s_scale[kbin]));
                         if (WGT)
                             add_fixed96(&s_w[slot], &s_w[ns + slot], &s_w[2 * ns + slot],
-                                        __double2ll_rn((double)(T)(wp * S.sw[k]) * w_scale));
+                                        __double2ll_rn((double)(T)(wp * sw[k]) * w_scale));
                     } else {
                         atomicAdd(&P.npairs[slot], 1ULL);
                         if (AVG) atomicAdd(&P.sum_sep[slot], (double)sep);
-                        if (WGT) atomicAdd(&P.sum_w[slot], (double)(T)(wp * S.sw[k]));
+                        if (WGT) atomicAdd(&P.sum_w[slot], (double)(T)(wp * sw[k]));
                     }
                 }
             }
