@@ -249,7 +249,7 @@ def run_ours(args, cfg):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        kern_ms, grid_ms, n_eval, launches = [], [], 0, 0
+        kern_ms, grid_ms, dev_ms, n_eval, launches = [], [], [], 0, 0
         barrier()
         t_acc = 0.0
         for _ in range(args.steps):
@@ -262,6 +262,7 @@ def run_ours(args, cfg):
             s = _lib.last_stats()
             kern_ms.append(s["ms_pairs"])
             grid_ms.append(s["ms_gridlink"])
+            dev_ms.append(s["ms_total_device"])
             n_eval = s["n_eval"]
             launches += s["kernel_launches"]
         barrier()
@@ -341,7 +342,8 @@ def run_ours(args, cfg):
                                                               "" if not args.npart else " (REDUCED N, not the headline size)"),
                    "l2": "inputs larger than L2" if not need_flush else "256 MiB L2 flush between iterations",
                    "reference_lattice": list(st0["nmesh"]), "refine": list(st0["refine"]), "device_lattice": list(st0["fine"]),
-                   "timing": "host clock around synchronous C-ABI calls (device-synchronised on both sides), max over ranks; kernel time by CUDA events on the launch stream"},
+                   "timing": "host clock around synchronous C-ABI calls (device-synchronised on both sides), max over ranks; kernel time by CUDA events on the launch stream",
+                   "device_ms_per_step": float(np.mean(dev_ms))},
         "e2e": {"value": n_cand / t_e2e, "unit": "pair_evals/s", "ms_per_step": t_e2e * 1e3,
                 "h2d_bytes_per_step": int(input_bytes), "d2h_bytes_per_step": int(len(bins) * 24 + 64)},
         "gpu_launches": int(launches),
