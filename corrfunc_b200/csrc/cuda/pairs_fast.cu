@@ -47,6 +47,9 @@
 #ifndef FAST_SPI2_NL
 #define FAST_SPI2_NL 2
 #endif
+#ifndef FAST_F64_SPI1
+#define FAST_F64_SPI1 999 // double kernel: bodies with primaries x levels >= this take 1 secondary per iteration (off: 4, 8 and 12 measured 1-5 % slower)
+#endif
 #ifndef FAST_MINB_F32
 #define FAST_MINB_F32 4 // resident blocks per SM the float kernel is compiled for (register budget); 5 and 6 measured no faster
 #endif
@@ -266,14 +269,22 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
     double E[NL];
 #pragma unroll
     for (int l = 0; l < NL; l++) E[l] = Es[l];
+    // one secondary per iteration for the long bodies (many primaries x levels): same instruction-cache
+    // consideration as in chunk_f32
+    constexpr int SPI = (PA * NL >= FAST_F64_SPI1) ? 1 : 2;
 #pragma unroll 1
-    for (int j = 0; j < m4; j += 2) {
-        const double2 X = *reinterpret_cast<const double2 *>(sx + j);
-        const double2 Y = *reinterpret_cast<const double2 *>(sy + j);
-        const double2 Z = *reinterpret_cast<const double2 *>(sz + j);
-        const double xs[2] = {X.x, X.y}, ys[2] = {Y.x, Y.y}, zs[2] = {Z.x, Z.y};
+    for (int j = 0; j < m4; j += SPI) {
+        double xs[SPI], ys[SPI], zs[SPI];
+        if constexpr (SPI == 2) {
+            const double2 X = *reinterpret_cast<const double2 *>(sx + j);
+            const double2 Y = *reinterpret_cast<const double2 *>(sy + j);
+            const double2 Z = *reinterpret_cast<const double2 *>(sz + j);
+            xs[0] = X.x, xs[1] = X.y, ys[0] = Y.x, ys[1] = Y.y, zs[0] = Z.x, zs[1] = Z.y;
+        } else {
+            xs[0] = sx[j], ys[0] = sy[j], zs[0] = sz[j];
+        }
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < SPI; h++) {
 #pragma unroll
             for (int p = 0; p < PA; p++) {
                 const double dx = xs[h] - xq[p], dy = ys[h] - yq[p], dz = zs[h] - zq[p];

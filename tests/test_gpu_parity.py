@@ -636,3 +636,20 @@ def test_DDtheta_refined_lattice(dtype, autocorr, link, occ):
     assert np.array_equal(got["npairs"], ref["npairs"])
     _close(got["thetaavg"], ref["ravg"], 1e-9 if dtype == np.float64 else 1e-4, "thetaavg")
     _close(got["weightavg"], ref["weightavg"], TOL[dtype], "weightavg")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_DDrppi_histogram_too_large_for_shared_memory(dtype):
+    """(nbin+1)*(npibin+1) = 27*251 slots x (count + two 96-bit sums) exceed the block's shared-memory budget: the
+    generic kernel then accumulates straight into global memory (native 64-bit / double atomics)."""
+    T = _theory()
+    L, N, pimax = 600.0, 30000, 250.0
+    x, y, z, w = H.box_points(71, N, L, dtype)
+    bins = np.logspace(-0.5, np.log10(40.0), 27)
+    got = T.DDrppi(1, 2, pimax, bins, x, y, z, weights1=w, weight_type="pair_product", periodic=True, boxsize=L,
+                   output_rpavg=True)
+    ref = H.oracle_theory("DDrppi", x, y, z, bins, w1=w, weight_type="pair_product", periodic=True, boxsize=L,
+                          need_avg=True, pimax=pimax)
+    assert np.array_equal(got["npairs"], ref["npairs"].ravel())
+    _close(got["rpavg"], ref["ravg"].ravel(), TOL[dtype], "rpavg")
+    _close(got["weightavg"], ref["weightavg"].ravel(), TOL[dtype], "weightavg")
