@@ -292,7 +292,7 @@ static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells, double scale)
     // scan -> starts / tile ids
     if (cfb_ensure(S.start, (size_t)ncells * 4)) return 1;
     if (cfb_ensure(S.tstart, (size_t)ncells * 4)) return 1;
-    unsigned long long *oob = (unsigned long long *)c.scratch.p;
+    // scratch: [0] out-of-bounds counter (written by the cell-index kernel), +64: {padded total, tile total}
     long long *totals = (long long *)((char *)c.scratch.p + 64);
     k_scan_cells<<<1, 1024, 0, c.stream>>>(ncells, (const int *)S.count.p, (int *)S.start.p, (int *)S.tstart.p, totals);
     c.launches++;
