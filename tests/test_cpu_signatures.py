@@ -1,0 +1,61 @@
+"""Drop-in check of the Python API: every wrapper takes the reference's parameters, in the reference's order, with
+the reference's defaults (tests/golden/reference_signatures.json was extracted from /root/reference/Corrfunc by
+tests/golden/make_golden_signatures.py)."""
+import inspect
+import json
+import os
+
+import pytest
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_signatures.json")))
+
+
+def _ours(name):
+    if name == "DDtheta_mocks":
+        from corrfunc_b200.mocks import DDtheta_mocks
+
+        return DDtheta_mocks
+    if name.startswith("convert_"):
+        import corrfunc_b200.utils as U
+
+        return getattr(U, name)
+    import corrfunc_b200.theory as T
+
+    return getattr(T, name)
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_signature_matches_reference(name):
+    sig = inspect.signature(_ours(name))
+    params = list(sig.parameters.values())
+    want = GOLD[name]
+    assert [p.name for p in params] == want["args"], want["source"]
+    for p in params:
+        if p.name in want["defaults"]:
+            assert p.default == want["defaults"][p.name], (p.name, want["source"])
+        else:
+            assert p.default is inspect.Parameter.empty, (p.name, want["source"])
+
+
+def test_compat_package_exposes_the_reference_import_paths():
+    """`compat/` holds a package named Corrfunc that forwards the reference's import paths to this library."""
+    import importlib
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "compat"))
+    try:
+        for mod, attr in (("Corrfunc.theory.DD", "DD"), ("Corrfunc.theory.DDrppi", "DDrppi"),
+                          ("Corrfunc.theory.DDsmu", "DDsmu"), ("Corrfunc.theory.wp", "wp"), ("Corrfunc.theory.xi", "xi"),
+                          ("Corrfunc.mocks.DDtheta_mocks", "DDtheta_mocks"), ("Corrfunc.theory", "DD"),
+                          ("Corrfunc.mocks", "DDtheta_mocks"), ("Corrfunc.utils", "convert_3d_counts_to_cf"),
+                          ("Corrfunc.utils", "convert_rp_pi_counts_to_wp")):
+            m = importlib.import_module(mod)
+            assert callable(getattr(m, attr)), (mod, attr)
+        import Corrfunc
+
+        assert Corrfunc.__version__
+    finally:
+        sys.path.pop(0)
+        for k in [k for k in sys.modules if k == "Corrfunc" or k.startswith("Corrfunc.")]:
+            del sys.modules[k]
