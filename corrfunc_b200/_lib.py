@@ -64,7 +64,7 @@ def last_stats() -> dict:
 
 
 def set_shard(rank: int, nranks: int, reduce_fn=None):
-    """Shard the primary tiles over `nranks` processes (one per GPU).  `reduce_fn(npairs, sum_sep,
+    """Shard the primary cells over `nranks` processes (one per GPU).  `reduce_fn(npairs, sum_sep,
     sum_w)` receives numpy views of the raw per-bin histograms and must sum them across ranks in
     place (see corrfunc_b200.parallel.enable_distributed)."""
     global _hook_keepalive

@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing: one process per GPU (torchrun), particles replicated, primary tiles sharded,
+"""Multi-GPU plumbing: one process per GPU (torchrun), particles replicated, primary cells sharded,
 per-bin histograms summed with one all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests).
 
 The path has no data-path exchange step: cell pairs are independent work units whose only shared

@@ -10,7 +10,7 @@
 extern "C" {
 #endif
 
-/* Multi-GPU: each process (rank) counts a disjoint share of the primary tiles against a full replica
+/* Multi-GPU: each process (rank) counts a disjoint share of the primary cells against a full replica
  * of the particles; the small per-bin histograms are then summed across ranks by `fn` (e.g. an NCCL
  * all-reduce issued through torch.distributed) BEFORE the host epilogue (x2, self pairs, averages,
  * xi/wp estimators) runs, so every rank returns the complete result.  Integer sums are exact, hence
