@@ -160,6 +160,7 @@ struct FastJob {
 #define JOB_TRI (1 << 20)
 #define JOB_ZCUT (1 << 21)
 #define JOB_TOPM (1 << 22)
+#define JOB_DIRZ (1 << 23)  // wp, two different reference cells: the reference's one-sided pi cut (see chunk_f32)
 
 template <typename T>
 struct FastWarp {
@@ -179,7 +180,7 @@ struct FastShared {
 
 // ------------------------------------------------------------------------------------------------
 // One chunk of secondaries against the lane's 4 primaries; cnt[l] += #{pairs with v < E[l]}.
-template <int MODE, int NL, int PA, bool ZCUT>
+template <int MODE, int NL, int PA, int ZCUT>
 __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, const float *sz, const int m4,
                                           const float (&xq)[FAST_PRIM], const float (&yq)[FAST_PRIM],
                                           const float (&zq)[FAST_PRIM], const float *Es, const float pimax,
@@ -193,6 +194,9 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
         c[l] = 0u;
     }
     const u64 th_a = pk(8388608.0f, 8388608.0f), th_b = pk(-16777216.0f, -16777216.0f);
+    float tz[PA];  // target_z = zpos - pimax of the reference's fast-forward (ZCUT == 2 only)
+#pragma unroll
+    for (int p = 0; p < PA; p++) tz[p] = zq[p] - pimax;
     // The kernel holds one loop per (levels, primaries) variant and the warps of an SM run different ones:
     // unrolling them all 4x overflowed the instruction cache (measured: 26 "no instruction" stall cycles per
     // issued instruction, 5x slower).  Only the variants that carry ~95 % of the iterations (3 primaries per
@@ -236,12 +240,24 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
                     // -cos(theta) * 2^24 = chord^2 * 2^23 - 2^24 (countpairs_theta_mocks_kernels.c.src:1062-1066)
                     if (MODE == CFB_THETA) v2 = fma2(v2, th_a, th_b);
                 }
-                if (ZCUT) {  // -pimax < dz < pimax (wp_kernels.c.src:207-221)
+                if (ZCUT == 1) {  // same reference cell (j after i in z order, dz >= 0): dz < pimax, here as |dz| < pimax
                     float v0, v1, z0, z1;
                     upk(v2, v0, v1);
                     upk(dz, z0, z1);
                     v0 = fabsf(z0) < pimax ? v0 : CUDART_INF_F;
                     v1 = fabsf(z1) < pimax ? v1 : CUDART_INF_F;
+                    v2 = pk(v0, v1);
+                }
+                if (ZCUT == 2) {
+                    // two reference cells: the reference fast-forwards over the secondaries with z1 <= zpos - pimax
+                    // (wp_kernels.c.src:139-142) and then masks with the SIGNED dz < pimax (:207-221).  A survivor
+                    // whose dz rounds to exactly -pimax is therefore counted; |dz| < pimax would drop it.
+                    float v0, v1, z0, z1, s0, s1;
+                    upk(v2, v0, v1);
+                    upk(dz, z0, z1);
+                    upk(zs[h], s0, s1);
+                    v0 = (s0 > tz[p] && z0 < pimax) ? v0 : CUDART_INF_F;
+                    v1 = (s1 > tz[p] && z1 < pimax) ? v1 : CUDART_INF_F;
                     v2 = pk(v0, v1);
                 }
                 // [v < E] is the sign bit of the rounded difference v - E (x - x = +0; NaN and +inf give
@@ -260,7 +276,7 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
     for (int l = 0; l < NL; l++) cnt[l] += (int)c[l];
 }
 
-template <int MODE, int NL, int PA, bool ZCUT>
+template <int MODE, int NL, int PA, int ZCUT>
 __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, const double *sz, const int m4,
                                           const double (&xq)[FAST_PRIM], const double (&yq)[FAST_PRIM],
                                           const double (&zq)[FAST_PRIM], const double *Es,
@@ -295,7 +311,8 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
                     v = __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
                     if (MODE == CFB_THETA) v = __fma_rn(v, 0.5, -1.0);  // -(1 - chord^2/2), exactly
                 }
-                if (ZCUT) v = fabs(dz) < pimax ? v : CUDART_INF;
+                if (ZCUT == 1) v = fabs(dz) < pimax ? v : CUDART_INF;
+                if (ZCUT == 2) v = (zs[h] > zq[p] - pimax && dz < pimax) ? v : CUDART_INF;  // see chunk_f32
 #pragma unroll
                 for (int l = 0; l < NL; l++) cnt[l] += (v < E[l]) ? 1 : 0;
             }
@@ -303,7 +320,7 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
     }
 }
 
-template <typename T, int MODE, int NL, int PA, bool ZCUT>
+template <typename T, int MODE, int NL, int PA, int ZCUT>
 __device__ __forceinline__ void chunk_T(const T *sx, const T *sy, const T *sz, const int m4, const T (&xq)[FAST_PRIM],
                                         const T (&yq)[FAST_PRIM], const T (&zq)[FAST_PRIM], const T *E,
                                         const T pimax, int (&cnt)[FAST_LMAX])
@@ -314,7 +331,7 @@ __device__ __forceinline__ void chunk_T(const T *sx, const T *sy, const T *sz, c
         chunk_f64<MODE, NL, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
 }
 
-template <typename T, int MODE, int PA, bool ZCUT>
+template <typename T, int MODE, int PA, int ZCUT>
 __device__ __forceinline__ void chunk_dispatch_nl(const int nl, const T *sx, const T *sy, const T *sz, const int m4,
                                                   const T (&xq)[FAST_PRIM], const T (&yq)[FAST_PRIM],
                                                   const T (&zq)[FAST_PRIM], const T *E, const T pimax,
@@ -336,7 +353,7 @@ __device__ __forceinline__ void chunk_dispatch_nl(const int nl, const T *sx, con
 }
 
 // pa = primaries per lane actually in use in this tile (1..4): empty register slots are not evaluated
-template <typename T, int MODE, bool ZCUT>
+template <typename T, int MODE, int ZCUT>
 __device__ __forceinline__ void chunk_dispatch(const int nl, const int pa, const T *sx, const T *sy, const T *sz,
                                                const int m4, const T (&xq)[FAST_PRIM], const T (&yq)[FAST_PRIM],
                                                const T (&zq)[FAST_PRIM], const T *E, const T pimax,
@@ -495,6 +512,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                         // the host lists every unordered pair of reference cells once (and a cell with itself):
                         // inside one reference cell every unordered pair of fine cells is taken once
                         if (P.autocorr && refQ == refP && cellQ > cellP) keep = false;
+                        if (!(P.autocorr && refQ == refP)) flags |= JOB_DIRZ;
                     } else {
                         const unsigned iy = fdiv((unsigned)cand, P.m_wz);
                         const int t[3] = {gx + row - rx, gy + (int)iy - ry, gz + (cand - (int)iy * wz) - rz};
@@ -534,9 +552,11 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                                 // cell every unordered pair of fine cells is taken once
                                 const long long refB = ((long long)rb[0] * P.g.n[1] + rb[1]) * P.g.n[2] + rb[2];
                                 if (refB > refA || (refB == refA && cellQ < cellP)) keep = false;
+                                if (refB != refA) flags |= JOB_DIRZ;
                                 // a cell against its own periodic image: |d| >= L/2 > rmax, nothing to count
                                 if (cellQ == cellP && code != 0) keep = false;
-                            }
+                            } else
+                                flags |= JOB_DIRZ;
                         }
                     }
                     int nQ = 0;
@@ -735,10 +755,13 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                         int cnt[FAST_LMAX];
 #pragma unroll
                         for (int l = 0; l < FAST_LMAX; l++) cnt[l] = 0;
-                        if (MODE == CFB_WP && (jb.meta & JOB_ZCUT))
-                            chunk_dispatch<T, MODE, true>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
-                        else
-                            chunk_dispatch<T, MODE, false>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                        if (MODE == CFB_WP && (jb.meta & JOB_ZCUT)) {
+                            if (jb.meta & JOB_DIRZ)
+                                chunk_dispatch<T, MODE, 2>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                            else
+                                chunk_dispatch<T, MODE, 1>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                        } else
+                            chunk_dispatch<T, MODE, 0>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
                         // ---- warp totals -> warp histogram: +C at the level's slot, -C one above ----
                         // a lane counts at most FAST_PRIM * FAST_CH = 512 pairs per level here and the warp 2^14:
                         // two levels share one 32-bit warp reduction

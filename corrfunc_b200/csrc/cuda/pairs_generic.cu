@@ -20,6 +20,7 @@
 
 #define GEN_CH 64   // secondaries staged per chunk, per warp (shared memory per block decides the occupancy)
 #define GEN_WARPS (CFB_TILE / 32)
+#define GEN_DIRZ 64  // queue-entry flag next to the 6-bit wrap code: primary and secondary lie in different reference cells
 
 template <typename T>
 __device__ __forceinline__ T fma_t(T a, T b, T c);
@@ -217,6 +218,7 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                 const int refQ = P.list_cells[list0 + li];
                 cellQ = refQ * sub2 + (cand - li * sub2);
                 if (P.autocorr && refQ == refP && cellQ > cellP) keep = false;  // fine pairs of one reference cell: once
+                if (!(P.autocorr && refQ == refP)) code |= GEN_DIRZ;
             } else {
                 const int dz = cand % wz - P.g.reach[2];
                 const int dy = (cand / wz) % wy - P.g.reach[1];
@@ -262,7 +264,9 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         const long long refB =
                             ((long long)(q[0] / P.g.s[0]) * P.g.n[1] + q[1] / P.g.s[1]) * P.g.n[2] + q[2] / P.g.s[2];
                         if (refB > refA || (refB == refA && cellQ < cellP)) keep = false;
-                    }
+                        if (refB != refA) code |= GEN_DIRZ;
+                    } else
+                        code |= GEN_DIRZ;
                 }
             }
             if (keep && B.count[cellQ] == 0) keep = false;
@@ -315,6 +319,8 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                 if (cz) zpos = zp + (cz == 1 ? (T)P.wrap[2] : -(T)P.wrap[2]);
             }
             const bool tri = P.autocorr && (cellQ == cellP);  // same cell: only j > i
+            const bool dirz = (code & GEN_DIRZ) != 0;
+            const T tz = zpos - pimax;
             const int nQ = B.count[cellQ];
             const int startQ = B.start[cellQ];
             if (valid) my_eval += tri ? (unsigned long long)(nQ - 1 - iloc > 0 ? nQ - 1 - iloc : 0) : (unsigned long long)nQ;
@@ -354,7 +360,10 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         if (AVG) sep = sqrt_t<T>(r2);
                     } else if (MODE == CFB_WP) {
                         const T r2 = fma_t<T>(dy, dy, dx * dx);
-                        if (!(dz > -pimax && dz < pimax)) continue;
+                        // two reference cells: the reference fast-forwards over z1 <= zpos - pimax and then masks with
+                        // the SIGNED dz < pimax (wp_kernels.c.src:139-142, 207-221), so a survivor whose dz rounds to
+                        // exactly -pimax counts; inside one reference cell j follows i in z order (dz >= 0)
+                        if (dirz ? !(sz[k] > tz && dz < pimax) : !(dz > -pimax && dz < pimax)) continue;
                         if (!(r2 < e_hi && r2 >= e_lo)) continue;
                         int kb;
                         for (kb = nedges - 1; kb >= 1; kb--)
@@ -364,7 +373,9 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         if (AVG) sep = sqrt_t<T>(r2);
                     } else if (MODE == CFB_RPPI) {
                         const T r2 = fma_t<T>(dy, dy, dx * dx);
-                        if (!(dz > -pimax)) continue;
+                        // two reference cells: survivors of the fast-forward over z1 <= zpos - pimax
+                        // (countpairs_rp_pi_kernels.c.src:139-142), then |dz| < pimax (:196-207)
+                        if (dirz ? !(sz[k] > tz) : !(dz > -pimax)) continue;
                         const T adz = dz < 0 ? -dz : dz;
                         if (!(adz < pimax)) continue;
                         if (!(r2 < e_hi && r2 >= e_lo)) continue;

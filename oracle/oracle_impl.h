@@ -11,8 +11,19 @@
  * inverse, truncating cell index with the ix-- clamp), the cell-pair set with periodic wrap,
  * first/second roles, duplicate suppression and the autocorr icell2<=icell filter, the per-pair
  * arithmetic in the AVX-512 kernels' FMA association, the 2-D bin index evaluated in floating
- * point, and the epilogues.  What is NOT restated: the z-sorted early exits inside a cell pair
- * (pure pruning aids; the reference's own sweep tests show results do not depend on them).
+ * point, and the epilogues.  What is NOT restated by default: the z-sorted early exits inside a cell pair
+ * (pruning aids; in double they never change a count).
+ *
+ * LITERAL mode (oracle_set_literal_kernels(1)): for wp and DDrppi the cells are z-sorted and the AVX-512
+ * kernels' control flow is followed chunk by chunk (16 float / 8 double lanes) -- the fast-forward over
+ * secondaries with z1 <= zpos - pimax and the "some lane reached pimax -> last chunk" exit.  In float a
+ * secondary that survives the fast-forward can still round to dz == -pimax exactly; the reference then
+ *   wp     : counts it, because its mask is the SIGNED dz < pimax   (wp_kernels.c.src:196-207)
+ *   DDrppi : takes |dz| first, sees |dz| >= pimax, and stops after this chunk -- every later secondary
+ *            of this primary is dropped                             (countpairs_rp_pi_kernels.c.src:196-207)
+ * Literal mode reproduces both, which is what makes the full-size float goldens bit-identical
+ * (tests/test_cpu_oracle.py::test_literal_*).  The per-primary minimum-separation shortcut (:130-137) is
+ * not restated: it needs two independent rounding coincidences and has never changed a count.
  */
 
 #define CAT_(a, b) a##_##b
@@ -79,6 +90,45 @@ static void FN(o_free_lattice)(FN(olattice) * L)
     free(L->z);
     free(L->w);
     free(L);
+}
+
+/* utils/gridlink_impl.c.src:398-420 (sort_cell_in_z): ascending z inside every cell.  Ties keep the input
+ * order (the reference's quicksort leaves them unspecified; they only matter on a chunk boundary). */
+typedef struct {
+    REAL z;
+    int64_t i;
+} FN(ozkey);
+static int FN(o_zkey_cmp)(const void *a, const void *b)
+{
+    const FN(ozkey) *p = a, *q = b;
+    if (p->z < q->z) return -1;
+    if (p->z > q->z) return 1;
+    return (p->i > q->i) - (p->i < q->i);
+}
+static void FN(o_sort_cells_in_z)(FN(olattice) * L)
+{
+    int64_t nmax = 1;
+    for (int64_t c = 0; c < L->totncells; c++)
+        if (L->cells[c].n > nmax) nmax = L->cells[c].n;
+    FN(ozkey) *key = malloc(sizeof(*key) * (size_t)nmax);
+    REAL *tmp = malloc(sizeof(REAL) * (size_t)nmax);
+    for (int64_t c = 0; c < L->totncells; c++) {
+        const int64_t n = L->cells[c].n, s0 = L->cells[c].start;
+        if (n < 2) continue;
+        for (int64_t i = 0; i < n; i++) {
+            key[i].z = L->z[s0 + i];
+            key[i].i = i;
+        }
+        qsort(key, (size_t)n, sizeof(*key), FN(o_zkey_cmp));
+        REAL *arr[4] = {L->x, L->y, L->z, L->w};
+        for (int a = 0; a < 4; a++) {
+            if (!arr[a]) continue;
+            for (int64_t i = 0; i < n; i++) tmp[i] = arr[a][s0 + key[i].i];
+            memcpy(arr[a] + s0, tmp, sizeof(REAL) * (size_t)n);
+        }
+    }
+    free(key);
+    free(tmp);
 }
 
 /* utils/gridlink_impl.c.src:65-436 (copy_particles=1 branch; per-cell z sort omitted: pruning aid) */
@@ -151,6 +201,7 @@ static FN(olattice) * FN(o_gridlink)(const int64_t N, const REAL *X, const REAL 
         if (Z[i] > c->zb[1]) c->zb[1] = Z[i];
     }
     free(idx);
+    if (orc_literal_kernels) FN(o_sort_cells_in_z)(L);
     return L;
 }
 
@@ -319,7 +370,10 @@ static void FN(o_count_cellpair)(const FN(okern) * K, const int64_t N0, const RE
             } break;
             case ORC_WP: {
                 const REAL r2 = FMA_R(dy, dy, dx * dx);
-                if (!(dz > -K->pimax && dz < K->pimax)) continue;
+                /* two cells: fast-forward over z1 <= zpos - pimax (:139-142), then the SIGNED mask dz < pimax
+                 * (:207-221) -- a survivor whose dz rounds to exactly -pimax counts.  Same cell: j follows i in
+                 * z order, dz >= 0, written symmetrically here because the cells are not z-sorted. */
+                if (same ? !(dz > -K->pimax && dz < K->pimax) : !(z1[j] > zpos - K->pimax && dz < K->pimax)) continue;
                 if (!(r2 < E[nbin - 1] && r2 >= E[0])) continue;
                 int k;
                 for (k = nbin - 1; k >= 1; k--)
@@ -329,7 +383,8 @@ static void FN(o_count_cellpair)(const FN(okern) * K, const int64_t N0, const RE
             } break;
             case ORC_RPPI: {
                 const REAL r2 = FMA_R(dy, dy, dx * dx);
-                if (!(dz > -K->pimax)) continue;
+                /* two cells: fast-forward over z1 <= zpos - pimax (rp_pi_kernels:139-142), then |dz| < pimax */
+                if (same ? !(dz > -K->pimax) : !(z1[j] > zpos - K->pimax)) continue;
                 const REAL adz = FABS_R(dz);
                 if (!(adz < K->pimax)) continue;
                 if (!(r2 < E[nbin - 1] && r2 >= E[0])) continue;
@@ -378,6 +433,71 @@ static void FN(o_count_cellpair)(const FN(okern) * K, const int64_t N0, const RE
             K->npairs[slot]++;
             if (K->need_avg) K->avg[slot] += (double)sep;
             if (K->need_w) K->wavg[slot] += (double)(REAL)(w0[i] * w1[j]); /* weight_functions.h.src:71-73 */
+        }
+    }
+}
+
+/* LITERAL mode, wp and DDrppi: the control flow of wp_avx512_intrinsics (wp_kernels.c.src:76-262) and
+ * countpairs_rp_pi_avx512_intrinsics (countpairs_rp_pi_kernels.c.src:81-267) over z-sorted cells. */
+static void FN(o_count_cellpair_literal)(const FN(okern) * K, const int64_t N0, const REAL *x0, const REAL *y0,
+                                         const REAL *z0, const REAL *w0, const int64_t N1, const REAL *x1,
+                                         const REAL *y1, const REAL *z1, const REAL *w1, const int same,
+                                         const REAL offx, const REAL offy, const REAL offz)
+{
+    const int nbin = K->nbin;
+    const REAL *E = K->edges;
+    const REAL pimax = K->pimax;
+    const int NVEC = (int)(64 / sizeof(REAL));
+    const int rppi = K->mode == ORC_RPPI;
+    int64_t p = 0; /* the reference's z1 pointer: only ever moves forward */
+    if (N1 == 0) return;
+    for (int64_t i = 0; i < N0; i++) {
+        const REAL xpos = x0[i] + offx, ypos = y0[i] + offy, zpos = z0[i] + offz;
+        const REAL this_dz = z1[p] - zpos;
+        if (this_dz >= pimax) continue;
+        if (same) {
+            p++;
+        } else {
+            const REAL target_z = zpos - pimax;
+            while (p < N1 && z1[p] <= target_z) p++;
+        }
+        if (p == N1) break;
+        for (int64_t j = p; j < N1; j += NVEC) {
+            const int lanes = (N1 - j) >= NVEC ? NVEC : (int)(N1 - j);
+            REAL dz[16];
+            int any_gt_neg = 0, any_geq = 0, any_lt = 0;
+            for (int l = 0; l < lanes; l++) {
+                dz[l] = z1[j + l] - zpos;
+                any_gt_neg |= dz[l] > -pimax;
+            }
+            if (!any_gt_neg) continue;
+            for (int l = 0; l < lanes; l++) {
+                if (rppi) dz[l] = FABS_R(dz[l]);
+                any_geq |= dz[l] >= pimax;
+                any_lt |= dz[l] < pimax;
+            }
+            const int64_t jbase = j;
+            if (any_geq) j = N1; /* "do not break yet": this chunk is still processed */
+            if (!any_lt) break;
+            for (int l = 0; l < lanes; l++) {
+                if (!(dz[l] < pimax)) continue;
+                const int64_t jj = jbase + l;
+                const REAL dx = x1[jj] - xpos, dy = y1[jj] - ypos;
+                const REAL r2 = FMA_R(dy, dy, dx * dx);
+                if (!(r2 < E[nbin - 1] && r2 >= E[0])) continue;
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (r2 >= E[k - 1]) break;
+                int64_t slot = k;
+                if (rppi) {
+                    const REAL pibin = dz[l] * K->inv_dpi;
+                    const REAL lin = (REAL)k * (REAL)(K->npibin + 1);
+                    slot = (int64_t)(int)(lin + pibin);
+                }
+                K->npairs[slot]++;
+                if (K->need_avg) K->avg[slot] += (double)SQRT_R(r2);
+                if (K->need_w) K->wavg[slot] += (double)(REAL)(w0[i] * w1[jj]);
+            }
         }
     }
 }
@@ -571,7 +691,9 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
 #endif
         for (int64_t p = 0; p < ncp; p++) {
             const FN(ocell) *a = &L1->cells[CP[p].c1], *b = &L2->cells[CP[p].c2];
-            FN(o_count_cellpair)(&k, a->n, L1->x + a->start, L1->y + a->start, L1->z + a->start,
+            (orc_literal_kernels && (mode == ORC_WP || mode == ORC_RPPI) ? FN(o_count_cellpair_literal)
+                                                                          : FN(o_count_cellpair))(
+                                 &k, a->n, L1->x + a->start, L1->y + a->start, L1->z + a->start,
                                  need_w ? L1->w + a->start : NULL, b->n, L2->x + b->start, L2->y + b->start,
                                  L2->z + b->start, need_w ? L2->w + b->start : NULL, CP[p].same, CP[p].xw, CP[p].yw,
                                  CP[p].zw);

@@ -27,6 +27,10 @@
 #define ORC_PI_OVER_180 0.017453292519943295769236907684886127134428718885417254560971
 #define ORC_INV_PI_OVER_180 57.29577951308232087679815481410517033240547246656432154916024
 
+/* 1: wp / DDrppi follow the AVX-512 kernels' z-sorted, chunked control flow (see oracle_impl.h) */
+static int orc_literal_kernels = 0;
+void oracle_set_literal_kernels(int on) { orc_literal_kernels = on; }
+
 #define REAL float
 #define SUFFIX float
 #define REAL_IS_DOUBLE 0

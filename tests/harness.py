@@ -103,6 +103,24 @@ def oracle_theory(stat, X1, Y1, Z1, bins, *, w1=None, X2=None, Y2=None, Z2=None,
     return dict(npairs=npairs[1:], ravg=avg[1:], weightavg=wavg[1:], cf=cf[1:], lattice=lat)
 
 
+def oracle_config(name, literal=0, nthreads=None):
+    """A BASELINE config (bench.CONFIGS, bench.py's own seeded input) through the oracle; literal=1 follows the
+    AVX-512 kernels' z-sorted chunked control flow for wp / DDrppi (oracle_impl.h)."""
+    import bench
+
+    cfg = bench.CONFIGS[name]
+    dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
+    pts = bench.gen_points(cfg, cfg["N"], dtype)
+    lib = load_oracle()
+    lib.oracle_set_literal_kernels(int(literal))
+    try:
+        return oracle_theory(cfg["stat"], pts["x"], pts["y"], pts["z"], bench.make_bins(cfg["bins"]),
+                             pimax=cfg.get("pimax", 0.0), periodic=True, boxsize=cfg["L"],
+                             nthreads=nthreads or os.cpu_count())
+    finally:
+        lib.oracle_set_literal_kernels(0)
+
+
 def oracle_theta(RA1, DEC1, bins, *, w1=None, RA2=None, DEC2=None, w2=None, autocorr=True, link_in_dec=True,
                  link_in_ra=True, ra_refine=2, dec_refine=2, max_cells=100, enable_min_sep=True, need_avg=False,
                  weight_type=None, fast_acos=False, nthreads=None):

@@ -137,3 +137,44 @@ def test_oracle_vs_live_reference(dtype):
     r = capi.call_DDtheta(ref, 1, 4, tb, ra, dec, options=o)
     a = H.oracle_theta(ra, dec, tb, need_avg=True)
     assert np.array_equal(a["npairs"], r["npairs"])
+
+
+# ---- the oracle at BASELINE config-2 size against the unmodified reference's float output ------------
+
+def test_oracle_full_size_wp_float_matches_reference():
+    """c2wp32 (1.2 M points, float): the oracle's per-pair conditions (fast-forward survivors, signed dz < pimax,
+    wp_kernels.c.src:139-142 / 207-221) reproduce the reference's AVX-512 output bit for bit."""
+    ref = np.load(os.path.join(H.GOLDEN, "ref_fullsize_c2wp32.npz"))["npairs"]
+    assert np.array_equal(H.oracle_config("c2wp32")["npairs"], ref)
+
+
+def test_oracle_literal_mode_pins_the_float_DDrppi_quirk():
+    """c2rppi32: LITERAL mode (z-sorted cells, 16-lane chunks, the |dz|-before-exit order of
+    countpairs_rp_pi_kernels.c.src:196-207) is bit-identical to the reference; the default mode differs from it
+    by exactly the committed `dropped` pairs (296 ordered pairs in 82 bins, none at |dz| >= 35)."""
+    ref = np.load(os.path.join(H.GOLDEN, "ref_fullsize_c2rppi32.npz"))["npairs"].astype(np.int64)
+    dropped = np.load(os.path.join(H.GOLDEN, "ref_fullsize_c2rppi32_dropped.npz"))["dropped"].astype(np.int64)
+    lit = H.oracle_config("c2rppi32", literal=1)["npairs"].astype(np.int64).reshape(ref.shape)
+    assert np.array_equal(lit, ref)
+    dflt = H.oracle_config("c2rppi32")["npairs"].astype(np.int64).reshape(ref.shape)
+    assert np.array_equal(dflt - ref, dropped)
+    assert dropped.sum() == 296 and dropped[:, 35:].sum() == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("stat", ["wp", "DDrppi"])
+def test_oracle_literal_equals_default_on_small_inputs(stat, dtype):
+    """On inputs where no dz rounds onto -pimax the early exits are pure pruning: both modes agree, weights too."""
+    L, N = 420.0, 60000
+    x, y, z, w = H.box_points(5, N, L, dtype)
+    edges = np.logspace(np.log10(0.1), np.log10(25.0), 15)
+    kw = dict(pimax=40.0, periodic=True, boxsize=L, w1=w, weight_type="pair_product", need_avg=True)
+    a = H.oracle_theory(stat, x, y, z, edges, **kw)
+    lib = H.load_oracle()
+    lib.oracle_set_literal_kernels(1)
+    try:
+        b = H.oracle_theory(stat, x, y, z, edges, **kw)
+    finally:
+        lib.oracle_set_literal_kernels(0)
+    assert np.array_equal(a["npairs"], b["npairs"])
+    assert np.allclose(a["ravg"], b["ravg"], rtol=1e-12) and np.allclose(a["weightavg"], b["weightavg"], rtol=1e-12)
