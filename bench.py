@@ -49,6 +49,19 @@ FLOP_PER_EVAL = {"DD": 8, "xi": 8, "wp": 6, "DDrppi": 7, "DDsmu": 9, "DDtheta": 
 INSTR_PER_EVAL = {"DD": 6, "xi": 6, "wp": 5, "DDrppi": 6, "DDsmu": 7, "DDtheta": 8}
 
 
+def config_by_name(name):
+    """CONFIGS[name], or '<cfg>sd<N>M': that config at the same number density with N million points
+    (what --npart N --same-density runs), e.g. c5sd10M."""
+    if name in CONFIGS:
+        return dict(CONFIGS[name])
+    base, _, n = name.partition("sd")
+    cfg = dict(CONFIGS[base])
+    npart = int(float(n.rstrip("M")) * 1e6)
+    cfg["L"] = float(cfg["L"] * (npart / cfg["N"]) ** (1.0 / 3.0))
+    cfg["N"] = npart
+    return cfg
+
+
 def make_bins(spec):
     kind, lo, hi, n = spec
     return np.logspace(np.log10(lo), np.log10(hi), n)

@@ -2,6 +2,7 @@
 """Full-size goldens: the UNMODIFIED reference (oracle/_ref, AVX-512F kernels) run on the exact synthetic inputs of the
 BASELINE configs as bench.py generates them (same seeds, same dtype), npairs saved to tests/golden/ref_fullsize_<cfg>.npz.
   python tests/golden/make_golden_fullsize.py c1 c2 c2wp32 c2rppi c2rppi32 c3 c4      (about two minutes on 8 cores)
+  python tests/golden/make_golden_fullsize.py c5sd10M                                 (config 5 at the same density, 10 M points)
   python tests/golden/make_golden_fullsize.py c5                                      (100 M points: ~40 minutes)
 Run in the build container only (needs /root/reference to build oracle/_ref)."""
 import os
@@ -21,7 +22,7 @@ ref = H.load_ref()
 assert ref is not None, "build oracle/_ref first (python -c 'import __graft_entry__ as g; g.build()')"
 nthreads = os.cpu_count()
 for name in sys.argv[1:]:
-    cfg = bench.CONFIGS[name]
+    cfg = bench.config_by_name(name)
     dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
     bins = bench.make_bins(cfg["bins"])
     pts = bench.gen_points(cfg, cfg["N"], dtype)

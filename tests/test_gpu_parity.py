@@ -663,7 +663,7 @@ def _run_config(lib, name):
     import bench
     from corrfunc_b200 import _capi
 
-    cfg = bench.CONFIGS[name]
+    cfg = bench.config_by_name(name)
     dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
     bins = bench.make_bins(cfg["bins"])
     pts = bench.gen_points(cfg, cfg["N"], dtype)
@@ -685,7 +685,7 @@ def _run_config(lib, name):
     return _capi.call_DDtheta(lib, 0, 1, bins, pts["ra"], pts["dec"], RA2=pts["ra2"], DEC2=pts["dec2"], options=o)
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c2wp32", "c2rppi", "c2rppi32", "c3", "c4"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c2wp32", "c2rppi", "c2rppi32", "c3", "c4", "c5sd10M"])
 def test_full_size_config_vs_reference_golden(name):
     """BASELINE configs 1-4 at their full sizes (1.2M / 10M / 2M+2M points): npairs bit-exact against the
     committed outputs of the UNMODIFIED reference (oracle/_ref, AVX-512F kernels) on the same seeded inputs
