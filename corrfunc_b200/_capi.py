@@ -127,6 +127,14 @@ class ResultsSMu(C.Structure):
                 ("mu_min", C.c_double), ("weightavg", _f64p), ("nsbin", C.c_int), ("nmu_bins", C.c_int)]
 
 
+class ResultsMocksRpPi(ResultsRpPi):  # results_countpairs_mocks (countpairs_rp_pi_mocks.h:18-26): same layout
+    pass
+
+
+class ResultsMocksSMu(ResultsSMu):  # results_countpairs_mocks_s_mu (countpairs_s_mu_mocks.h:19-28): same layout
+    pass
+
+
 class ResultsWp(C.Structure):
     _fields_ = [("npairs", _u64p), ("wp", _f64p), ("rupp", _f64p), ("rpavg", _f64p), ("weightavg", _f64p),
                 ("pimax", C.c_double), ("nbin", C.c_int)]
@@ -145,7 +153,7 @@ class ResultsTheta(C.Structure):
 def default_options(dtype, *, verbose=False, periodic=True, need_avg_sep=False, boxsize=None,
                     bin_refine_factors=(2, 2, 1), max_cells_per_dim=100, copy_particles=True,
                     enable_min_sep_opt=True, c_api_timer=False, isa=-1, link_in_dec=True, link_in_ra=True,
-                    fast_acos=False, custom_refine=False) -> ConfigOptions:
+                    fast_acos=False, custom_refine=False, is_comoving_dist=False) -> ConfigOptions:
     """Python twin of ``get_config_options()`` plus the kwargs the reference's extension sets
     (theory/python_bindings/_countpairs.c:1153-1260)."""
     o = ConfigOptions()
@@ -167,6 +175,7 @@ def default_options(dtype, *, verbose=False, periodic=True, need_avg_sep=False, 
     o.link_in_dec = int(bool(link_in_dec))
     o.link_in_ra = int(bool(link_in_ra))
     o.fast_acos = int(bool(fast_acos))
+    o.is_comoving_dist = int(bool(is_comoving_dist))
     o.enable_min_sep_opt = int(bool(enable_min_sep_opt))
     o.copy_particles = int(bool(copy_particles))
     for i in range(3):
@@ -257,6 +266,16 @@ def _declare(lib):
                  ("free_results_xi", ResultsXi), ("free_results_countpairs_theta", ResultsTheta)):
         getattr(lib, f).argtypes = [C.POINTER(t)]
         getattr(lib, f).restype = None
+    # mocks/DDrppi_mocks, mocks/DDsmu_mocks (absent from reference builds without them)
+    if hasattr(lib, "countpairs_mocks"):
+        lib.countpairs_mocks.argtypes = [i64, vp, vp, vp, i64, vp, vp, vp, ci, ci, cs, cd, ci,
+                                         C.POINTER(ResultsMocksRpPi), C.POINTER(ConfigOptions), C.POINTER(ExtraOptions)]
+        lib.countpairs_mocks_s_mu.argtypes = [i64, vp, vp, vp, i64, vp, vp, vp, ci, ci, cs, cd, ci, ci,
+                                              C.POINTER(ResultsMocksSMu), C.POINTER(ConfigOptions), C.POINTER(ExtraOptions)]
+        lib.countpairs_mocks.restype = lib.countpairs_mocks_s_mu.restype = ci
+        lib.free_results_mocks.argtypes = [C.POINTER(ResultsMocksRpPi)]
+        lib.free_results_mocks_s_mu.argtypes = [C.POINTER(ResultsMocksSMu)]
+        lib.free_results_mocks.restype = lib.free_results_mocks_s_mu.restype = None
     lib._cf_declared = True
 
 
@@ -347,6 +366,71 @@ def call_DDsmu(lib, autocorr, nthreads, bins, mu_max, nmu_bins, X1, Y1, Z1, w1=N
                ravg=grid(res.savg, np.float64), weightavg=grid(res.weightavg, np.float64), nmu_bins=nmu,
                mu_max=res.mu_max, api_time=options.c_api_time)
     lib.free_results_s_mu(C.byref(res))
+    return out
+
+
+def call_DDrppi_mocks(lib, autocorr, cosmology, nthreads, pimax, bins, RA1, DEC1, CZ1, w1=None, RA2=None, DEC2=None,
+                      CZ2=None, w2=None, weight_type=None, options=None, dtype=None):
+    """countpairs_mocks (mocks/DDrppi_mocks/countpairs_rp_pi_mocks.h:28-37).  The C routine may shift RA/DEC in
+    place (check_ra_dec_cz) -> private copies."""
+    _declare(lib)
+    dtype = np.dtype(dtype or np.asarray(RA1).dtype)
+    RA1, DEC1, CZ1, RA2, DEC2, CZ2 = (None if a is None else np.array(a, dtype=dtype, order="C", copy=True)
+                                      for a in (RA1, DEC1, CZ1, RA2, DEC2, CZ2))
+    if autocorr:
+        RA2, DEC2, CZ2 = RA1, DEC1, CZ1
+    extra, keep = make_extra(w1, w2 if not autocorr else w1, weight_type, dtype)
+    res = ResultsMocksRpPi()
+    n2 = 0 if RA2 is None else RA2.size
+    with binfile_for(bins) as bf:
+        st = lib.countpairs_mocks(RA1.size, _ptr(RA1), _ptr(DEC1), _ptr(CZ1), n2, _ptr(RA2), _ptr(DEC2), _ptr(CZ2),
+                                  int(nthreads), int(autocorr), bf, float(pimax), int(cosmology), C.byref(res),
+                                  C.byref(options), C.byref(extra))
+    if st != 0:
+        raise RuntimeError("countpairs_mocks returned %d" % st)
+    nb, npi = res.nbin, res.npibin
+    tot = (nb + 1) * (npi + 1)
+
+    def grid(p, dt):
+        a = _arr(p, tot, dt).reshape(nb + 1, npi + 1)
+        return a[1:nb, :npi].copy()
+
+    out = dict(npairs=grid(res.npairs, np.uint64), rupp=_arr(res.rupp, nb, np.float64),
+               ravg=grid(res.rpavg, np.float64), weightavg=grid(res.weightavg, np.float64), npibin=npi,
+               pimax=res.pimax, api_time=options.c_api_time)
+    lib.free_results_mocks(C.byref(res))
+    return out
+
+
+def call_DDsmu_mocks(lib, autocorr, cosmology, nthreads, mu_max, nmu_bins, bins, RA1, DEC1, CZ1, w1=None, RA2=None,
+                     DEC2=None, CZ2=None, w2=None, weight_type=None, options=None, dtype=None):
+    """countpairs_mocks_s_mu (mocks/DDsmu_mocks/countpairs_s_mu_mocks.h:30-41)."""
+    _declare(lib)
+    dtype = np.dtype(dtype or np.asarray(RA1).dtype)
+    RA1, DEC1, CZ1, RA2, DEC2, CZ2 = (None if a is None else np.array(a, dtype=dtype, order="C", copy=True)
+                                      for a in (RA1, DEC1, CZ1, RA2, DEC2, CZ2))
+    if autocorr:
+        RA2, DEC2, CZ2 = RA1, DEC1, CZ1
+    extra, keep = make_extra(w1, w2 if not autocorr else w1, weight_type, dtype)
+    res = ResultsMocksSMu()
+    n2 = 0 if RA2 is None else RA2.size
+    with binfile_for(bins) as bf:
+        st = lib.countpairs_mocks_s_mu(RA1.size, _ptr(RA1), _ptr(DEC1), _ptr(CZ1), n2, _ptr(RA2), _ptr(DEC2),
+                                       _ptr(CZ2), int(nthreads), int(autocorr), bf, float(mu_max), int(nmu_bins),
+                                       int(cosmology), C.byref(res), C.byref(options), C.byref(extra))
+    if st != 0:
+        raise RuntimeError("countpairs_mocks_s_mu returned %d" % st)
+    nb, nmu = res.nsbin, res.nmu_bins
+    tot = (nb + 1) * (nmu + 1)
+
+    def grid(p, dt):
+        a = _arr(p, tot, dt).reshape(nb + 1, nmu + 1)
+        return a[1:nb, :nmu].copy()
+
+    out = dict(npairs=grid(res.npairs, np.uint64), rupp=_arr(res.supp, nb, np.float64),
+               ravg=grid(res.savg, np.float64), weightavg=grid(res.weightavg, np.float64), nmu_bins=nmu,
+               mu_max=res.mu_max, api_time=options.c_api_time)
+    lib.free_results_mocks_s_mu(C.byref(res))
     return out
 
 

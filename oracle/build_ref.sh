@@ -34,11 +34,11 @@ expand() { # expand <src template> <dst dir>  -> writes <name>_float.<ext> and <
 }
 
 mkdir -p "$TMP/gen"
-for d in utils theory/DD theory/DDrppi theory/DDsmu theory/wp theory/xi mocks/DDtheta_mocks; do
+for d in utils theory/DD theory/DDrppi theory/DDsmu theory/wp theory/xi mocks/DDtheta_mocks mocks/DDrppi_mocks mocks/DDsmu_mocks; do
   for f in "$REF/$d"/*.src; do expand "$f" "$TMP/gen"; done
 done
 
-INCL="-I$TMP/gen -I$REF/utils -I$REF/io -I$REF/theory/DD -I$REF/theory/DDrppi -I$REF/theory/DDsmu -I$REF/theory/wp -I$REF/theory/xi -I$REF/mocks/DDtheta_mocks"
+INCL="-I$TMP/gen -I$REF/utils -I$REF/io -I$REF/theory/DD -I$REF/theory/DDrppi -I$REF/theory/DDsmu -I$REF/theory/wp -I$REF/theory/xi -I$REF/mocks/DDtheta_mocks -I$REF/mocks/DDrppi_mocks -I$REF/mocks/DDsmu_mocks -I$HERE/gsl_shim"
 COMMON="-std=c99 -m64 -O3 -fPIC -D_POSIX_SOURCE=200809L -D_GNU_SOURCE -DVERSION=\"2.5.3\" -DUSE_OMP -fopenmp \
  -funroll-loops -fno-strict-aliasing -ftree-vectorize -DPERIODIC -DENABLE_MIN_SEP_OPT -DCOPY_PARTICLES -DOUTPUT_RPAVG \
  -DLINK_IN_DEC -DLINK_IN_RA -DDOUBLE_PREC -w"
@@ -50,6 +50,11 @@ SRCS=(
   "$REF/theory/wp/countpairs_wp.c" "$TMP/gen/countpairs_wp_impl_float.c" "$TMP/gen/countpairs_wp_impl_double.c"
   "$REF/theory/xi/countpairs_xi.c" "$TMP/gen/countpairs_xi_impl_float.c" "$TMP/gen/countpairs_xi_impl_double.c"
   "$REF/mocks/DDtheta_mocks/countpairs_theta_mocks.c" "$TMP/gen/countpairs_theta_mocks_impl_float.c" "$TMP/gen/countpairs_theta_mocks_impl_double.c"
+  # SURVEY 8(f) rank 1.  GSL is absent: gsl_shim/ stands in for <gsl/gsl_interp.h> and for set_cosmo_dist (both only
+  # reached with is_comoving_dist == 0, which the tests never use); the reference sources themselves are unmodified.
+  "$REF/mocks/DDrppi_mocks/countpairs_rp_pi_mocks.c" "$TMP/gen/countpairs_rp_pi_mocks_impl_float.c" "$TMP/gen/countpairs_rp_pi_mocks_impl_double.c"
+  "$REF/mocks/DDsmu_mocks/countpairs_s_mu_mocks.c" "$TMP/gen/countpairs_s_mu_mocks_impl_float.c" "$TMP/gen/countpairs_s_mu_mocks_impl_double.c"
+  "$REF/utils/cosmology_params.c" "$HERE/gsl_shim/cosmo_stub.c"
   "$TMP/gen/gridlink_impl_float.c" "$TMP/gen/gridlink_impl_double.c"
   "$TMP/gen/gridlink_mocks_impl_float.c" "$TMP/gen/gridlink_mocks_impl_double.c"
   "$TMP/gen/gridlink_utils_float.c" "$TMP/gen/gridlink_utils_double.c"

@@ -1,0 +1,42 @@
+/* TEST INFRASTRUCTURE ONLY -- stand-in for <gsl/gsl_interp.h> (GSL is not installed in this image).
+ * The reference's mocks/DDrppi_mocks and mocks/DDsmu_mocks include this header for the cz -> comoving
+ * distance table lookup, a branch that runs only when options->is_comoving_dist == 0.  oracle/build_ref.sh
+ * puts this directory on the include path so the UNMODIFIED reference sources compile; the parity tests
+ * only ever call them with is_comoving_dist = 1 (distances given), where none of this is reached.
+ * Written from the documented GSL interface (linear interpolation); no GSL code is used. */
+#pragma once
+#include <stdlib.h>
+
+typedef struct { int kind; } gsl_interp_type;
+static const gsl_interp_type gsl_shim_linear_type = {0};
+#define gsl_interp_linear (&gsl_shim_linear_type)
+typedef struct { size_t size; } gsl_interp;
+typedef struct { size_t cache; } gsl_interp_accel;
+
+static inline gsl_interp_accel *gsl_interp_accel_alloc(void) { return (gsl_interp_accel *)calloc(1, sizeof(gsl_interp_accel)); }
+static inline void gsl_interp_accel_free(gsl_interp_accel *a) { free(a); }
+static inline gsl_interp *gsl_interp_alloc(const gsl_interp_type *t, size_t n)
+{
+    (void)t;
+    gsl_interp *p = (gsl_interp *)calloc(1, sizeof(gsl_interp));
+    if (p) p->size = n;
+    return p;
+}
+static inline int gsl_interp_init(gsl_interp *p, const double *x, const double *y, size_t n)
+{
+    (void)x, (void)y;
+    p->size = n;
+    return 0;
+}
+static inline void gsl_interp_free(gsl_interp *p) { free(p); }
+static inline double gsl_interp_eval(const gsl_interp *p, const double *x, const double *y, double xv, gsl_interp_accel *a)
+{
+    size_t lo = 0, hi = p->size - 1;
+    (void)a;
+    while (hi - lo > 1) {
+        const size_t mid = (lo + hi) / 2;
+        if (x[mid] > xv) hi = mid; else lo = mid;
+    }
+    const double dx = x[lo + 1] - x[lo];
+    return dx > 0.0 ? y[lo] + (xv - x[lo]) / dx * (y[lo + 1] - y[lo]) : y[lo];
+}

@@ -318,6 +318,7 @@ typedef struct {
     int npibin;           /* rppi */
     REAL inv_dpi;         /* rppi */
     REAL sqr_mumax;       /* smu */
+    REAL sqr_max_sep, sqr_pimax; /* rppi mocks: rp_pi_mocks_kernels:56-57 */
     int nmu;              /* smu */
     REAL inv_dmu;         /* smu */
     int need_avg, need_w; /* accumulate sums? */
@@ -412,6 +413,46 @@ static void FN(o_count_cellpair)(const FN(okern) * K, const int64_t N0, const RE
                 const REAL lin = (REAL)k * (REAL)(K->nmu + 1);
                 slot = (int64_t)(int)(lin + mubin);
                 if (K->need_avg) sep = SQRT_R(s2);
+            } break;
+            case ORC_RPPI_MOCKS: { /* countpairs_rp_pi_mocks_kernels.c.src:200-300: line of sight = pair midpoint */
+                const REAL parx = x1[j] + xpos, pary = y1[j] + ypos, parz = z1[j] + zpos;
+                const REAL term1 = parx * dx, term2 = pary * dy;
+                const REAL s_dot_l = FMA_R(parz, dz, term1 + term2);
+                const REAL sqr_s_dot_l = s_dot_l * s_dot_l;
+                const REAL sqr_sep = FMA_R(dx, dx, FMA_R(dy, dy, dz * dz));
+                if (!(sqr_sep < K->sqr_max_sep)) continue;
+                const REAL sqr_norm_l = FMA_R(parx, parx, FMA_R(pary, pary, parz * parz));
+                if (!(sqr_s_dot_l < K->sqr_pimax * sqr_norm_l)) continue;
+                const REAL sqr_Dpar = sqr_s_dot_l / sqr_norm_l; /* fast_divide_and_NR_steps == 0 */
+                const REAL sqr_Dperp = sqr_sep - sqr_Dpar;
+                if (!(sqr_Dpar < K->sqr_pimax && sqr_Dperp < E[nbin - 1] && sqr_Dperp >= E[0])) continue;
+                const REAL Dpar = SQRT_R(sqr_Dpar);
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (sqr_Dperp >= E[k - 1]) break;
+                const REAL pibin = Dpar * K->inv_dpi;
+                const REAL lin = (REAL)k * (REAL)(K->npibin + 1);
+                slot = (int64_t)(int)(lin + pibin);
+                if (K->need_avg) sep = SQRT_R(sqr_Dperp);
+            } break;
+            case ORC_SMU_MOCKS: { /* countpairs_s_mu_mocks_kernels.c.src:196-290 */
+                const REAL parx = x1[j] + xpos, pary = y1[j] + ypos, parz = z1[j] + zpos;
+                const REAL term1 = parx * dx, term2 = pary * dy;
+                const REAL s_dot_l = FMA_R(parz, dz, term1 + term2);
+                const REAL sqr_s_dot_l = s_dot_l * s_dot_l;
+                const REAL sqr_s = FMA_R(dx, dx, FMA_R(dy, dy, dz * dz));
+                if (!(sqr_s < E[nbin - 1])) continue;
+                const REAL sqr_norm_l = FMA_R(parx, parx, FMA_R(pary, pary, parz * parz));
+                const REAL sqr_mu = sqr_s_dot_l / (sqr_norm_l * sqr_s);
+                const REAL mu = SQRT_R(sqr_mu);
+                if (!(sqr_mu < K->sqr_mumax && sqr_s >= E[0])) continue;
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (sqr_s >= E[k - 1]) break;
+                const REAL mubin = mu * K->inv_dmu;
+                const REAL lin = (REAL)k * (REAL)(K->nmu + 1);
+                slot = (int64_t)(int)(lin + mubin);
+                if (K->need_avg) sep = SQRT_R(sqr_s);
             } break;
             case ORC_THETA: {
                 const REAL chord2 = FMA_R(dz, dz, FMA_R(dy, dy, dx * dx));
@@ -529,6 +570,31 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
     for (int i = 0; i < nbin; i++) esq[i] = rupp[i] * rupp[i]; /* double product rounded to REAL (DD impl:435-438) */
 
     const int is_box = (mode == ORC_XI || mode == ORC_WP);
+    const int is_mocks = (mode == ORC_RPPI_MOCKS || mode == ORC_SMU_MOCKS);
+    REAL *conv[6] = {NULL, NULL, NULL, NULL, NULL, NULL};
+    if (is_mocks) {
+        /* inputs are RA, DEC (degrees) and the comoving distance (is_comoving_dist = 1):
+         * countpairs_rp_pi_mocks_impl.c.src:364-391 */
+        if (!(rmin > 0.0)) { /* :304 -- the mocks statistics do not accept rmin = 0 */
+            free(esq);
+            return EXIT_FAILURE;
+        }
+        for (int sidx = 0; sidx < (autocorr ? 1 : 2); sidx++) {
+            const int64_t n = sidx ? ND2 : ND1;
+            const REAL *ra = sidx ? X2 : X1, *dec = sidx ? Y2 : Y1, *D = sidx ? Z2 : Z1;
+            REAL *x = malloc(sizeof(REAL) * (n > 0 ? n : 1)), *y = malloc(sizeof(REAL) * (n > 0 ? n : 1)),
+                 *z = malloc(sizeof(REAL) * (n > 0 ? n : 1));
+            for (int64_t i = 0; i < n; i++) {
+                x[i] = D[i] * COSD_R(dec[i]) * COSD_R(ra[i]);
+                y[i] = D[i] * COSD_R(dec[i]) * SIND_R(ra[i]);
+                z[i] = D[i] * SIND_R(dec[i]);
+            }
+            conv[3 * sidx] = x, conv[3 * sidx + 1] = y, conv[3 * sidx + 2] = z;
+        }
+        X1 = conv[0], Y1 = conv[1], Z1 = conv[2];
+        if (!autocorr) X2 = conv[3], Y2 = conv[4], Z2 = conv[5];
+        periodic = 0;
+    }
     REAL xmin, xmax, ymin, ymax, zmin, zmax, xwrap, ywrap, zwrap;
     int px, py, pz;
     REAL max_x, max_y, max_z; /* gridlink cell sizes */
@@ -603,6 +669,25 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
             max_z = pimax_in;
             max2 = rmax;
             max1 = pimax_in;
+        } else if (is_mocks) {
+            REAL max_sep;
+            if (mode == ORC_RPPI_MOCKS) { /* rp_pi_mocks_impl:307-308 */
+                pimax = pimax_in;
+                npibin = (int)pimax_in;
+                const REAL sqr_max_sep = rmax * rmax + pimax * pimax;
+                max_sep = SQRT_R(sqr_max_sep);
+            } else { /* s_mu_mocks_impl:312-326, 424-432 */
+                if (mu_max_in <= 0.0 || mu_max_in > 1.0 || nmu_bins < 1) return EXIT_FAILURE;
+                mu_max = (REAL)mu_max_in;
+                max_sep = rmax;
+            }
+            if (!binning_cust) { /* :413-423 */
+                if (max_sep < 0.05 * (xmax - xmin)) rf[0] = 1;
+                if (max_sep < 0.05 * (ymax - ymin)) rf[1] = 1;
+                if (max_sep < 0.05 * (zmax - zmin)) rf[2] = 1;
+            }
+            max_x = max_y = max_z = max_sep;
+            max3 = max_sep;
         } else { /* ORC_SMU: s_mu impl:212-234, 305-345 */
             if (mu_max_in <= 0.0 || mu_max_in > 1.0 || nmu_bins < 1) return EXIT_FAILURE;
             mu_max = (REAL)mu_max_in;
@@ -618,7 +703,11 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
                                       max_y, max_z, xwrap, ywrap, zwrap, rf[0], rf[1], rf[2], max_cells);
     if (!L1) return EXIT_FAILURE;
     if (mode != ORC_SMU) { /* boost: DD impl:298-332 (smu's boost multiplies by BOOST_BIN_REF=1: no-op) */
-        const double avg_np = ((double)ND1) / ((double)L1->nmesh[0] * L1->nmesh[1] * L1->nmesh[2]);
+        double avg_np = ((double)ND1) / ((double)L1->nmesh[0] * L1->nmesh[1] * L1->nmesh[2]);
+        if (mode == ORC_RPPI_MOCKS) { /* rp_pi_mocks_impl:442-444: the larger of the two sets (ND2 also when autocorr) */
+            const double avg_np2 = ((double)ND2) / ((double)L1->nmesh[0] * L1->nmesh[1] * L1->nmesh[2]);
+            if (avg_np2 > avg_np) avg_np = avg_np2;
+        }
         const int max_nmesh = (int)fmax(L1->nmesh[0], fmax(L1->nmesh[1], L1->nmesh[2]));
         if ((max_nmesh <= 10 || avg_np >= 250) && max_nmesh < max_cells && !binning_cust) {
             FN(o_free_lattice)(L1);
@@ -654,12 +743,14 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
     K.need_avg = need_avg;
     K.need_w = need_w;
     K.pimax = pimax;
-    if (mode == ORC_RPPI) { /* rp_pi_kernels:65-66 */
+    if (mode == ORC_RPPI || mode == ORC_RPPI_MOCKS) { /* rp_pi_kernels:65-66, rp_pi_mocks_kernels:56-68 */
         K.npibin = npibin;
         const REAL dpi = pimax / npibin;
         K.inv_dpi = 1.0 / dpi;
+        K.sqr_max_sep = esq[nbin - 1] + pimax * pimax;
+        K.sqr_pimax = pimax * pimax;
         nslots = (int64_t)(npibin + 1) * (nbin + 1);
-    } else if (mode == ORC_SMU) { /* s_mu_kernels:65-68 */
+    } else if (mode == ORC_SMU || mode == ORC_SMU_MOCKS) { /* s_mu_kernels:65-68, s_mu_mocks_kernels:52-61 */
         K.nmu = nmu_bins;
         K.sqr_mumax = mu_max * mu_max;
         const REAL dmu = mu_max / (REAL)nmu_bins;
@@ -769,6 +860,7 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
     free(avg);
     free(wavg);
     free(esq);
+    for (int i = 0; i < 6; i++) free(conv[i]);
     if (L2 != L1) FN(o_free_lattice)(L2);
     FN(o_free_lattice)(L1);
     return EXIT_SUCCESS;

@@ -22,6 +22,8 @@
 #define ORC_WP 3
 #define ORC_SMU 4
 #define ORC_THETA 5
+#define ORC_RPPI_MOCKS 6 /* X,Y,Z arguments carry RA, DEC (deg) and the comoving distance */
+#define ORC_SMU_MOCKS 7
 
 /* utils/function_precision.h:20-21 */
 #define ORC_PI_OVER_180 0.017453292519943295769236907684886127134428718885417254560971

@@ -9,7 +9,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 
-MODES = dict(DD=0, xi=1, DDrppi=2, wp=3, DDsmu=4, DDtheta=5)
+MODES = dict(DD=0, xi=1, DDrppi=2, wp=3, DDsmu=4, DDtheta=5, DDrppi_mocks=6, DDsmu_mocks=7)
 
 
 def _cpu_flags():
@@ -67,9 +67,9 @@ def oracle_theory(stat, X1, Y1, Z1, bins, *, w1=None, X2=None, Y2=None, Z2=None,
     edges = np.sort(np.asarray(bins, dtype=np.float64))
     nbin = edges.size  # reference's nbin = nlines+1 = number of edges
     mode = MODES[stat]
-    if stat == "DDrppi":
+    if stat in ("DDrppi", "DDrppi_mocks"):
         nslots = (nbin + 1) * (int(pimax) + 1)
-    elif stat == "DDsmu":
+    elif stat in ("DDsmu", "DDsmu_mocks"):
         nslots = (nbin + 1) * (nmu_bins + 1)
     else:
         nslots = nbin
@@ -93,11 +93,11 @@ def oracle_theory(stat, X1, Y1, Z1, bins, *, w1=None, X2=None, Y2=None, Z2=None,
             C.c_int(int(need_w)), _p(npairs), _p(avg), _p(wavg), _p(cf), _p(lat))
     if st != 0:
         raise RuntimeError("oracle failed")
-    if stat == "DDrppi":
+    if stat in ("DDrppi", "DDrppi_mocks"):
         npi = int(pimax)
         g = lambda a: a.reshape(nbin + 1, npi + 1)[1:nbin, :npi].copy()
         return dict(npairs=g(npairs), ravg=g(avg), weightavg=g(wavg), lattice=lat)
-    if stat == "DDsmu":
+    if stat in ("DDsmu", "DDsmu_mocks"):
         g = lambda a: a.reshape(nbin + 1, nmu_bins + 1)[1:nbin, :nmu_bins].copy()
         return dict(npairs=g(npairs), ravg=g(avg), weightavg=g(wavg), lattice=lat)
     return dict(npairs=npairs[1:], ravg=avg[1:], weightavg=wavg[1:], cf=cf[1:], lattice=lat)
