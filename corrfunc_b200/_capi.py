@@ -281,7 +281,9 @@ def _declare(lib):
 
 EXPORTED_SYMBOLS = ("countpairs", "free_results", "countpairs_rp_pi", "free_results_rp_pi", "countpairs_s_mu",
                     "free_results_s_mu", "countpairs_wp", "free_results_wp", "countpairs_xi", "free_results_xi",
-                    "countpairs_theta_mocks", "free_results_countpairs_theta") + tuple(
+                    "countpairs_theta_mocks", "free_results_countpairs_theta", "countpairs_mocks", "free_results_mocks",
+                    "countpairs_mocks_s_mu", "free_results_mocks_s_mu", "countpairs_mocks_float",
+                    "countpairs_mocks_double", "countpairs_mocks_s_mu_float", "countpairs_mocks_s_mu_double") + tuple(
     "%s_%s" % (f, t) for f in ("countpairs", "countpairs_rp_pi", "countpairs_s_mu", "countpairs_wp", "countpairs_xi",
                                "countpairs_theta_mocks") for t in ("float", "double"))
 

@@ -448,7 +448,8 @@ extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat,
         if (sub[k] > 1 && lat->inv[k] > 0) {
             // fine cells more than ceil(maxsep / fine size) + 1 away (two cells of slack) cannot hold a pair in range
             const double rmax = sqrt(bin->edges[bin->nedges - 1]);
-            const double sep = (k == 2 && (bin->mode == CFB_WP || bin->mode == CFB_RPPI)) ? bin->pimax : rmax;
+            double sep = (k == 2 && (bin->mode == CFB_WP || bin->mode == CFB_RPPI)) ? bin->pimax : rmax;
+            if (bin->mode == CFB_RPPI_MOCKS) sep = sqrt(bin->edges[bin->nedges - 1] + bin->pimax * bin->pimax);  // 3-D
             const double cells = ceil(sep * lat->inv[k] * sub[k] * (1.0 + 1e-6)) + 1.0;
             if (cells < P.g.reach[k]) P.g.reach[k] = (int)cells;
         }

@@ -197,9 +197,11 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
     const T pimax = (T)P.pimax;
     const T inv_dpi = (T)P.inv_dpi, inv_dmu = (T)P.inv_dmu, sqr_mumax = (T)P.sqr_mumax;
     const T npi_p1 = (T)(P.npibin + 1), nmu_p1 = (T)(P.nmu_bins + 1);
+    const T sqr_pimax = pimax * pimax;  // rppi mocks (countpairs_rp_pi_mocks_kernels.c.src:56-57)
     unsigned long long my_eval = 0, my_tp = 0;
     __syncthreads();
     const T e_lo = s_edges[0], e_hi = s_edges[nedges - 1];
+    const T sqr_max_sep = e_hi + sqr_pimax;
     const int lane = tid & 31, wid = tid >> 5;
     T *sx = S.sx[wid], *sy = S.sy[wid], *sz = S.sz[wid], *sw = S.sw[wid];
     const bool warp_has_work = __any_sync(0xffffffffu, valid);
@@ -401,6 +403,47 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
                         slot = (int64_t)(int)fin;
                         kbin = kb;
                         if (AVG) sep = sqrt_t<T>(s2);
+                    } else if (MODE == CFB_RPPI_MOCKS) {
+                        // line of sight = pair midpoint: pi^2 = (s.l)^2 / l^2, rp^2 = s^2 - pi^2
+                        // (countpairs_rp_pi_mocks_kernels.c.src:200-262)
+                        const T parx = sx[k] + xpos, pary = sy[k] + ypos, parz = sz[k] + zpos;
+                        const T term1 = parx * dx, term2 = pary * dy;
+                        const T s_dot_l = fma_t<T>(parz, dz, term1 + term2);
+                        const T sqr_s_dot_l = s_dot_l * s_dot_l;
+                        const T sqr_sep = fma_t<T>(dx, dx, fma_t<T>(dy, dy, dz * dz));
+                        if (!(sqr_sep < sqr_max_sep)) continue;
+                        const T sqr_norm_l = fma_t<T>(parx, parx, fma_t<T>(pary, pary, parz * parz));
+                        if (!(sqr_s_dot_l < sqr_pimax * sqr_norm_l)) continue;
+                        const T sqr_Dpar = divi_t<T>(sqr_s_dot_l, sqr_norm_l);  // fast_divide_and_NR_steps == 0
+                        const T sqr_Dperp = sqr_sep - sqr_Dpar;
+                        if (!(sqr_Dpar < sqr_pimax && sqr_Dperp < e_hi && sqr_Dperp >= e_lo)) continue;
+                        const T Dpar = sqrt_t<T>(sqr_Dpar);
+                        int kb;
+                        for (kb = nedges - 1; kb >= 1; kb--)
+                            if (sqr_Dperp >= s_edges[kb - 1]) break;
+                        const T fin = (T)kb * npi_p1 + Dpar * inv_dpi;  // :283-290, evaluated in T, then truncated
+                        slot = (int64_t)(int)fin;
+                        kbin = kb;
+                        if (AVG) sep = sqrt_t<T>(sqr_Dperp);
+                    } else if (MODE == CFB_SMU_MOCKS) {
+                        // mu^2 = (s.l)^2 / (l^2 s^2) (countpairs_s_mu_mocks_kernels.c.src:196-290)
+                        const T parx = sx[k] + xpos, pary = sy[k] + ypos, parz = sz[k] + zpos;
+                        const T term1 = parx * dx, term2 = pary * dy;
+                        const T s_dot_l = fma_t<T>(parz, dz, term1 + term2);
+                        const T sqr_s_dot_l = s_dot_l * s_dot_l;
+                        const T s2 = fma_t<T>(dx, dx, fma_t<T>(dy, dy, dz * dz));
+                        if (!(s2 < e_hi && s2 >= e_lo)) continue;
+                        const T sqr_norm_l = fma_t<T>(parx, parx, fma_t<T>(pary, pary, parz * parz));
+                        const T sqr_mu = divi_t<T>(sqr_s_dot_l, sqr_norm_l * s2);
+                        if (!(sqr_mu < sqr_mumax)) continue;
+                        const T mu = sqrt_t<T>(sqr_mu);
+                        int kb;
+                        for (kb = nedges - 1; kb >= 1; kb--)
+                            if (s2 >= s_edges[kb - 1]) break;
+                        const T fin = (T)kb * nmu_p1 + mu * inv_dmu;
+                        slot = (int64_t)(int)fin;
+                        kbin = kb;
+                        if (AVG) sep = sqrt_t<T>(s2);
                     } else {  // CFB_THETA: cos(theta) = 1 - chord^2/2, edges are cos(theta_upp) (decreasing)
                         const T chord2 = fma_t<T>(dz, dz, fma_t<T>(dy, dy, dx * dx));
                         const T ct = (T)1.0 - (T)0.5 * chord2;
@@ -440,7 +483,9 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
             if (v) {
                 atomicAdd(&P.npairs[i], v);
                 if (AVG) {
-                    const int kb = MODE == CFB_RPPI ? (int)(i / (P.npibin + 1)) : (MODE == CFB_SMU ? (int)(i / (P.nmu_bins + 1)) : (int)i);
+                    const int kb = (MODE == CFB_RPPI || MODE == CFB_RPPI_MOCKS)
+                                       ? (int)(i / (P.npibin + 1))
+                                       : ((MODE == CFB_SMU || MODE == CFB_SMU_MOCKS) ? (int)(i / (P.nmu_bins + 1)) : (int)i);
                     atomicAdd(&P.sum_sep[i], fixed96_to_double(s_sep[i], s_sep[ns + i], s_sep[2 * ns + i]) / s_scale[kb < nedges ? kb : nedges - 1]);
                 }
                 if (WGT) atomicAdd(&P.sum_w[i], fixed96_to_double(s_w[i], s_w[ns + i], s_w[2 * ns + i]) / w_scale);
@@ -526,6 +571,8 @@ static int launch_T(const cfb_binning *bin, const PairParams &P, bool list_mode)
     case CFB_WP: return launch_mode<T, CFB_WP, false>(bin, P, SA, SB, c.stream);
     case CFB_RPPI: return launch_mode<T, CFB_RPPI, false>(bin, P, SA, SB, c.stream);
     case CFB_SMU: return launch_mode<T, CFB_SMU, false>(bin, P, SA, SB, c.stream);
+    case CFB_RPPI_MOCKS: return launch_mode<T, CFB_RPPI_MOCKS, false>(bin, P, SA, SB, c.stream);
+    case CFB_SMU_MOCKS: return launch_mode<T, CFB_SMU_MOCKS, false>(bin, P, SA, SB, c.stream);
     default: return cfb_fail("unknown mode %d", bin->mode);
     }
 }

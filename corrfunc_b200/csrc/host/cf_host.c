@@ -19,7 +19,9 @@
 #include "corrfunc_b200_device.h"
 #include "countpairs.h"
 #include "countpairs_rp_pi.h"
+#include "countpairs_rp_pi_mocks.h"
 #include "countpairs_s_mu.h"
+#include "countpairs_s_mu_mocks.h"
 #include "countpairs_theta_mocks.h"
 #include "countpairs_wp.h"
 #include "countpairs_xi.h"
@@ -372,6 +374,73 @@ int countpairs_theta_mocks(const int64_t ND1, void *phi1, void *theta1, const in
 /* ------------------------------------------------------------------------------------------------
  * Precision-suffixed entry points (the reference's *_impl.h.src prototypes): typed pointers; the
  * options' float_type is overridden for the call and restored afterwards. */
+/* ---- survey geometry: mocks/DDrppi_mocks/countpairs_rp_pi_mocks.c:33-77, DDsmu_mocks ---- */
+void free_results_mocks(results_countpairs_mocks *r)
+{
+    if (r == NULL) return;
+    free(r->npairs); free(r->rupp); free(r->rpavg); free(r->weightavg);
+    r->npairs = NULL; r->rupp = NULL; r->rpavg = NULL; r->weightavg = NULL;
+}
+
+void free_results_mocks_s_mu(results_countpairs_mocks_s_mu *r)
+{
+    if (r == NULL) return;
+    free(r->npairs); free(r->supp); free(r->savg); free(r->weightavg);
+    r->npairs = NULL; r->supp = NULL; r->savg = NULL; r->weightavg = NULL;
+}
+
+int countpairs_mocks(const int64_t ND1, void *phi1, void *theta1, void *czD1, const int64_t ND2, void *phi2, void *theta2,
+                     void *czD2, const int numthreads, const int autocorr, const char *binfile, const double pimax,
+                     const int cosmology, results_countpairs_mocks *results, struct config_options *options,
+                     struct extra_options *extra)
+{
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_box_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_mocks_f32(CFB_RPPI_MOCKS, ND1, phi1, theta1, czD1, ND2, phi2, theta2, czD2, numthreads, autocorr,
+                                      binfile, (double)(float)pimax, 0.0, 0, cosmology, options, extra, &o)
+                       : cf_mocks_f64(CFB_RPPI_MOCKS, ND1, phi1, theta1, czD1, ND2, phi2, theta2, czD2, numthreads, autocorr,
+                                      binfile, pimax, 0.0, 0, cosmology, options, extra, &o);
+    if (st != EXIT_SUCCESS || o.npairs == NULL) return st; /* empty input: success, results untouched */
+    results->nbin = o.nbin;
+    results->npibin = o.n2;
+    results->pimax = options->float_type == sizeof(float) ? (double)(float)pimax : pimax;
+    results->npairs = o.npairs;
+    results->rupp = o.rupp;
+    results->rpavg = o.avg;
+    results->weightavg = o.wavg;
+    free(o.cf);
+    return EXIT_SUCCESS;
+}
+
+int countpairs_mocks_s_mu(const int64_t ND1, void *phi1, void *theta1, void *czD1, const int64_t ND2, void *phi2,
+                          void *theta2, void *czD2, const int numthreads, const int autocorr, const char *sbinfile,
+                          const double mu_max, const int nmu_bins, const int cosmology,
+                          results_countpairs_mocks_s_mu *results, struct config_options *options,
+                          struct extra_options *extra)
+{
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_box_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_mocks_f32(CFB_SMU_MOCKS, ND1, phi1, theta1, czD1, ND2, phi2, theta2, czD2, numthreads, autocorr,
+                                      sbinfile, 0.0, mu_max, nmu_bins, cosmology, options, extra, &o)
+                       : cf_mocks_f64(CFB_SMU_MOCKS, ND1, phi1, theta1, czD1, ND2, phi2, theta2, czD2, numthreads, autocorr,
+                                      sbinfile, 0.0, mu_max, nmu_bins, cosmology, options, extra, &o);
+    if (st != EXIT_SUCCESS || o.npairs == NULL) return st;
+    results->nsbin = o.nbin;
+    results->nmu_bins = nmu_bins;
+    results->mu_max = mu_max;
+    results->mu_min = 0.0;
+    results->npairs = o.npairs;
+    results->supp = o.rupp;
+    results->savg = o.avg;
+    results->weightavg = o.wavg;
+    free(o.cf);
+    return EXIT_SUCCESS;
+}
+
 #define CF_TYPED(call)                                                      \
     do {                                                                    \
         if (!options) {                                                     \
@@ -431,3 +500,25 @@ int countpairs_theta_mocks(const int64_t ND1, void *phi1, void *theta1, const in
 
 CF_TYPED_FUNCS(float, float)
 CF_TYPED_FUNCS(double, double)
+
+#define CF_TYPED_MOCKS(SUF, REAL)                                                                                        \
+    int countpairs_mocks_##SUF(const int64_t ND1, REAL *X1, REAL *theta1, REAL *czD1, const int64_t ND2, REAL *phi2,     \
+                               REAL *theta2, REAL *czD2, const int numthreads, const int autocorr, const char *binfile,  \
+                               const REAL pimax, const int cosmology, results_countpairs_mocks *results,                \
+                               struct config_options *options, struct extra_options *extra)                             \
+    {                                                                                                                    \
+        CF_TYPED(countpairs_mocks(ND1, X1, theta1, czD1, ND2, phi2, theta2, czD2, numthreads, autocorr, binfile,         \
+                                  (double)pimax, cosmology, results, options, extra));                                  \
+    }                                                                                                                    \
+    int countpairs_mocks_s_mu_##SUF(const int64_t ND1, REAL *X1, REAL *theta1, REAL *czD1, const int64_t ND2,            \
+                                    REAL *phi2, REAL *theta2, REAL *czD2, const int numthreads, const int autocorr,      \
+                                    const char *sbinfile, const double mu_max, const int nmu_bins, const int cosmology,  \
+                                    results_countpairs_mocks_s_mu *results, struct config_options *options,             \
+                                    struct extra_options *extra)                                                         \
+    {                                                                                                                    \
+        CF_TYPED(countpairs_mocks_s_mu(ND1, X1, theta1, czD1, ND2, phi2, theta2, czD2, numthreads, autocorr, sbinfile,   \
+                                       mu_max, nmu_bins, cosmology, results, options, extra));                          \
+    }
+
+CF_TYPED_MOCKS(float, float)
+CF_TYPED_MOCKS(double, double)

@@ -16,12 +16,14 @@
 #define H_SIND(X) sin((X) * CF_PI_OVER_180)
 #define H_ASIN(X) asin(X)
 #define H_FABS(X) fabs(X)
+#define H_SQRT(X) sqrt(X)
 #define H_MAXPOS DBL_MAX
 #else
 #define H_COSD(X) cosf((X) * CF_PI_OVER_180)
 #define H_SIND(X) sinf((X) * CF_PI_OVER_180)
 #define H_ASIN(X) asinf(X)
 #define H_FABS(X) fabsf(X)
+#define H_SQRT(X) sqrtf(X)
 #define H_MAXPOS FLT_MAX
 #endif
 
@@ -95,6 +97,8 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
         return EXIT_FAILURE;
     }
     const int is_box = (mode == CFB_XI || mode == CFB_WP);
+    /* survey geometry (mocks/DDrppi_mocks, mocks/DDsmu_mocks): X/Y/Z are the Cartesian positions HFN(cf_mocks) made */
+    const int is_mocks = (mode == CFB_RPPI_MOCKS || mode == CFB_SMU_MOCKS);
     if (is_box) { /* countpairs_xi_impl.c.src:176-178, countpairs_wp_impl.c.src:191-193 */
         options->periodic = 1;
         options->autocorr = 1;
@@ -113,7 +117,7 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
         fprintf(stderr, "Warning: Max. cells per dimension is set to 0 - resetting to `NLATMAX' = %d\n", NLATMAX);
         options->max_cells_per_dim = NLATMAX;
     }
-    if (mode == CFB_SMU && options->fast_divide_and_NR_steps >= MAX_FAST_DIVIDE_NR_STEPS) {
+    if ((mode == CFB_SMU || is_mocks) && options->fast_divide_and_NR_steps >= MAX_FAST_DIVIDE_NR_STEPS) {
         options->fast_divide_and_NR_steps = 0;
     }
     if (!(autocorr == 0 || autocorr == 1)) {
@@ -125,13 +129,14 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
     double *rupp = NULL, rpmin, rpmax;
     int nrpbin;
     if (cf_setup_bins(binfile, &rpmin, &rpmax, &nrpbin, &rupp, 0) != EXIT_SUCCESS) return EXIT_FAILURE;
-    if (!(rpmin >= 0.0 && rpmax > 0.0 && rpmin < rpmax && nrpbin > 0)) {
+    /* the mocks statistics insist on rmin > 0 (countpairs_rp_pi_mocks_impl.c.src:304, countpairs_s_mu_mocks_impl.c.src:304) */
+    if (!((is_mocks ? rpmin > 0.0 : rpmin >= 0.0) && rpmax > 0.0 && rpmin < rpmax && nrpbin > 0)) {
         fprintf(stderr, "Error: Could not setup with R bins correctly. (rmin = %lf, rmax = %lf, with nbins = %d). "
                         "Expected non-zero rmin/rmax with rmax > rmin and nbins >=1 \n", rpmin, rpmax, nrpbin);
         free(rupp);
         return EXIT_FAILURE;
     }
-    if (mode == CFB_SMU) { /* countpairs_s_mu_impl.c.src:212-223 */
+    if (mode == CFB_SMU || mode == CFB_SMU_MOCKS) { /* countpairs_s_mu_impl.c.src:212-223, s_mu_mocks_impl:309-319 */
         if (max_mu <= 0.0 || max_mu > 1.0) {
             fprintf(stderr, "Error: max_mu (max. value for the cosine of the angle with line of sight) must be greater than 0 and at most 1).\n"
                             "The passed value is max_mu = %lf. Please change it to be > 0 and <= 1.0\n", max_mu);
@@ -208,7 +213,8 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
             lo[a] = (REAL)lohi[a];
             hi[a] = (REAL)lohi[3 + a];
         }
-        if (options->periodic && options->boxsize == BOXSIZE_NOTGIVEN) { /* countpairs_impl.c.src:231-235 */
+        const int want_periodic = is_mocks ? 0 : options->periodic; /* a survey footprint never wraps */
+        if (want_periodic && options->boxsize == BOXSIZE_NOTGIVEN) { /* countpairs_impl.c.src:231-235 */
             fprintf(stderr, "boxsize = %g must be specified with periodic wrap. Please specify a non-zero boxsize, or zero to detect the particle extent, or -1 to make a dimension non-periodic.\n",
                     options->boxsize);
             free(rupp); free(rupp_sqr);
@@ -218,7 +224,7 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
                               options->boxsize_y == BOXSIZE_NOTGIVEN ? options->boxsize : options->boxsize_y,
                               options->boxsize_z == BOXSIZE_NOTGIVEN ? options->boxsize : options->boxsize_z};
         for (int a = 0; a < 3; a++) { /* countpairs_impl.c.src:244-251 */
-            periodic[a] = options->periodic && bs[a] >= 0;
+            periodic[a] = want_periodic && bs[a] >= 0;
             wrap[a] = periodic[a] ? (bs[a] > 0 ? bs[a] : (hi[a] - lo[a])) : 0.;
         }
         if (mode == CFB_DD) {
@@ -247,6 +253,31 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
             maxsize[2] = pimax_in;
             max_sep[1] = (double)(REAL)rpmax;
             max_sep[2] = (double)(REAL)pimax_in;
+        } else if (is_mocks) {
+            REAL max_sep_r;
+            double heur; /* what the 0.05 * extent rule compares against */
+            if (mode == CFB_RPPI_MOCKS) { /* countpairs_rp_pi_mocks_impl.c.src:281, 307-308 */
+                pimax = pimax_in;
+                npibin = (int)pimax;
+                if (npibin < 1) {
+                    fprintf(stderr, "Error: pimax = %lf must be at least 1 (the pi bins are 1 unit wide)\n", pimax_in);
+                    free(rupp); free(rupp_sqr);
+                    return EXIT_FAILURE;
+                }
+                const REAL sqr_max_sep = rpmax * rpmax + pimax * pimax;
+                max_sep_r = H_SQRT(sqr_max_sep);
+                heur = (double)max_sep_r;
+            } else { /* countpairs_s_mu_mocks_impl.c.src:408, 424-432, 438 */
+                mu_max = (REAL)max_mu;
+                max_sep_r = (REAL)rpmax;
+                heur = rpmax;
+            }
+            if (get_bin_refine_scheme(options) == BINNING_DFL) {
+                for (int a = 0; a < 3; a++)
+                    if (heur < 0.05 * (hi[a] - lo[a])) options->bin_refine_factors[a] = 1;
+            }
+            maxsize[0] = maxsize[1] = maxsize[2] = max_sep_r;
+            max_sep[0] = (double)max_sep_r;
         } else { /* CFB_SMU: countpairs_s_mu_impl.c.src:231-234 */
             mu_max = (REAL)max_mu;
             pimax = rpmax * mu_max;
@@ -264,7 +295,11 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
         return EXIT_FAILURE;
     }
     if (mode != CFB_SMU) { /* countpairs_impl.c.src:298-332; DDsmu's boost multiplies by BOOST_BIN_REF=1 (no-op) */
-        const double avg_np = ((double)ND1) / ((double)M.nmesh[0] * M.nmesh[1] * M.nmesh[2]);
+        double avg_np = ((double)ND1) / ((double)M.nmesh[0] * M.nmesh[1] * M.nmesh[2]);
+        if (mode == CFB_RPPI_MOCKS) { /* the larger set, with ND2 as passed even when autocorr (rp_pi_mocks_impl:442-444) */
+            const double avg_np2 = ((double)ND2) / ((double)M.nmesh[0] * M.nmesh[1] * M.nmesh[2]);
+            if (avg_np2 > avg_np) avg_np = avg_np2;
+        }
         const int max_nmesh = (int)fmax(M.nmesh[0], fmax(M.nmesh[1], M.nmesh[2]));
         if ((max_nmesh <= BOOST_CELL_THRESH || avg_np >= BOOST_NUMPART_THRESH) &&
             max_nmesh < options->max_cells_per_dim && get_bin_refine_scheme(options) == BINNING_DFL) {
@@ -293,14 +328,14 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
     B.need_weights = need_weightavg;
     int64_t nslots = nrpbin;
     int n2 = 0;
-    if (mode == CFB_RPPI) { /* countpairs_rp_pi_kernels.c.src:65-66 */
+    if (mode == CFB_RPPI || mode == CFB_RPPI_MOCKS) { /* countpairs_rp_pi_kernels.c.src:65-66, rp_pi_mocks_kernels:64-65 */
         const REAL dpi = pimax / npibin;
         const REAL inv_dpi = 1.0 / dpi;
         B.npibin = npibin;
         B.inv_dpi = (double)inv_dpi;
         n2 = npibin;
         nslots = (int64_t)(npibin + 1) * (nrpbin + 1);
-    } else if (mode == CFB_SMU) { /* countpairs_s_mu_kernels.c.src:65-68 */
+    } else if (mode == CFB_SMU || mode == CFB_SMU_MOCKS) { /* countpairs_s_mu_kernels.c.src:65-68, s_mu_mocks_kernels:52-61 */
         const REAL sqr_mumax = mu_max * mu_max;
         const REAL dmu = mu_max / (REAL)nmu_bins;
         const REAL inv_dmu = 1.0 / dmu;
@@ -428,6 +463,87 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
         options->c_api_time = (mode == CFB_WP) ? (t_end - t_start) * 1.0e6 : (t_end - t_start) * 1.0e-3;
     }
     return EXIT_SUCCESS;
+}
+
+/* ========================================================================================== */
+/* DDrppi_mocks / DDsmu_mocks: (RA, DEC, comoving distance) -> Cartesian on the host, then the box driver   */
+
+/* check_ra_dec_cz_DOUBLE (mocks/DDrppi_mocks/countpairs_rp_pi_mocks_impl.c.src:43-110): RA in [-180,180] and DEC in
+ * [0,180] are shifted IN PLACE like the reference does.  (Its third fix, z -> cz, belongs to the cz branch.) */
+static int HFN(cf_check_ra_dec_cz)(const int64_t N, REAL *phi, REAL *theta, REAL *cz)
+{
+    if (N == 0) return EXIT_SUCCESS;
+    if (phi == NULL || theta == NULL || cz == NULL) {
+        fprintf(stderr, "Input arrays can not be NULL. Have RA = %p DEC = %p cz = %p\n", (void *)phi, (void *)theta, (void *)cz);
+        return EXIT_FAILURE;
+    }
+    int fix_ra = 0, fix_dec = 0;
+    for (int64_t i = 0; i < N; i++) {
+        if (phi[i] < 0.0) fix_ra = 1;
+        if (theta[i] > 90.0) fix_dec = 1;
+        if (theta[i] > 180) {
+            fprintf(stderr, "theta[%" PRId64 "] = %lf should be less than 180 deg\n", i, (double)theta[i]);
+            return EXIT_FAILURE;
+        }
+    }
+    if (fix_ra) fprintf(stderr, "%s> Out of range values found for ra. Expected ra to be in the range [0.0,360.0]. Found ra values in [-180,180] -- fixing that\n", __func__);
+    if (fix_dec) fprintf(stderr, "%s> Out of range values found for dec. Expected dec to be in the range [-90.0,90.0]. Found dec values in [0,180] -- fixing that\n", __func__);
+    if (fix_ra || fix_dec)
+        for (int64_t i = 0; i < N; i++) {
+            if (fix_ra) phi[i] += (REAL)180.0;
+            if (fix_dec) theta[i] -= (REAL)90.0;
+        }
+    return EXIT_SUCCESS;
+}
+
+static int HFN(cf_mocks)(const int mode, const int64_t ND1, void *vra1, void *vdec1, void *vd1, const int64_t ND2,
+                         void *vra2, void *vdec2, void *vd2, const int numthreads, const int autocorr,
+                         const char *binfile, const double pimax, const double max_mu, const int nmu_bins,
+                         const int cosmology, struct config_options *options, struct extra_options *extra,
+                         cf_box_out *out)
+{
+    if (options->float_type != sizeof(REAL)) {
+        fprintf(stderr, "ERROR: In %s> Can only handle arrays of size=%zu. Got an array of size = %zu\n", __func__,
+                sizeof(REAL), options->float_type);
+        return EXIT_FAILURE;
+    }
+    if (ND1 == 0 || (autocorr == 0 && ND2 == 0)) return EXIT_SUCCESS; /* rp_pi_mocks_impl:243-245: results untouched */
+    REAL *ra[2] = {(REAL *)vra1, (REAL *)vra2}, *dec[2] = {(REAL *)vdec1, (REAL *)vdec2}, *D[2] = {(REAL *)vd1, (REAL *)vd2};
+    const int64_t N[2] = {ND1, ND2};
+    const int nsets = autocorr ? 1 : 2;
+    for (int s = 0; s < nsets; s++)
+        if (HFN(cf_check_ra_dec_cz)(N[s], ra[s], dec[s], D[s])) return EXIT_FAILURE;
+    if (!(cosmology == 1 || cosmology == 2)) { /* init_cosmology, utils/cosmology_params.c:21-54 */
+        fprintf(stderr, "ERROR: In %s> Cosmology=%d not implemented\n", "init_cosmology", cosmology);
+        return EXIT_FAILURE;
+    }
+    if (options->is_comoving_dist == 0) {
+        /* rp_pi_mocks_impl:326-362 tabulates the comoving distance with GSL's adaptive integrator to 1e-7 and
+         * interpolates linearly: positions that depend on GSL's rounding cannot be matched without GSL. */
+        fprintf(stderr, "Error: In %s> cz -> comoving distance is not available in the B200 build (the reference's table "
+                        "comes from GSL); convert to comoving distances and set is_comoving_dist = 1\n", __func__);
+        return EXIT_FAILURE;
+    }
+    REAL *xyz[2][3] = {{NULL, NULL, NULL}, {NULL, NULL, NULL}};
+    int status = EXIT_SUCCESS;
+    for (int s = 0; s < nsets && status == EXIT_SUCCESS; s++) {
+        for (int a = 0; a < 3; a++) {
+            xyz[s][a] = malloc(sizeof(REAL) * (size_t)(N[s] > 0 ? N[s] : 1));
+            if (!xyz[s][a]) status = EXIT_FAILURE;
+        }
+        if (status != EXIT_SUCCESS) break;
+        for (int64_t i = 0; i < N[s]; i++) { /* rp_pi_mocks_impl:370-391 */
+            xyz[s][0][i] = D[s][i] * H_COSD(dec[s][i]) * H_COSD(ra[s][i]);
+            xyz[s][1][i] = D[s][i] * H_COSD(dec[s][i]) * H_SIND(ra[s][i]);
+            xyz[s][2][i] = D[s][i] * H_SIND(dec[s][i]);
+        }
+    }
+    if (status == EXIT_SUCCESS)
+        status = HFN(cf_box)(mode, ND1, xyz[0][0], xyz[0][1], xyz[0][2], ND2, xyz[1][0], xyz[1][1], xyz[1][2], numthreads,
+                             autocorr, binfile, pimax, max_mu, nmu_bins, 0.0, options, extra, out);
+    for (int s = 0; s < 2; s++)
+        for (int a = 0; a < 3; a++) free(xyz[s][a]);
+    return status;
 }
 
 /* ========================================================================================== */
@@ -837,6 +953,7 @@ static int HFN(cf_theta)(const int64_t ND1, void *vra1, void *vdec1, const int64
 #undef H_SIND
 #undef H_ASIN
 #undef H_FABS
+#undef H_SQRT
 #undef H_MAXPOS
 #undef HCAT_
 #undef HCAT

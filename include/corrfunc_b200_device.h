@@ -20,7 +20,12 @@
 extern "C" {
 #endif
 
-enum cfb_mode { CFB_DD = 0, CFB_XI = 1, CFB_RPPI = 2, CFB_WP = 3, CFB_SMU = 4, CFB_THETA = 5 };
+enum cfb_mode {
+    CFB_DD = 0, CFB_XI = 1, CFB_RPPI = 2, CFB_WP = 3, CFB_SMU = 4, CFB_THETA = 5,
+    /* survey geometry, line of sight = pair midpoint (mocks/DDrppi_mocks, mocks/DDsmu_mocks): the box lattice is the
+     * non-periodic one over the Cartesian positions, max_sep[0] = the 3-D pruning radius */
+    CFB_RPPI_MOCKS = 6, CFB_SMU_MOCKS = 7
+};
 
 #define CFB_MAX_EDGES 4096
 
@@ -31,7 +36,7 @@ typedef struct {
     int autocorr;  /* 1: secondaries are set 0 again, count each unordered pair once */
     int nedges;    /* reference's `nbin` = number of bin edges */
     const double *edges; /* rupp_sqr[] (box modes) or costheta_upp[] (theta), REAL-valued */
-    double pimax;        /* wp, rppi (REAL-valued) */
+    double pimax;        /* wp, rppi, rppi mocks (REAL-valued) */
     int npibin;          /* rppi */
     double inv_dpi;      /* rppi */
     double sqr_mumax;    /* smu */

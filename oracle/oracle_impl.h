@@ -681,10 +681,11 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
                 mu_max = (REAL)mu_max_in;
                 max_sep = rmax;
             }
-            if (!binning_cust) { /* :413-423 */
-                if (max_sep < 0.05 * (xmax - xmin)) rf[0] = 1;
-                if (max_sep < 0.05 * (ymax - ymin)) rf[1] = 1;
-                if (max_sep < 0.05 * (zmax - zmin)) rf[2] = 1;
+            if (!binning_cust) { /* :413-423; DDsmu_mocks compares the double smax (s_mu_mocks_impl:424-432) */
+                const double heur = (mode == ORC_SMU_MOCKS) ? rmax : (double)max_sep;
+                if (heur < 0.05 * (xmax - xmin)) rf[0] = 1;
+                if (heur < 0.05 * (ymax - ymin)) rf[1] = 1;
+                if (heur < 0.05 * (zmax - zmin)) rf[2] = 1;
             }
             max_x = max_y = max_z = max_sep;
             max3 = max_sep;

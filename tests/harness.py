@@ -103,6 +103,17 @@ def oracle_theory(stat, X1, Y1, Z1, bins, *, w1=None, X2=None, Y2=None, Z2=None,
     return dict(npairs=npairs[1:], ravg=avg[1:], weightavg=wavg[1:], cf=cf[1:], lattice=lat)
 
 
+def mock_points(seed, n, dtype):
+    """Seeded synthetic survey wedge: RA 40-90 deg, DEC -10..30 deg, comoving distance 300-700 (uniform in volume
+    along the radius), weights in [0.5, 1.5)."""
+    rng = np.random.default_rng(seed)
+    ra = (40.0 + 50.0 * rng.random(n)).astype(dtype)
+    dec = (-10.0 + 40.0 * rng.random(n)).astype(dtype)
+    d = (300.0 + 400.0 * rng.random(n) ** (1.0 / 3.0)).astype(dtype)
+    w = (0.5 + rng.random(n)).astype(dtype)
+    return ra, dec, d, w
+
+
 def oracle_config(name, literal=0, nthreads=None):
     """A BASELINE config (bench.CONFIGS, bench.py's own seeded input) through the oracle; literal=1 follows the
     AVX-512 kernels' z-sorted chunked control flow for wp / DDrppi (oracle_impl.h)."""

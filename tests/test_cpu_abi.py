@@ -24,7 +24,8 @@ def test_headers_compile_as_c_and_cxx_and_offsets_agree(tmp_path):
     src = tmp_path / "t.c"
     src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "countpairs.h"\n#include "countpairs_rp_pi.h"\n'
                    '#include "countpairs_s_mu.h"\n#include "countpairs_wp.h"\n#include "countpairs_xi.h"\n'
-                   '#include "countpairs_theta_mocks.h"\n#include "corrfunc_b200.h"\n'
+                   '#include "countpairs_theta_mocks.h"\n#include "countpairs_rp_pi_mocks.h"\n#include "countpairs_s_mu_mocks.h"\n'
+                   '#include "corrfunc_b200.h"\n'
                    'int main(void){struct config_options o=get_config_options();'
                    'printf("%zu %zu %zu %zu %zu %zu %s\\n",sizeof(struct config_options),sizeof(struct extra_options),'
                    'offsetof(struct config_options,float_type),offsetof(struct config_options,version),'
@@ -95,6 +96,14 @@ def test_bad_inputs_rejected_before_the_device():
         T.DD(1, 1, [0.1, 1.0], x, x.astype(np.float32), x, boxsize=10.0)
     with pytest.raises(ValueError):
         T.DDsmu(1, 1, [0.1, 1.0], 1.5, 10, x, x, x, boxsize=10.0)
+    import corrfunc_b200.mocks as M
+
+    with pytest.raises(NotImplementedError):  # cz -> comoving distance needs the reference's GSL table
+        M.DDrppi_mocks(1, 1, 1, 10.0, [0.1, 1.0], x, x, x + 100.0)
+    with pytest.raises(ValueError):
+        M.DDsmu_mocks(0, 1, 1, 0.5, 4, [0.1, 1.0], x, x, x + 100.0, is_comoving_dist=True)  # cross without second set
+    with pytest.raises(ValueError):
+        M.DDsmu_mocks(1, 1, 1, 1.5, 4, [0.1, 1.0], x, x, x + 100.0, is_comoving_dist=True)  # mu_max > 1
     o = _capi.default_options(np.float64, boxsize=10.0)
     o.version = b"1.0.0"
     with pytest.raises(RuntimeError):

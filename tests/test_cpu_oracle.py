@@ -178,3 +178,75 @@ def test_oracle_literal_equals_default_on_small_inputs(stat, dtype):
         lib.oracle_set_literal_kernels(0)
     assert np.array_equal(a["npairs"], b["npairs"])
     assert np.allclose(a["ravg"], b["ravg"], rtol=1e-12) and np.allclose(a["weightavg"], b["weightavg"], rtol=1e-12)
+
+
+# ---- survey geometry: mocks/DDrppi_mocks and mocks/DDsmu_mocks -----------------------
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_mocks_match_committed_reference_outputs(dtype):
+    """tests/golden/ref_mocks_*.npz: the unmodified reference (AVX-512F kernels) on seeded survey wedges."""
+    g = np.load(os.path.join(H.GOLDEN, "ref_mocks_%s.npz" % np.dtype(dtype).name))
+    ra, dec, d, w = H.mock_points(int(g["seed"]), int(g["N1"]), dtype)
+    ra2, dec2, d2, w2 = H.mock_points(int(g["seed"]) + 1, int(g["N2"]), dtype)
+    tol = 1e-10 if dtype == np.float64 else 1e-4  # the reference's float path sums in float
+    for autocorr in (1, 0):
+        tag = "auto" if autocorr else "cross"
+        kw = dict(w1=w, weight_type="pair_product", need_avg=True, autocorr=bool(autocorr), periodic=False)
+        if not autocorr:
+            kw.update(X2=ra2, Y2=dec2, Z2=d2, w2=w2)
+        a = H.oracle_theory("DDrppi_mocks", ra, dec, d, g["edges"], pimax=float(g["pimax"]), **kw)
+        assert np.array_equal(a["npairs"], g["DDrppi_mocks_%s__npairs" % tag])
+        assert np.allclose(a["ravg"], g["DDrppi_mocks_%s__ravg" % tag], rtol=tol)
+        assert np.allclose(a["weightavg"], g["DDrppi_mocks_%s__weightavg" % tag], rtol=tol)
+        a = H.oracle_theory("DDsmu_mocks", ra, dec, d, g["edges"], mu_max=float(g["mu_max"]), nmu_bins=int(g["nmu"]), **kw)
+        assert np.array_equal(a["npairs"], g["DDsmu_mocks_%s__npairs" % tag])
+        assert np.allclose(a["ravg"], g["DDsmu_mocks_%s__ravg" % tag], rtol=tol)
+        assert np.allclose(a["weightavg"], g["DDsmu_mocks_%s__weightavg" % tag], rtol=tol)
+
+
+def test_oracle_mocks_brute_force():
+    """Independent numpy restatement of the definitions (pi = |s.l|/|l|, rp^2 = s^2 - pi^2, mu = pi/s with
+    l the pair midpoint), all pairs, no lattice: counts agree except where a pair sits within rounding of an edge."""
+    ra, dec, d, _ = H.mock_points(21, 1500, np.float64)
+    x = d * np.cos(np.radians(dec)) * np.cos(np.radians(ra))
+    y = d * np.cos(np.radians(dec)) * np.sin(np.radians(ra))
+    z = d * np.sin(np.radians(dec))
+    p = np.stack([x, y, z], 1)
+    i, j = np.triu_indices(len(p), 1)
+    s = p[j] - p[i]
+    l = p[j] + p[i]
+    s2 = (s * s).sum(1)
+    pi2 = (s * l).sum(1) ** 2 / (l * l).sum(1)
+    rp2 = s2 - pi2
+    edges = np.logspace(np.log10(0.5), np.log10(60.0), 9)
+    pimax, mu_max, nmu = 30.0, 0.8, 5
+    ok = (pi2 < pimax ** 2) & (rp2 >= edges[0] ** 2) & (rp2 < edges[-1] ** 2)
+    want = np.histogram2d(np.sqrt(rp2[ok]), np.sqrt(pi2[ok]), bins=[edges, np.arange(int(pimax) + 1)])[0] * 2
+    a = H.oracle_theory("DDrppi_mocks", ra, dec, d, edges, pimax=pimax, periodic=False)
+    assert np.abs(a["npairs"].astype(np.int64) - want.astype(np.int64)).sum() <= 4
+    mu = np.sqrt(pi2 / s2)
+    ok = (mu < mu_max) & (s2 >= edges[0] ** 2) & (s2 < edges[-1] ** 2)
+    want = np.histogram2d(np.sqrt(s2[ok]), mu[ok], bins=[edges, np.linspace(0, mu_max, nmu + 1)])[0] * 2
+    a = H.oracle_theory("DDsmu_mocks", ra, dec, d, edges, mu_max=mu_max, nmu_bins=nmu, periodic=False)
+    assert np.abs(a["npairs"].astype(np.int64) - want.astype(np.int64)).sum() <= 4
+
+
+@pytest.mark.skipif(H.load_ref() is None or not hasattr(H.load_ref(), "countpairs_mocks"),
+                    reason="oracle/_ref was not prebuilt with the mocks statistics")
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("refine", [(2, 2, 1), (1, 1, 1), (3, 2, 2)])
+def test_oracle_mocks_vs_live_reference(dtype, refine):
+    from corrfunc_b200 import _capi as capi
+
+    ref = H.load_ref()
+    ra, dec, d, w = H.mock_points(31, 20000, dtype)
+    edges = np.logspace(np.log10(1.0), np.log10(25.0), 8)
+    custom = refine != (2, 2, 1)
+    o = capi.default_options(dtype, isa=H.ref_isa(), is_comoving_dist=True, bin_refine_factors=refine, custom_refine=custom)
+    r = capi.call_DDrppi_mocks(ref, 1, 1, 4, 20.0, edges, ra, dec, d, options=o)
+    a = H.oracle_theory("DDrppi_mocks", ra, dec, d, edges, pimax=20.0, periodic=False, refine=refine, custom_refine=custom)
+    assert np.array_equal(a["npairs"], r["npairs"])
+    o = capi.default_options(dtype, isa=H.ref_isa(), is_comoving_dist=True, bin_refine_factors=refine, custom_refine=custom)
+    r = capi.call_DDsmu_mocks(ref, 1, 1, 4, 1.0, 7, edges, ra, dec, d, options=o)
+    a = H.oracle_theory("DDsmu_mocks", ra, dec, d, edges, mu_max=1.0, nmu_bins=7, periodic=False, refine=refine, custom_refine=custom)
+    assert np.array_equal(a["npairs"], r["npairs"])
