@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Extracts the Python-level signatures of the reference's six hot-path wrappers (names, order, defaults) by parsing
+"""Extracts the Python-level signatures of the reference's hot-path wrappers (names, order, defaults) by parsing
 their sources with `ast` -- no import, the reference package needs `future`/`wurlitzer` -- into
 tests/golden/reference_signatures.json.  Run in the build container only."""
 import ast
@@ -8,7 +8,8 @@ import os
 
 REF = "/root/reference/Corrfunc"
 FUNCS = {"DD": "theory/DD.py", "DDrppi": "theory/DDrppi.py", "DDsmu": "theory/DDsmu.py", "wp": "theory/wp.py",
-         "xi": "theory/xi.py", "DDtheta_mocks": "mocks/DDtheta_mocks.py",
+         "xi": "theory/xi.py", "DDtheta_mocks": "mocks/DDtheta_mocks.py", "DDrppi_mocks": "mocks/DDrppi_mocks.py",
+         "DDsmu_mocks": "mocks/DDsmu_mocks.py",
          "convert_3d_counts_to_cf": "utils.py", "convert_rp_pi_counts_to_wp": "utils.py"}
 out = {}
 for name, rel in FUNCS.items():

@@ -11,10 +11,10 @@ GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "
 
 
 def _ours(name):
-    if name == "DDtheta_mocks":
-        from corrfunc_b200.mocks import DDtheta_mocks
+    if name.endswith("_mocks"):
+        import corrfunc_b200.mocks as M
 
-        return DDtheta_mocks
+        return getattr(M, name)
     if name.startswith("convert_"):
         import corrfunc_b200.utils as U
 
@@ -48,7 +48,9 @@ def test_compat_package_exposes_the_reference_import_paths():
         for mod, attr in (("Corrfunc.theory.DD", "DD"), ("Corrfunc.theory.DDrppi", "DDrppi"),
                           ("Corrfunc.theory.DDsmu", "DDsmu"), ("Corrfunc.theory.wp", "wp"), ("Corrfunc.theory.xi", "xi"),
                           ("Corrfunc.mocks.DDtheta_mocks", "DDtheta_mocks"), ("Corrfunc.theory", "DD"),
-                          ("Corrfunc.mocks", "DDtheta_mocks"), ("Corrfunc.utils", "convert_3d_counts_to_cf"),
+                          ("Corrfunc.mocks", "DDtheta_mocks"), ("Corrfunc.mocks.DDrppi_mocks", "DDrppi_mocks"),
+                          ("Corrfunc.mocks.DDsmu_mocks", "DDsmu_mocks"), ("Corrfunc.mocks", "DDsmu_mocks"),
+                          ("Corrfunc.utils", "convert_3d_counts_to_cf"),
                           ("Corrfunc.utils", "convert_rp_pi_counts_to_wp")):
             m = importlib.import_module(mod)
             assert callable(getattr(m, attr)), (mod, attr)
