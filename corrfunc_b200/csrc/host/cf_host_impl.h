@@ -525,25 +525,30 @@ static int HFN(cf_mocks)(const int mode, const int64_t ND1, void *vra1, void *vd
         return EXIT_FAILURE;
     }
     REAL *xyz[2][3] = {{NULL, NULL, NULL}, {NULL, NULL, NULL}};
-    int status = EXIT_SUCCESS;
-    for (int s = 0; s < nsets && status == EXIT_SUCCESS; s++) {
+    for (int s = 0; s < nsets; s++) {
         for (int a = 0; a < 3; a++) {
-            xyz[s][a] = malloc(sizeof(REAL) * (size_t)(N[s] > 0 ? N[s] : 1));
-            if (!xyz[s][a]) status = EXIT_FAILURE;
+            /* pinned, persistent across calls (no page faults, full-rate upload); owned by the device context */
+            xyz[s][a] = cfb_host_scratch(3 * s + a, sizeof(REAL) * (size_t)(N[s] > 0 ? N[s] : 1));
+            if (!xyz[s][a]) {
+                fprintf(stderr, "Error: could not get host staging memory for %" PRId64 " positions: %s\n", N[s], cfb_last_error());
+                return EXIT_FAILURE;
+            }
         }
-        if (status != EXIT_SUCCESS) break;
-        for (int64_t i = 0; i < N[s]; i++) { /* rp_pi_mocks_impl:370-391 */
-            xyz[s][0][i] = D[s][i] * H_COSD(dec[s][i]) * H_COSD(ra[s][i]);
-            xyz[s][1][i] = D[s][i] * H_COSD(dec[s][i]) * H_SIND(ra[s][i]);
-            xyz[s][2][i] = D[s][i] * H_SIND(dec[s][i]);
+        REAL *X = xyz[s][0], *Y = xyz[s][1], *Z = xyz[s][2];
+        const REAL *r = ra[s], *dc = dec[s], *dist = D[s];
+        const int64_t n = N[s];
+        /* rp_pi_mocks_impl:370-391, element by element with glibc trig: independent of the thread count */
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static)
+#endif
+        for (int64_t i = 0; i < n; i++) {
+            X[i] = dist[i] * H_COSD(dc[i]) * H_COSD(r[i]);
+            Y[i] = dist[i] * H_COSD(dc[i]) * H_SIND(r[i]);
+            Z[i] = dist[i] * H_SIND(dc[i]);
         }
     }
-    if (status == EXIT_SUCCESS)
-        status = HFN(cf_box)(mode, ND1, xyz[0][0], xyz[0][1], xyz[0][2], ND2, xyz[1][0], xyz[1][1], xyz[1][2], numthreads,
-                             autocorr, binfile, pimax, max_mu, nmu_bins, 0.0, options, extra, out);
-    for (int s = 0; s < 2; s++)
-        for (int a = 0; a < 3; a++) free(xyz[s][a]);
-    return status;
+    return HFN(cf_box)(mode, ND1, xyz[0][0], xyz[0][1], xyz[0][2], ND2, xyz[1][0], xyz[1][1], xyz[1][2], numthreads,
+                       autocorr, binfile, pimax, max_mu, nmu_bins, 0.0, options, extra, out);
 }
 
 /* ========================================================================================== */
