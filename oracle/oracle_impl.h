@@ -14,16 +14,18 @@
  * point, and the epilogues.  What is NOT restated by default: the z-sorted early exits inside a cell pair
  * (pruning aids; in double they never change a count).
  *
- * LITERAL mode (oracle_set_literal_kernels(1)): for wp and DDrppi the cells are z-sorted and the AVX-512
+ * LITERAL mode (oracle_set_literal_kernels(1)): for wp, DDrppi, DD and xi the cells are z-sorted and the AVX-512
  * kernels' control flow is followed chunk by chunk (16 float / 8 double lanes) -- the fast-forward over
  * secondaries with z1 <= zpos - pimax and the "some lane reached pimax -> last chunk" exit.  In float a
  * secondary that survives the fast-forward can still round to dz == -pimax exactly; the reference then
  *   wp     : counts it, because its mask is the SIGNED dz < pimax   (wp_kernels.c.src:196-207)
  *   DDrppi : takes |dz| first, sees |dz| >= pimax, and stops after this chunk -- every later secondary
  *            of this primary is dropped                             (countpairs_rp_pi_kernels.c.src:196-207)
- * Literal mode reproduces both, which is what makes the full-size float goldens bit-identical
- * (tests/test_cpu_oracle.py::test_literal_*).  The per-primary minimum-separation shortcut (:130-137) is
- * not restated: it needs two independent rounding coincidences and has never changed a count.
+ *   DD, xi : never visits a secondary outside the per-primary window |dz| < max_dz (see
+ *            o_count_cellpair_literal_dd): at most a pair on the very edge of the last bin
+ * Literal mode reproduces these, which is what makes the full-size float goldens bit-identical
+ * (tests/test_cpu_oracle.py::test_*literal*).  For wp / DDrppi the per-primary minimum-separation shortcut
+ * (:130-137) is not restated: it has never changed a count.
  */
 
 #define CAT_(a, b) a##_##b
@@ -209,6 +211,8 @@ typedef struct {
     int64_t c1, c2;
     REAL xw, yw, zw;
     int same;
+    /* struct cell_pair_DOUBLE's pruning fields (utils/cell_pair.h.src:20-36), used by the literal kernels only */
+    REAL min_dx, min_dy, min_dz, closest_x1, closest_y1, closest_z1;
 } FN(opair);
 
 /* utils/gridlink_impl.c.src:439-625 */
@@ -261,6 +265,7 @@ static FN(opair) * FN(o_cell_pairs)(const FN(olattice) * L1, const FN(olattice) 
                         if (dup) continue;
                     }
                     const FN(ocell) *second = &L2->cells[icell2];
+                    REAL cp_min[3] = {0, 0, 0}, cp_closest[3] = {0, 0, 0};
                     if (enable_min_sep) { /* gridlink_impl.c.src:538-589 */
                         const REAL x_low = first->xb[0] + offx, x_hi = first->xb[1] + offx;
                         const REAL y_low = first->yb[0] + offy, y_hi = first->yb[1] + offy;
@@ -274,6 +279,10 @@ static FN(opair) * FN(o_cell_pairs)(const FN(olattice) * L1, const FN(olattice) 
                         const REAL first_z = iiz < 0 ? z_low : z_hi;
                         const REAL second_z = iiz < 0 ? second->zb[1] : second->zb[0];
                         const REAL min_dz = iiz != 0 ? (first_z - second_z) : 0;
+                        cp_min[0] = min_dx, cp_min[1] = min_dy, cp_min[2] = min_dz;
+                        cp_closest[0] = iix < 0 ? x_low : (iix > 0 ? x_hi : 0); /* :543-545 */
+                        cp_closest[1] = iiy < 0 ? y_low : (iiy > 0 ? y_hi : 0);
+                        cp_closest[2] = iiz < 0 ? z_low : (iiz > 0 ? z_hi : 0);
                         if (max_3D > 0) {
                             const REAL s = min_dx * min_dx + min_dy * min_dy + min_dz * min_dz;
                             if (s >= max_3D * max_3D) continue;
@@ -293,6 +302,8 @@ static FN(opair) * FN(o_cell_pairs)(const FN(olattice) * L1, const FN(olattice) 
                     P[np].yw = offy;
                     P[np].zw = offz;
                     P[np].same = (autocorr == 1 && icell2 == icell) ? 1 : 0;
+                    P[np].min_dx = cp_min[0], P[np].min_dy = cp_min[1], P[np].min_dz = cp_min[2];
+                    P[np].closest_x1 = cp_closest[0], P[np].closest_y1 = cp_closest[1], P[np].closest_z1 = cp_closest[2];
                     np++;
                     nthis++;
                 }
@@ -543,6 +554,69 @@ static void FN(o_count_cellpair_literal)(const FN(okern) * K, const int64_t N0, 
     }
 }
 
+/* LITERAL mode, DD and xi: countpairs_avx512_intrinsics (theory/DD/countpairs_kernels.c.src:76-254) and
+ * xi_avx512_intrinsics (theory/xi/xi_kernels.c.src:76-250) over z-sorted cells: the per-primary window
+ * |dz| < max_dz = sqrt(rmax^2 - min_dx^2 - min_dy^2) built from the cell pair's bounding-box separations, the
+ * fast-forward below the window and the "some lane reached max_dz -> last chunk" exit.  Inside a processed chunk
+ * only r2 is tested.  In float, on coordinates much larger than rmax, the window can close a hair too early and a
+ * pair with r2 < rmax^2 at the very edge of the last bin is never visited. */
+static void FN(o_count_cellpair_literal_dd)(const FN(okern) * K, const FN(opair) * cp, const REAL rpmax, const int64_t N0,
+                                            const REAL *x0, const REAL *y0, const REAL *z0, const REAL *w0,
+                                            const int64_t N1, const REAL *x1, const REAL *y1, const REAL *z1,
+                                            const REAL *w1)
+{
+    const int nbin = K->nbin;
+    const REAL *E = K->edges;
+    const REAL sqr_rpmax = E[nbin - 1], sqr_rpmin = E[0];
+    const int NVEC = (int)(64 / sizeof(REAL));
+    const REAL min_xdiff = cp->min_dx, min_ydiff = cp->min_dy, min_zdiff = cp->min_dz;
+    /* DD squares the REAL rpmax (:77), xi takes the squared edge (xi_kernels:77) */
+    const REAL max_all_dz = (K->mode == ORC_DD) ? SQRT_R(rpmax * rpmax - min_xdiff * min_xdiff - min_ydiff * min_ydiff)
+                                                : SQRT_R(sqr_rpmax - min_xdiff * min_xdiff - min_ydiff * min_ydiff);
+    int64_t p = 0;
+    if (N1 == 0) return;
+    for (int64_t i = 0; i < N0; i++) {
+        const REAL xpos = x0[i] + cp->xw, ypos = y0[i] + cp->yw, zpos = z0[i] + cp->zw;
+        REAL max_dz = max_all_dz;
+        const REAL this_dz = z1[p] - zpos;
+        if (this_dz >= max_all_dz) continue;
+        if (cp->same) {
+            p++;
+        } else {
+            const REAL min_dx = min_xdiff > 0 ? min_xdiff + FABS_R(xpos - cp->closest_x1) : min_xdiff;
+            const REAL min_dy = min_ydiff > 0 ? min_ydiff + FABS_R(ypos - cp->closest_y1) : min_ydiff;
+            const REAL min_dz = min_zdiff > 0 ? (this_dz > 0 ? this_dz : min_zdiff + FABS_R(zpos - cp->closest_z1)) : min_zdiff;
+            const REAL sqr_min_sep_this_point = min_dx * min_dx + min_dy * min_dy + min_dz * min_dz;
+            if (sqr_min_sep_this_point >= sqr_rpmax) continue;
+            max_dz = SQRT_R(sqr_rpmax - min_dx * min_dx - min_dy * min_dy);
+            const REAL target_z = zpos - max_all_dz;
+            while (p < N1 && z1[p] <= target_z) p++;
+        }
+        if (p == N1) break;
+        int64_t lp = p;
+        const REAL target_z = zpos - max_dz;
+        while (lp != N1 && z1[lp] <= target_z) lp++;
+        for (int64_t j = lp; j < N1; j += NVEC) {
+            const int lanes = (N1 - j) >= NVEC ? NVEC : (int)(N1 - j);
+            const int64_t jbase = j;
+            for (int l = 0; l < lanes; l++)
+                if (z1[jbase + l] - zpos >= max_dz) j = N1; /* "do not break yet": this chunk is still processed */
+            for (int l = 0; l < lanes; l++) {
+                const int64_t jj = jbase + l;
+                const REAL dx = x1[jj] - xpos, dy = y1[jj] - ypos, dz = z1[jj] - zpos;
+                const REAL r2 = FMA_R(dz, dz, FMA_R(dy, dy, dx * dx));
+                if (!(r2 < sqr_rpmax && r2 >= sqr_rpmin)) continue;
+                int k;
+                for (k = nbin - 1; k >= 1; k--)
+                    if (r2 >= E[k - 1]) break;
+                K->npairs[k]++;
+                if (K->need_avg) K->avg[k] += (double)SQRT_R(r2);
+                if (K->need_w) K->wavg[k] += (double)(REAL)(w0[i] * w1[jj]);
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* theory entry point: DD / xi / wp / DDrppi / DDsmu                                            */
 /* Follows theory/DD/countpairs_impl.c.src:136-707 and its four siblings.                       */
@@ -783,6 +857,13 @@ int FN(oracle_theory)(const int mode, const int64_t ND1, const REAL *X1, const R
 #endif
         for (int64_t p = 0; p < ncp; p++) {
             const FN(ocell) *a = &L1->cells[CP[p].c1], *b = &L2->cells[CP[p].c2];
+            if (orc_literal_kernels && (mode == ORC_DD || mode == ORC_XI)) {
+                FN(o_count_cellpair_literal_dd)(&k, &CP[p], (REAL)rmax, a->n, L1->x + a->start, L1->y + a->start,
+                                                L1->z + a->start, need_w ? L1->w + a->start : NULL, b->n,
+                                                L2->x + b->start, L2->y + b->start, L2->z + b->start,
+                                                need_w ? L2->w + b->start : NULL);
+                continue;
+            }
             (orc_literal_kernels && (mode == ORC_WP || mode == ORC_RPPI) ? FN(o_count_cellpair_literal)
                                                                           : FN(o_count_cellpair))(
                                  &k, a->n, L1->x + a->start, L1->y + a->start, L1->z + a->start,

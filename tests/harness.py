@@ -103,6 +103,19 @@ def oracle_theory(stat, X1, Y1, Z1, bins, *, w1=None, X2=None, Y2=None, Z2=None,
     return dict(npairs=npairs[1:], ravg=avg[1:], weightavg=wavg[1:], cf=cf[1:], lattice=lat)
 
 
+FLOAT_WINDOW_CASES = {"DD": 0, "xi": 2}  # statistic -> seed (found by search; see make_golden_float_window.py)
+
+
+def float_window_case(stat):
+    """2 M float32 points in a 60000-wide periodic box, bins up to rmax = 1200: coordinates 50x larger than rmax and
+    ~2 particles per cell make the reference's float z-window drop one pair on the edge of the last bin."""
+    n, L, rmax = 2000000, 60000.0, 1200.0
+    rng = np.random.default_rng(FLOAT_WINDOW_CASES[stat])
+    x, y, z = [(rng.random(n) * L).astype(np.float32) for _ in range(3)]
+    edges = np.logspace(np.log10(rmax / 50), np.log10(rmax), 8)
+    return x, y, z, L, edges
+
+
 def mock_points(seed, n, dtype):
     """Seeded synthetic survey wedge: RA 40-90 deg, DEC -10..30 deg, comoving distance 300-700 (uniform in volume
     along the radius), weights in [0.5, 1.5)."""

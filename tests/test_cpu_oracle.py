@@ -250,3 +250,40 @@ def test_oracle_mocks_vs_live_reference(dtype, refine):
     r = capi.call_DDsmu_mocks(ref, 1, 1, 4, 1.0, 7, edges, ra, dec, d, options=o)
     a = H.oracle_theory("DDsmu_mocks", ra, dec, d, edges, mu_max=1.0, nmu_bins=7, periodic=False, refine=refine, custom_refine=custom)
     assert np.array_equal(a["npairs"], r["npairs"])
+
+
+@pytest.mark.parametrize("stat", ["DD", "xi"])
+def test_oracle_literal_mode_pins_the_float_z_window_of_DD_and_xi(stat):
+    """Float32, coordinates 50x rmax, ~2 particles per cell: the reference never visits one pair that lies inside
+    the last bin (its per-primary window |dz| < max_dz closes a rounding error early).  LITERAL mode reproduces the
+    reference bit for bit; the default mode (every pair, the reference's own r2 arithmetic) counts that pair --
+    the same +2 in the last bin, and nothing else, that separates the GPU from the reference."""
+    ref = np.load(os.path.join(H.GOLDEN, "ref_float_window.npz"))[stat].astype(np.int64)
+    x, y, z, L, edges = H.float_window_case(stat)
+    lib = H.load_oracle()
+    lib.oracle_set_literal_kernels(1)
+    try:
+        lit = H.oracle_theory(stat, x, y, z, edges, periodic=True, boxsize=L)["npairs"].astype(np.int64)
+    finally:
+        lib.oracle_set_literal_kernels(0)
+    assert np.array_equal(lit, ref)
+    dflt = H.oracle_theory(stat, x, y, z, edges, periodic=True, boxsize=L)["npairs"].astype(np.int64)
+    assert np.array_equal((dflt - ref)[:-1], np.zeros(ref.size - 1, dtype=np.int64)) and (dflt - ref)[-1] == 2
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("stat,periodic", [("DD", True), ("DD", False), ("xi", True)])
+def test_oracle_literal_equals_default_for_DD_xi_on_small_inputs(stat, periodic, dtype):
+    L, N = 420.0, 60000
+    x, y, z, w = H.box_points(6, N, L, dtype)
+    edges = np.logspace(np.log10(0.1), np.log10(25.0), 15)
+    kw = dict(periodic=periodic, boxsize=L, w1=w, weight_type="pair_product", need_avg=True)
+    a = H.oracle_theory(stat, x, y, z, edges, **kw)
+    lib = H.load_oracle()
+    lib.oracle_set_literal_kernels(1)
+    try:
+        b = H.oracle_theory(stat, x, y, z, edges, **kw)
+    finally:
+        lib.oracle_set_literal_kernels(0)
+    assert np.array_equal(a["npairs"], b["npairs"])
+    assert np.allclose(a["ravg"], b["ravg"], rtol=1e-12) and np.allclose(a["weightavg"], b["weightavg"], rtol=1e-12)

@@ -17,6 +17,6 @@ lib = _lib.load()
 for spec in sys.argv[1:]:
     name, _, kind = spec.partition(":")
     lib.cfb_force_kernel({"": -1, "generic": 0, "fast": 1}[kind])
-    r = P._run_config(lib, name)
+    r = P._run_config(lib, name)  # bench.config_by_name: c1..c5 or e.g. c5sd10M
     np.save(os.path.join(ROOT, "gpurun_out", "gpu_fullsize_%s.npy" % spec.replace(":", "_")), np.asarray(r["npairs"], dtype=np.uint64))
     print(spec, int(np.asarray(r["npairs"], dtype=np.uint64).sum()))
