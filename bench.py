@@ -42,11 +42,18 @@ CONFIGS = {
     "c3": dict(stat="DDsmu", N=10_000_000, L=1000.0, bins=("log", 0.1, 50.0, 21), dtype="f64", seed=1003,
                mu_max=1.0, nmu=20, weights=True, avg=True),
     "c4": dict(stat="DDtheta", N=2_000_000, L=0.0, bins=("log", 0.01, 10.0, 21), dtype="f64", seed=1004),
+    # survey geometry (full-sky shell 500 < D < 1500, uniform in volume), comoving distances
+    "m1": dict(stat="DDrppi_mocks", N=4_000_000, L=0.0, bins=("log", 0.1, 25.0, 15), dtype="f64", seed=1011, pimax=40.0),
+    "m2": dict(stat="DDsmu_mocks", N=4_000_000, L=0.0, bins=("log", 0.1, 50.0, 21), dtype="f64", seed=1012,
+               mu_max=1.0, nmu=20, weights=True, avg=True),
     "c5d": dict(stat="xi", N=100_000_000, L=2000.0, bins=("log", 0.1, 150.0, 31), dtype="f64", seed=1006),
     "c5": dict(stat="xi", N=100_000_000, L=2000.0, bins=("log", 0.1, 150.0, 31), dtype="f32", seed=1006),
 }
-FLOP_PER_EVAL = {"DD": 8, "xi": 8, "wp": 6, "DDrppi": 7, "DDsmu": 9, "DDtheta": 10}
-INSTR_PER_EVAL = {"DD": 6, "xi": 6, "wp": 5, "DDrppi": 6, "DDsmu": 7, "DDtheta": 8}
+# mocks: up to the first range test of a pair -- 3 sub + 3 add (perp, par), 2 mul + add + fma (s.l), its square,
+# mul + 2 fma (s^2): 14 lane-instructions, 17 FLOP
+FLOP_PER_EVAL = {"DD": 8, "xi": 8, "wp": 6, "DDrppi": 7, "DDsmu": 9, "DDtheta": 10, "DDrppi_mocks": 17, "DDsmu_mocks": 17}
+INSTR_PER_EVAL = {"DD": 6, "xi": 6, "wp": 5, "DDrppi": 6, "DDsmu": 7, "DDtheta": 8, "DDrppi_mocks": 14, "DDsmu_mocks": 14}
+HOST_ONLY = ("DDtheta", "DDrppi_mocks", "DDsmu_mocks")  # the host layer converts the angles itself: host buffers only
 
 
 def config_by_name(name):
@@ -76,6 +83,13 @@ def gen_points(cfg, n, dtype):
         ra2 = (360.0 * rng2.random(n)).astype(dtype)
         dec2 = np.degrees(np.arcsin(2.0 * rng2.random(n) - 1.0)).astype(dtype)
         return dict(ra=ra, dec=dec, ra2=ra2, dec2=dec2)
+    if cfg["stat"].endswith("_mocks"):
+        out = dict(ra=(360.0 * rng.random(n)).astype(dtype),
+                   dec=np.degrees(np.arcsin(2.0 * rng.random(n) - 1.0)).astype(dtype),
+                   d=np.cbrt(500.0 ** 3 + (1500.0 ** 3 - 500.0 ** 3) * rng.random(n)).astype(dtype))
+        if cfg.get("weights"):
+            out["w"] = (1.0 - rng.random(n)).astype(dtype)
+        return out
     out = {}
     for k in "xyz":  # one axis at a time keeps the peak host memory at ~2 arrays
         out[k] = (rng.random(n) * cfg["L"]).astype(dtype)
@@ -100,6 +114,53 @@ def n_cand_box(counts, refine, periodic=True):
                 seen.add(key)
                 s += np.roll(c, shift=(dx, dy, dz), axis=(0, 1, 2))
     return float((c * s).sum() - c.sum()) / 2.0
+
+
+def n_cand_open(counts, refine):
+    """n_cand_box for a lattice without periodic wrap (zero padding instead of roll)."""
+    c = counts.astype(np.float64)
+    rx, ry, rz = refine
+    pad = np.pad(c, ((rx, rx), (ry, ry), (rz, rz)))
+    s = np.zeros_like(c)
+    for dx in range(2 * rx + 1):
+        for dy in range(2 * ry + 1):
+            for dz in range(2 * rz + 1):
+                s += pad[dx:dx + c.shape[0], dy:dy + c.shape[1], dz:dz + c.shape[2]]
+    return float((c * s).sum() - c.sum()) / 2.0
+
+
+def n_cand_data_extent(cfg, pts, n, bins):
+    """Candidate pairs of the reference's lattice over the DATA extent, for the statistics whose lattice is not the
+    [0,L]^3 one: DDsmu (periodic; countpairs_s_mu_impl.c.src:190-234, no 0.05 rule, boost is a no-op) and the mocks
+    statistics (open; countpairs_rp_pi_mocks_impl.c.src:404-470).  Computed in double: a throughput denominator."""
+    stat = cfg["stat"]
+    rmax = float(bins[-1])
+    if stat.endswith("_mocks"):
+        ra, dec, d = (np.asarray(pts[k][:n], dtype=np.float64) for k in ("ra", "dec", "d"))
+        xyz = [d * np.cos(np.radians(dec)) * np.cos(np.radians(ra)), d * np.cos(np.radians(dec)) * np.sin(np.radians(ra)),
+               d * np.sin(np.radians(dec))]
+        sep = np.sqrt(rmax ** 2 + cfg["pimax"] ** 2) if stat == "DDrppi_mocks" else rmax
+        maxsize = [sep, sep, sep]
+    else:
+        xyz = [np.asarray(pts[k][:n], dtype=np.float64) for k in "xyz"]
+        maxsize = [rmax, rmax, rmax * cfg["mu_max"]]
+    lo = [float(a.min()) for a in xyz]
+    ext = [float(a.max()) - l for a, l in zip(xyz, lo)]
+    rf = [2, 2, 1]
+    if stat.endswith("_mocks"):
+        rf = [1 if maxsize[0] < 0.05 * e else r for r, e in zip(rf, ext)]
+
+    def mesh(rf):
+        return [max(2, min(100, int(r * e / m))) for r, e, m in zip(rf, ext, maxsize)]
+
+    nm = mesh(rf)
+    if stat.endswith("_mocks") and (max(nm) <= 10 or n / (nm[0] * nm[1] * nm[2]) >= 250) and max(nm) < 100:
+        rf = [rf[0] + 1, rf[1] + 1, rf[2]]
+        nm = mesh(rf)
+    idx = [np.minimum((((a - l) * (m / e)).astype(np.int64)), m - 1) for a, l, m, e in zip(xyz, lo, nm, ext)]
+    lin = (idx[0] * nm[1] + idx[1]) * nm[2] + idx[2]
+    counts = np.bincount(lin, minlength=nm[0] * nm[1] * nm[2]).reshape(nm)
+    return n_cand_open(counts, rf) if stat.endswith("_mocks") else n_cand_box(counts, rf)
 
 
 def ref_cell_counts(pts, L, nmesh, dtype):
@@ -191,7 +252,8 @@ def run_ours(args, cfg):
     # host copies in pinned memory (e2e) and device-resident copies (value)
     pinned = {k: torch.from_numpy(pts[k]).pin_memory() for k in keys}
     resident = {k: pinned[k].to(dev) for k in keys}
-    opt_kw = dict(periodic=True, need_avg_sep=bool(cfg.get("avg")), boxsize=cfg["L"] if cfg["L"] > 0 else None)
+    opt_kw = dict(periodic=True, need_avg_sep=bool(cfg.get("avg")), boxsize=cfg["L"] if cfg["L"] > 0 else None,
+                  is_comoving_dist=stat.endswith("_mocks"))
     wtype = "pair_product" if cfg.get("weights") else None
     _capi._declare(lib)
 
@@ -233,12 +295,25 @@ def run_ours(args, cfg):
                                             N, C.c_void_p(pinned["ra2"].data_ptr()), C.c_void_p(pinned["dec2"].data_ptr()),
                                             1, 0, bf, C.byref(r), C.byref(o), C.byref(e))
             free = lib.free_results_countpairs_theta
+        elif stat in ("DDrppi_mocks", "DDsmu_mocks"):
+            # RA/DEC/distance -> Cartesian happens on the host (glibc trig, for bit parity): host buffers only
+            H3 = [C.c_void_p(pinned[k].data_ptr()) for k in ("ra", "dec", "d")]
+            if stat == "DDrppi_mocks":
+                r = _capi.ResultsMocksRpPi()
+                st = lib.countpairs_mocks(N, H3[0], H3[1], H3[2], N, H3[0], H3[1], H3[2], 1, 1, bf, cfg["pimax"], 1,
+                                          C.byref(r), C.byref(o), C.byref(e))
+                free = lib.free_results_mocks
+            else:
+                r = _capi.ResultsMocksSMu()
+                st = lib.countpairs_mocks_s_mu(N, H3[0], H3[1], H3[2], N, H3[0], H3[1], H3[2], 1, 1, bf, cfg["mu_max"],
+                                               cfg["nmu"], 1, C.byref(r), C.byref(o), C.byref(e))
+                free = lib.free_results_mocks_s_mu
         else:
             raise ValueError(stat)
         if st != 0:
             raise RuntimeError("C call failed: %s" % lib.cfb_last_error())
         nb = r.nbin if hasattr(r, "nbin") else r.nsbin
-        tot = int(np.ctypeslib.as_array(r.npairs, shape=(nb,)).astype(np.uint64)[1:].sum()) if stat not in ("DDsmu", "DDrppi") else -1
+        tot = int(np.ctypeslib.as_array(r.npairs, shape=(nb,)).astype(np.uint64)[1:].sum()) if stat not in ("DDsmu", "DDrppi", "DDrppi_mocks", "DDsmu_mocks") else -1
         free(C.byref(r))
         return tot
 
@@ -289,7 +364,7 @@ def run_ours(args, cfg):
                 flush.zero_()
                 torch.cuda.synchronize()
             t0 = time.perf_counter()
-            if world > 1 and stat != "DDtheta":
+            if world > 1 and stat not in HOST_ONLY:
                 # each rank uploads 1/world of the host arrays, one NVLink all-gather completes the replicas
                 dev_t = parallel.replicate_from_host([pinned[k] for k in keys], dev, dist)
                 torch.cuda.current_stream().synchronize()
@@ -322,6 +397,8 @@ def run_ours(args, cfg):
     if stat in ("xi", "wp", "DD", "DDrppi"):
         counts = ref_cell_counts(pts, cfg["L"], st0["nmesh"], dtype)
         n_cand = n_cand_box(counts, st0["refine"])
+    elif stat in ("DDsmu", "DDrppi_mocks", "DDsmu_mocks"):
+        n_cand = n_cand_data_extent(cfg, pts, N, bins)
     else:
         n_cand = float(n_eval_total)  # no cheap closed form: use the device's own evaluation count
     peaks = {}
@@ -405,6 +482,13 @@ def ref_call(ref, cfg, pts, n, bins, nthreads):
                          w1=None if w is None else w[:n], weight_type=wt, options=o)
     elif stat == "DDtheta":
         _capi.call_DDtheta(ref, 0, nthreads, bins, pts["ra"][:n], pts["dec"][:n], RA2=pts["ra2"][:n], DEC2=pts["dec2"][:n], options=o)
+    elif stat == "DDrppi_mocks":
+        o.is_comoving_dist = 1
+        _capi.call_DDrppi_mocks(ref, 1, 1, nthreads, cfg["pimax"], bins, pts["ra"][:n], pts["dec"][:n], pts["d"][:n], options=o)
+    elif stat == "DDsmu_mocks":
+        o.is_comoving_dist = 1
+        _capi.call_DDsmu_mocks(ref, 1, 1, nthreads, cfg["mu_max"], cfg["nmu"], bins, pts["ra"][:n], pts["dec"][:n],
+                               pts["d"][:n], w1=None if w is None else w[:n], weight_type=wt, options=o)
     return time.perf_counter() - t0
 
 
@@ -452,6 +536,8 @@ def cpu_baseline(cfg, args, budget_s=15.0, steps=1, n_cand_full=None):
         nm, rf = ref_lattice_for(cfg, n_s, bins)
         counts = ref_cell_counts({k: pts[k][:n_s] for k in "xyz"}, cfg["L"], nm, dtype)
         n_cand = n_cand_box(counts, rf)
+    elif stat in ("DDsmu", "DDrppi_mocks", "DDsmu_mocks"):
+        n_cand = n_cand_data_extent(cfg, pts, n_s, bins)
     elif n_cand_full:
         # no closed form for this lattice: the device's own count of the full workload, scaled to the sample
         # (candidate pairs of a uniform catalogue grow with the square of the point count)

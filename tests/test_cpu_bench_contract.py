@@ -5,15 +5,16 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 import harness as H
 
 
-def test_reference_arm_prints_one_json_line():
+@pytest.mark.parametrize("config", ["c1", "c3", "m1"])
+def test_reference_arm_prints_one_json_line(config):
     if H.load_ref() is None:
-        import pytest
-
         pytest.skip("oracle/_ref not built")
-    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--config", "c1",
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--config", config,
                           "--npart", "60000", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
