@@ -42,6 +42,11 @@ CONFIGS = {
     "c3": dict(stat="DDsmu", N=10_000_000, L=1000.0, bins=("log", 0.1, 50.0, 21), dtype="f64", seed=1003,
                mu_max=1.0, nmu=20, weights=True, avg=True),
     "c4": dict(stat="DDtheta", N=2_000_000, L=0.0, bins=("log", 0.01, 10.0, 21), dtype="f64", seed=1004),
+    # float32 twins of configs 1, 3 and 4: parity cases only (full-size goldens), not bench lines
+    "c1f32": dict(stat="DD", N=1_200_000, L=420.0, bins=("log", 0.1, 25.0, 15), dtype="f32", seed=1001),
+    "c3f32": dict(stat="DDsmu", N=10_000_000, L=1000.0, bins=("log", 0.1, 50.0, 21), dtype="f32", seed=1003,
+                  mu_max=1.0, nmu=20, weights=True, avg=True),
+    "c4f32": dict(stat="DDtheta", N=2_000_000, L=0.0, bins=("log", 0.01, 10.0, 21), dtype="f32", seed=1004),
     # survey geometry (full-sky shell 500 < D < 1500, uniform in volume), comoving distances
     "m1": dict(stat="DDrppi_mocks", N=4_000_000, L=0.0, bins=("log", 0.1, 25.0, 15), dtype="f64", seed=1011, pimax=40.0),
     "m2": dict(stat="DDsmu_mocks", N=4_000_000, L=0.0, bins=("log", 0.1, 50.0, 21), dtype="f64", seed=1012,
