@@ -551,6 +551,7 @@ def cpu_baseline(cfg, args, budget_s=15.0, steps=1, n_cand_full=None):
         n_cand = float("nan")
     return {"value": n_cand / t, "unit": "pair_evals/s", "cores": cores, "kind": "reference",
             "isa": "avx512f" if H.ref_variant() == "v4" else "avx", "seconds": t, "n_cand": n_cand,
+            "omp": {"proc_bind": os.environ.get("OMP_PROC_BIND"), "places": os.environ.get("OMP_PLACES")},
             "sample": "first %d of the %d points (same box, same bins): reference %s, %d OpenMP threads" % (n_s, n_full, stat, cores)}
 
 
@@ -581,6 +582,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.impl == "reference":
+        # the reference's OpenMP threads pinned to cores.  Only this arm: it is a process of its own
+        # (rank 0), and libgomp reads these when it is first loaded -- in the GPU arm, whose ranks share the host,
+        # pinning every rank's initial thread to the first core would serialise them.
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
     cfg = dict(CONFIGS[args.config])
     if args.npart and args.same_density and cfg["L"] > 0:
         cfg["L"] = float(cfg["L"] * (args.npart / cfg["N"]) ** (1.0 / 3.0))
