@@ -699,13 +699,14 @@ def test_float_z_window_case(stat):
     assert not d[:-1].any() and d[-1] == 2, d
 
 
-@pytest.mark.parametrize("name", ["c1", "c1f32", "c2", "c2wp32", "c2rppi", "c2rppi32", "c3", "c4", "c4f32", "c5sd10M", "c5"])
+@pytest.mark.parametrize("name", ["c1", "c1f32", "c2", "c2wp32", "c2rppi", "c2rppi32", "c3", "c3f32", "c4", "c4f32", "c5sd10M", "c5"])
 def test_full_size_config_vs_reference_golden(name):
     """BASELINE configs 1-4 at their full sizes (1.2M / 10M / 2M+2M points): npairs bit-exact against the
     committed outputs of the UNMODIFIED reference (oracle/_ref, AVX-512F kernels) on the same seeded inputs
     (tests/golden/make_golden_fullsize.py); ravg / weightavg of config 3 within 1e-10 relative.
 
-    c1f32 / c4f32 are configs 1 and 4 on float32 inputs (the CPU oracle agrees with the reference on both at full size).
+    c1f32 / c3f32 / c4f32 are configs 1, 3 and 4 on float32 inputs (the CPU oracle agrees with the reference on all
+    three at full size: no early-exit effect there).
     Config 5 itself (xi, 100 M points, float; the reference needs 25 minutes on 8 cores for it): 29 of the 30 bins are
     bit-exact and the last one holds 4 more (2 unordered pairs of 8.8e12) than the reference, whose float z-window
     never visits them (test_float_z_window_case).
@@ -729,5 +730,7 @@ def test_full_size_config_vs_reference_golden(name):
     nflip = int(np.count_nonzero(got != want))
     assert nflip == 0, "%s: %d bins differ from the reference, max |diff| %d" % (name, nflip, int(np.abs(got - want).max()))
     for k in ("ravg", "weightavg"):
-        if k in g.files:
+        # float goldens: npairs only -- the reference sums separations in float, which at 1e8 pairs per bin has
+        # lost most of its digits, so its float averages are not a standard to hold the GPU to
+        if k in g.files and not name.endswith("f32"):
             _close(np.asarray(r[k]).reshape(g[k].shape), g[k], 1e-10, k)
