@@ -135,6 +135,63 @@ static int reduce_across_ranks(uint64_t *np, double *ss, double *sw, int64_t nsl
 }
 
 /* what every statistic hands back to its public wrapper (arrays are malloc'ed, caller owns them) */
+/* ---- redshift -> comoving distance (mocks statistics with is_comoving_dist == 0) ---------------------------- */
+#define CF_SPEED_OF_LIGHT 299800.0 /* utils/set_cosmo_dist.h:19 */
+
+/* utils/set_cosmo_dist.c:27-75 with the parameters of utils/cosmology_params.c:21-54; same statements in the same
+ * order (compiled with -ffp-contract=off like the reference's -std=c99), so the table is bit-identical */
+int corrfunc_b200_cosmo_dist_table(double zmax, int max_size, double *zc, double *dc, int cosmology)
+{
+    double OMEGA_M;
+    switch (cosmology) {
+    case 1: OMEGA_M = 0.25; break;
+    case 2: OMEGA_M = 0.302; break;
+    default: fprintf(stderr, "ERROR: In %s> Cosmology=%d not implemented\n", "init_cosmology", cosmology); return -1;
+    }
+    const double OMEGA_L = 1.0 - OMEGA_M;
+    int i = 0;
+    const double smallh = 1.0;
+    const double Omegak = 1.0 - OMEGA_M - OMEGA_L;
+    const double Dh = CF_SPEED_OF_LIGHT * 0.01 / smallh;
+    const double Deltaz = 1.0 / max_size;
+    const double dz = 1e-2 * Deltaz;
+    const double epsilon = 1e-10;
+    double Eint = 0.0, E2 = 1.0, z2 = Deltaz;
+#define CF_CUBE(x) ((x) * (x) * (x))
+    for (double z = 2.0 * dz; z < zmax; z += 2.0 * dz) {
+        const double E0 = E2;
+        const double E1 = 1.0 / sqrt(OMEGA_M * CF_CUBE(1 + z - dz) + Omegak * (1 + z - dz) + OMEGA_L);
+        E2 = 1.0 / sqrt(OMEGA_M * CF_CUBE(1 + z) + Omegak * (1 + z) + OMEGA_L);
+        Eint += dz * (E0 + 4. * E1 + E2) / 3.;
+        if (z > (z2 - epsilon) && z < (z2 + epsilon)) {
+            if (i >= max_size) break;
+            zc[i] = z;
+            dc[i] = Eint * Dh;
+            z2 += Deltaz;
+            i++;
+        }
+    }
+#undef CF_CUBE
+    return i;
+}
+
+/* GSL 2.x interpolation/linear.c:linear_eval + interpolation/bsearch.c:gsl_interp_bsearch (GSL is a dependency of the
+ * reference that is absent here; restated from its published source).  Returns 1 when x is outside the table. */
+static int cf_interp_linear(const double *xa, const double *ya, const int n, const double x, double *y)
+{
+    if (n < 2 || x < xa[0] || x > xa[n - 1]) return 1; /* gsl_interp_eval: GSL_EDOM -> the default handler aborts */
+    size_t ilo = 0, ihi = (size_t)n - 1;
+    while (ihi > ilo + 1) {
+        const size_t i = (ihi + ilo) / 2;
+        if (xa[i] > x) ihi = i; else ilo = i;
+    }
+    const double x_lo = xa[ilo], x_hi = xa[ilo + 1], y_lo = ya[ilo], y_hi = ya[ilo + 1];
+    const double dx = x_hi - x_lo;
+    if (!(dx > 0.0)) return 1;
+    *y = y_lo + (x - x_lo) / dx * (y_hi - y_lo);
+    return 0;
+}
+
 typedef struct {
     int nbin;         /* number of edges = reference's nbin */
     int n2;           /* npibin / nmu_bins for the 2-D statistics */
@@ -374,6 +431,24 @@ int countpairs_theta_mocks(const int64_t ND1, void *phi1, void *theta1, const in
 /* ------------------------------------------------------------------------------------------------
  * Precision-suffixed entry points (the reference's *_impl.h.src prototypes): typed pointers; the
  * options' float_type is overridden for the call and restored afterwards. */
+int corrfunc_b200_cz_to_comoving(int prec, int64_t n, const void *cz, int cosmology, void *dist)
+{
+    if (prec == 4) {
+        float czmax = 0.0f;
+        for (int64_t i = 0; i < n; i++)
+            if (((const float *)cz)[i] > czmax) czmax = ((const float *)cz)[i];
+        return cf_cz_to_dist_f32(n, (const float *)cz, czmax, cosmology, (float *)dist);
+    }
+    if (prec == 8) {
+        double czmax = 0.0;
+        for (int64_t i = 0; i < n; i++)
+            if (((const double *)cz)[i] > czmax) czmax = ((const double *)cz)[i];
+        return cf_cz_to_dist_f64(n, (const double *)cz, czmax, cosmology, (double *)dist);
+    }
+    fprintf(stderr, "Error: In %s> element size must be 4 or 8 (got %d)\n", __func__, prec);
+    return EXIT_FAILURE;
+}
+
 /* ---- survey geometry: mocks/DDrppi_mocks/countpairs_rp_pi_mocks.c:33-77, DDsmu_mocks ---- */
 void free_results_mocks(results_countpairs_mocks *r)
 {

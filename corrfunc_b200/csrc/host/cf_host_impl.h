@@ -468,17 +468,60 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
 /* ========================================================================================== */
 /* DDrppi_mocks / DDsmu_mocks: (RA, DEC, comoving distance) -> Cartesian on the host, then the box driver   */
 
+/* cz -> comoving distance of one particle set (countpairs_rp_pi_mocks_impl.c.src:326-362).  czmax is the maximum over
+ * BOTH sets of a cross-correlation: it only sets how far the table reaches (its entries do not depend on it). */
+static int HFN(cf_cz_to_dist)(const int64_t N, const REAL *cz, const REAL czmax, const int cosmology, REAL *D)
+{
+    const REAL inv_speed_of_light = 1.0 / CF_SPEED_OF_LIGHT;
+    const double zmax = czmax * inv_speed_of_light + 0.01;
+    const int workspace_size = 10000;
+    double *zc = calloc((size_t)workspace_size, sizeof(double)), *dc = calloc((size_t)workspace_size, sizeof(double));
+    if (!zc || !dc) {
+        free(zc); free(dc);
+        return EXIT_FAILURE;
+    }
+    const int Nzdc = corrfunc_b200_cosmo_dist_table(zmax, workspace_size, zc, dc, cosmology);
+    int64_t bad = -1;
+    if (Nzdc >= 2) {
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static)
+#endif
+        for (int64_t i = 0; i < N; i++) {
+            double y = 0.0;
+            if (cf_interp_linear(zc, dc, Nzdc, cz[i] * inv_speed_of_light, &y)) {
+#if defined(_OPENMP)
+#pragma omp critical
+#endif
+                bad = i;
+            }
+            D[i] = y;
+        }
+    }
+    free(zc);
+    free(dc);
+    if (Nzdc < 2) return EXIT_FAILURE;
+    if (bad >= 0) {
+        fprintf(stderr, "Error: cz[%" PRId64 "] = %g is outside the redshift range [1e-4, %g] of the distance table "
+                        "(the reference's GSL interpolation aborts here)\n", bad, (double)cz[bad], zmax);
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}
+
 /* check_ra_dec_cz_DOUBLE (mocks/DDrppi_mocks/countpairs_rp_pi_mocks_impl.c.src:43-110): RA in [-180,180] and DEC in
- * [0,180] are shifted IN PLACE like the reference does.  (Its third fix, z -> cz, belongs to the cz branch.) */
-static int HFN(cf_check_ra_dec_cz)(const int64_t N, REAL *phi, REAL *theta, REAL *cz)
+ * [0,180] are shifted, and redshifts passed as cz are scaled, IN PLACE like the reference does. */
+static int HFN(cf_check_ra_dec_cz)(const int64_t N, REAL *phi, REAL *theta, REAL *cz, const int is_comoving_dist)
 {
     if (N == 0) return EXIT_SUCCESS;
     if (phi == NULL || theta == NULL || cz == NULL) {
         fprintf(stderr, "Input arrays can not be NULL. Have RA = %p DEC = %p cz = %p\n", (void *)phi, (void *)theta, (void *)cz);
         return EXIT_FAILURE;
     }
-    int fix_ra = 0, fix_dec = 0;
+    int fix_ra = 0, fix_dec = 0, fix_cz = 0;
+    const REAL max_cz_threshold = 10.0; /* a maximum below this means redshifts were passed instead of cz */
+    REAL max_cz = 0.0;
     for (int64_t i = 0; i < N; i++) {
+        if (cz[i] > max_cz) max_cz = cz[i];
         if (phi[i] < 0.0) fix_ra = 1;
         if (theta[i] > 90.0) fix_dec = 1;
         if (theta[i] > 180) {
@@ -488,10 +531,15 @@ static int HFN(cf_check_ra_dec_cz)(const int64_t N, REAL *phi, REAL *theta, REAL
     }
     if (fix_ra) fprintf(stderr, "%s> Out of range values found for ra. Expected ra to be in the range [0.0,360.0]. Found ra values in [-180,180] -- fixing that\n", __func__);
     if (fix_dec) fprintf(stderr, "%s> Out of range values found for dec. Expected dec to be in the range [-90.0,90.0]. Found dec values in [0,180] -- fixing that\n", __func__);
-    if (fix_ra || fix_dec)
+    if ((max_cz < max_cz_threshold) && (is_comoving_dist == 0)) fix_cz = 1;
+    if (fix_cz)
+        fprintf(stderr, "%s> Out of range values found for cz. Expected input to be `cz' but found `z' instead. max_cz (found in input) = %g threshold = %g\n",
+                __func__, (double)max_cz, (double)max_cz_threshold);
+    if (fix_ra || fix_dec || fix_cz)
         for (int64_t i = 0; i < N; i++) {
             if (fix_ra) phi[i] += (REAL)180.0;
             if (fix_dec) theta[i] -= (REAL)90.0;
+            if (fix_cz) cz[i] *= (REAL)CF_SPEED_OF_LIGHT; /* input was z -> convert to cz */
         }
     return EXIT_SUCCESS;
 }
@@ -512,17 +560,25 @@ static int HFN(cf_mocks)(const int mode, const int64_t ND1, void *vra1, void *vd
     const int64_t N[2] = {ND1, ND2};
     const int nsets = autocorr ? 1 : 2;
     for (int s = 0; s < nsets; s++)
-        if (HFN(cf_check_ra_dec_cz)(N[s], ra[s], dec[s], D[s])) return EXIT_FAILURE;
+        if (HFN(cf_check_ra_dec_cz)(N[s], ra[s], dec[s], D[s], options->is_comoving_dist)) return EXIT_FAILURE;
     if (!(cosmology == 1 || cosmology == 2)) { /* init_cosmology, utils/cosmology_params.c:21-54 */
         fprintf(stderr, "ERROR: In %s> Cosmology=%d not implemented\n", "init_cosmology", cosmology);
         return EXIT_FAILURE;
     }
-    if (options->is_comoving_dist == 0) {
-        /* rp_pi_mocks_impl:326-362 tabulates the comoving distance with GSL's adaptive integrator to 1e-7 and
-         * interpolates linearly: positions that depend on GSL's rounding cannot be matched without GSL. */
-        fprintf(stderr, "Error: In %s> cz -> comoving distance is not available in the B200 build (the reference's table "
-                        "comes from GSL); convert to comoving distances and set is_comoving_dist = 1\n", __func__);
-        return EXIT_FAILURE;
+    REAL *conv[2] = {NULL, NULL};
+    if (options->is_comoving_dist == 0) { /* rp_pi_mocks_impl:326-362: cz -> comoving distance through the table */
+        REAL czmax = 0.0;
+        for (int s = 0; s < nsets; s++)
+            for (int64_t i = 0; i < N[s]; i++)
+                if (D[s][i] > czmax) czmax = D[s][i];
+        for (int s = 0; s < nsets; s++) {
+            conv[s] = malloc(sizeof(REAL) * (size_t)(N[s] > 0 ? N[s] : 1));
+            if (!conv[s] || HFN(cf_cz_to_dist)(N[s], D[s], czmax, cosmology, conv[s])) {
+                free(conv[0]); free(conv[1]);
+                return EXIT_FAILURE;
+            }
+            D[s] = conv[s];
+        }
     }
     REAL *xyz[2][3] = {{NULL, NULL, NULL}, {NULL, NULL, NULL}};
     for (int s = 0; s < nsets; s++) {
@@ -531,6 +587,7 @@ static int HFN(cf_mocks)(const int mode, const int64_t ND1, void *vra1, void *vd
             xyz[s][a] = cfb_host_scratch(3 * s + a, sizeof(REAL) * (size_t)(N[s] > 0 ? N[s] : 1));
             if (!xyz[s][a]) {
                 fprintf(stderr, "Error: could not get host staging memory for %" PRId64 " positions: %s\n", N[s], cfb_last_error());
+                free(conv[0]); free(conv[1]);
                 return EXIT_FAILURE;
             }
         }
@@ -547,6 +604,8 @@ static int HFN(cf_mocks)(const int mode, const int64_t ND1, void *vra1, void *vd
             Z[i] = dist[i] * H_SIND(dc[i]);
         }
     }
+    free(conv[0]);
+    free(conv[1]);
     return HFN(cf_box)(mode, ND1, xyz[0][0], xyz[0][1], xyz[0][2], ND2, xyz[1][0], xyz[1][1], xyz[1][2], numthreads,
                        autocorr, binfile, pimax, max_mu, nmu_bins, 0.0, options, extra, out);
 }

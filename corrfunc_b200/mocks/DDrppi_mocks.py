@@ -11,16 +11,11 @@ from .DDtheta_mocks import fix_ra_dec
 def _mock_options(dtype, *, is_comoving_dist, verbose, need_avg, refine, max_cells_per_dim, copy_particles,
                   enable_min_sep_opt, c_api_timer, isa, fast_divide_and_NR_steps):
     translate_isa_string_to_enum(isa)
-    if not is_comoving_dist:
-        # the reference integrates the cz -> distance table with GSL (utils/set_cosmo_dist.c); its rounding cannot be
-        # reproduced without GSL, so the conversion is refused rather than approximated
-        raise NotImplementedError("the B200 build takes comoving distances only: convert CZ to comoving distance and "
-                                  "pass is_comoving_dist=True")
     custom = tuple(int(r) for r in refine) != (2, 2, 1)  # _countpairs_mocks.c:1200-1207
     opt = _capi.default_options(dtype, verbose=verbose, need_avg_sep=need_avg, bin_refine_factors=refine,
                                 max_cells_per_dim=max_cells_per_dim, copy_particles=copy_particles,
                                 enable_min_sep_opt=enable_min_sep_opt, c_api_timer=c_api_timer, isa=-1,
-                                custom_refine=custom, is_comoving_dist=True)
+                                custom_refine=custom, is_comoving_dist=is_comoving_dist)
     opt.fast_divide_and_NR_steps = int(fast_divide_and_NR_steps)
     return opt
 
@@ -30,8 +25,8 @@ def DDrppi_mocks(autocorr, cosmology, nthreads, pimax, binfile, RA1, DEC1, CZ1, 
                  fast_divide_and_NR_steps=0, xbin_refine_factor=2, ybin_refine_factor=2, zbin_refine_factor=1,
                  max_cells_per_dim=100, copy_particles=True, enable_min_sep_opt=True, c_api_timer=False,
                  isa="fastest", weight_type=None):
-    """Survey-geometry pair counts DD(rp, pi) from RA, DEC (degrees) and comoving distance, line of sight = pair
-    midpoint.  Returns a structured array (rmin, rmax, rpavg, pimax, npairs, weightavg), rp-major with
+    """Survey-geometry pair counts DD(rp, pi) from RA, DEC (degrees) and CZ (km/s; or the comoving distance with
+    ``is_comoving_dist=True``), line of sight = pair midpoint.  ``cosmology``: 1 (LasDamas) or 2 (Planck).  Returns a structured array (rmin, rmax, rpavg, pimax, npairs, weightavg), rp-major with
     ``int(pimax)`` unit-width pi bins [and the C call's wall time when ``c_api_timer``]."""
     if not autocorr and (RA2 is None or DEC2 is None or CZ2 is None):
         raise ValueError("Must pass valid arrays for RA2/DEC2/CZ2 for computing cross-correlation")

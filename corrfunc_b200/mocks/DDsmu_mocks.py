@@ -14,8 +14,8 @@ def DDsmu_mocks(autocorr, cosmology, nthreads, mu_max, nmu_bins, binfile, RA1, D
                 fast_divide_and_NR_steps=0, xbin_refine_factor=2, ybin_refine_factor=2, zbin_refine_factor=1,
                 max_cells_per_dim=100, copy_particles=True, enable_min_sep_opt=True, c_api_timer=False,
                 isa="fastest", weight_type=None):
-    """Survey-geometry pair counts DD(s, mu) from RA, DEC (degrees) and comoving distance, mu measured against the
-    pair-midpoint line of sight.  Returns a structured array (smin, smax, savg, mumax, npairs, weightavg), s-major
+    """Survey-geometry pair counts DD(s, mu) from RA, DEC (degrees) and CZ (km/s; or the comoving distance with
+    ``is_comoving_dist=True``), mu measured against the pair-midpoint line of sight.  Returns a structured array (smin, smax, savg, mumax, npairs, weightavg), s-major
     with ``nmu_bins`` mu bins up to ``mu_max`` [and the C call's wall time when ``c_api_timer``]."""
     if not autocorr and (RA2 is None or DEC2 is None or CZ2 is None):
         raise ValueError("Must pass valid arrays for RA2/DEC2/CZ2 for computing cross-correlation")

@@ -31,6 +31,17 @@ const corrfunc_b200_stats *corrfunc_b200_last_stats(void);
 
 const char *corrfunc_b200_version(void);
 
+/* cz (km/s) -> comoving distance (Mpc/h) exactly as countpairs_mocks / countpairs_mocks_s_mu do it for
+ * is_comoving_dist == 0 (mocks/DDrppi_mocks/countpairs_rp_pi_mocks_impl.c.src:326-362): the redshift -> distance table
+ * of utils/set_cosmo_dist.c:27-75 (Simpson's rule, 10000 points per unit redshift; plain C despite its GSL include),
+ * then GSL's linear interpolation (interpolation/linear.c of GSL 2.x: y_lo + (x - x_lo) / dx * (y_hi - y_lo) on the
+ * bracket found by bisection).  prec = 4 | 8 selects float / double arrays; cosmology = 1 (LasDamas) | 2 (Planck).
+ * Returns 0, or 1 with a message on stderr (unknown cosmology, redshift outside the table's [1e-4, zmax] domain --
+ * where GSL's error handler would abort the reference).  Pure host code: usable without a GPU. */
+int corrfunc_b200_cz_to_comoving(int prec, int64_t n, const void *cz, int cosmology, void *dist);
+/* The table itself (for tests): fills zc[], dc[] (max_size entries each) and returns the number of entries, -1 on error. */
+int corrfunc_b200_cosmo_dist_table(double zmax, int max_size, double *zc, double *dc, int cosmology);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,9 +2,11 @@
  * Replaces the reference interface mocks/DDrppi_mocks/countpairs_rp_pi_mocks.h:18-39 (Corrfunc v2.5.3): same symbol
  * names, argument order/meaning, result layout and error behaviour (EXIT_SUCCESS / EXIT_FAILURE + stderr message).
  * Inputs are HOST pointers of element size options->float_type (4 or 8): RA and DEC in degrees and the third array
- * as a COMOVING DISTANCE -- options->is_comoving_dist must be 1.  The reference's cz -> distance table is integrated
- * with GSL (utils/set_cosmo_dist.c), whose rounding cannot be reproduced without it, so that branch is refused
- * loudly instead of being approximated.  RA / DEC out of range are shifted in place like the reference does
+ * as cz in km/s (options->is_comoving_dist = 0) or as a comoving distance (= 1).  cz is converted like the reference
+ * does: its own redshift -> distance table (utils/set_cosmo_dist.c:27-75, plain Simpson's rule, reproduced bit for
+ * bit) and GSL's linear interpolation, restated from GSL's source because GSL itself is absent (see
+ * corrfunc_b200_cz_to_comoving in corrfunc_b200.h); a redshift outside the table returns EXIT_FAILURE where GSL's
+ * error handler would abort.  RA / DEC out of range are shifted, and redshifts passed as cz are scaled, in place
  * (countpairs_rp_pi_mocks_impl.c.src:43-110).  Line of sight = pair midpoint.  The pair counting runs on the GPU
  * (sm_100a); there is no CPU fallback.
  */

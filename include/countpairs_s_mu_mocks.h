@@ -1,7 +1,7 @@
 /* countpairs_s_mu_mocks.h -- drop-in C ABI for survey-geometry pair counts DD(s, mu) from (RA, DEC, distance).
  * Replaces the reference interface mocks/DDsmu_mocks/countpairs_s_mu_mocks.h:19-43 (Corrfunc v2.5.3): same symbol
  * names, argument order/meaning, result layout and error behaviour.  See countpairs_rp_pi_mocks.h for the input
- * contract (host pointers, degrees, COMOVING distances only: options->is_comoving_dist must be 1).
+ * contract (host pointers, degrees, cz in km/s or comoving distance per options->is_comoving_dist).
  */
 #ifndef CORRFUNC_B200_COUNTPAIRS_S_MU_MOCKS_H
 #define CORRFUNC_B200_COUNTPAIRS_S_MU_MOCKS_H

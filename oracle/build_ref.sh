@@ -50,11 +50,12 @@ SRCS=(
   "$REF/theory/wp/countpairs_wp.c" "$TMP/gen/countpairs_wp_impl_float.c" "$TMP/gen/countpairs_wp_impl_double.c"
   "$REF/theory/xi/countpairs_xi.c" "$TMP/gen/countpairs_xi_impl_float.c" "$TMP/gen/countpairs_xi_impl_double.c"
   "$REF/mocks/DDtheta_mocks/countpairs_theta_mocks.c" "$TMP/gen/countpairs_theta_mocks_impl_float.c" "$TMP/gen/countpairs_theta_mocks_impl_double.c"
-  # SURVEY 8(f) rank 1.  GSL is absent: gsl_shim/ stands in for <gsl/gsl_interp.h> and for set_cosmo_dist (both only
-  # reached with is_comoving_dist == 0, which the tests never use); the reference sources themselves are unmodified.
+  # SURVEY 8(f) rank 1.  GSL is absent: gsl_shim/ stands in for <gsl/gsl_interp.h> (linear interpolation, restated from
+  # GSL's source; only reached with is_comoving_dist == 0) and for the unused <gsl/gsl_integration.h> include of
+  # set_cosmo_dist.c; the reference sources themselves are compiled unmodified.
   "$REF/mocks/DDrppi_mocks/countpairs_rp_pi_mocks.c" "$TMP/gen/countpairs_rp_pi_mocks_impl_float.c" "$TMP/gen/countpairs_rp_pi_mocks_impl_double.c"
   "$REF/mocks/DDsmu_mocks/countpairs_s_mu_mocks.c" "$TMP/gen/countpairs_s_mu_mocks_impl_float.c" "$TMP/gen/countpairs_s_mu_mocks_impl_double.c"
-  "$REF/utils/cosmology_params.c" "$HERE/gsl_shim/cosmo_stub.c"
+  "$REF/utils/cosmology_params.c" "$REF/utils/set_cosmo_dist.c"
   "$TMP/gen/gridlink_impl_float.c" "$TMP/gen/gridlink_impl_double.c"
   "$TMP/gen/gridlink_mocks_impl_float.c" "$TMP/gen/gridlink_mocks_impl_double.c"
   "$TMP/gen/gridlink_utils_float.c" "$TMP/gen/gridlink_utils_double.c"

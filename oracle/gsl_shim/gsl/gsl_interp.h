@@ -1,9 +1,13 @@
 /* TEST INFRASTRUCTURE ONLY -- stand-in for <gsl/gsl_interp.h> (GSL is not installed in this image).
  * The reference's mocks/DDrppi_mocks and mocks/DDsmu_mocks include this header for the cz -> comoving
  * distance table lookup, a branch that runs only when options->is_comoving_dist == 0.  oracle/build_ref.sh
- * puts this directory on the include path so the UNMODIFIED reference sources compile; the parity tests
- * only ever call them with is_comoving_dist = 1 (distances given), where none of this is reached.
- * Written from the documented GSL interface (linear interpolation); no GSL code is used. */
+ * puts this directory on the include path so the UNMODIFIED reference sources compile.  Restated from GSL 2.x's
+ * published source -- interpolation/linear.c:linear_eval (y_lo + (x - x_lo) / dx * (y_hi - y_lo)) and
+ * interpolation/bsearch.c:gsl_interp_bsearch (bisection to x_array[i] <= x < x_array[i+1]); the accelerator only
+ * caches the bracket, so it is ignored.  Out-of-range x: GSL raises GSL_EDOM (its default handler aborts); here NaN.
+ * Parity for cz input is therefore pinned on the reference's own table code (utils/set_cosmo_dist.c, compiled
+ * unmodified) plus this restatement of a 10-line GSL routine -- stated as such in DESIGN.md section 4c. */
+#include <math.h>
 #pragma once
 #include <stdlib.h>
 
@@ -33,6 +37,7 @@ static inline double gsl_interp_eval(const gsl_interp *p, const double *x, const
 {
     size_t lo = 0, hi = p->size - 1;
     (void)a;
+    if (xv < x[0] || xv > x[p->size - 1]) return NAN;
     while (hi - lo > 1) {
         const size_t mid = (lo + hi) / 2;
         if (x[mid] > xv) hi = mid; else lo = mid;

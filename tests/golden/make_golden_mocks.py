@@ -36,4 +36,21 @@ for dtype in (np.float64, np.float32):
         for k in ("npairs", "ravg", "weightavg"):
             out["DDsmu_mocks_%s__%s" % (tag, k)] = r[k]
         print(np.dtype(dtype).name, tag, int(out["DDrppi_mocks_%s__npairs" % tag].sum()), int(out["DDsmu_mocks_%s__npairs" % tag].sum()))
+    # cz input (is_comoving_dist = 0): the reference's own distance table (utils/set_cosmo_dist.c, compiled unmodified)
+    # + GSL's linear interpolation as restated in oracle/gsl_shim; cz = 60 * (the distances above), cosmology 2
+    cz, cz2 = (d * dtype(60.0)).astype(dtype), (d2 * dtype(60.0)).astype(dtype)
+    o = _capi.default_options(dtype, need_avg_sep=True, isa=H.ref_isa(), is_comoving_dist=False)
+    r = _capi.call_DDrppi_mocks(ref, 0, 2, os.cpu_count(), PIMAX, edges, ra, dec, cz, RA2=ra2, DEC2=dec2, CZ2=cz2, options=o)
+    out["DDrppi_mocks_cz_cross__npairs"], out["DDrppi_mocks_cz_cross__ravg"] = r["npairs"], r["ravg"]
+    o = _capi.default_options(dtype, need_avg_sep=True, isa=H.ref_isa(), is_comoving_dist=False)
+    r = _capi.call_DDsmu_mocks(ref, 1, 2, os.cpu_count(), MU_MAX, NMU, edges, ra, dec, cz, options=o)
+    out["DDsmu_mocks_cz_auto__npairs"], out["DDsmu_mocks_cz_auto__ravg"] = r["npairs"], r["ravg"]
+    print(np.dtype(dtype).name, "cz", int(out["DDrppi_mocks_cz_cross__npairs"].sum()), int(out["DDsmu_mocks_cz_auto__npairs"].sum()))
+    # a sample of the reference's redshift -> distance table itself
+    import ctypes as C
+    ref.set_cosmo_dist.restype = C.c_int
+    for cosmo in (1, 2):
+        zc, dc = np.zeros(10000), np.zeros(10000)
+        n = ref.set_cosmo_dist(C.c_double(0.35), C.c_int(10000), zc.ctypes.data_as(C.c_void_p), dc.ctypes.data_as(C.c_void_p), C.c_int(cosmo))
+        out["table%d_n" % cosmo], out["table%d_zc" % cosmo], out["table%d_dc" % cosmo] = n, zc[:n:97].copy(), dc[:n:97].copy()
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_mocks_%s.npz" % np.dtype(dtype).name), **out)

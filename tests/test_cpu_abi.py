@@ -98,8 +98,6 @@ def test_bad_inputs_rejected_before_the_device():
         T.DDsmu(1, 1, [0.1, 1.0], 1.5, 10, x, x, x, boxsize=10.0)
     import corrfunc_b200.mocks as M
 
-    with pytest.raises(NotImplementedError):  # cz -> comoving distance needs the reference's GSL table
-        M.DDrppi_mocks(1, 1, 1, 10.0, [0.1, 1.0], x, x, x + 100.0)
     with pytest.raises(ValueError):
         M.DDsmu_mocks(0, 1, 1, 0.5, 4, [0.1, 1.0], x, x, x + 100.0, is_comoving_dist=True)  # cross without second set
     with pytest.raises(ValueError):

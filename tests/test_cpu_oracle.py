@@ -287,3 +287,57 @@ def test_oracle_literal_equals_default_for_DD_xi_on_small_inputs(stat, periodic,
         lib.oracle_set_literal_kernels(0)
     assert np.array_equal(a["npairs"], b["npairs"])
     assert np.allclose(a["ravg"], b["ravg"], rtol=1e-12) and np.allclose(a["weightavg"], b["weightavg"], rtol=1e-12)
+
+
+def _cz_to_comoving(cz, cosmology):
+    import ctypes as C
+
+    from corrfunc_b200 import _lib
+
+    lib = _lib.load()
+    lib.corrfunc_b200_cz_to_comoving.restype = C.c_int
+    out = np.zeros_like(cz)
+    st = lib.corrfunc_b200_cz_to_comoving(C.c_int(cz.itemsize), C.c_int64(cz.size), cz.ctypes.data_as(C.c_void_p),
+                                          C.c_int(cosmology), out.ctypes.data_as(C.c_void_p))
+    if st != 0:
+        raise RuntimeError("corrfunc_b200_cz_to_comoving failed")
+    return out
+
+
+@pytest.mark.parametrize("cosmology", [1, 2])
+def test_redshift_distance_table_is_the_references(cosmology):
+    """corrfunc_b200_cosmo_dist_table (host code, no GPU) against a committed sample of the table the reference's
+    utils/set_cosmo_dist.c produces -- every 97th of its 3499 entries up to z = 0.35, bit for bit."""
+    import ctypes as C
+
+    from corrfunc_b200 import _lib
+
+    g = np.load(os.path.join(H.GOLDEN, "ref_mocks_float64.npz"))
+    lib = _lib.load()
+    lib.corrfunc_b200_cosmo_dist_table.restype = C.c_int
+    zc, dc = np.zeros(10000), np.zeros(10000)
+    n = lib.corrfunc_b200_cosmo_dist_table(C.c_double(0.35), C.c_int(10000), zc.ctypes.data_as(C.c_void_p),
+                                           dc.ctypes.data_as(C.c_void_p), C.c_int(cosmology))
+    assert n == int(g["table%d_n" % cosmology])
+    assert np.array_equal(zc[:n:97], g["table%d_zc" % cosmology]) and np.array_equal(dc[:n:97], g["table%d_dc" % cosmology])
+    assert lib.corrfunc_b200_cosmo_dist_table(C.c_double(0.35), C.c_int(10000), zc.ctypes.data_as(C.c_void_p),
+                                              dc.ctypes.data_as(C.c_void_p), C.c_int(3)) == -1  # unknown cosmology
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cz_input_matches_committed_reference_outputs(dtype):
+    """is_comoving_dist = 0: the library's host-side cz -> distance conversion (table + linear interpolation), fed to
+    the oracle, reproduces what the reference returns for the cz input itself."""
+    g = np.load(os.path.join(H.GOLDEN, "ref_mocks_%s.npz" % np.dtype(dtype).name))
+    ra, dec, d, _ = H.mock_points(int(g["seed"]), int(g["N1"]), dtype)
+    ra2, dec2, d2, _ = H.mock_points(int(g["seed"]) + 1, int(g["N2"]), dtype)
+    cz, cz2 = (d * dtype(60.0)).astype(dtype), (d2 * dtype(60.0)).astype(dtype)
+    # the table's reach is set by the larger of the two sets; its entries are the same either way
+    D, D2 = _cz_to_comoving(cz, 2), _cz_to_comoving(cz2, 2)
+    a = H.oracle_theory("DDrppi_mocks", ra, dec, D, g["edges"], pimax=float(g["pimax"]), autocorr=False, X2=ra2, Y2=dec2,
+                        Z2=D2, periodic=False)
+    assert np.array_equal(a["npairs"], g["DDrppi_mocks_cz_cross__npairs"])
+    a = H.oracle_theory("DDsmu_mocks", ra, dec, D, g["edges"], mu_max=float(g["mu_max"]), nmu_bins=int(g["nmu"]), periodic=False)
+    assert np.array_equal(a["npairs"], g["DDsmu_mocks_cz_auto__npairs"])
+    with pytest.raises(RuntimeError):  # z < 1e-4: below the table, where GSL would abort the reference
+        _cz_to_comoving(np.full(4, 20.0, dtype=dtype), 1)

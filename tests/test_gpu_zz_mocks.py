@@ -129,8 +129,8 @@ def test_mocks_python_wrappers_and_errors():
     lib = _lib.load()
     with pytest.raises(RuntimeError):  # init_cosmology: only 1 and 2 exist (utils/cosmology_params.c:21-54)
         _capi.call_DDrppi_mocks(lib, 1, 3, 1, 25.0, edges, ra, dec, d, options=_capi.default_options(dtype, is_comoving_dist=True))
-    with pytest.raises(RuntimeError):  # cz input: refused loudly, never approximated
-        _capi.call_DDrppi_mocks(lib, 1, 1, 1, 25.0, edges, ra, dec, d, options=_capi.default_options(dtype))
+    with pytest.raises(RuntimeError):  # cz = 20 km/s is z < 1e-4: below the distance table (the reference's GSL call aborts)
+        _capi.call_DDrppi_mocks(lib, 1, 1, 1, 25.0, edges, ra, dec, np.full_like(d, 20.0), options=_capi.default_options(dtype))
     with pytest.raises(RuntimeError):  # rmin = 0 is not accepted by the mocks statistics
         _capi.call_DDsmu_mocks(lib, 1, 1, 1, 0.8, 4, np.array([0.0, 1.0, 5.0]), ra, dec, d,
                                options=_capi.default_options(dtype, is_comoving_dist=True))

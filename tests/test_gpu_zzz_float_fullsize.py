@@ -11,3 +11,36 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", ["c1f32", "c4f32", "c3f32"])
 def test_full_size_float_twin_vs_reference_golden(name):
     P._check_full_size(name)
+
+
+# ---- cz input of the mocks statistics (is_comoving_dist = 0): host-side conversion, added with the tests above -------
+
+import os  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+import harness as H  # noqa: E402
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_mocks_cz_input_vs_reference_golden(dtype):
+    """countpairs_mocks / countpairs_mocks_s_mu with cz (km/s) instead of distances, against the committed outputs of
+    the reference for the same cz input (its own distance table + GSL's linear interpolation as restated in
+    oracle/gsl_shim).  The conversion is host code and is checked bit for bit on the CPU (tests/test_cpu_oracle.py)."""
+    from corrfunc_b200 import _capi, _lib
+    from corrfunc_b200.mocks import DDsmu_mocks
+
+    g = np.load(os.path.join(H.GOLDEN, "ref_mocks_%s.npz" % np.dtype(dtype).name))
+    ra, dec, d, _ = H.mock_points(int(g["seed"]), int(g["N1"]), dtype)
+    ra2, dec2, d2, _ = H.mock_points(int(g["seed"]) + 1, int(g["N2"]), dtype)
+    cz, cz2 = (d * dtype(60.0)).astype(dtype), (d2 * dtype(60.0)).astype(dtype)
+    o = _capi.default_options(dtype, need_avg_sep=True, is_comoving_dist=False)
+    r = _capi.call_DDrppi_mocks(_lib.load(), 0, 2, 1, float(g["pimax"]), g["edges"], ra, dec, cz, RA2=ra2, DEC2=dec2,
+                                CZ2=cz2, options=o)
+    assert np.array_equal(r["npairs"], g["DDrppi_mocks_cz_cross__npairs"])
+    s = DDsmu_mocks(1, 2, 1, float(g["mu_max"]), int(g["nmu"]), g["edges"], ra, dec, cz)  # the wrapper's default: cz
+    assert np.array_equal(s["npairs"], g["DDsmu_mocks_cz_auto__npairs"].ravel())
+    # redshifts passed where cz is expected (maximum below 10): scaled by the speed of light like the reference does
+    z_in = (cz / dtype(299800.0)).astype(dtype)
+    s2 = DDsmu_mocks(1, 2, 1, float(g["mu_max"]), int(g["nmu"]), g["edges"], ra, dec, z_in)
+    assert abs(int(s2["npairs"].sum()) - int(s["npairs"].sum())) <= 1e-4 * int(s["npairs"].sum())
