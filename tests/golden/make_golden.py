@@ -3,8 +3,10 @@ the GPU box has no /root/reference).  Usage: python tests/golden/make_golden.py
 
 Fixtures:
   Mr19_mock_northonly_radecw.npz  <- mocks/tests/data/Mr19_mock_northonly.rdcz.ff (fast-food binary,
-                                     docs/source/modules/fast_food_binary.rst): RA, DEC, weight as float64
+                                     docs/source/modules/fast_food_binary.rst): RA, DEC, cz, weight as float64
   Mr19_mock_wtheta_DD.txt         <- mocks/tests/Mr19_mock_wtheta.DD (npairs thetaavg thetamin thetamax weightavg)
+  Mr19_mock_DDrppi_DD.txt         <- mocks/tests/Mr19_mock.DD (DDrppi_mocks autocorr, cz input: npairs rpavg . pi_upper weightavg)
+  mocks_bins.txt                  <- mocks/tests/bins
   angular_bins.txt                <- mocks/tests/angular_bins
   theory_bins.txt                 <- theory/tests/bins (14 log bins 0.1675-23.8755)
   ref_synthetic_*.npz             <- outputs of the UNMODIFIED reference (oracle/_ref, AVX-512 kernels) on small
@@ -52,7 +54,11 @@ def synthetic_inputs(seed, n, boxsize, dtype):
 
 def main():
     ra, dec, cz, w = read_fastfood(os.path.join(REF, "mocks/tests/data/Mr19_mock_northonly.rdcz.ff"))
-    np.savez_compressed(os.path.join(HERE, "Mr19_mock_northonly_radecw.npz"), ra=ra, dec=dec, w=w)
+    np.savez_compressed(os.path.join(HERE, "Mr19_mock_northonly_radecw.npz"), ra=ra, dec=dec, w=w, cz=cz)
+    # the reference's own known-answer file for DDrppi_mocks on this catalogue (cz input, cosmology 1, pimax 40;
+    # Corrfunc/tests/test_mocks.py:15-34) and its rp bins
+    shutil.copy(os.path.join(REF, "mocks/tests/Mr19_mock.DD"), os.path.join(HERE, "Mr19_mock_DDrppi_DD.txt"))
+    shutil.copy(os.path.join(REF, "mocks/tests/bins"), os.path.join(HERE, "mocks_bins.txt"))
     shutil.copy(os.path.join(REF, "mocks/tests/Mr19_mock_wtheta.DD"), os.path.join(HERE, "Mr19_mock_wtheta_DD.txt"))
     shutil.copy(os.path.join(REF, "mocks/tests/angular_bins"), os.path.join(HERE, "angular_bins.txt"))
     shutil.copy(os.path.join(REF, "theory/tests/bins"), os.path.join(HERE, "theory_bins.txt"))

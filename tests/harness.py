@@ -189,6 +189,17 @@ def load_mr19_mock():
     return d["ra"], d["dec"], d["w"]
 
 
+def load_mr19_mock_cz():
+    d = np.load(os.path.join(GOLDEN, "Mr19_mock_northonly_radecw.npz"))
+    return d["ra"], d["dec"], d["cz"], d["w"]
+
+
+def load_ddrppi_mocks_golden():
+    """mocks/tests/Mr19_mock.DD: rows rp-major x 40 pi bins; columns npairs rpavg . pi_upper weightavg."""
+    g = np.loadtxt(os.path.join(GOLDEN, "Mr19_mock_DDrppi_DD.txt"))
+    return dict(npairs=g[:, 0].astype(np.uint64), ravg=g[:, 1], weightavg=g[:, 4])
+
+
 def load_wtheta_golden():
     g = np.loadtxt(os.path.join(GOLDEN, "Mr19_mock_wtheta_DD.txt"))
     return dict(npairs=g[:, 0].astype(np.uint64), ravg=g[:, 1], weightavg=g[:, 4])

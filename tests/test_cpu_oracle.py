@@ -341,3 +341,20 @@ def test_cz_input_matches_committed_reference_outputs(dtype):
     assert np.array_equal(a["npairs"], g["DDsmu_mocks_cz_auto__npairs"])
     with pytest.raises(RuntimeError):  # z < 1e-4: below the table, where GSL would abort the reference
         _cz_to_comoving(np.full(4, 20.0, dtype=dtype), 1)
+
+
+def test_oracle_matches_reference_golden_DDrppi_mocks():
+    """The reference's own known-answer test for DDrppi_mocks (Corrfunc/tests/test_mocks.py:15-34): autocorrelation of
+    the Mr19 mock from RA, DEC and **cz** (cosmology 1, pimax 40, PAIR_PRODUCT weights, rpavg) vs
+    mocks/tests/Mr19_mock.DD -- a file written upstream by a build with the real GSL.  All 560 npairs exact and the
+    averages to the file's print precision: this pins the whole cz path (distance table, the restated GSL
+    interpolation, the Cartesian conversion, the pair-midpoint arithmetic)."""
+    ra, dec, cz, w = H.load_mr19_mock_cz()
+    bins = H.load_bins_file("mocks_bins.txt")
+    gold = H.load_ddrppi_mocks_golden()
+    D = _cz_to_comoving(cz, 1)
+    a = H.oracle_theory("DDrppi_mocks", ra, dec, D, bins, pimax=40.0, w1=w, weight_type="pair_product", need_avg=True,
+                        periodic=False)
+    assert np.array_equal(a["npairs"].ravel(), gold["npairs"])
+    assert np.allclose(a["ravg"].ravel(), gold["ravg"], atol=1e-8, rtol=1e-6)  # common.py:83-105 tolerances
+    assert np.allclose(a["weightavg"].ravel(), gold["weightavg"], atol=1e-8, rtol=1e-6)

@@ -44,3 +44,17 @@ def test_mocks_cz_input_vs_reference_golden(dtype):
     z_in = (cz / dtype(299800.0)).astype(dtype)
     s2 = DDsmu_mocks(1, 2, 1, float(g["mu_max"]), int(g["nmu"]), g["edges"], ra, dec, z_in)
     assert abs(int(s2["npairs"].sum()) - int(s["npairs"].sum())) <= 1e-4 * int(s["npairs"].sum())
+
+
+def test_DDrppi_mocks_reference_golden_file():
+    """The reference's own known-answer test (Corrfunc/tests/test_mocks.py:15-34): DDrppi_mocks autocorr of the Mr19
+    mock from RA, DEC, cz vs mocks/tests/Mr19_mock.DD, atol 1e-9 / rtol 1e-6 as in common.py:83-105."""
+    from corrfunc_b200.mocks import DDrppi_mocks
+
+    ra, dec, cz, w = H.load_mr19_mock_cz()
+    bins = H.load_bins_file("mocks_bins.txt")
+    gold = H.load_ddrppi_mocks_golden()
+    r = DDrppi_mocks(1, 1, 4, 40.0, bins, ra, dec, cz, weights1=w, weight_type="pair_product", output_rpavg=True)
+    assert np.array_equal(r["npairs"], gold["npairs"])
+    assert np.allclose(r["rpavg"], gold["ravg"], atol=1e-9, rtol=1e-6)
+    assert np.allclose(r["weightavg"], gold["weightavg"], atol=1e-9, rtol=1e-6)
