@@ -42,5 +42,18 @@ dd2 = rng.integers(0, 10 ** 6, n2).astype(np.uint64)
 dr2 = rng.integers(0, 3 * 10 ** 6, n2).astype(np.uint64)
 out.update(wp_N=np.array([ND1, ND1, NR1, NR1]), wp_dd=dd2, wp_dr=dr2, wp_rr=rr2, wp_nrp=nrp, wp_pimax=pimax, wp_dpi=dpi,
            wp_out=ref.convert_rp_pi_counts_to_wp(ND1, ND1, NR1, NR1, dd2, dr2, dr2, rr2, nrp, pimax, dpi=dpi))
+# the smaller helpers of Corrfunc/utils.py (gridlink_sphere :599-863, compute_nbins :521-596)
+SPHERE_CASES = [dict(thetamax=10.0), dict(thetamax=3.0, link_in_ra=False),
+                dict(thetamax=2.5, ra_limits=[20.0, 200.0], dec_limits=[-30.0, 65.0], ra_refine_factor=2, dec_refine_factor=3),
+                dict(thetamax=0.4, max_ra_cells=37, max_dec_cells=50), dict(thetamax=0.2, dec_limits=[-1.5, 1.5], input_in_degrees=False)]
+for i, kw in enumerate(SPHERE_CASES):
+    if kw.get("link_in_ra", True):
+        grid, nra = ref.gridlink_sphere(return_num_ra_cells=True, **kw)
+        out["sphere%d_nra" % i] = nra
+    else:
+        grid = ref.gridlink_sphere(**kw)
+    out["sphere%d_dec" % i], out["sphere%d_ra" % i] = grid["dec_limit"], grid["ra_limit"]
+out["nbins_cases"] = np.array([[180.0, 10.0, 1, 0], [180.0, 10.0, 2, 20], [0.5, 10.0, 3, 0], [359.9, 0.7, 2, 100]])
+out["nbins_out"] = np.array([ref.compute_nbins(a, b, refine_factor=int(c), max_nbins=int(d) or None) for a, b, c, d in out["nbins_cases"]])
 np.savez(os.path.join(os.path.dirname(os.path.abspath(__file__)), "estimators.npz"), **out)
 print("wrote estimators.npz", {k: np.asarray(v).shape for k, v in out.items()})

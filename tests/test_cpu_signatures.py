@@ -15,9 +15,9 @@ def _ours(name):
         import corrfunc_b200.mocks as M
 
         return getattr(M, name)
-    if name.startswith("convert_"):
-        import corrfunc_b200.utils as U
+    import corrfunc_b200.utils as U
 
+    if hasattr(U, name):
         return getattr(U, name)
     import corrfunc_b200.theory as T
 
