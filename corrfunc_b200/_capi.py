@@ -135,6 +135,11 @@ class ResultsMocksSMu(ResultsSMu):  # results_countpairs_mocks_s_mu (countpairs_
     pass
 
 
+class ResultsVpfMocks(C.Structure):  # results_countspheres_mocks (mocks/vpf_mocks/countspheres_mocks.h:20-26)
+    _fields_ = [("pN", C.POINTER(C.POINTER(C.c_double))), ("rmax", C.c_double), ("nbin", C.c_int), ("nc", C.c_int),
+                ("num_pN", C.c_int)]
+
+
 class ResultsWp(C.Structure):
     _fields_ = [("npairs", _u64p), ("wp", _f64p), ("rupp", _f64p), ("rpavg", _f64p), ("weightavg", _f64p),
                 ("pimax", C.c_double), ("nbin", C.c_int)]
@@ -276,13 +281,20 @@ def _declare(lib):
         lib.free_results_mocks.argtypes = [C.POINTER(ResultsMocksRpPi)]
         lib.free_results_mocks_s_mu.argtypes = [C.POINTER(ResultsMocksSMu)]
         lib.free_results_mocks.restype = lib.free_results_mocks_s_mu.restype = None
+    if hasattr(lib, "countspheres_mocks"):  # mocks/vpf_mocks
+        lib.countspheres_mocks.argtypes = [i64, vp, vp, vp, i64, vp, vp, vp, ci, cd, ci, ci, ci, cs, ci,
+                                           C.POINTER(ResultsVpfMocks), C.POINTER(ConfigOptions), C.POINTER(ExtraOptions)]
+        lib.countspheres_mocks.restype = ci
+        lib.free_results_countspheres_mocks.argtypes = [C.POINTER(ResultsVpfMocks)]
+        lib.free_results_countspheres_mocks.restype = None
     lib._cf_declared = True
 
 
 EXPORTED_SYMBOLS = ("countpairs", "free_results", "countpairs_rp_pi", "free_results_rp_pi", "countpairs_s_mu",
                     "free_results_s_mu", "countpairs_wp", "free_results_wp", "countpairs_xi", "free_results_xi",
                     "countpairs_theta_mocks", "free_results_countpairs_theta", "countpairs_mocks", "free_results_mocks",
-                    "countpairs_mocks_s_mu", "free_results_mocks_s_mu", "countpairs_mocks_float",
+                    "countpairs_mocks_s_mu", "free_results_mocks_s_mu", "countspheres_mocks",
+                    "free_results_countspheres_mocks", "countpairs_mocks_float",
                     "countpairs_mocks_double", "countpairs_mocks_s_mu_float", "countpairs_mocks_s_mu_double") + tuple(
     "%s_%s" % (f, t) for f in ("countpairs", "countpairs_rp_pi", "countpairs_s_mu", "countpairs_wp", "countpairs_xi",
                                "countpairs_theta_mocks") for t in ("float", "double"))
@@ -433,6 +445,30 @@ def call_DDsmu_mocks(lib, autocorr, cosmology, nthreads, mu_max, nmu_bins, bins,
                ravg=grid(res.savg, np.float64), weightavg=grid(res.weightavg, np.float64), nmu_bins=nmu,
                mu_max=res.mu_max, api_time=options.c_api_time)
     lib.free_results_mocks_s_mu(C.byref(res))
+    return out
+
+
+def call_vpf_mocks(lib, rmax, nbin, nc, num_pN, threshold_neighbors, centers_file, cosmology, RA, DEC, CZ,
+                   RAND_RA=None, RAND_DEC=None, RAND_CZ=None, options=None, dtype=None):
+    """countspheres_mocks (mocks/vpf_mocks/countspheres_mocks.h:28-37): counts-in-spheres -> pN[nbin][num_pN]."""
+    _declare(lib)
+    dtype = np.dtype(dtype or np.asarray(RA).dtype)
+    arrs = [None if a is None else np.array(a, dtype=dtype, order="C", copy=True)
+            for a in (RA, DEC, CZ, RAND_RA, RAND_DEC, RAND_CZ)]
+    RA, DEC, CZ, RR, RD, RC = arrs
+    if RR is None:
+        RR, RD, RC = RA, DEC, CZ
+    extra, keep = make_extra(None, None, None, dtype)
+    res = ResultsVpfMocks()
+    st = lib.countspheres_mocks(RA.size, _ptr(RA), _ptr(DEC), _ptr(CZ), RR.size, _ptr(RR), _ptr(RD), _ptr(RC),
+                                int(threshold_neighbors), float(rmax), int(nbin), int(nc), int(num_pN),
+                                os.fsencode(centers_file), int(cosmology), C.byref(res), C.byref(options),
+                                C.byref(extra))
+    if st != 0:
+        raise RuntimeError("countspheres_mocks returned %d" % st)
+    pN = np.array([[res.pN[i][j] for j in range(res.num_pN)] for i in range(res.nbin)], dtype=np.float64)
+    out = dict(pN=pN, rmax=res.rmax, nbin=res.nbin, nc=res.nc, api_time=options.c_api_time)
+    lib.free_results_countspheres_mocks(C.byref(res))
     return out
 
 

@@ -1,0 +1,159 @@
+// spheres.cu -- counts-in-spheres for the void probability function on survey catalogues
+// (mocks/vpf_mocks/countspheres_mocks_impl.c.src:206-638, vpf_mocks_kernels.c.src:20-100).
+//
+// One warp per sphere centre: the particles of the 27 lattice cells around the centre are tried against it, lanes
+// striding over a cell's contiguous run in the cell-sorted SoA (coalesced).  The per-centre shell counts live in the
+// warp's slice of shared memory (native 32-bit ATOMS.ADD) and are written out once.  HBM/L2 bound in principle
+// (each centre re-reads ~27 cells that its neighbours also read, so they come from L2); the work is tiny next to the
+// pair counts: 1e5 centres x a few hundred candidates each.
+#include <math_constants.h>
+
+#include "cfb_internal.cuh"
+
+static DevBuf g_cen[3], g_out, g_edges;
+
+template <typename T>
+__device__ __forceinline__ T sph_fma(T a, T b, T c);
+template <>
+__device__ __forceinline__ float sph_fma<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <>
+__device__ __forceinline__ double sph_fma<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// SHELLS = true : r2 = fma(dz,dz, fma(dy,dy, dx*dx)) and the AVX-512 kernel's shell assignment (vpf_mocks_kernels:63-92)
+// SHELLS = false: r2 = dx*dx + dy*dy + dz*dz and a plain count of r2 < rmax_sqr (count_neighbors, impl:140-204)
+template <typename T, bool SHELLS>
+__global__ void k_spheres(const int64_t ncen, const T *__restrict__ xc, const T *__restrict__ yc, const T *__restrict__ zc,
+                          const SetView<T> B, const int n0, const int n1, const int n2, const T inv, const T rmax_sqr,
+                          const int nbin, const T *__restrict__ edges, unsigned *__restrict__ out)
+{
+    extern __shared__ unsigned char sph_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    T *s_E = (T *)sph_smem;
+    unsigned *s_cnt = (unsigned *)(sph_smem + (((size_t)nbin * sizeof(T) + 15) & ~(size_t)15)) + (size_t)wid * nbin;
+    for (int k = threadIdx.x; k < nbin; k += blockDim.x) s_E[k] = SHELLS ? edges[k] : (T)0;
+    for (int k = lane; k < nbin; k += 32) s_cnt[k] = 0u;
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * nw + wid;
+    if (c >= ncen) return;
+    const T X = xc[c], Y = yc[c], Z = zc[c];
+    int ix = (int)(X * inv), iy = (int)(Y * inv), iz = (int)(Z * inv);
+    ix = min(max(ix, 0), n0 - 1);
+    iy = min(max(iy, 0), n1 - 1);
+    iz = min(max(iz, 0), n2 - 1);
+    for (int cx = max(ix - 1, 0); cx <= min(ix + 1, n0 - 1); cx++)
+        for (int cy = max(iy - 1, 0); cy <= min(iy + 1, n1 - 1); cy++)
+            for (int cz = max(iz - 1, 0); cz <= min(iz + 1, n2 - 1); cz++) {
+                const int cell = (cx * n1 + cy) * n2 + cz;
+                const int n = B.count[cell], s0 = B.start[cell];
+                for (int j = lane; j < n; j += 32) {
+                    const T dx = X - B.x[s0 + j], dy = Y - B.y[s0 + j], dz = Z - B.z[s0 + j];
+                    if (SHELLS) {
+                        const T r2 = sph_fma<T>(dz, dz, sph_fma<T>(dy, dy, dx * dx));
+                        if (!(r2 < rmax_sqr)) continue;
+                        // lane by lane what the masked loop over k = nbin-1 .. 1 does: the shell with E[k-1] <= r2 < E[k];
+                        // whoever is left after k == 1 goes to shell 0; with one shell the loop never runs
+                        bool left = true;
+                        for (int k = nbin - 1; k >= 1; k--)
+                            if (r2 < s_E[k] && r2 >= s_E[k - 1]) {
+                                atomicAdd(&s_cnt[k], 1u);
+                                left = false;
+                                break;
+                            }
+                        if (left && nbin >= 2) atomicAdd(&s_cnt[0], 1u);
+                    } else {
+                        const T r2 = dx * dx + dy * dy + dz * dz;  // -fmad=false: no contraction
+                        if (r2 < rmax_sqr) atomicAdd(&s_cnt[0], 1u);
+                    }
+                }
+            }
+    __syncwarp();
+    for (int k = lane; k < nbin; k += 32) out[c * nbin + k] = s_cnt[k];
+}
+
+template <typename T>
+static int count_spheres_T(Ctx &c, ParticleSet &S, double extent, int regrid, int64_t ncen, const void *xc, const void *yc,
+                           const void *zc, double rmax, double rmax_sqr, int nbin, const double *edges, int shells,
+                           uint32_t *counts)
+{
+    // internal lattice over [0, extent]^3: cells a little larger than rmax, so that the 27 cells around a centre hold
+    // every particle within rmax whatever way the two cell indices round; the counts do not depend on this choice
+    int nm = (int)floor(extent / (rmax * 1.001));
+    nm = nm < 1 ? 1 : (nm > 128 ? 128 : nm);
+    if (regrid || !S.gridded) {
+        cfb_box_lattice lat;
+        memset(&lat, 0, sizeof(lat));
+        for (int k = 0; k < 3; k++) {
+            lat.nmesh[k] = nm;
+            lat.refine[k] = 1;
+            lat.lo[k] = 0.0;
+            lat.inv[k] = (double)((T)nm / (T)extent);
+            lat.max_sep[k] = -1.0;
+        }
+        const int sub[3] = {1, 1, 1};
+        if (cfb_gridlink_box_set(S, &lat, sub, 1.0)) return 1;
+    }
+    const size_t cb = (size_t)(ncen > 0 ? ncen : 1) * sizeof(T);
+    const void *src[3] = {xc, yc, zc};
+    for (int a = 0; a < 3; a++) {
+        if (cfb_ensure(g_cen[a], cb)) return 1;
+        CK(cudaMemcpyAsync(g_cen[a].p, src[a], (size_t)ncen * sizeof(T), cudaMemcpyHostToDevice, c.stream));
+    }
+    if (cfb_ensure(g_out, (size_t)(ncen > 0 ? ncen : 1) * nbin * 4)) return 1;
+    if (cfb_ensure(g_edges, (size_t)nbin * sizeof(T))) return 1;
+    if (shells) {
+        T *h = (T *)malloc((size_t)nbin * sizeof(T));
+        if (!h) return cfb_fail("out of host memory");
+        for (int k = 0; k < nbin; k++) h[k] = (T)edges[k];
+        cudaError_t e = cudaMemcpyAsync(g_edges.p, h, (size_t)nbin * sizeof(T), cudaMemcpyHostToDevice, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        free(h);
+        if (e != cudaSuccess) return cfb_fail("CUDA error %s uploading the shell edges", cudaGetErrorName(e));
+    }
+    if (ncen > 0) {
+        SetView<T> V;
+        V.x = (const T *)S.sorted[0].p;
+        V.y = (const T *)S.sorted[1].p;
+        V.z = (const T *)S.sorted[2].p;
+        V.w = nullptr;
+        V.count = (const int *)S.count.p;
+        V.start = (const int *)S.start.p;
+        V.bounds = (const T *)S.bounds.p;
+        const int warps = 8;
+        const size_t smem = (((size_t)nbin * sizeof(T) + 15) & ~(size_t)15) + (size_t)warps * nbin * 4;
+        if (smem > 96 * 1024) return cfb_fail("too many radial bins (%d) for the counts-in-spheres kernel", nbin);
+        const int64_t nblk = (ncen + warps - 1) / warps;
+        if (nblk >= 2147483647LL) return cfb_fail("too many sphere centres (%lld)", (long long)ncen);
+        const T inv = (T)nm / (T)extent;
+        if (shells) {
+            CK(cudaFuncSetAttribute(k_spheres<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            k_spheres<T, true><<<(unsigned)nblk, warps * 32, smem, c.stream>>>(
+                ncen, (const T *)g_cen[0].p, (const T *)g_cen[1].p, (const T *)g_cen[2].p, V, nm, nm, nm, inv, (T)rmax_sqr,
+                nbin, (const T *)g_edges.p, (unsigned *)g_out.p);
+        } else {
+            CK(cudaFuncSetAttribute(k_spheres<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            k_spheres<T, false><<<(unsigned)nblk, warps * 32, smem, c.stream>>>(
+                ncen, (const T *)g_cen[0].p, (const T *)g_cen[1].p, (const T *)g_cen[2].p, V, nm, nm, nm, inv, (T)rmax_sqr,
+                nbin, (const T *)g_edges.p, (unsigned *)g_out.p);
+        }
+        c.launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(counts, g_out.p, (size_t)ncen * nbin * 4, cudaMemcpyDeviceToHost, c.stream));
+    }
+    CK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+extern "C" int cfb_count_spheres(int slot, int prec, double extent, int regrid, int64_t ncen, const void *xc, const void *yc,
+                                 const void *zc, double rmax, double rmax_sqr, int nbin, const double *edges, int shells,
+                                 uint32_t *counts)
+{
+    Ctx &c = cfb_ctx();
+    if (!c.ready) return cfb_fail("cfb_count_spheres before cfb_upload");
+    if (slot < 0 || slot > 1) return cfb_fail("bad particle slot %d", slot);
+    CK(cudaSetDevice(c.dev));
+    ParticleSet &S = c.set[slot];
+    if (S.prec != prec) return cfb_fail("particle set %d precision mismatch", slot);
+    if (!(extent > 0.0) || !(rmax > 0.0) || nbin < 1) return cfb_fail("bad counts-in-spheres parameters");
+    return prec == 4 ? count_spheres_T<float>(c, S, extent, regrid, ncen, xc, yc, zc, rmax, rmax_sqr, nbin, edges, shells, counts)
+                     : count_spheres_T<double>(c, S, extent, regrid, ncen, xc, yc, zc, rmax, rmax_sqr, nbin, edges, shells, counts);
+}

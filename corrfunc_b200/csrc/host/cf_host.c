@@ -20,6 +20,7 @@
 #include "countpairs.h"
 #include "countpairs_rp_pi.h"
 #include "countpairs_rp_pi_mocks.h"
+#include "countspheres_mocks.h"
 #include "countpairs_s_mu.h"
 #include "countpairs_s_mu_mocks.h"
 #include "countpairs_theta_mocks.h"
@@ -201,6 +202,11 @@ typedef struct {
     double *wavg;     /* [nslots] */
     double *cf;       /* [nbin] xi or wp, NULL otherwise */
 } cf_box_out;
+
+typedef struct { /* counts-in-spheres result (cf_vpf_mocks) */
+    int nbin, num_pN;
+    double **pN;
+} cf_vpf_out;
 
 #define REAL float
 #define SFX f32
@@ -513,6 +519,44 @@ int countpairs_mocks_s_mu(const int64_t ND1, void *phi1, void *theta1, void *czD
     results->savg = o.avg;
     results->weightavg = o.wavg;
     free(o.cf);
+    return EXIT_SUCCESS;
+}
+
+/* ---- counts-in-spheres: mocks/vpf_mocks/countspheres_mocks.c ---- */
+void free_results_countspheres_mocks(results_countspheres_mocks *r)
+{
+    if (r == NULL || r->pN == NULL) return;
+    for (int i = 0; i < r->nbin; i++) free(r->pN[i]);
+    free(r->pN);
+    r->pN = NULL;
+}
+
+int countspheres_mocks(const int64_t Ngal, void *xgal, void *ygal, void *zgal, const int64_t Nran, void *xran, void *yran,
+                       void *zran, const int threshold_neighbors, const double rmax, const int nbin, const int nc,
+                       const int num_pN, const char *centers_file, const int cosmology, results_countspheres_mocks *results,
+                       struct config_options *options, struct extra_options *extra)
+{
+    (void)extra;
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_vpf_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_vpf_mocks_f32(Ngal, xgal, ygal, zgal, Nran, xran, yran, zran, threshold_neighbors, (float)rmax, nbin, nc,
+                                          num_pN, centers_file, cosmology, options, &o)
+                       : cf_vpf_mocks_f64(Ngal, xgal, ygal, zgal, Nran, xran, yran, zran, threshold_neighbors, rmax, nbin, nc,
+                                          num_pN, centers_file, cosmology, options, &o);
+    if (st != EXIT_SUCCESS) {
+        if (o.pN) {
+            for (int i = 0; i < nbin; i++) free(o.pN[i]);
+            free(o.pN);
+        }
+        return st;
+    }
+    results->rmax = rmax;
+    results->nbin = nbin;
+    results->nc = nc;
+    results->num_pN = num_pN;
+    results->pN = o.pN;
     return EXIT_SUCCESS;
 }
 

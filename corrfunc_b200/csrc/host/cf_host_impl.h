@@ -611,6 +611,210 @@ static int HFN(cf_mocks)(const int mode, const int64_t ND1, void *vra1, void *vd
 }
 
 /* ========================================================================================== */
+/* vpf_mocks: counts-in-spheres (mocks/vpf_mocks/countspheres_mocks_impl.c.src:206-638)                          */
+
+static int HFN(cf_vpf_mocks)(const int64_t Ngal, void *vra, void *vdec, void *vcz, const int64_t Nran, void *vrra,
+                             void *vrdec, void *vrcz, const int threshold_neighbors, const REAL rmax, const int nbin,
+                             const int nc, const int num_pN, const char *centers_file, const int cosmology,
+                             struct config_options *options, cf_vpf_out *out)
+{
+    const double t_start = now_ms();
+    if (options->float_type != sizeof(REAL)) {
+        fprintf(stderr, "ERROR: In %s> Can only handle arrays of size=%zu. Got an array of size = %zu\n", __func__,
+                sizeof(REAL), options->float_type);
+        return EXIT_FAILURE;
+    }
+    if (!(rmax > 0.0)) { fprintf(stderr, "rmax=%lf has to be positive", (double)rmax); return EXIT_FAILURE; }
+    if (nbin < 1) { fprintf(stderr, "Number of bins=%d has to be at least 1", nbin); return EXIT_FAILURE; }
+    if (nc < 1) { fprintf(stderr, "Number of spheres=%d has to be at least 1", nc); return EXIT_FAILURE; }
+    if (num_pN < 1) { fprintf(stderr, "Number of pN's=%d requested must be at least 1", num_pN); return EXIT_FAILURE; }
+    if (!(cosmology == 1 || cosmology == 2)) {
+        fprintf(stderr, "ERROR: In %s> Cosmology=%d not implemented\n", "init_cosmology", cosmology);
+        return EXIT_FAILURE;
+    }
+    options->periodic = 0;
+    const REAL *RA = (const REAL *)vra, *DEC = (const REAL *)vdec, *CZ = (const REAL *)vcz;
+    const REAL *RRA = (const REAL *)vrra, *RDEC = (const REAL *)vrdec, *RCZ = (const REAL *)vrcz;
+
+    /* ---- centres file: usable when its first radius covers rmax and it has at least nc lines (:256-283) ---- */
+    int need_randoms = 1;
+    FILE *fpcen = fopen(centers_file, "r");
+    if (fpcen != NULL) {
+        double rr = 0.0;
+        if (fscanf(fpcen, "%*f %*f %*f %lf", &rr) != 1) {
+            fprintf(stderr, "Could not read max. sphere radius from the centers file");
+            fclose(fpcen);
+            return EXIT_FAILURE;
+        }
+        if (rr >= rmax && count_data_lines(centers_file) >= nc) {
+            need_randoms = 0;
+            rewind(fpcen);
+        } else {
+            fclose(fpcen);
+            fpcen = NULL;
+        }
+    }
+    if (need_randoms) {
+        fpcen = fopen(centers_file, "w"); /* the reference rewrites the file with the centres it places */
+        if (fpcen == NULL) {
+            fprintf(stderr, "Error: could not open centers file `%s' for writing\n", centers_file);
+            return EXIT_FAILURE;
+        }
+    }
+
+    int status = EXIT_FAILURE;
+    REAL *gal[3] = {NULL, NULL, NULL}, *ran[3] = {NULL, NULL, NULL}, *Dg = NULL, *Dr = NULL;
+    REAL *cen[3] = {NULL, NULL, NULL};
+    uint32_t *counts = NULL, *ngb = NULL;
+    uint64_t *pN = NULL;
+    double *edges = NULL;
+    const int64_t nr_used = need_randoms ? Nran : 0;
+    for (int a = 0; a < 3; a++) {
+        gal[a] = malloc(sizeof(REAL) * (size_t)(Ngal > 0 ? Ngal : 1));
+        ran[a] = malloc(sizeof(REAL) * (size_t)(nr_used > 0 ? nr_used : 1));
+        cen[a] = malloc(sizeof(REAL) * (size_t)nc);
+    }
+    Dg = malloc(sizeof(REAL) * (size_t)(Ngal > 0 ? Ngal : 1));
+    Dr = malloc(sizeof(REAL) * (size_t)(nr_used > 0 ? nr_used : 1));
+    counts = malloc(sizeof(uint32_t) * (size_t)nc * (size_t)nbin);
+    pN = calloc((size_t)nbin * (size_t)num_pN, sizeof(uint64_t));
+    edges = malloc(sizeof(double) * (size_t)nbin);
+    if (!gal[0] || !gal[1] || !gal[2] || !ran[0] || !ran[1] || !ran[2] || !cen[0] || !cen[1] || !cen[2] || !Dg || !Dr ||
+        !counts || !pN || !edges) {
+        fprintf(stderr, "Error: In %s> out of memory\n", __func__);
+        goto done;
+    }
+
+    /* ---- distances (:285-317), Cartesian positions and the shift into [0, 2 rcube] (:338-392) ---- */
+    if (options->is_comoving_dist == 0) {
+        REAL czmax = 0.0;
+        for (int64_t i = 0; i < Ngal; i++) if (CZ[i] > czmax) czmax = CZ[i];
+        for (int64_t i = 0; i < nr_used; i++) if (RCZ[i] > czmax) czmax = RCZ[i];
+        if (HFN(cf_cz_to_dist)(Ngal, CZ, czmax, cosmology, Dg)) goto done;
+        if (nr_used > 0 && HFN(cf_cz_to_dist)(nr_used, RCZ, czmax, cosmology, Dr)) goto done;
+    } else {
+        memcpy(Dg, CZ, sizeof(REAL) * (size_t)Ngal);
+        if (nr_used > 0) memcpy(Dr, RCZ, sizeof(REAL) * (size_t)nr_used);
+    }
+    REAL rcube = 0.0;
+    for (int64_t i = 0; i < Ngal; i++) {
+        const REAL dc = Dg[i];
+        if (dc > rcube) rcube = dc;
+        gal[0][i] = dc * H_COSD(DEC[i]) * H_COSD(RA[i]);
+        gal[1][i] = dc * H_COSD(DEC[i]) * H_SIND(RA[i]);
+        gal[2][i] = dc * H_SIND(DEC[i]);
+    }
+    for (int64_t i = 0; i < nr_used; i++) {
+        const REAL dc = Dr[i];
+        if (dc > rcube) rcube = dc;
+        ran[0][i] = dc * H_COSD(RDEC[i]) * H_COSD(RRA[i]);
+        ran[1][i] = dc * H_COSD(RDEC[i]) * H_SIND(RRA[i]);
+        ran[2][i] = dc * H_SIND(RDEC[i]);
+    }
+    rcube = rcube + 1.;
+    for (int a = 0; a < 3; a++) {
+        for (int64_t i = 0; i < Ngal; i++) gal[a][i] += rcube;
+        for (int64_t i = 0; i < nr_used; i++) ran[a][i] += rcube;
+    }
+    rcube = 2.0 * rcube;
+
+    if (cfb_upload(0, (int)sizeof(REAL), Ngal, gal[0], gal[1], gal[2], NULL, NULL, NULL)) goto done;
+    if (need_randoms && cfb_upload(1, (int)sizeof(REAL), nr_used, ran[0], ran[1], ran[2], NULL, NULL, NULL)) goto done;
+
+    /* ---- the centres (:470-505) ---- */
+    const REAL rmax_sqr = rmax * rmax;
+    int isucceed = 0;
+    if (!need_randoms) {
+        char buffer[10000];
+        for (; isucceed < nc; isucceed++) {
+            double rr = 0.0, c3[3];
+            if (fgets(buffer, (int)sizeof(buffer), fpcen) == NULL) {
+                fprintf(stderr, "ERROR: Could not read-in co-ordinates for the centers of the randoms spheres from file %s\n", centers_file);
+                goto done;
+            }
+            /* the reference parses straight into REAL ("%f" / "%lf") */
+            const int nitems = REAL_IS_DOUBLE ? sscanf(buffer, "%lf %lf %lf %lf", &c3[0], &c3[1], &c3[2], &rr) : 0;
+            if (REAL_IS_DOUBLE) {
+                if (nitems != 4) { fprintf(stderr, "ERROR in parsing centers file: buffer = `%s' \n", buffer); goto done; }
+                for (int a = 0; a < 3; a++) cen[a][isucceed] = (REAL)c3[a];
+            } else {
+                float f3[3];
+                if (sscanf(buffer, "%f %f %f %lf", &f3[0], &f3[1], &f3[2], &rr) != 4) {
+                    fprintf(stderr, "ERROR in parsing centers file: buffer = `%s' \n", buffer);
+                    goto done;
+                }
+                for (int a = 0; a < 3; a++) cen[a][isucceed] = (REAL)f3[a];
+            }
+            if (!(rr >= rmax)) { fprintf(stderr, "Rmax from the center file is >= rmax"); goto done; }
+        }
+    } else {
+        /* randoms with more than threshold_neighbors randoms (itself included) within rmax, in input order, until nc
+         * are placed (:478-490 with count_neighbors :140-204); the GPU counts a chunk of candidates at a time */
+        const int64_t chunk = 1 << 16;
+        ngb = malloc(sizeof(uint32_t) * (size_t)chunk);
+        if (!ngb) goto done;
+        int first = 1;
+        for (int64_t base = 0; base < Nran && isucceed < nc; base += chunk) {
+            const int64_t m = (Nran - base) < chunk ? (Nran - base) : chunk;
+            if (cfb_count_spheres(1, (int)sizeof(REAL), (double)rcube, first, m, ran[0] + base, ran[1] + base, ran[2] + base,
+                                  (double)rmax, (double)rmax_sqr, 1, NULL, 0, ngb)) goto done;
+            first = 0;
+            for (int64_t i = 0; i < m && isucceed < nc; i++)
+                if ((int64_t)ngb[i] > (int64_t)threshold_neighbors) {
+                    for (int a = 0; a < 3; a++) cen[a][isucceed] = ran[a][base + i];
+                    fprintf(fpcen, "%lf \t %lf \t %lf \t %lf\n", (double)ran[0][base + i], (double)ran[1][base + i],
+                            (double)ran[2][base + i], (double)rmax);
+                    isucceed++;
+                }
+        }
+    }
+    if (isucceed <= 0) {
+        fprintf(stderr, "ERROR: Could not place even a single sphere within the volume. Please reduce the radius of the sphere (currently set to %lf)\n", (double)rmax);
+        goto done;
+    } else if (isucceed < nc) {
+        fprintf(stderr, "WARNING: Could only place `%d' out of requested `%d' spheres. Increase the random-sample size might improve the situation\n", isucceed, nc);
+    }
+
+    /* ---- shell counts per centre on the GPU, then cumulative counts and pN on the host (:565-580) ---- */
+    {
+        const REAL rstep = rmax / (REAL)nbin; /* vpf_mocks_kernels.c.src:38-46 */
+        for (int k = 0; k < nbin; k++) {
+            const REAL e = (k + 1) * rstep * rstep * (k + 1);
+            edges[k] = (double)e;
+        }
+        if (cfb_count_spheres(0, (int)sizeof(REAL), (double)rcube, 1, isucceed, cen[0], cen[1], cen[2], (double)rmax,
+                              (double)rmax_sqr, nbin, edges, 1, counts)) goto done;
+        for (int64_t c = 0; c < isucceed; c++) {
+            uint64_t cum = 0;
+            for (int k = 0; k < nbin; k++) {
+                cum += counts[c * nbin + k];
+                if (cum < (uint64_t)num_pN) pN[(size_t)k * num_pN + cum]++;
+            }
+        }
+    }
+    out->nbin = nbin;
+    out->num_pN = num_pN;
+    out->pN = calloc((size_t)nbin, sizeof(double *));
+    if (!out->pN) goto done;
+    {
+        const REAL inv_nc = ((REAL)1.0) / (REAL)isucceed; /* :616-621 */
+        for (int k = 0; k < nbin; k++) {
+            out->pN[k] = malloc(sizeof(double) * (size_t)num_pN);
+            if (!out->pN[k]) goto done; /* rows allocated so far are released by the caller's free_results */
+            for (int i = 0; i < num_pN; i++) out->pN[k][i] = (double)(REAL)((REAL)pN[(size_t)k * num_pN + i] * inv_nc);
+        }
+    }
+    reset_bin_refine_factors(options);
+    if (options->c_api_timer) options->c_api_time = (now_ms() - t_start) * 1.0e-3;
+    status = EXIT_SUCCESS;
+done:
+    if (fpcen) fclose(fpcen);
+    for (int a = 0; a < 3; a++) { free(gal[a]); free(ran[a]); free(cen[a]); }
+    free(Dg); free(Dr); free(counts); free(ngb); free(pN); free(edges);
+    return status;
+}
+
+/* ========================================================================================== */
 /* DDtheta                                                                                     */
 
 /* find_closest_pos_DOUBLE (utils/gridlink_utils.c.src:91-113): min 1-D separation of two intervals */

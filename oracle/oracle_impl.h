@@ -1269,6 +1269,91 @@ int FN(oracle_theta)(const int64_t ND1, const REAL *RA1, const REAL *DEC1, const
     return EXIT_SUCCESS;
 }
 
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* Counts-in-spheres on a survey catalogue: mocks/vpf_mocks/countspheres_mocks_impl.c.src:206-638 with the        */
+/* AVX-512 kernel of vpf_mocks_kernels.c.src:20-100.  Centres are given (the reference reads them from its        */
+/* centres file, or takes the randoms that pass o_vpf_neighbours below); the result does not depend on the        */
+/* lattice, so every galaxy is tried against every centre.                                                        */
+int FN(oracle_vpf_mocks)(const int64_t Ngal, const REAL *RA, const REAL *DEC, const REAL *D /* comoving */,
+                         const int64_t nc, const REAL *xc, const REAL *yc, const REAL *zc /* shifted, as in the file */,
+                         const double rmax_in, const int nbin, const int num_pN, double *pN_out /* [nbin][num_pN] */,
+                         const double dmax_randoms /* largest distance among the randoms when they are in play, else 0 */,
+                         double *rcube_out)
+{
+    if (!(rmax_in > 0.0) || nbin < 1 || nc < 1 || num_pN < 1) return EXIT_FAILURE;
+    const REAL rmax = rmax_in;
+    REAL *x = malloc(sizeof(REAL) * (Ngal > 0 ? Ngal : 1)), *y = malloc(sizeof(REAL) * (Ngal > 0 ? Ngal : 1)),
+         *z = malloc(sizeof(REAL) * (Ngal > 0 ? Ngal : 1));
+    REAL rcube = (REAL)dmax_randoms; /* :351-372: the randoms widen the bounding cube too */
+    for (int64_t i = 0; i < Ngal; i++) { /* :338-349 */
+        const REAL dc = D[i];
+        if (dc > rcube) rcube = dc;
+        x[i] = dc * COSD_R(DEC[i]) * COSD_R(RA[i]);
+        y[i] = dc * COSD_R(DEC[i]) * SIND_R(RA[i]);
+        z[i] = dc * SIND_R(DEC[i]);
+    }
+    rcube = rcube + 1.; /* :385-392: shift into [0, 2 rcube] */
+    for (int64_t i = 0; i < Ngal; i++) {
+        x[i] += rcube;
+        y[i] += rcube;
+        z[i] += rcube;
+    }
+    if (rcube_out) *rcube_out = (double)rcube;
+    const REAL rstep = rmax / (REAL)nbin; /* vpf_mocks_kernels:38-46 */
+    const REAL rmax_sqr = rmax * rmax;
+    REAL *E = malloc(sizeof(REAL) * nbin);
+    for (int k = 0; k < nbin; k++) E[k] = (k + 1) * rstep * rstep * (k + 1);
+    double *pN = calloc((size_t)nbin * num_pN, sizeof(double));
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        uint64_t *counts = calloc((size_t)nbin, sizeof(uint64_t));
+        double *mine = calloc((size_t)nbin * num_pN, sizeof(double));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+        for (int64_t c = 0; c < nc; c++) {
+            for (int k = 0; k < nbin; k++) counts[k] = 0;
+            for (int64_t j = 0; j < Ngal; j++) {
+                const REAL dx = xc[c] - x[j], dy = yc[c] - y[j], dz = zc[c] - z[j];
+                const REAL r2 = FMA_R(dz, dz, FMA_R(dy, dy, dx * dx));
+                if (!(r2 < rmax_sqr)) continue;
+                /* :80-92 lane by lane: the bin with E[k-1] <= r2 < E[k]; whoever is left after k == 1 lands in bin 0
+                 * (also an r2 at or above the last edge); with a single bin the loop never runs and nothing counts */
+                int left = 1;
+                for (int k = nbin - 1; k >= 1; k--)
+                    if (r2 < E[k] && r2 >= E[k - 1]) {
+                        counts[k]++;
+                        left = 0;
+                        break;
+                    }
+                if (left && nbin >= 2) counts[0]++;
+            }
+            for (int k = 1; k < nbin; k++) counts[k] += counts[k - 1]; /* impl:565-567 */
+            for (int k = 0; k < nbin; k++)
+                if (counts[k] < (uint64_t)num_pN) mine[(size_t)k * num_pN + counts[k]] += 1.0;
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        for (int64_t i = 0; i < (int64_t)nbin * num_pN; i++) pN[i] += mine[i];
+        free(counts);
+        free(mine);
+    }
+    const REAL inv_nc = ((REAL)1.0) / (REAL)nc; /* :616-621, arithmetic in REAL */
+    for (int k = 0; k < nbin; k++)
+        for (int i = 0; i < num_pN; i++) pN_out[(size_t)k * num_pN + i] = (double)(REAL)((REAL)pN[(size_t)k * num_pN + i] * inv_nc);
+    free(pN);
+    free(E);
+    free(x);
+    free(y);
+    free(z);
+    return EXIT_SUCCESS;
+}
+
 #undef FMA_R
 #undef SQRT_R
 #undef FABS_R

@@ -7,6 +7,7 @@ Fixtures:
   Mr19_mock_wtheta_DD.txt         <- mocks/tests/Mr19_mock_wtheta.DD (npairs thetaavg thetamin thetamax weightavg)
   Mr19_mock_DDrppi_DD.txt         <- mocks/tests/Mr19_mock.DD (DDrppi_mocks autocorr, cz input: npairs rpavg . pi_upper weightavg)
   mocks_bins.txt                  <- mocks/tests/bins
+  Mr19_centers_xyz_forVPF_rmax_10Mpc.txt, Mr19_mock_vpf.txt <- mocks/tests/data/..., mocks/tests/Mr19_mock_vpf (vpf_mocks)
   angular_bins.txt                <- mocks/tests/angular_bins
   theory_bins.txt                 <- theory/tests/bins (14 log bins 0.1675-23.8755)
   ref_synthetic_*.npz             <- outputs of the UNMODIFIED reference (oracle/_ref, AVX-512 kernels) on small
@@ -59,6 +60,9 @@ def main():
     # Corrfunc/tests/test_mocks.py:15-34) and its rp bins
     shutil.copy(os.path.join(REF, "mocks/tests/Mr19_mock.DD"), os.path.join(HERE, "Mr19_mock_DDrppi_DD.txt"))
     shutil.copy(os.path.join(REF, "mocks/tests/bins"), os.path.join(HERE, "mocks_bins.txt"))
+    # the reference's known-answer test for vpf_mocks (Corrfunc/tests/test_mocks.py:82-110): sphere centres + pN table
+    shutil.copy(os.path.join(REF, "mocks/tests/data/Mr19_centers_xyz_forVPF_rmax_10Mpc.txt"), HERE)
+    shutil.copy(os.path.join(REF, "mocks/tests/Mr19_mock_vpf"), os.path.join(HERE, "Mr19_mock_vpf.txt"))
     shutil.copy(os.path.join(REF, "mocks/tests/Mr19_mock_wtheta.DD"), os.path.join(HERE, "Mr19_mock_wtheta_DD.txt"))
     shutil.copy(os.path.join(REF, "mocks/tests/angular_bins"), os.path.join(HERE, "angular_bins.txt"))
     shutil.copy(os.path.join(REF, "theory/tests/bins"), os.path.join(HERE, "theory_bins.txt"))

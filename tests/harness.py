@@ -116,6 +116,25 @@ def float_window_case(stat):
     return x, y, z, L, edges
 
 
+def oracle_vpf_mocks(RA, DEC, D, xc, yc, zc, rmax, nbin, num_pN, nthreads=None, dmax_randoms=0.0):
+    """Counts-in-spheres oracle: galaxies as RA, DEC (deg) and comoving distance, centres in the shifted Cartesian
+    frame of the reference's centres file.  Returns pN[nbin, num_pN] and the shift the reference applies."""
+    lib = load_oracle()
+    if nthreads:
+        lib.oracle_set_num_threads(int(nthreads))
+    dtype = np.asarray(RA).dtype
+    fn = lib.oracle_vpf_mocks_double if dtype == np.float64 else lib.oracle_vpf_mocks_float
+    fn.restype = C.c_int
+    RA, DEC, D, xc, yc, zc = [np.ascontiguousarray(a, dtype=dtype) for a in (RA, DEC, D, xc, yc, zc)]
+    pN = np.zeros((nbin, num_pN))
+    rcube = C.c_double(0.0)
+    st = fn(C.c_int64(RA.size), _p(RA), _p(DEC), _p(D), C.c_int64(xc.size), _p(xc), _p(yc), _p(zc), C.c_double(rmax),
+            C.c_int(nbin), C.c_int(num_pN), _p(pN), C.c_double(float(dmax_randoms)), C.byref(rcube))
+    if st != 0:
+        raise RuntimeError("oracle_vpf_mocks failed")
+    return pN, rcube.value
+
+
 def mock_points(seed, n, dtype):
     """Seeded synthetic survey wedge: RA 40-90 deg, DEC -10..30 deg, comoving distance 300-700 (uniform in volume
     along the radius), weights in [0.5, 1.5)."""
@@ -198,6 +217,55 @@ def load_ddrppi_mocks_golden():
     """mocks/tests/Mr19_mock.DD: rows rp-major x 40 pi bins; columns npairs rpavg . pi_upper weightavg."""
     g = np.loadtxt(os.path.join(GOLDEN, "Mr19_mock_DDrppi_DD.txt"))
     return dict(npairs=g[:, 0].astype(np.uint64), ravg=g[:, 1], weightavg=g[:, 4])
+
+
+VPF_CENTERS = os.path.join(GOLDEN, "Mr19_centers_xyz_forVPF_rmax_10Mpc.txt")
+
+
+def load_vpf_golden():
+    """mocks/tests/Mr19_mock_vpf: one row per radius 1..10: r, p0..p5."""
+    return np.genfromtxt(os.path.join(GOLDEN, "Mr19_mock_vpf.txt"), usecols=range(1, 7), dtype=np.float64)
+
+
+def cz_to_comoving(cz, cosmology):
+    """The library's host-side redshift -> distance conversion (no GPU needed)."""
+    from corrfunc_b200 import _lib
+
+    lib = _lib.load()
+    lib.corrfunc_b200_cz_to_comoving.restype = C.c_int
+    out = np.zeros_like(cz)
+    st = lib.corrfunc_b200_cz_to_comoving(C.c_int(cz.itemsize), C.c_int64(cz.size), cz.ctypes.data_as(C.c_void_p),
+                                          C.c_int(cosmology), out.ctypes.data_as(C.c_void_p))
+    if st != 0:
+        raise RuntimeError("corrfunc_b200_cz_to_comoving failed")
+    return out
+
+
+def vpf_centres_from_randoms(RA, DEC, D, rcube, rmax, threshold, nc):
+    """The reference's choice of sphere centres when it has no usable centres file (countspheres_mocks_impl.c.src:
+    140-204, 478-490): the first nc randoms, in input order, with more than `threshold` randoms (itself included)
+    within rmax; r2 = dx*dx + dy*dy + dz*dz in the run precision, without FMA.  rcube = the shift (max distance + 1).
+    Brute force: small inputs only."""
+    dt = RA.dtype.type
+    cosd = lambda a: np.cos(a.astype(dt) * np.float64(np.pi / 180.0) if False else (a * 0.017453292519943295769236907684886127134428718885417254560971)).astype(dt)  # noqa: E731
+    sind = lambda a: np.sin(a * 0.017453292519943295769236907684886127134428718885417254560971).astype(dt)  # noqa: E731
+    if dt == np.float32:  # COSD(x) = cosf((float)(x * PI_OVER_180)): the product is a double rounded to float first
+        cosd = lambda a: np.cos((a.astype(np.float64) * 0.017453292519943295769236907684886127134428718885417254560971).astype(np.float32))  # noqa: E731
+        sind = lambda a: np.sin((a.astype(np.float64) * 0.017453292519943295769236907684886127134428718885417254560971).astype(np.float32))  # noqa: E731
+    x = (D * cosd(DEC) * cosd(RA)).astype(dt) + dt(rcube)
+    y = (D * cosd(DEC) * sind(RA)).astype(dt) + dt(rcube)
+    z = (D * sind(DEC)).astype(dt) + dt(rcube)
+    r2max = dt(rmax) * dt(rmax)
+    keep = []
+    for i in range(x.size):
+        dx, dy, dz = x - x[i], y - y[i], z - z[i]
+        r2 = dx * dx + dy * dy + dz * dz
+        if np.count_nonzero(r2 < r2max) > threshold:
+            keep.append(i)
+            if len(keep) == nc:
+                break
+    keep = np.asarray(keep, dtype=np.int64)
+    return x[keep], y[keep], z[keep]
 
 
 def load_wtheta_golden():

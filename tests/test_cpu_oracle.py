@@ -358,3 +358,39 @@ def test_oracle_matches_reference_golden_DDrppi_mocks():
     assert np.array_equal(a["npairs"].ravel(), gold["npairs"])
     assert np.allclose(a["ravg"].ravel(), gold["ravg"], atol=1e-8, rtol=1e-6)  # common.py:83-105 tolerances
     assert np.allclose(a["weightavg"].ravel(), gold["weightavg"], atol=1e-8, rtol=1e-6)
+
+
+# ---- counts-in-spheres on survey catalogues: mocks/vpf_mocks ------------------------------------
+
+def test_oracle_matches_reference_golden_vpf_mocks():
+    """The reference's own known-answer test for vpf_mocks (Corrfunc/tests/test_mocks.py:82-110): 10 000 spheres from
+    its centres file on the Mr19 mock (cz input, cosmology 1), radii 1..10, p0..p5, vs mocks/tests/Mr19_mock_vpf."""
+    ra, dec, cz, _ = H.load_mr19_mock_cz()
+    cen = np.loadtxt(H.VPF_CENTERS)
+    pN, _ = H.oracle_vpf_mocks(ra, dec, H.cz_to_comoving(cz, 1), cen[:, 0], cen[:, 1], cen[:, 2], 10.0, 10, 6)
+    assert np.allclose(pN, H.load_vpf_golden(), atol=1e-9, rtol=1e-6)  # common.py:107-116 tolerances
+
+
+@pytest.mark.skipif(H.load_ref() is None or not hasattr(H.load_ref(), "countspheres_mocks"),
+                    reason="oracle/_ref was not prebuilt with vpf_mocks")
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_oracle_vpf_mocks_vs_live_reference_with_randoms(dtype, tmp_path):
+    """No centres file: the reference places the spheres on the randoms that have enough neighbours and writes the
+    file; harness.vpf_centres_from_randoms restates that choice and the oracle the counting."""
+    from corrfunc_b200 import _capi as capi
+
+    ra, dec, d, _ = H.mock_points(41, 20000, dtype)
+    rra, rdec, rd, _ = H.mock_points(42, 3000, dtype)
+    cfile = str(tmp_path / "centres.txt")
+    o = capi.default_options(dtype, isa=H.ref_isa(), bin_refine_factors=(1, 1, 1), is_comoving_dist=True)
+    nc = 150
+    r = capi.call_vpf_mocks(H.load_ref(), 12.0, 6, nc, 4, 2, cfile, 1, ra, dec, d, RAND_RA=rra, RAND_DEC=rdec, RAND_CZ=rd,
+                            options=o)
+    rcube = dtype(max(d.max(), rd.max())) + dtype(1.0)
+    xc, yc, zc = H.vpf_centres_from_randoms(rra, rdec, rd, rcube, 12.0, 2, nc)
+    written = np.loadtxt(cfile)
+    assert xc.size == nc and written.shape == (nc, 4)
+    assert np.allclose(written[:, 0], xc, atol=1e-4) and np.allclose(written[:, 2], zc, atol=1e-4) and np.all(written[:, 3] == 12.0)
+    pN, rc = H.oracle_vpf_mocks(ra, dec, d, xc, yc, zc, 12.0, 6, 4, dmax_randoms=rd.max())
+    assert rc == float(rcube)
+    assert np.allclose(pN, r["pN"], atol=1e-6 if dtype == np.float32 else 1e-12)

@@ -58,3 +58,42 @@ def test_DDrppi_mocks_reference_golden_file():
     assert np.array_equal(r["npairs"], gold["npairs"])
     assert np.allclose(r["rpavg"], gold["ravg"], atol=1e-9, rtol=1e-6)
     assert np.allclose(r["weightavg"], gold["weightavg"], atol=1e-9, rtol=1e-6)
+
+
+# ---- counts-in-spheres (mocks/vpf_mocks), added with the tests above ------------------------------------------------
+
+def test_vpf_mocks_reference_golden_file():
+    """The reference's own known-answer test (Corrfunc/tests/test_mocks.py:82-110): 10 000 spheres from its centres
+    file on the Mr19 mock, radii 1..10, p0..p5 vs mocks/tests/Mr19_mock_vpf (atol 1e-9 / rtol 1e-6, common.py:107-116)."""
+    from corrfunc_b200.mocks import vpf_mocks
+
+    ra, dec, cz, _ = H.load_mr19_mock_cz()
+    r = vpf_mocks(10.0, 10, 10000, 6, 1, H.VPF_CENTERS, 1, ra, dec, cz, ra, dec, cz)
+    assert r.dtype.names == ("rmax", "pN") and np.allclose(r["rmax"], np.arange(1, 11))
+    assert np.allclose(r["pN"], H.load_vpf_golden(), atol=1e-9, rtol=1e-6)
+    # the same through the float path, against the oracle in float
+    raf, decf, czf = (a.astype(np.float32) for a in (ra, dec, cz))
+    cen = np.loadtxt(H.VPF_CENTERS).astype(np.float32)
+    want, _ = H.oracle_vpf_mocks(raf, decf, H.cz_to_comoving(czf, 1), cen[:, 0], cen[:, 1], cen[:, 2], 10.0, 10, 6)
+    rf = vpf_mocks(10.0, 10, 10000, 6, 1, H.VPF_CENTERS, 1, raf, decf, czf, raf, decf, czf)
+    assert np.array_equal(rf["pN"], want)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_vpf_mocks_centres_from_randoms(dtype, tmp_path):
+    """Without a usable centres file the spheres go on the first randoms with enough neighbours and the file is
+    rewritten (countspheres_mocks_impl.c.src:478-562): centres, file and pN against the restatement in tests/harness.py
+    and the oracle (both checked against the live reference on the CPU)."""
+    from corrfunc_b200.mocks import vpf_mocks
+
+    ra, dec, d, _ = H.mock_points(41, 20000, dtype)
+    rra, rdec, rd, _ = H.mock_points(42, 3000, dtype)
+    cfile = str(tmp_path / "centres.txt")
+    nc = 150
+    r = vpf_mocks(12.0, 6, nc, 4, 2, cfile, 1, ra, dec, d, rra, rdec, rd, is_comoving_dist=True)
+    rcube = dtype(max(d.max(), rd.max())) + dtype(1.0)
+    xc, yc, zc = H.vpf_centres_from_randoms(rra, rdec, rd, rcube, 12.0, 2, nc)
+    written = np.loadtxt(cfile)
+    assert written.shape == (nc, 4) and np.allclose(written[:, 0], xc, atol=1e-4) and np.allclose(written[:, 1], yc, atol=1e-4)
+    want, _ = H.oracle_vpf_mocks(ra, dec, d, xc, yc, zc, 12.0, 6, 4, dmax_randoms=rd.max())
+    assert np.array_equal(r["pN"], want)
