@@ -124,6 +124,8 @@ __host__ __device__ __forceinline__ bool cfb_owns_cell(const int cell, const int
 // scale: power of two applied to the sorted copy of the positions (1 unless the fast float kernel runs)
 int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3], double scale);
 int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t ncells /* reference cells */);
+// counts-in-spheres buffers (spheres.cu)
+void cfb_spheres_release();
 // pair kernels (pairs_generic.cu)
 int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode);
 // fast 1-D kernel (pairs_fast.cu); P.edges / P.wrap / P.pimax are in the kernel's scaled units

@@ -87,6 +87,7 @@ extern "C" void cfb_shutdown(void)
         rel(S.tile_cell); rel(S.tile_off);
         S = ParticleSet();
     }
+    cfb_spheres_release();
     rel(c.scratch); rel(c.hist); rel(c.edges); rel(c.list_off); rel(c.list_cells); rel(c.ngrid_ra); rel(c.ra_off);
     if (c.pinned) cudaFreeHost(c.pinned);
     c.pinned = nullptr;

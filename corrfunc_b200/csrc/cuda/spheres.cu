@@ -12,6 +12,16 @@
 
 static DevBuf g_cen[3], g_out, g_edges;
 
+void cfb_spheres_release()  // called by cfb_shutdown
+{
+    DevBuf *all[5] = {&g_cen[0], &g_cen[1], &g_cen[2], &g_out, &g_edges};
+    for (DevBuf *b : all) {
+        if (b->p) cudaFree(b->p);
+        b->p = nullptr;
+        b->cap = 0;
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ T sph_fma(T a, T b, T c);
 template <>
