@@ -1,0 +1,57 @@
+"""The HOST layer of countspheres_mocks without a GPU: cf_host.c (the product's own host code) is linked with
+tests/stub_device/stub_device.c -- a brute-force CPU stand-in for the CUDA layer's C ABI, test infrastructure only --
+into a throw-away library, and driven through the same ctypes helpers as the real one.  Checks what the CUDA kernel
+does not decide: centres file parsing, cz -> distance, the shift, the choice of centres on the randoms and the
+rewritten file, cumulative counts and pN.  (The kernel itself is checked by the -m gpu tests.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import harness as H
+from corrfunc_b200 import _capi
+
+
+@pytest.fixture(scope="module")
+def hostlib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("hoststub") / "libcorrfunc_hoststub.so")
+    host = os.path.join(H.ROOT, "corrfunc_b200", "csrc", "host")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fopenmp",
+                           "-I", os.path.join(H.ROOT, "include"), "-I", host, os.path.join(host, "cf_host.c"),
+                           os.path.join(H.ROOT, "tests", "stub_device", "stub_device.c"), "-o", out, "-lm"])
+    return C.CDLL(out, mode=os.RTLD_LOCAL)
+
+
+def test_host_layer_reproduces_the_reference_golden_vpf(hostlib):
+    ra, dec, cz, _ = H.load_mr19_mock_cz()
+    o = _capi.default_options(np.float64, bin_refine_factors=(1, 1, 1))
+    r = _capi.call_vpf_mocks(hostlib, 10.0, 10, 10000, 6, 1, H.VPF_CENTERS, 1, ra, dec, cz, options=o)
+    assert np.allclose(r["pN"], H.load_vpf_golden(), atol=1e-9, rtol=1e-6)
+    assert r["nbin"] == 10 and r["nc"] == 10000 and r["rmax"] == 10.0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_host_layer_places_centres_on_the_randoms(hostlib, dtype, tmp_path):
+    ra, dec, d, _ = H.mock_points(41, 20000, dtype)
+    rra, rdec, rd, _ = H.mock_points(42, 3000, dtype)
+    cfile = str(tmp_path / "centres.txt")
+    nc = 150
+    o = _capi.default_options(dtype, bin_refine_factors=(1, 1, 1), is_comoving_dist=True, c_api_timer=True)
+    r = _capi.call_vpf_mocks(hostlib, 12.0, 6, nc, 4, 2, cfile, 1, ra, dec, d, RAND_RA=rra, RAND_DEC=rdec, RAND_CZ=rd,
+                             options=o)
+    rcube = dtype(max(d.max(), rd.max())) + dtype(1.0)
+    xc, yc, zc = H.vpf_centres_from_randoms(rra, rdec, rd, rcube, 12.0, 2, nc)
+    written = np.loadtxt(cfile)
+    assert written.shape == (nc, 4) and np.allclose(written[:, 0], xc, atol=1e-4) and np.all(written[:, 3] == 12.0)
+    want, _ = H.oracle_vpf_mocks(ra, dec, d, xc, yc, zc, 12.0, 6, 4, dmax_randoms=rd.max())
+    assert np.array_equal(r["pN"], want)
+    assert r["api_time"] > 0
+    # errors are loud: unknown cosmology, too few randoms to place a single sphere
+    with pytest.raises(RuntimeError):
+        _capi.call_vpf_mocks(hostlib, 12.0, 6, nc, 4, 2, cfile, 7, ra, dec, d, RAND_RA=rra, RAND_DEC=rdec, RAND_CZ=rd,
+                             options=_capi.default_options(dtype, is_comoving_dist=True))
+    with pytest.raises(RuntimeError):
+        _capi.call_vpf_mocks(hostlib, 12.0, 6, nc, 4, 10 ** 6, str(tmp_path / "none.txt"), 1, ra, dec, d, RAND_RA=rra,
+                             RAND_DEC=rdec, RAND_CZ=rd, options=_capi.default_options(dtype, is_comoving_dist=True))
