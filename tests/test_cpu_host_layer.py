@@ -55,3 +55,39 @@ def test_host_layer_places_centres_on_the_randoms(hostlib, dtype, tmp_path):
     with pytest.raises(RuntimeError):
         _capi.call_vpf_mocks(hostlib, 12.0, 6, nc, 4, 10 ** 6, str(tmp_path / "none.txt"), 1, ra, dec, d, RAND_RA=rra,
                              RAND_DEC=rdec, RAND_CZ=rd, options=_capi.default_options(dtype, is_comoving_dist=True))
+
+
+# ---- host layer of countpairs_mocks / countpairs_mocks_s_mu (angles, cz, extents, bins, epilogue) -----------------
+
+def test_host_layer_reproduces_the_reference_golden_DDrppi_mocks(hostlib):
+    """mocks/tests/Mr19_mock.DD (cz input, written upstream with real GSL) through the product's host code."""
+    ra, dec, cz, w = H.load_mr19_mock_cz()
+    bins = H.load_bins_file("mocks_bins.txt")
+    gold = H.load_ddrppi_mocks_golden()
+    o = _capi.default_options(np.float64, need_avg_sep=True, is_comoving_dist=False)
+    r = _capi.call_DDrppi_mocks(hostlib, 1, 1, 4, 40.0, bins, ra, dec, cz, w1=w, weight_type="pair_product", options=o)
+    assert np.array_equal(r["npairs"].ravel(), gold["npairs"])
+    assert np.allclose(r["ravg"].ravel(), gold["ravg"], atol=1e-9, rtol=1e-6)
+    assert np.allclose(r["weightavg"].ravel(), gold["weightavg"], atol=1e-9, rtol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_host_layer_mocks_vs_committed_reference_outputs(hostlib, dtype):
+    g = np.load(os.path.join(H.GOLDEN, "ref_mocks_%s.npz" % np.dtype(dtype).name))
+    n1, n2 = 20000, 12000  # a subsample keeps the brute force short: compared with the oracle, not the goldens
+    ra, dec, d, w = H.mock_points(int(g["seed"]), n1, dtype)
+    ra2, dec2, d2, w2 = H.mock_points(int(g["seed"]) + 1, n2, dtype)
+    cz, cz2 = (d * dtype(60.0)).astype(dtype), (d2 * dtype(60.0)).astype(dtype)
+    o = _capi.default_options(dtype, need_avg_sep=True, is_comoving_dist=False)
+    r = _capi.call_DDsmu_mocks(hostlib, 0, 2, 1, 0.9, 10, g["edges"], ra - dtype(180.0), dec + dtype(90.0), cz, w1=w,
+                               RA2=ra2, DEC2=dec2, CZ2=cz2, w2=w2, weight_type="pair_product", options=o)
+    raf, decf = (ra - dtype(180.0)) + dtype(180.0), (dec + dtype(90.0)) - dtype(90.0)  # shifted back in place by the host layer
+    czmax = max(cz.max(), cz2.max())
+    D = H.cz_to_comoving(np.append(cz, czmax).astype(dtype), 2)[:-1]
+    D2 = H.cz_to_comoving(np.append(cz2, czmax).astype(dtype), 2)[:-1]
+    a = H.oracle_theory("DDsmu_mocks", raf, decf, D, g["edges"], mu_max=0.9, nmu_bins=10, autocorr=False, X2=ra2, Y2=dec2,
+                        Z2=D2, w1=w, w2=w2, weight_type="pair_product", need_avg=True, periodic=False)
+    assert np.array_equal(r["npairs"], a["npairs"])
+    tol = 1e-10 if dtype == np.float64 else 1e-5
+    ok = a["npairs"] > 0
+    assert np.allclose(r["ravg"][ok], a["ravg"][ok], rtol=tol) and np.allclose(r["weightavg"][ok], a["weightavg"][ok], rtol=tol)
