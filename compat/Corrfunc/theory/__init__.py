@@ -3,7 +3,8 @@ the functions, and the sub-modules of the same names stay importable."""
 from .DD import DD
 from .DDrppi import DDrppi
 from .DDsmu import DDsmu
+from .vpf import vpf
 from .wp import wp
 from .xi import xi
 
-__all__ = ["DD", "DDrppi", "DDsmu", "wp", "xi"]
+__all__ = ["DD", "DDrppi", "DDsmu", "wp", "xi", "vpf"]

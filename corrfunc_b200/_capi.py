@@ -281,6 +281,12 @@ def _declare(lib):
         lib.free_results_mocks.argtypes = [C.POINTER(ResultsMocksRpPi)]
         lib.free_results_mocks_s_mu.argtypes = [C.POINTER(ResultsMocksSMu)]
         lib.free_results_mocks.restype = lib.free_results_mocks_s_mu.restype = None
+    if hasattr(lib, "countspheres"):  # theory/vpf
+        lib.countspheres.argtypes = [i64, vp, vp, vp, cd, ci, ci, ci, C.c_ulong, C.POINTER(ResultsVpfMocks),
+                                     C.POINTER(ConfigOptions), C.POINTER(ExtraOptions)]
+        lib.countspheres.restype = ci
+        lib.free_results_countspheres.argtypes = [C.POINTER(ResultsVpfMocks)]
+        lib.free_results_countspheres.restype = None
     if hasattr(lib, "countspheres_mocks"):  # mocks/vpf_mocks
         lib.countspheres_mocks.argtypes = [i64, vp, vp, vp, i64, vp, vp, vp, ci, cd, ci, ci, ci, cs, ci,
                                            C.POINTER(ResultsVpfMocks), C.POINTER(ConfigOptions), C.POINTER(ExtraOptions)]
@@ -294,7 +300,7 @@ EXPORTED_SYMBOLS = ("countpairs", "free_results", "countpairs_rp_pi", "free_resu
                     "free_results_s_mu", "countpairs_wp", "free_results_wp", "countpairs_xi", "free_results_xi",
                     "countpairs_theta_mocks", "free_results_countpairs_theta", "countpairs_mocks", "free_results_mocks",
                     "countpairs_mocks_s_mu", "free_results_mocks_s_mu", "countspheres_mocks",
-                    "free_results_countspheres_mocks", "countpairs_mocks_float",
+                    "free_results_countspheres_mocks", "countspheres", "free_results_countspheres", "countpairs_mocks_float",
                     "countpairs_mocks_double", "countpairs_mocks_s_mu_float", "countpairs_mocks_s_mu_double") + tuple(
     "%s_%s" % (f, t) for f in ("countpairs", "countpairs_rp_pi", "countpairs_s_mu", "countpairs_wp", "countpairs_xi",
                                "countpairs_theta_mocks") for t in ("float", "double"))
@@ -445,6 +451,23 @@ def call_DDsmu_mocks(lib, autocorr, cosmology, nthreads, mu_max, nmu_bins, bins,
                ravg=grid(res.savg, np.float64), weightavg=grid(res.weightavg, np.float64), nmu_bins=nmu,
                mu_max=res.mu_max, api_time=options.c_api_time)
     lib.free_results_mocks_s_mu(C.byref(res))
+    return out
+
+
+def call_vpf(lib, rmax, nbin, nc, num_pN, seed, X, Y, Z, options=None, dtype=None):
+    """countspheres (theory/vpf/countspheres.h:28-35; results_countspheres has the layout of ResultsVpfMocks)."""
+    _declare(lib)
+    dtype = np.dtype(dtype or np.asarray(X).dtype)
+    X, Y, Z = _prep((X, Y, Z), dtype)
+    extra, keep = make_extra(None, None, None, dtype)
+    res = ResultsVpfMocks()
+    st = lib.countspheres(X.size, _ptr(X), _ptr(Y), _ptr(Z), float(rmax), int(nbin), int(nc), int(num_pN), int(seed),
+                          C.byref(res), C.byref(options), C.byref(extra))
+    if st != 0:
+        raise RuntimeError("countspheres returned %d" % st)
+    pN = np.array([[res.pN[i][j] for j in range(res.num_pN)] for i in range(res.nbin)], dtype=np.float64)
+    out = dict(pN=pN, rmax=res.rmax, nbin=res.nbin, nc=res.nc, api_time=options.c_api_time)
+    lib.free_results_countspheres(C.byref(res))
     return out
 
 

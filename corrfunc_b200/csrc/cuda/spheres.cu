@@ -29,12 +29,22 @@ __device__ __forceinline__ float sph_fma<float>(float a, float b, float c) { ret
 template <>
 __device__ __forceinline__ double sph_fma<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
 
-// SHELLS = true : r2 = fma(dz,dz, fma(dy,dy, dx*dx)) and the AVX-512 kernel's shell assignment (vpf_mocks_kernels:63-92)
+struct SphGeom {
+    int n[3];         // lattice cells per axis
+    int periodic[3];  // axis wraps
+    double lo[3], inv[3], wrap[3];  // REAL-valued
+};
+
+// SHELLS = true : r2 = fma(dz,dz, fma(dy,dy, dx*dx)) and the AVX-512 kernel's shell assignment (vpf_mocks_kernels:63-92,
+//                 theory/vpf/vpf_kernels.c.src alike)
 // SHELLS = false: r2 = dx*dx + dy*dy + dz*dz and a plain count of r2 < rmax_sqr (count_neighbors, impl:140-204)
+// Periodic axes (theory vpf): the reference shifts the centre by -+wrap for the neighbour cells across the box edge
+// (countspheres_impl.c.src:331-380); a particle that can count is always met with its nearest image, so the image is
+// chosen per particle here (d > wrap/2 -> centre + wrap, d < -wrap/2 -> centre - wrap), whatever the lattice.
 template <typename T, bool SHELLS>
 __global__ void k_spheres(const int64_t ncen, const T *__restrict__ xc, const T *__restrict__ yc, const T *__restrict__ zc,
-                          const SetView<T> B, const int n0, const int n1, const int n2, const T inv, const T rmax_sqr,
-                          const int nbin, const T *__restrict__ edges, unsigned *__restrict__ out)
+                          const SetView<T> B, const SphGeom G, const T rmax_sqr, const int nbin,
+                          const T *__restrict__ edges, unsigned *__restrict__ out)
 {
     extern __shared__ unsigned char sph_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -45,20 +55,49 @@ __global__ void k_spheres(const int64_t ncen, const T *__restrict__ xc, const T 
     __syncthreads();
     const int64_t c = (int64_t)blockIdx.x * nw + wid;
     if (c >= ncen) return;
-    const T X = xc[c], Y = yc[c], Z = zc[c];
-    int ix = (int)(X * inv), iy = (int)(Y * inv), iz = (int)(Z * inv);
-    ix = min(max(ix, 0), n0 - 1);
-    iy = min(max(iy, 0), n1 - 1);
-    iz = min(max(iz, 0), n2 - 1);
-    for (int cx = max(ix - 1, 0); cx <= min(ix + 1, n0 - 1); cx++)
-        for (int cy = max(iy - 1, 0); cy <= min(iy + 1, n1 - 1); cy++)
-            for (int cz = max(iz - 1, 0); cz <= min(iz + 1, n2 - 1); cz++) {
-                const int cell = (cx * n1 + cy) * n2 + cz;
+    const T C[3] = {xc[c], yc[c], zc[c]};
+    int first[3], cnt[3];  // per axis: the run of neighbour cells (taken modulo n on a periodic axis)
+    T wrap[3], half[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        int i = (int)((C[a] - (T)G.lo[a]) * (T)G.inv[a]);
+        i = min(max(i, 0), G.n[a] - 1);
+        wrap[a] = (T)G.wrap[a];
+        half[a] = (T)0.5 * wrap[a];
+        if (G.periodic[a]) {
+            if (G.n[a] >= 3) {
+                first[a] = i - 1 + G.n[a];
+                cnt[a] = 3;
+            } else {
+                first[a] = 0;
+                cnt[a] = G.n[a];
+            }
+        } else {
+            first[a] = max(i - 1, 0);
+            cnt[a] = min(i + 1, G.n[a] - 1) - first[a] + 1;
+        }
+    }
+    for (int tx = 0; tx < cnt[0]; tx++)
+        for (int ty = 0; ty < cnt[1]; ty++)
+            for (int tz = 0; tz < cnt[2]; tz++) {
+                const int cx = (first[0] + tx) % G.n[0], cy = (first[1] + ty) % G.n[1], cz = (first[2] + tz) % G.n[2];
+                const int cell = (cx * G.n[1] + cy) * G.n[2] + cz;
                 const int n = B.count[cell], s0 = B.start[cell];
                 for (int j = lane; j < n; j += 32) {
-                    const T dx = X - B.x[s0 + j], dy = Y - B.y[s0 + j], dz = Z - B.z[s0 + j];
+                    const T P[3] = {B.x[s0 + j], B.y[s0 + j], B.z[s0 + j]};
+                    T d[3];
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        T cen = C[a];
+                        if (G.periodic[a]) {
+                            const T raw = P[a] - C[a];
+                            if (raw > half[a]) cen = C[a] + wrap[a];
+                            else if (raw < -half[a]) cen = C[a] - wrap[a];
+                        }
+                        d[a] = cen - P[a];
+                    }
                     if (SHELLS) {
-                        const T r2 = sph_fma<T>(dz, dz, sph_fma<T>(dy, dy, dx * dx));
+                        const T r2 = sph_fma<T>(d[2], d[2], sph_fma<T>(d[1], d[1], d[0] * d[0]));
                         if (!(r2 < rmax_sqr)) continue;
                         // lane by lane what the masked loop over k = nbin-1 .. 1 does: the shell with E[k-1] <= r2 < E[k];
                         // whoever is left after k == 1 goes to shell 0; with one shell the loop never runs
@@ -71,7 +110,7 @@ __global__ void k_spheres(const int64_t ncen, const T *__restrict__ xc, const T 
                             }
                         if (left && nbin >= 2) atomicAdd(&s_cnt[0], 1u);
                     } else {
-                        const T r2 = dx * dx + dy * dy + dz * dz;  // -fmad=false: no contraction
+                        const T r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];  // -fmad=false: no contraction
                         if (r2 < rmax_sqr) atomicAdd(&s_cnt[0], 1u);
                     }
                 }
@@ -81,22 +120,30 @@ __global__ void k_spheres(const int64_t ncen, const T *__restrict__ xc, const T 
 }
 
 template <typename T>
-static int count_spheres_T(Ctx &c, ParticleSet &S, double extent, int regrid, int64_t ncen, const void *xc, const void *yc,
-                           const void *zc, double rmax, double rmax_sqr, int nbin, const double *edges, int shells,
-                           uint32_t *counts)
+static int count_spheres_T(Ctx &c, ParticleSet &S, const double lo[3], const double ext[3], const int periodic[3],
+                           const double wrap[3], int regrid, int64_t ncen, const void *xc, const void *yc, const void *zc,
+                           double rmax, double rmax_sqr, int nbin, const double *edges, int shells, uint32_t *counts)
 {
-    // internal lattice over [0, extent]^3: cells a little larger than rmax, so that the 27 cells around a centre hold
-    // every particle within rmax whatever way the two cell indices round; the counts do not depend on this choice
-    int nm = (int)floor(extent / (rmax * 1.001));
-    nm = nm < 1 ? 1 : (nm > 128 ? 128 : nm);
+    // internal lattice over the particles' extent: cells a little larger than rmax, so that the 27 cells around a centre
+    // hold every particle within rmax whatever way the two cell indices round; the counts do not depend on this choice
+    SphGeom G;
+    for (int k = 0; k < 3; k++) {
+        int nm = ext[k] > 0 ? (int)floor(ext[k] / (rmax * 1.001)) : 1;
+        nm = nm < 1 ? 1 : (nm > 128 ? 128 : nm);
+        G.n[k] = nm;
+        G.periodic[k] = periodic[k];
+        G.lo[k] = (double)(T)lo[k];
+        G.inv[k] = ext[k] > 0 ? (double)((T)nm / (T)ext[k]) : 0.0;
+        G.wrap[k] = (double)(T)wrap[k];
+    }
     if (regrid || !S.gridded) {
         cfb_box_lattice lat;
         memset(&lat, 0, sizeof(lat));
         for (int k = 0; k < 3; k++) {
-            lat.nmesh[k] = nm;
+            lat.nmesh[k] = G.n[k];
             lat.refine[k] = 1;
-            lat.lo[k] = 0.0;
-            lat.inv[k] = (double)((T)nm / (T)extent);
+            lat.lo[k] = G.lo[k];
+            lat.inv[k] = G.inv[k];
             lat.max_sep[k] = -1.0;
         }
         const int sub[3] = {1, 1, 1};
@@ -133,17 +180,16 @@ static int count_spheres_T(Ctx &c, ParticleSet &S, double extent, int regrid, in
         if (smem > 96 * 1024) return cfb_fail("too many radial bins (%d) for the counts-in-spheres kernel", nbin);
         const int64_t nblk = (ncen + warps - 1) / warps;
         if (nblk >= 2147483647LL) return cfb_fail("too many sphere centres (%lld)", (long long)ncen);
-        const T inv = (T)nm / (T)extent;
         if (shells) {
             CK(cudaFuncSetAttribute(k_spheres<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             k_spheres<T, true><<<(unsigned)nblk, warps * 32, smem, c.stream>>>(
-                ncen, (const T *)g_cen[0].p, (const T *)g_cen[1].p, (const T *)g_cen[2].p, V, nm, nm, nm, inv, (T)rmax_sqr,
-                nbin, (const T *)g_edges.p, (unsigned *)g_out.p);
+                ncen, (const T *)g_cen[0].p, (const T *)g_cen[1].p, (const T *)g_cen[2].p, V, G, (T)rmax_sqr, nbin,
+                (const T *)g_edges.p, (unsigned *)g_out.p);
         } else {
             CK(cudaFuncSetAttribute(k_spheres<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             k_spheres<T, false><<<(unsigned)nblk, warps * 32, smem, c.stream>>>(
-                ncen, (const T *)g_cen[0].p, (const T *)g_cen[1].p, (const T *)g_cen[2].p, V, nm, nm, nm, inv, (T)rmax_sqr,
-                nbin, (const T *)g_edges.p, (unsigned *)g_out.p);
+                ncen, (const T *)g_cen[0].p, (const T *)g_cen[1].p, (const T *)g_cen[2].p, V, G, (T)rmax_sqr, nbin,
+                (const T *)g_edges.p, (unsigned *)g_out.p);
         }
         c.launches++;
         CK(cudaGetLastError());
@@ -153,7 +199,8 @@ static int count_spheres_T(Ctx &c, ParticleSet &S, double extent, int regrid, in
     return 0;
 }
 
-extern "C" int cfb_count_spheres(int slot, int prec, double extent, int regrid, int64_t ncen, const void *xc, const void *yc,
+extern "C" int cfb_count_spheres(int slot, int prec, const double lo[3], const double ext[3], const int periodic[3],
+                                 const double wrap[3], int regrid, int64_t ncen, const void *xc, const void *yc,
                                  const void *zc, double rmax, double rmax_sqr, int nbin, const double *edges, int shells,
                                  uint32_t *counts)
 {
@@ -163,7 +210,9 @@ extern "C" int cfb_count_spheres(int slot, int prec, double extent, int regrid, 
     CK(cudaSetDevice(c.dev));
     ParticleSet &S = c.set[slot];
     if (S.prec != prec) return cfb_fail("particle set %d precision mismatch", slot);
-    if (!(extent > 0.0) || !(rmax > 0.0) || nbin < 1) return cfb_fail("bad counts-in-spheres parameters");
-    return prec == 4 ? count_spheres_T<float>(c, S, extent, regrid, ncen, xc, yc, zc, rmax, rmax_sqr, nbin, edges, shells, counts)
-                     : count_spheres_T<double>(c, S, extent, regrid, ncen, xc, yc, zc, rmax, rmax_sqr, nbin, edges, shells, counts);
+    if (!(rmax > 0.0) || nbin < 1) return cfb_fail("bad counts-in-spheres parameters");
+    return prec == 4 ? count_spheres_T<float>(c, S, lo, ext, periodic, wrap, regrid, ncen, xc, yc, zc, rmax, rmax_sqr, nbin,
+                                              edges, shells, counts)
+                     : count_spheres_T<double>(c, S, lo, ext, periodic, wrap, regrid, ncen, xc, yc, zc, rmax, rmax_sqr, nbin,
+                                               edges, shells, counts);
 }

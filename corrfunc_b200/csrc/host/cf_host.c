@@ -21,6 +21,7 @@
 #include "countpairs_rp_pi.h"
 #include "countpairs_rp_pi_mocks.h"
 #include "countspheres_mocks.h"
+#include "countspheres.h"
 #include "countpairs_s_mu.h"
 #include "countpairs_s_mu_mocks.h"
 #include "countpairs_theta_mocks.h"
@@ -202,6 +203,49 @@ typedef struct {
     double *wavg;     /* [nslots] */
     double *cf;       /* [nbin] xi or wp, NULL otherwise */
 } cf_box_out;
+
+/* ---- MT19937 as GSL's gsl_rng_mt19937 runs it (theory/vpf draws its sphere centres from it, countspheres_impl.c.src:
+ * 190-192, 303-305).  GSL is absent here; this is the published generator of Matsumoto & Nishimura with the 2002
+ * initialisation that GSL 2.x's rng/mt.c implements (seed 0 -> 4357), gsl_rng_uniform = next word / 2^32. */
+typedef struct {
+    uint32_t mt[624];
+    int mti;
+} cf_mt19937;
+
+static void cf_mt_set(cf_mt19937 *r, unsigned long seed)
+{
+    uint32_t s = (uint32_t)(seed & 0xffffffffUL);
+    if (seed == 0) s = 4357u;
+    r->mt[0] = s;
+    for (int i = 1; i < 624; i++) r->mt[i] = 1812433253u * (r->mt[i - 1] ^ (r->mt[i - 1] >> 30)) + (uint32_t)i;
+    r->mti = 624;
+}
+
+static double cf_mt_uniform(cf_mt19937 *r)
+{
+    uint32_t *const mt = r->mt;
+    if (r->mti >= 624) {
+        for (int kk = 0; kk < 624; kk++) {
+            const uint32_t y = (mt[kk] & 0x80000000u) | (mt[(kk + 1) % 624] & 0x7fffffffu);
+            mt[kk] = mt[(kk + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        r->mti = 0;
+    }
+    uint32_t k = mt[r->mti++];
+    k ^= (k >> 11);
+    k ^= (k << 7) & 0x9d2c5680u;
+    k ^= (k << 15) & 0xefc60000u;
+    k ^= (k >> 18);
+    return k / 4294967296.0;
+}
+
+/* the first n uniforms of that stream (for tests) */
+void corrfunc_b200_mt19937_uniform(unsigned long seed, int64_t n, double *out)
+{
+    cf_mt19937 r;
+    cf_mt_set(&r, seed);
+    for (int64_t i = 0; i < n; i++) out[i] = cf_mt_uniform(&r);
+}
 
 typedef struct { /* counts-in-spheres result (cf_vpf_mocks) */
     int nbin, num_pN;
@@ -519,6 +563,40 @@ int countpairs_mocks_s_mu(const int64_t ND1, void *phi1, void *theta1, void *czD
     results->savg = o.avg;
     results->weightavg = o.wavg;
     free(o.cf);
+    return EXIT_SUCCESS;
+}
+
+/* ---- counts-in-spheres in a simulation box: theory/vpf/countspheres.c ---- */
+void free_results_countspheres(results_countspheres *r)
+{
+    if (r == NULL || r->pN == NULL) return;
+    for (int i = 0; i < r->nbin; i++) free(r->pN[i]);
+    free(r->pN);
+    r->pN = NULL;
+}
+
+int countspheres(const int64_t np, void *X, void *Y, void *Z, const double rmax, const int nbin, const int nc, const int num_pN,
+                 unsigned long seed, results_countspheres *results, struct config_options *options, struct extra_options *extra)
+{
+    (void)extra;
+    if (check_common(options, __func__)) return EXIT_FAILURE;
+    cf_vpf_out o;
+    memset(&o, 0, sizeof(o));
+    const int st = options->float_type == sizeof(float)
+                       ? cf_vpf_theory_f32(np, X, Y, Z, rmax, nbin, nc, num_pN, seed, options, &o)
+                       : cf_vpf_theory_f64(np, X, Y, Z, rmax, nbin, nc, num_pN, seed, options, &o);
+    if (st != EXIT_SUCCESS) {
+        if (o.pN) {
+            for (int i = 0; i < nbin; i++) free(o.pN[i]);
+            free(o.pN);
+        }
+        return st;
+    }
+    results->rmax = rmax;
+    results->nbin = nbin;
+    results->nc = nc;
+    results->num_pN = num_pN;
+    results->pN = o.pN;
     return EXIT_SUCCESS;
 }
 

@@ -717,6 +717,8 @@ static int HFN(cf_vpf_mocks)(const int64_t Ngal, void *vra, void *vdec, void *vc
         for (int64_t i = 0; i < nr_used; i++) ran[a][i] += rcube;
     }
     rcube = 2.0 * rcube;
+    const double cube_lo[3] = {0.0, 0.0, 0.0}, cube_ext[3] = {(double)rcube, (double)rcube, (double)rcube};
+    const int no_wrap[3] = {0, 0, 0};
 
     if (cfb_upload(0, (int)sizeof(REAL), Ngal, gal[0], gal[1], gal[2], NULL, NULL, NULL)) goto done;
     if (need_randoms && cfb_upload(1, (int)sizeof(REAL), nr_used, ran[0], ran[1], ran[2], NULL, NULL, NULL)) goto done;
@@ -756,8 +758,8 @@ static int HFN(cf_vpf_mocks)(const int64_t Ngal, void *vra, void *vdec, void *vc
         int first = 1;
         for (int64_t base = 0; base < Nran && isucceed < nc; base += chunk) {
             const int64_t m = (Nran - base) < chunk ? (Nran - base) : chunk;
-            if (cfb_count_spheres(1, (int)sizeof(REAL), (double)rcube, first, m, ran[0] + base, ran[1] + base, ran[2] + base,
-                                  (double)rmax, (double)rmax_sqr, 1, NULL, 0, ngb)) goto done;
+            if (cfb_count_spheres(1, (int)sizeof(REAL), cube_lo, cube_ext, no_wrap, cube_lo, first, m, ran[0] + base,
+                                  ran[1] + base, ran[2] + base, (double)rmax, (double)rmax_sqr, 1, NULL, 0, ngb)) goto done;
             first = 0;
             for (int64_t i = 0; i < m && isucceed < nc; i++)
                 if ((int64_t)ngb[i] > (int64_t)threshold_neighbors) {
@@ -782,8 +784,8 @@ static int HFN(cf_vpf_mocks)(const int64_t Ngal, void *vra, void *vdec, void *vc
             const REAL e = (k + 1) * rstep * rstep * (k + 1);
             edges[k] = (double)e;
         }
-        if (cfb_count_spheres(0, (int)sizeof(REAL), (double)rcube, 1, isucceed, cen[0], cen[1], cen[2], (double)rmax,
-                              (double)rmax_sqr, nbin, edges, 1, counts)) goto done;
+        if (cfb_count_spheres(0, (int)sizeof(REAL), cube_lo, cube_ext, no_wrap, cube_lo, 1, isucceed, cen[0], cen[1], cen[2],
+                              (double)rmax, (double)rmax_sqr, nbin, edges, 1, counts)) goto done;
         for (int64_t c = 0; c < isucceed; c++) {
             uint64_t cum = 0;
             for (int k = 0; k < nbin; k++) {
@@ -811,6 +813,135 @@ done:
     if (fpcen) fclose(fpcen);
     for (int a = 0; a < 3; a++) { free(gal[a]); free(ran[a]); free(cen[a]); }
     free(Dg); free(Dr); free(counts); free(ngb); free(pN); free(edges);
+    return status;
+}
+
+/* ========================================================================================== */
+/* theory vpf: counts-in-spheres in a simulation box (theory/vpf/countspheres_impl.c.src:138-479)                 */
+
+static int HFN(cf_vpf_theory)(const int64_t np, void *vX, void *vY, void *vZ, const double rmax, const int nbin, const int nc,
+                              const int num_pN, unsigned long seed, struct config_options *options, cf_vpf_out *out)
+{
+    const double t_start = now_ms();
+    if (options->float_type != sizeof(REAL)) {
+        fprintf(stderr, "ERROR: In %s> Can only handle arrays of size=%zu. Got an array of size = %zu\n", __func__,
+                sizeof(REAL), options->float_type);
+        return EXIT_FAILURE;
+    }
+    if (!(rmax > 0.0 && nbin > 0 && nc > 0 && num_pN > 0)) {
+        fprintf(stderr, "Error: Invalid input parameters. Expected rmax > 0, number of bins > 0, number of random spheres > 0, number of pN's to calculate > 0.\n"
+                        "Found rmax = %lf, nbin = %d nspheres = %d num_pN = %d\n", rmax, nbin, nc, num_pN);
+        return EXIT_FAILURE;
+    }
+    if (np <= 0) {
+        fprintf(stderr, "Error: In %s> no particles\n", __func__);
+        return EXIT_FAILURE;
+    }
+    const REAL *P[3] = {(const REAL *)vX, (const REAL *)vY, (const REAL *)vZ};
+    REAL lo[3], hi[3], wrap[3];
+    for (int a = 0; a < 3; a++) { /* get_max_min_DOUBLE */
+        lo[a] = H_MAXPOS;
+        hi[a] = -H_MAXPOS;
+        for (int64_t i = 0; i < np; i++) {
+            if (P[a][i] < lo[a]) lo[a] = P[a][i];
+            if (P[a][i] > hi[a]) hi[a] = P[a][i];
+        }
+    }
+    if (options->periodic && options->boxsize == BOXSIZE_NOTGIVEN) {
+        fprintf(stderr, "boxsize = %g must be specified with periodic wrap. Please specify a non-zero boxsize, or zero to detect the particle extent, or -1 to make a dimension non-periodic.\n",
+                options->boxsize);
+        return EXIT_FAILURE;
+    }
+    const double bs[3] = {options->boxsize_x, options->boxsize_y == BOXSIZE_NOTGIVEN ? options->boxsize : options->boxsize_y,
+                          options->boxsize_z == BOXSIZE_NOTGIVEN ? options->boxsize : options->boxsize_z};
+    int periodic[3];
+    for (int a = 0; a < 3; a++) { /* :227-233 */
+        periodic[a] = options->periodic && bs[a] >= 0;
+        wrap[a] = (options->periodic && bs[a] > 0) ? bs[a] : (hi[a] - lo[a]);
+    }
+
+    int status = EXIT_FAILURE;
+    REAL *cen[3] = {NULL, NULL, NULL};
+    uint32_t *counts = NULL;
+    uint64_t *pN = NULL;
+    double *edges = NULL;
+    for (int a = 0; a < 3; a++) cen[a] = malloc(sizeof(REAL) * (size_t)nc);
+    counts = malloc(sizeof(uint32_t) * (size_t)nc * (size_t)nbin);
+    pN = calloc((size_t)nbin * (size_t)num_pN, sizeof(uint64_t));
+    edges = malloc(sizeof(double) * (size_t)nbin);
+    if (!cen[0] || !cen[1] || !cen[2] || !counts || !pN || !edges) {
+        fprintf(stderr, "Error: In %s> out of memory\n", __func__);
+        goto done;
+    }
+
+    /* ---- the centres: three draws per trial; without periodic wrap a sphere that reaches past the data is redrawn
+     * (:299-316).  Bounded so that an rmax larger than the box cannot spin forever. ---- */
+    {
+        cf_mt19937 rng;
+        cf_mt_set(&rng, seed);
+        int ic = 0;
+        int64_t trials = 0;
+        const int64_t max_trials = 1000000 + 100000 * (int64_t)nc;
+        while (ic < nc) {
+            if (++trials > max_trials) {
+                fprintf(stderr, "Error: In %s> could not place %d spheres of radius %lf inside the particle extent\n", __func__, nc, rmax);
+                goto done;
+            }
+            const REAL xc = wrap[0] * cf_mt_uniform(&rng) + lo[0];
+            const REAL yc = wrap[1] * cf_mt_uniform(&rng) + lo[1];
+            const REAL zc = wrap[2] * cf_mt_uniform(&rng) + lo[2];
+            if (!options->periodic) {
+                if ((xc - lo[0]) < rmax || (hi[0] - xc) < rmax || (yc - lo[1]) < rmax || (hi[1] - yc) < rmax ||
+                    (zc - lo[2]) < rmax || (hi[2] - zc) < rmax)
+                    continue;
+            }
+            cen[0][ic] = xc, cen[1][ic] = yc, cen[2][ic] = zc;
+            ic++;
+        }
+    }
+
+    if (cfb_upload(0, (int)sizeof(REAL), np, vX, vY, vZ, NULL, NULL, NULL)) goto done;
+    {
+        const REAL rmax_r = (REAL)rmax; /* the kernels take rmax as DOUBLE (vpf_kernels.c.src:20-40) */
+        const REAL rstep = rmax_r / (REAL)nbin;
+        const REAL rmax_sqr = rmax_r * rmax_r;
+        for (int k = 0; k < nbin; k++) {
+            const REAL e = (k + 1) * rstep * rstep * (k + 1);
+            edges[k] = (double)e;
+        }
+        const double dlo[3] = {(double)lo[0], (double)lo[1], (double)lo[2]};
+        const double dext[3] = {(double)(hi[0] - lo[0]), (double)(hi[1] - lo[1]), (double)(hi[2] - lo[2])};
+        const double dwrap[3] = {(double)wrap[0], (double)wrap[1], (double)wrap[2]};
+        const int per[3] = {options->periodic ? 1 : 0, options->periodic ? 1 : 0, options->periodic ? 1 : 0}; /* :332-380 */
+        (void)periodic;
+        if (cfb_count_spheres(0, (int)sizeof(REAL), dlo, dext, per, dwrap, 1, nc, cen[0], cen[1], cen[2], (double)rmax_r,
+                              (double)rmax_sqr, nbin, edges, 1, counts)) goto done;
+    }
+    for (int64_t c = 0; c < nc; c++) { /* :401-416 */
+        uint64_t cum = 0;
+        for (int k = 0; k < nbin; k++) {
+            cum += counts[c * nbin + k];
+            if (cum < (uint64_t)num_pN) pN[(size_t)k * num_pN + cum]++;
+        }
+    }
+    out->nbin = nbin;
+    out->num_pN = num_pN;
+    out->pN = calloc((size_t)nbin, sizeof(double *));
+    if (!out->pN) goto done;
+    {
+        const REAL inv_nc = ((REAL)1.0) / (REAL)nc; /* :451-462: integer count times a REAL */
+        for (int k = 0; k < nbin; k++) {
+            out->pN[k] = malloc(sizeof(double) * (size_t)num_pN);
+            if (!out->pN[k]) goto done;
+            for (int i = 0; i < num_pN; i++) out->pN[k][i] = (double)(REAL)((int)pN[(size_t)k * num_pN + i] * inv_nc);
+        }
+    }
+    reset_bin_refine_factors(options);
+    if (options->c_api_timer) options->c_api_time = (now_ms() - t_start) * 1.0e-3;
+    status = EXIT_SUCCESS;
+done:
+    for (int a = 0; a < 3; a++) free(cen[a]);
+    free(counts); free(pN); free(edges);
     return status;
 }
 

@@ -153,3 +153,23 @@ def xi(boxsize, nthreads, binfile, X, Y, Z, weights=None, weight_type=None, verb
     res["rmin"], res["rmax"] = r["rupp"][:-1], r["rupp"][1:]
     res["ravg"], res["xi"], res["npairs"], res["weightavg"] = r["ravg"], r["cf"], r["npairs"], r["weightavg"]
     return (res, r["api_time"]) if c_api_timer else res
+
+
+def vpf(rmax, nbins, nspheres, numpN, seed, X, Y, Z, verbose=False, periodic=True, boxsize=None, xbin_refine_factor=1,
+        ybin_refine_factor=1, zbin_refine_factor=1, max_cells_per_dim=100, copy_particles=True, c_api_timer=False,
+        isa="fastest"):
+    """Counts-in-spheres in a simulation box (``Corrfunc.theory.vpf``, Corrfunc/theory/vpf.py:17-200): the probability
+    pN that a sphere of radius r holds exactly N points, for ``nbins`` radii up to ``rmax`` and N < ``numpN``, from
+    ``nspheres`` centres drawn with MT19937 seeded by ``seed``.  Returns a structured array (rmax, pN[numpN])."""
+    if periodic and boxsize is None:
+        raise ValueError("Must specify a boxsize if periodic=True")
+    dtype = check_same_dtype(X, Y, Z)
+    opt = _options(dtype, periodic=periodic, boxsize=boxsize, verbose=verbose, need_avg=False,
+                   refine=(xbin_refine_factor, ybin_refine_factor, zbin_refine_factor), default_refine=(1, 1, 1),
+                   max_cells_per_dim=max_cells_per_dim, copy_particles=copy_particles, enable_min_sep_opt=True,
+                   c_api_timer=c_api_timer, isa=isa)
+    r = _capi.call_vpf(_lib.load(), rmax, nbins, nspheres, numpN, seed, X, Y, Z, options=opt, dtype=dtype)
+    res = np.zeros(r["nbin"], dtype=[("rmax", np.float64), ("pN", (np.float64, numpN))])
+    res["rmax"] = (np.arange(r["nbin"]) + 1) * (rmax / float(nbins))  # _countpairs.c: r = (ibin + 1) * rstep
+    res["pN"] = r["pN"] if numpN > 1 else r["pN"][:, 0]
+    return (res, r["api_time"]) if c_api_timer else res

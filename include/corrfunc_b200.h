@@ -41,6 +41,9 @@ const char *corrfunc_b200_version(void);
 int corrfunc_b200_cz_to_comoving(int prec, int64_t n, const void *cz, int cosmology, void *dist);
 /* The table itself (for tests): fills zc[], dc[] (max_size entries each) and returns the number of entries, -1 on error. */
 int corrfunc_b200_cosmo_dist_table(double zmax, int max_size, double *zc, double *dc, int cosmology);
+/* The first n uniform deviates of the MT19937 stream countspheres draws its sphere centres from (what GSL's
+ * gsl_rng_mt19937 + gsl_rng_uniform give for this seed); for tests. */
+void corrfunc_b200_mt19937_uniform(unsigned long seed, int64_t n, double *out);
 
 #ifdef __cplusplus
 }

@@ -124,15 +124,17 @@ int cfb_theta_gridlink(int slot, int prec, const cfb_theta_lattice *lat, int64_t
 int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int64_t *ngb_offsets /* [ncells+1] */,
                     const int32_t *ngb_cells, cfb_hist *out, cfb_stats *stats);
 
-/* Counts-in-spheres (mocks/vpf_mocks): for each of ncen centres (host arrays of element size prec), the number of
- * particles of `slot` per radial shell -> counts[ncen][nbin] (host).  The particles must lie in [0, extent]^3; they are
- * gridded on an internal lattice with cells a little larger than rmax (regrid = 0 reuses the lattice of the previous
- * call on this slot); the counts do not depend on it.  shells = 1: edges[nbin] are the squared upper shell edges
+/* Counts-in-spheres (theory/vpf, mocks/vpf_mocks): for each of ncen centres (host arrays of element size prec), the
+ * number of particles of `slot` per radial shell -> counts[ncen][nbin] (host).  The particles must lie in
+ * [lo, lo + ext] per axis; they are gridded on an internal lattice with cells a little larger than rmax (regrid = 0
+ * reuses the lattice of the previous call on this slot); the counts do not depend on it.  On a periodic axis the centre
+ * is shifted by -+wrap[axis] towards a particle more than half a wrap away (the reference does the same per neighbour
+ * cell, theory/vpf/countspheres_impl.c.src:331-380).  shells = 1: edges[nbin] are the squared upper shell edges
  * (REAL-valued), r2 = fma(dz,dz, fma(dy,dy, dx*dx)), shell assignment as in vpf_mocks_kernels.c.src:63-92.
  * shells = 0: nbin must be 1, r2 = dx*dx + dy*dy + dz*dz, counts = #{r2 < rmax_sqr} (count_neighbors). */
-int cfb_count_spheres(int slot, int prec, double extent, int regrid, int64_t ncen, const void *xc, const void *yc,
-                      const void *zc, double rmax, double rmax_sqr, int nbin, const double *edges, int shells,
-                      uint32_t *counts);
+int cfb_count_spheres(int slot, int prec, const double lo[3], const double ext[3], const int periodic[3],
+                      const double wrap[3], int regrid, int64_t ncen, const void *xc, const void *yc, const void *zc,
+                      double rmax, double rmax_sqr, int nbin, const double *edges, int shells, uint32_t *counts);
 
 /* Tunables (mostly for tests / benchmarks). */
 void cfb_set_target_occupancy(int particles_per_fine_cell); /* 0 = default */

@@ -34,11 +34,11 @@ expand() { # expand <src template> <dst dir>  -> writes <name>_float.<ext> and <
 }
 
 mkdir -p "$TMP/gen"
-for d in utils theory/DD theory/DDrppi theory/DDsmu theory/wp theory/xi mocks/DDtheta_mocks mocks/DDrppi_mocks mocks/DDsmu_mocks mocks/vpf_mocks; do
+for d in utils theory/vpf theory/DD theory/DDrppi theory/DDsmu theory/wp theory/xi mocks/DDtheta_mocks mocks/DDrppi_mocks mocks/DDsmu_mocks mocks/vpf_mocks; do
   for f in "$REF/$d"/*.src; do expand "$f" "$TMP/gen"; done
 done
 
-INCL="-I$TMP/gen -I$REF/utils -I$REF/io -I$REF/theory/DD -I$REF/theory/DDrppi -I$REF/theory/DDsmu -I$REF/theory/wp -I$REF/theory/xi -I$REF/mocks/DDtheta_mocks -I$REF/mocks/DDrppi_mocks -I$REF/mocks/DDsmu_mocks -I$REF/mocks/vpf_mocks -I$HERE/gsl_shim"
+INCL="-I$TMP/gen -I$REF/utils -I$REF/io -I$REF/theory/vpf -I$REF/theory/DD -I$REF/theory/DDrppi -I$REF/theory/DDsmu -I$REF/theory/wp -I$REF/theory/xi -I$REF/mocks/DDtheta_mocks -I$REF/mocks/DDrppi_mocks -I$REF/mocks/DDsmu_mocks -I$REF/mocks/vpf_mocks -I$HERE/gsl_shim"
 COMMON="-std=c99 -m64 -O3 -fPIC -D_POSIX_SOURCE=200809L -D_GNU_SOURCE -DVERSION=\"2.5.3\" -DUSE_OMP -fopenmp \
  -funroll-loops -fno-strict-aliasing -ftree-vectorize -DPERIODIC -DENABLE_MIN_SEP_OPT -DCOPY_PARTICLES -DOUTPUT_RPAVG \
  -DLINK_IN_DEC -DLINK_IN_RA -DDOUBLE_PREC -w"
@@ -55,6 +55,7 @@ SRCS=(
   # set_cosmo_dist.c; the reference sources themselves are compiled unmodified.
   "$REF/mocks/DDrppi_mocks/countpairs_rp_pi_mocks.c" "$TMP/gen/countpairs_rp_pi_mocks_impl_float.c" "$TMP/gen/countpairs_rp_pi_mocks_impl_double.c"
   "$REF/mocks/DDsmu_mocks/countpairs_s_mu_mocks.c" "$TMP/gen/countpairs_s_mu_mocks_impl_float.c" "$TMP/gen/countpairs_s_mu_mocks_impl_double.c"
+  "$REF/theory/vpf/countspheres.c" "$TMP/gen/countspheres_impl_float.c" "$TMP/gen/countspheres_impl_double.c"
   "$REF/mocks/vpf_mocks/countspheres_mocks.c" "$TMP/gen/countspheres_mocks_impl_float.c" "$TMP/gen/countspheres_mocks_impl_double.c"
   "$REF/utils/cosmology_params.c" "$REF/utils/set_cosmo_dist.c"
   "$TMP/gen/gridlink_impl_float.c" "$TMP/gen/gridlink_impl_double.c"

@@ -1354,6 +1354,75 @@ int FN(oracle_vpf_mocks)(const int64_t Ngal, const REAL *RA, const REAL *DEC, co
     return EXIT_SUCCESS;
 }
 
+/* Counts-in-spheres in a simulation box: theory/vpf/countspheres_impl.c.src:138-479 with the AVX-512 kernel of
+ * theory/vpf/vpf_kernels.c.src.  The centres are given (the reference draws them from gsl_rng_mt19937).  On a periodic
+ * axis the reference shifts the centre by -+wrap for neighbour cells across the box edge; a particle that can count is
+ * always met with its nearest image, which is what the brute force below takes. */
+int FN(oracle_vpf_theory)(const int64_t np, const REAL *X, const REAL *Y, const REAL *Z, const int64_t nc, const REAL *xc,
+                          const REAL *yc, const REAL *zc, const int periodic, const double wrapx, const double wrapy,
+                          const double wrapz, const double rmax_in, const int nbin, const int num_pN, double *pN_out)
+{
+    if (!(rmax_in > 0.0) || nbin < 1 || nc < 1 || num_pN < 1) return EXIT_FAILURE;
+    const REAL rmax = rmax_in;
+    const REAL wrap[3] = {(REAL)wrapx, (REAL)wrapy, (REAL)wrapz};
+    const REAL rstep = rmax / (REAL)nbin;
+    const REAL rmax_sqr = rmax * rmax;
+    REAL *E = malloc(sizeof(REAL) * nbin);
+    for (int k = 0; k < nbin; k++) E[k] = (k + 1) * rstep * rstep * (k + 1);
+    int64_t *pN = calloc((size_t)nbin * num_pN, sizeof(int64_t));
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+        uint64_t *counts = calloc((size_t)nbin, sizeof(uint64_t));
+        int64_t *mine = calloc((size_t)nbin * num_pN, sizeof(int64_t));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 16)
+#endif
+        for (int64_t c = 0; c < nc; c++) {
+            const REAL C3[3] = {xc[c], yc[c], zc[c]};
+            for (int k = 0; k < nbin; k++) counts[k] = 0;
+            for (int64_t j = 0; j < np; j++) {
+                const REAL P3[3] = {X[j], Y[j], Z[j]};
+                REAL d[3];
+                for (int a = 0; a < 3; a++) {
+                    REAL cen = C3[a];
+                    if (periodic) {
+                        const REAL raw = P3[a] - C3[a], half = (REAL)0.5 * wrap[a];
+                        if (raw > half) cen = C3[a] + wrap[a];
+                        else if (raw < -half) cen = C3[a] - wrap[a];
+                    }
+                    d[a] = cen - P3[a];
+                }
+                const REAL r2 = FMA_R(d[2], d[2], FMA_R(d[1], d[1], d[0] * d[0]));
+                if (!(r2 < rmax_sqr)) continue;
+                int left = 1;
+                for (int k = nbin - 1; k >= 1; k--)
+                    if (r2 < E[k] && r2 >= E[k - 1]) {
+                        counts[k]++;
+                        left = 0;
+                        break;
+                    }
+                if (left && nbin >= 2) counts[0]++;
+            }
+            for (int k = 1; k < nbin; k++) counts[k] += counts[k - 1];
+            for (int k = 0; k < nbin; k++)
+                if (counts[k] < (uint64_t)num_pN) mine[(size_t)k * num_pN + counts[k]]++;
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        for (int64_t i = 0; i < (int64_t)nbin * num_pN; i++) pN[i] += mine[i];
+        free(counts);
+        free(mine);
+    }
+    const REAL inv_nc = ((REAL)1.0) / (REAL)nc;
+    for (int64_t i = 0; i < (int64_t)nbin * num_pN; i++) pN_out[i] = (double)(REAL)((int)pN[i] * inv_nc);
+    free(pN);
+    free(E);
+    return EXIT_SUCCESS;
+}
+
 #undef FMA_R
 #undef SQRT_R
 #undef FABS_R

@@ -8,7 +8,7 @@ import os
 
 REF = "/root/reference/Corrfunc"
 FUNCS = {"DD": "theory/DD.py", "DDrppi": "theory/DDrppi.py", "DDsmu": "theory/DDsmu.py", "wp": "theory/wp.py",
-         "xi": "theory/xi.py", "DDtheta_mocks": "mocks/DDtheta_mocks.py", "DDrppi_mocks": "mocks/DDrppi_mocks.py",
+         "xi": "theory/xi.py", "vpf": "theory/vpf.py", "DDtheta_mocks": "mocks/DDtheta_mocks.py", "DDrppi_mocks": "mocks/DDrppi_mocks.py",
          "DDsmu_mocks": "mocks/DDsmu_mocks.py", "vpf_mocks": "mocks/vpf_mocks.py",
          "convert_3d_counts_to_cf": "utils.py", "convert_rp_pi_counts_to_wp": "utils.py",
          "return_file_with_rbins": "utils.py", "fix_cz": "utils.py", "fix_ra_dec": "utils.py",

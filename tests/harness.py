@@ -135,6 +135,52 @@ def oracle_vpf_mocks(RA, DEC, D, xc, yc, zc, rmax, nbin, num_pN, nthreads=None, 
     return pN, rcube.value
 
 
+def mt19937_uniform(seed, n):
+    """The library's restatement of gsl_rng_mt19937 + gsl_rng_uniform (host code, no GPU)."""
+    from corrfunc_b200 import _lib
+
+    lib = _lib.load()
+    out = np.zeros(n)
+    lib.corrfunc_b200_mt19937_uniform.restype = None
+    lib.corrfunc_b200_mt19937_uniform(C.c_ulong(seed), C.c_int64(n), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def vpf_theory_centres(X, Y, Z, rmax, nc, seed, periodic, boxsize):
+    """The sphere centres theory/vpf draws (countspheres_impl.c.src:299-316) from the library's MT19937 stream."""
+    dt = X.dtype.type
+    lo = [dt(a.min()) for a in (X, Y, Z)]
+    hi = [dt(a.max()) for a in (X, Y, Z)]
+    wrap = [dt(boxsize) if (periodic and boxsize > 0) else dt(h - l) for l, h in zip(lo, hi)]
+    u = mt19937_uniform(seed, 3 * (nc * 50 + 1000))
+    cen, t = [], 0
+    while len(cen) < nc:
+        c = [dt(np.float64(wrap[a]) * u[3 * t + a] + np.float64(lo[a])) for a in range(3)]
+        t += 1
+        if not periodic and any(np.float64(c[a] - lo[a]) < rmax or np.float64(hi[a] - c[a]) < rmax for a in range(3)):
+            continue
+        cen.append(c)
+    cen = np.array(cen, dtype=X.dtype)
+    return cen[:, 0].copy(), cen[:, 1].copy(), cen[:, 2].copy(), [float(w) for w in wrap]
+
+
+def oracle_vpf_theory(X, Y, Z, xc, yc, zc, periodic, wrap, rmax, nbin, num_pN, nthreads=None):
+    lib = load_oracle()
+    if nthreads:
+        lib.oracle_set_num_threads(int(nthreads))
+    dtype = np.asarray(X).dtype
+    fn = lib.oracle_vpf_theory_double if dtype == np.float64 else lib.oracle_vpf_theory_float
+    fn.restype = C.c_int
+    X, Y, Z, xc, yc, zc = [np.ascontiguousarray(a, dtype=dtype) for a in (X, Y, Z, xc, yc, zc)]
+    pN = np.zeros((nbin, num_pN))
+    st = fn(C.c_int64(X.size), _p(X), _p(Y), _p(Z), C.c_int64(xc.size), _p(xc), _p(yc), _p(zc), C.c_int(int(periodic)),
+            C.c_double(wrap[0]), C.c_double(wrap[1]), C.c_double(wrap[2]), C.c_double(rmax), C.c_int(nbin),
+            C.c_int(num_pN), _p(pN))
+    if st != 0:
+        raise RuntimeError("oracle_vpf_theory failed")
+    return pN
+
+
 def mock_points(seed, n, dtype):
     """Seeded synthetic survey wedge: RA 40-90 deg, DEC -10..30 deg, comoving distance 300-700 (uniform in volume
     along the radius), weights in [0.5, 1.5)."""

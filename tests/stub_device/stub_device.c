@@ -135,10 +135,20 @@ int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int64_t *off, 
 #define SPHERES(T, FMA)                                                                                              \
     for (int64_t c = 0; c < ncen; c++) {                                                                             \
         for (int k = 0; k < nbin; k++) counts[c * nbin + k] = 0;                                                     \
-        const T X = ((const T *)xc)[c], Y = ((const T *)yc)[c], Z = ((const T *)zc)[c];                              \
+        const T Cc[3] = {((const T *)xc)[c], ((const T *)yc)[c], ((const T *)zc)[c]};                                \
         for (int64_t j = 0; j < g_set[slot].n; j++) {                                                                \
-            const T dx = X - ((const T *)g_set[slot].x)[j], dy = Y - ((const T *)g_set[slot].y)[j],                  \
-                    dz = Z - ((const T *)g_set[slot].z)[j];                                                          \
+            const T Pp[3] = {((const T *)g_set[slot].x)[j], ((const T *)g_set[slot].y)[j], ((const T *)g_set[slot].z)[j]}; \
+            T dd[3];                                                                                                 \
+            for (int a = 0; a < 3; a++) { /* nearest image on a periodic axis, as the device kernel does */          \
+                T cen = Cc[a];                                                                                       \
+                if (periodic[a]) {                                                                                   \
+                    const T raw = Pp[a] - Cc[a], half = (T)0.5 * (T)wrap[a];                                         \
+                    if (raw > half) cen = Cc[a] + (T)wrap[a];                                                        \
+                    else if (raw < -half) cen = Cc[a] - (T)wrap[a];                                                  \
+                }                                                                                                    \
+                dd[a] = cen - Pp[a];                                                                                 \
+            }                                                                                                        \
+            const T dx = dd[0], dy = dd[1], dz = dd[2];                                                              \
             if (shells) {                                                                                            \
                 const T r2 = FMA(dz, dz, FMA(dy, dy, dx * dx));                                                      \
                 if (!(r2 < (T)rmax_sqr)) continue;                                                                   \
@@ -157,11 +167,11 @@ int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int64_t *off, 
         }                                                                                                            \
     }
 
-int cfb_count_spheres(int slot, int prec, double extent, int regrid, int64_t ncen, const void *xc, const void *yc,
-                      const void *zc, double rmax, double rmax_sqr, int nbin, const double *edges, int shells,
-                      uint32_t *counts)
+int cfb_count_spheres(int slot, int prec, const double lo[3], const double ext[3], const int periodic[3],
+                      const double wrap[3], int regrid, int64_t ncen, const void *xc, const void *yc, const void *zc,
+                      double rmax, double rmax_sqr, int nbin, const double *edges, int shells, uint32_t *counts)
 {
-    (void)extent, (void)regrid, (void)rmax;
+    (void)lo, (void)ext, (void)regrid, (void)rmax;
     if (g_set[slot].prec != prec) return 1;
     if (prec == 4) {
         SPHERES(float, fmaf)

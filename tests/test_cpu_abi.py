@@ -25,7 +25,7 @@ def test_headers_compile_as_c_and_cxx_and_offsets_agree(tmp_path):
     src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "countpairs.h"\n#include "countpairs_rp_pi.h"\n'
                    '#include "countpairs_s_mu.h"\n#include "countpairs_wp.h"\n#include "countpairs_xi.h"\n'
                    '#include "countpairs_theta_mocks.h"\n#include "countpairs_rp_pi_mocks.h"\n#include "countpairs_s_mu_mocks.h"\n'
-                   '#include "countspheres_mocks.h"\n'
+                   '#include "countspheres_mocks.h"\n#include "countspheres.h"\n'
                    '#include "corrfunc_b200.h"\n'
                    'int main(void){struct config_options o=get_config_options();'
                    'printf("%zu %zu %zu %zu %zu %zu %s\\n",sizeof(struct config_options),sizeof(struct extra_options),'

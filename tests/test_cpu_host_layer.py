@@ -91,3 +91,50 @@ def test_host_layer_mocks_vs_committed_reference_outputs(hostlib, dtype):
     tol = 1e-10 if dtype == np.float64 else 1e-5
     ok = a["npairs"] > 0
     assert np.allclose(r["ravg"][ok], a["ravg"][ok], rtol=tol) and np.allclose(r["weightavg"][ok], a["weightavg"][ok], rtol=tol)
+
+
+# ---- theory vpf: MT19937 stream, centres, host driver -------------------------------------------------------------
+
+def test_mt19937_stream_is_the_published_one():
+    """corrfunc_b200_mt19937_uniform (what countspheres draws its centres from) against numpy's independent MT19937
+    with the same (2002) initialisation, which is the stream gsl_rng_mt19937 + gsl_rng_uniform produce."""
+    for seed in (42, 1, 0):
+        bg = np.random.MT19937()
+        bg._legacy_seeding(seed if seed else 4357)  # GSL maps seed 0 to 4357
+        want = bg.random_raw(3000) / 4294967296.0
+        assert np.array_equal(H.mt19937_uniform(seed, 3000), want)
+
+
+@pytest.mark.skipif(H.load_ref() is None or not hasattr(H.load_ref(), "countspheres"),
+                    reason="oracle/_ref was not prebuilt with theory/vpf")
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("periodic", [True, False])
+def test_host_layer_theory_vpf_vs_live_reference(hostlib, dtype, periodic):
+    """theory/vpf of the unmodified reference (its GSL generator supplied by oracle/gsl_shim) vs the product's host
+    layer over the brute-force device stand-in vs the oracle on the centres of tests/harness.py."""
+    L, N = 300.0, 40000
+    x, y, z, _ = H.box_points(9, N, L, dtype)
+    rmax, nbin, nc, num_pN, seed = 12.0, 6, 800, 5, 77
+    o = _capi.default_options(dtype, periodic=periodic, boxsize=L if periodic else None, isa=H.ref_isa(), bin_refine_factors=(1, 1, 1))
+    r = _capi.call_vpf(H.load_ref(), rmax, nbin, nc, num_pN, seed, x, y, z, options=o)
+    o = _capi.default_options(dtype, periodic=periodic, boxsize=L if periodic else None, bin_refine_factors=(1, 1, 1))
+    h = _capi.call_vpf(hostlib, rmax, nbin, nc, num_pN, seed, x, y, z, options=o)
+    assert np.array_equal(h["pN"], r["pN"])
+    xc, yc, zc, wrap = H.vpf_theory_centres(x, y, z, rmax, nc, seed, periodic, L)
+    a = H.oracle_vpf_theory(x, y, z, xc, yc, zc, periodic, wrap, rmax, nbin, num_pN)
+    assert np.array_equal(a, r["pN"])
+    assert abs(r["pN"][:, :].sum(axis=1).max() - 1.0) < 0.5 and r["pN"][0, 0] > r["pN"][-1, 0]  # sanity: p0 falls with radius
+
+
+@pytest.mark.skipif(H.load_ref() is None or not hasattr(H.load_ref(), "countspheres"),
+                    reason="oracle/_ref was not prebuilt with theory/vpf")
+def test_theory_vpf_small_periodic_box_vs_live_reference(hostlib):
+    """Three cells per axis, spheres reaching through the periodic faces: nearest-image brute force == the reference's
+    per-cell centre shifts."""
+    x, y, z, _ = H.box_points(10, 3000, 40.0, np.float64)
+    o = _capi.default_options(np.float64, periodic=True, boxsize=40.0, isa=H.ref_isa(), bin_refine_factors=(1, 1, 1))
+    r = _capi.call_vpf(H.load_ref(), 12.0, 4, 300, 4, 5, x, y, z, options=o)
+    xc, yc, zc, wrap = H.vpf_theory_centres(x, y, z, 12.0, 300, 5, True, 40.0)
+    assert np.array_equal(H.oracle_vpf_theory(x, y, z, xc, yc, zc, True, wrap, 12.0, 4, 4), r["pN"])
+    o = _capi.default_options(np.float64, periodic=True, boxsize=40.0, bin_refine_factors=(1, 1, 1))
+    assert np.array_equal(_capi.call_vpf(hostlib, 12.0, 4, 300, 4, 5, x, y, z, options=o)["pN"], r["pN"])

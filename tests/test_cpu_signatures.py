@@ -49,7 +49,7 @@ def test_compat_package_exposes_the_reference_import_paths():
                           ("Corrfunc.theory.DDsmu", "DDsmu"), ("Corrfunc.theory.wp", "wp"), ("Corrfunc.theory.xi", "xi"),
                           ("Corrfunc.mocks.DDtheta_mocks", "DDtheta_mocks"), ("Corrfunc.theory", "DD"),
                           ("Corrfunc.mocks", "DDtheta_mocks"), ("Corrfunc.mocks.DDrppi_mocks", "DDrppi_mocks"),
-                          ("Corrfunc.mocks.DDsmu_mocks", "DDsmu_mocks"), ("Corrfunc.mocks", "DDsmu_mocks"), ("Corrfunc.mocks.vpf_mocks", "vpf_mocks"),
+                          ("Corrfunc.mocks.DDsmu_mocks", "DDsmu_mocks"), ("Corrfunc.mocks", "DDsmu_mocks"), ("Corrfunc.mocks.vpf_mocks", "vpf_mocks"), ("Corrfunc.theory.vpf", "vpf"), ("Corrfunc.theory", "vpf"),
                           ("Corrfunc.utils", "convert_3d_counts_to_cf"),
                           ("Corrfunc.utils", "convert_rp_pi_counts_to_wp")):
             m = importlib.import_module(mod)

@@ -97,3 +97,27 @@ def test_vpf_mocks_centres_from_randoms(dtype, tmp_path):
     assert written.shape == (nc, 4) and np.allclose(written[:, 0], xc, atol=1e-4) and np.allclose(written[:, 1], yc, atol=1e-4)
     want, _ = H.oracle_vpf_mocks(ra, dec, d, xc, yc, zc, 12.0, 6, 4, dmax_randoms=rd.max())
     assert np.array_equal(r["pN"], want)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("periodic", [True, False])
+def test_theory_vpf_vs_oracle(dtype, periodic):
+    """countspheres / Corrfunc.theory.vpf: centres from the MT19937 stream (restated in tests/harness.py from the
+    library's own stream, which equals numpy's), counts against the oracle -- both of which agree with the unmodified
+    reference on the CPU (tests/test_cpu_host_layer.py)."""
+    from corrfunc_b200.theory import vpf
+
+    L, N = 300.0, 40000
+    x, y, z, _ = H.box_points(9, N, L, dtype)
+    rmax, nbin, nc, num_pN, seed = 12.0, 6, 800, 5, 77
+    r = vpf(rmax, nbin, nc, num_pN, seed, x, y, z, periodic=periodic, boxsize=L if periodic else None)
+    xc, yc, zc, wrap = H.vpf_theory_centres(x, y, z, rmax, nc, seed, periodic, L)
+    a = H.oracle_vpf_theory(x, y, z, xc, yc, zc, periodic, wrap, rmax, nbin, num_pN)
+    assert r.dtype.names == ("rmax", "pN") and np.allclose(r["rmax"], 2.0 * np.arange(1, 7))
+    assert np.array_equal(r["pN"], a)
+    # a box only three cells wide per axis, spheres reaching through the periodic faces
+    if periodic:
+        xs, ys, zs, _ = H.box_points(10, 3000, 40.0, dtype)
+        r = vpf(12.0, 4, 300, 4, 5, xs, ys, zs, periodic=True, boxsize=40.0)
+        xc, yc, zc, wrap = H.vpf_theory_centres(xs, ys, zs, 12.0, 300, 5, True, 40.0)
+        assert np.array_equal(r["pN"], H.oracle_vpf_theory(xs, ys, zs, xc, yc, zc, True, wrap, 12.0, 4, 4))
