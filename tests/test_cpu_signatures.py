@@ -57,6 +57,10 @@ def test_compat_package_exposes_the_reference_import_paths():
         import Corrfunc
 
         assert Corrfunc.__version__
+        assert Corrfunc.which("sh") and callable(Corrfunc.read_text_file) and callable(Corrfunc.write_text_file)
+        import Corrfunc.io
+
+        assert callable(Corrfunc.io.read_catalog)
     finally:
         sys.path.pop(0)
         for k in [k for k in sys.modules if k == "Corrfunc" or k.startswith("Corrfunc.")]:
