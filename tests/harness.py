@@ -293,11 +293,14 @@ def vpf_centres_from_randoms(RA, DEC, D, rcube, rmax, threshold, nc):
     within rmax; r2 = dx*dx + dy*dy + dz*dz in the run precision, without FMA.  rcube = the shift (max distance + 1).
     Brute force: small inputs only."""
     dt = RA.dtype.type
-    cosd = lambda a: np.cos(a.astype(dt) * np.float64(np.pi / 180.0) if False else (a * 0.017453292519943295769236907684886127134428718885417254560971)).astype(dt)  # noqa: E731
-    sind = lambda a: np.sin(a * 0.017453292519943295769236907684886127134428718885417254560971).astype(dt)  # noqa: E731
-    if dt == np.float32:  # COSD(x) = cosf((float)(x * PI_OVER_180)): the product is a double rounded to float first
-        cosd = lambda a: np.cos((a.astype(np.float64) * 0.017453292519943295769236907684886127134428718885417254560971).astype(np.float32))  # noqa: E731
-        sind = lambda a: np.sin((a.astype(np.float64) * 0.017453292519943295769236907684886127134428718885417254560971).astype(np.float32))  # noqa: E731
+    k = 0.017453292519943295769236907684886127134428718885417254560971  # PI_OVER_180 (utils/function_precision.h)
+
+    def cosd(a):  # COSD(x): cos / cosf of the DOUBLE product x * PI_OVER_180, rounded to the run precision first
+        return np.cos((a.astype(np.float64) * k).astype(dt))
+
+    def sind(a):
+        return np.sin((a.astype(np.float64) * k).astype(dt))
+
     x = (D * cosd(DEC) * cosd(RA)).astype(dt) + dt(rcube)
     y = (D * cosd(DEC) * sind(RA)).astype(dt) + dt(rcube)
     z = (D * sind(DEC)).astype(dt) + dt(rcube)
