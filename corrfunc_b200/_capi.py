@@ -408,6 +408,10 @@ def call_DDrppi_mocks(lib, autocorr, cosmology, nthreads, pimax, bins, RA1, DEC1
                                   C.byref(options), C.byref(extra))
     if st != 0:
         raise RuntimeError("countpairs_mocks returned %d" % st)
+    if not res.npairs:  # an empty particle set: EXIT_SUCCESS with the results untouched (rp_pi_mocks_impl:243-245)
+        e = np.zeros((0, 0))
+        return dict(npairs=e.astype(np.uint64), rupp=np.zeros(0), ravg=e, weightavg=e, npibin=0, pimax=float(pimax),
+                    api_time=options.c_api_time)
     nb, npi = res.nbin, res.npibin
     tot = (nb + 1) * (npi + 1)
 
@@ -440,6 +444,10 @@ def call_DDsmu_mocks(lib, autocorr, cosmology, nthreads, mu_max, nmu_bins, bins,
                                        int(cosmology), C.byref(res), C.byref(options), C.byref(extra))
     if st != 0:
         raise RuntimeError("countpairs_mocks_s_mu returned %d" % st)
+    if not res.npairs:  # an empty particle set: EXIT_SUCCESS with the results untouched
+        e = np.zeros((0, 0))
+        return dict(npairs=e.astype(np.uint64), rupp=np.zeros(0), ravg=e, weightavg=e, nmu_bins=0, mu_max=float(mu_max),
+                    api_time=options.c_api_time)
     nb, nmu = res.nsbin, res.nmu_bins
     tot = (nb + 1) * (nmu + 1)
 

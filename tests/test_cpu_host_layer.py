@@ -138,3 +138,27 @@ def test_theory_vpf_small_periodic_box_vs_live_reference(hostlib):
     assert np.array_equal(H.oracle_vpf_theory(x, y, z, xc, yc, zc, True, wrap, 12.0, 4, 4), r["pN"])
     o = _capi.default_options(np.float64, periodic=True, boxsize=40.0, bin_refine_factors=(1, 1, 1))
     assert np.array_equal(_capi.call_vpf(hostlib, 12.0, 4, 300, 4, 5, x, y, z, options=o)["pN"], r["pN"])
+
+
+def test_host_layer_mocks_error_behaviour(hostlib):
+    """What the host layer decides before any device work: the reference's error returns, loudly."""
+    ra, dec, d, _ = H.mock_points(5, 2000, np.float64)
+    edges = np.logspace(0, 1.3, 6)
+    ok = lambda **kw: _capi.default_options(np.float64, **kw)  # noqa: E731
+    with pytest.raises(RuntimeError):  # init_cosmology knows 1 and 2 only
+        _capi.call_DDrppi_mocks(hostlib, 1, 3, 1, 25.0, edges, ra, dec, d, options=ok(is_comoving_dist=True))
+    with pytest.raises(RuntimeError):  # cz = 20 km/s is z < 1e-4: below the distance table
+        _capi.call_DDrppi_mocks(hostlib, 1, 1, 1, 25.0, edges, ra, dec, np.full_like(d, 20.0), options=ok())
+    with pytest.raises(RuntimeError):  # rmin = 0 is refused by the mocks statistics
+        _capi.call_DDsmu_mocks(hostlib, 1, 1, 1, 0.8, 4, np.array([0.0, 1.0, 5.0]), ra, dec, d, options=ok(is_comoving_dist=True))
+    with pytest.raises(RuntimeError):  # mu_max outside (0, 1]
+        _capi.call_DDsmu_mocks(hostlib, 1, 1, 1, 1.5, 4, edges, ra, dec, d, options=ok(is_comoving_dist=True))
+    with pytest.raises(RuntimeError):  # DEC beyond 180 degrees
+        _capi.call_DDrppi_mocks(hostlib, 1, 1, 1, 25.0, edges, ra, dec + 200.0, d, options=ok(is_comoving_dist=True))
+    with pytest.raises(RuntimeError):  # pimax below one bin
+        _capi.call_DDrppi_mocks(hostlib, 1, 1, 1, 0.5, edges, ra, dec, d, options=ok(is_comoving_dist=True))
+    empty = np.zeros(0)
+    r = _capi.call_DDrppi_mocks(hostlib, 1, 1, 1, 25.0, edges, empty, empty, empty, options=ok(is_comoving_dist=True))
+    assert r["npairs"].size == 0  # the reference returns EXIT_SUCCESS and leaves the results untouched
+    with pytest.raises(RuntimeError):  # vpf: nonsense parameters
+        _capi.call_vpf(hostlib, -1.0, 4, 10, 3, 1, ra, dec, d, options=ok(periodic=False))
