@@ -394,3 +394,16 @@ def test_oracle_vpf_mocks_vs_live_reference_with_randoms(dtype, tmp_path):
     pN, rc = H.oracle_vpf_mocks(ra, dec, d, xc, yc, zc, 12.0, 6, 4, dmax_randoms=rd.max())
     assert rc == float(rcube)
     assert np.allclose(pN, r["pN"], atol=1e-6 if dtype == np.float32 else 1e-12)
+
+
+@pytest.mark.skipif(H.load_ref() is None or not hasattr(H.load_ref(), "countpairs_mocks"), reason="oracle/_ref not prebuilt")
+@pytest.mark.parametrize("part,seed", [("box", 11), ("sky", 12)])
+def test_oracle_fuzz_against_live_reference(part, seed):
+    """A short seeded run of tools/fuzz_oracle_vs_reference.py (random options, all statistics): no mismatch."""
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "tools", "fuzz_oracle_vs_reference.py"), part, str(seed), "25"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-1500:]
+    assert "mismatches 0" in out.stdout and "ran 25" in out.stdout, out.stdout[-1500:]
