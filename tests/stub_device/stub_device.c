@@ -21,6 +21,9 @@ static void *g_scratch[6];
 
 const char *cfb_last_error(void) { return "stub device layer"; }
 int cfb_init(void) { return 0; }
+void cfb_shutdown(void) {}
+void cfb_set_target_occupancy(int n) { (void)n; }
+void cfb_force_kernel(int k) { (void)k; }
 void cfb_set_shard(int rank, int nranks) { (void)rank, (void)nranks; }
 void cfb_get_shard(int *rank, int *nranks) { *rank = 0, *nranks = 1; }
 void *cfb_host_scratch(int which, size_t bytes)
