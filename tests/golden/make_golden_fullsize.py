@@ -20,7 +20,7 @@ from corrfunc_b200 import _capi  # noqa: E402
 
 ref = H.load_ref()
 assert ref is not None, "build oracle/_ref first (python -c 'import __graft_entry__ as g; g.build()')"
-nthreads = os.cpu_count()
+nthreads = int(os.environ.get("GOLDEN_THREADS", os.cpu_count()))
 for name in sys.argv[1:]:
     cfg = bench.config_by_name(name)
     dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
