@@ -48,6 +48,7 @@ struct Ctx {
     int target_occ = 0;
     int theta_sub = 1;  // sub x sub fine cells per reference RA/DEC cell of the last theta gridlink
     int force_kernel = -1;
+    int last_kind = 0;  // kernel the last count ran: 0 legacy generic, 1 fast, 2 per-pair-sum
     int launches = 0;
     char err[512];
 };
@@ -110,6 +111,7 @@ struct PairParams {
     const double *wmax;  // device: max |weight| of the first and of the second set (generic kernel, weights on)
     unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs [2]=pairs binned without evaluation [3]=sum of evaluated pairs x levels [4]=next tile (persistent warps)
     int hist_in_smem;
+    int sum_copies_shift;  // per-pair-sum kernel: log2 of the number of shared-memory histogram copies
 };
 
 // Multi-rank sharding is by primary CELL, never by tile: every rank sorts its own replica and the order of the
@@ -128,5 +130,7 @@ int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t
 void cfb_spheres_release();
 // pair kernels (pairs_generic.cu)
 int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode);
+// per-pair-sum kernel (pairs_sum.cu): 0 launched, -1 not applicable (the caller falls back to the generic kernel), 1 error
+int cfb_launch_pairs_sum(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode);
 // fast 1-D kernel (pairs_fast.cu); P.edges / P.wrap / P.pimax are in the kernel's scaled units
 int cfb_launch_pairs_fast(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode);

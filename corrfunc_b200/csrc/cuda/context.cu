@@ -250,10 +250,10 @@ extern "C" int cfb_extent(int slot, int which, double lohi[6])
 // ---------------------------------------------------------------------------------------------
 // Fine lattice: every reference cell is split sub[] ways so that a fine cell holds about `target`
 // particles (one warp tile = up to 128) and is as close to a cube as the integer splits allow.
-static void choose_subdivision(const Ctx &c, const cfb_box_lattice *lat, int64_t nmax, int sub[3])
+static void choose_subdivision(const Ctx &c, const cfb_box_lattice *lat, int64_t nmax, int sub[3], int dflt)
 {
     sub[0] = sub[1] = sub[2] = 1;
-    const int target = c.target_occ > 0 ? c.target_occ : 112;  // mostly 4 primaries per lane (97..128 per tile): measured best on config 5
+    const int target = c.target_occ > 0 ? c.target_occ : dflt;  // mostly 4 primaries per lane (97..128 per tile): measured best on config 5
     const double ncell = (double)lat->nmesh[0] * lat->nmesh[1] * lat->nmesh[2];
     const double occ = (double)nmax / ncell;
     if (occ <= 1.3 * target) return;
@@ -422,9 +422,16 @@ extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat,
     int sub[3];
     int64_t nmax = c.set[0].n;
     if (nsets == 2 && c.set[1].n > nmax) nmax = c.set[1].n;
-    choose_subdivision(c, lat, nmax, sub);
     double scale = 1.0;
     const bool fast = fast_box_plan(c, bin, lat, &scale);
+    // fine cells: ~112 particles (4 primaries per lane) for the fast kernel; the per-pair-sum kernel works on 64-particle
+    // tiles and gains more from tighter pruning than it loses to more jobs
+    static int sum_occ = -1;
+    if (sum_occ < 0) {
+        const char *e = getenv("CORRFUNC_B200_SUM_OCC");
+        sum_occ = (e && atoi(e) > 0) ? atoi(e) : 56;
+    }
+    choose_subdivision(c, lat, nmax, sub, fast ? 112 : sum_occ);
     for (int s = 0; s < nsets; s++)
         if (cfb_gridlink_box_set(c.set[s], lat, sub, scale)) return 1;
     CK(cudaEventRecord(c.ev[1], c.stream));
@@ -474,7 +481,7 @@ extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat,
         if (fast ? cfb_launch_pairs_fast(bin, P, bin->prec, false) : cfb_launch_pairs_generic(bin, P, bin->prec, false))
             return 1;
     }
-    st.kernel_kind = fast ? 1 : 0;
+    st.kernel_kind = fast ? 1 : c.last_kind;
     CK(cudaEventRecord(c.ev[2], c.stream));
     if (fetch_hist(c, nslots, bin, out, &st)) return 1;
     float ms = 0;
@@ -599,7 +606,7 @@ extern "C" int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int
         if (fast ? cfb_launch_pairs_fast(bin, P, bin->prec, true) : cfb_launch_pairs_generic(bin, P, bin->prec, true))
             return 1;
     }
-    st.kernel_kind = fast ? 1 : 0;
+    st.kernel_kind = fast ? 1 : c.last_kind;
     CK(cudaEventRecord(c.ev[2], c.stream));
     if (fetch_hist(c, nslots, bin, out, &st)) return 1;
     float ms = 0;

@@ -15,6 +15,7 @@
 //
 // Compiled with -fmad=false: an FMA appears exactly where the reference's AVX-512 kernels have one.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "cfb_internal.cuh"
 
@@ -606,5 +607,20 @@ int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P0, int p
     if (bin->need_weights) {
         if (prec == 4 ? weight_maxima<float>(cfb_ctx(), bin, P) : weight_maxima<double>(cfb_ctx(), bin, P)) return 1;
     }
+    // the per-pair-sum kernel (pairs_sum.cu) serves everything it can hold in shared memory; this kernel remains for
+    // histograms too large for that, more than 256 edges, and as a cross-check (force_kernel 3 / CORRFUNC_B200_LEGACY_GENERIC)
+    static int legacy = -1;
+    if (legacy < 0) {
+        const char *e = getenv("CORRFUNC_B200_LEGACY_GENERIC");
+        legacy = (e && atoi(e) > 0) ? 1 : 0;
+    }
+    if (!legacy && cfb_ctx().force_kernel != 3) {
+        const int rc = cfb_launch_pairs_sum(bin, P, prec, list_mode);
+        if (rc >= 0) {
+            cfb_ctx().last_kind = 2;
+            return rc;
+        }
+    }
+    cfb_ctx().last_kind = 0;
     return prec == 4 ? launch_T<float>(bin, P, list_mode) : launch_T<double>(bin, P, list_mode);
 }

@@ -1,0 +1,1021 @@
+// pairs_sum.cu -- the per-pair-sum kernel: every statistic whose result needs something PER ACCEPTED PAIR -- a 2-D bin
+// (DDrppi, DDsmu and their survey-geometry twins), an average separation (ravg / thetaavg) or a PAIR_PRODUCT weight.
+//
+// Replaces the per-cell-pair CPU kernels (theory/DDrppi/countpairs_rp_pi_kernels.c.src:24-285,
+// theory/DDsmu/countpairs_s_mu_kernels.c.src:24-309, theory/DD/countpairs_kernels.c.src:25-279 with need_rpavg / weights,
+// theory/wp/wp_kernels.c.src:23-305, mocks/DDtheta_mocks/countpairs_theta_mocks_kernels.c.src:872-1141,
+// mocks/DDrppi_mocks/countpairs_rp_pi_mocks_kernels.c.src:200-300, mocks/DDsmu_mocks/countpairs_s_mu_mocks_kernels.c.src:196-290)
+// and the cell-pair enumeration of generate_cell_pairs_DOUBLE (utils/gridlink_impl.c.src:439-625).
+//
+// Design:
+//   * persistent warps; a warp owns one primary tile (up to 64 particles of one fine cell, 2 per lane in registers) and
+//     pulls its next tile from a global counter;
+//   * phase 1 (one candidate neighbour cell per lane): periodic index and wrap code, the reference's role filter, and --
+//     from the two cells' particle bounding boxes, in double with explicit rounding margins -- a conservative interval of
+//     the binned quantity.  It prunes the cell pair, and it leaves the few bin edges that can split its pairs: the bin
+//     search of an accepted pair is a count over those "levels" (1-3 compares) instead of a search over all edges;
+//   * phase 2: the neighbour's x|y|z|(w) runs are staged per warp in shared memory, double buffered, with 16-byte
+//     cp.async.  The HOT LOOP computes the separation of every (primary, secondary) with the reference's arithmetic
+//     (same subtraction order, same FMA association per statistic) and only the range test; accepted pairs are
+//     WARP-COMPACTED (ballot + prefix popcount) into a per-warp ring in shared memory;
+//   * the DRAIN takes 32 accepted pairs at a time with all lanes busy: level count -> separation bin, the 2-D bin index
+//     evaluated in floating point exactly as the reference does (IEEE divide and square roots), sqrt for the average,
+//     the weight product, and the histogram update.  Only 0.3 drains run per 32 separations, instead of a divergent
+//     accept branch in nearly every iteration;
+//   * histograms: per block in shared memory, 32-bit words updated with native ATOMS.ADD (counts two words, sums 96-bit
+//     fixed point: exact, order independent, reproducible), REPLICATED `copies` times with the copy chosen by the lane, so
+//     that lanes of one drain that hit the same slot or bank mostly do not serialise.
+//
+// Compiled with -fmad=false: an FMA appears exactly where the reference's AVX-512 kernels have one.
+#include <math_constants.h>
+#include <stdlib.h>
+
+#include "cfb_internal.cuh"
+
+#ifndef SUM_WARPS
+#define SUM_WARPS 4
+#endif
+#define SUM_PA 2                // primaries per lane
+#define SUM_TILE (32 * SUM_PA)  // primaries per tile; divides CFB_TILE
+#ifndef SUM_CH
+#define SUM_CH 64               // secondaries per staged chunk
+#endif
+#ifndef SUM_QCAP
+#define SUM_QCAP 80             // job queue entries per warp
+#endif
+#ifndef SUM_MINB
+#define SUM_MINB 5               // resident blocks per SM the kernel is compiled for (register budget): the kernel is latency bound, measured 25 % faster at 5 blocks than at 4
+#endif
+#define SUM_RING 160            // accepted-pair stack per warp: < 32 left over + up to 4 x 32 new ones per iteration
+#define SUM_MAX_EDGES 256
+
+typedef unsigned long long u64;
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ T fma_t(T a, T b, T c);
+template <>
+__device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <>
+__device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+template <typename T>
+__device__ __forceinline__ T sqrt_t(T a);
+template <>
+__device__ __forceinline__ float sqrt_t<float>(float a) { return __fsqrt_rn(a); }
+template <>
+__device__ __forceinline__ double sqrt_t<double>(double a) { return __dsqrt_rn(a); }
+template <typename T>
+__device__ __forceinline__ T divi_t(T a, T b);
+template <>
+__device__ __forceinline__ float divi_t<float>(float a, float b) { return __fdiv_rn(a, b); }
+template <>
+__device__ __forceinline__ double divi_t<double>(double a, double b) { return __ddiv_rn(a, b); }
+
+// utils/fast_acos.h:57-101 (degree-8 estimate, |err| < 3.7e-9)
+template <typename T>
+__device__ __forceinline__ T fast_acos_t(const T x)
+{
+    const T xa = x < 0 ? -x : x;
+    T poly = (T) + 7.1796493341480527e-04;
+    poly = (T)-4.1160981058965262e-03 + poly * xa;
+    poly = (T) + 1.1272900916992512e-02 + poly * xa;
+    poly = (T)-2.0949278766238422e-02 + poly * xa;
+    poly = (T) + 3.2683762943179318e-02 + poly * xa;
+    poly = (T)-5.0625279962389413e-02 + poly * xa;
+    poly = (T) + 8.9034700107934128e-02 + poly * xa;
+    poly = (T)-2.1460143648688035e-01 + poly * xa;
+    poly = (T) + 1.5707963267948966 + poly * xa;
+    poly = poly * sqrt_t<T>((T)1.0 - xa);
+    return (x < 0) ? (T)(3.14159265358979323846 - (double)poly) : poly;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// exact n / d for n * d < 2^32, magic = ceil(2^32 / d) (0 stands for d == 1)
+__device__ __forceinline__ unsigned fdiv(unsigned n, unsigned magic) { return magic ? __umulhi(n, magic) : n; }
+
+// Shared-memory accumulation with the native 32-bit integer ATOMS.ADD only (64-bit, float and double shared atomics
+// compile to compare-and-swap loops on sm_100a).  Measured with tools/ubench_atoms.cu: a full-warp ATOMS.ADD to spread
+// addresses sustains 10-15 word updates per clock and SM when the result is not used and 5-10 as a carry chain; an ATOMS
+// with 8 active lanes costs as much as one with 32 -- which is why the accepted pairs are compacted first.  Measured on
+// config 3 (10 M points): 96-bit sums as three carry-chained words 413 ms, four 16-bit limbs without carries 437 ms,
+// two words (44 bits) 307 ms.  What is used:
+//   count: one word, +1 per pair, result unused;
+//   sums : fixed point -- value * 2^k rounded to an integer below 2^59 in magnitude (k from the bin's upper edge, or from the
+//          largest weight product; 59 bits because a bin may hold a single pair whose value is a millionth of the bin's
+//          largest and is still compared at 1e-10) -- in three words: the low 15 bits go to a word of their own (result
+//          unused), bits 15-46 to a word whose returned old value gives the carry, and the signed top 12 bits + that carry to a
+//          third word (result unused).  One atomic per sum waits for its result, and nothing waits for that but one add.
+// The count word, the low word (< 2^15 per add) and the top word (< 2^12 + 1 per add) must not wrap: every warp
+// NORMALISES the block's histogram every SUM_NORM_DRAINS of its drains -- these words are exchanged with zero and what
+// they held goes to the global histogram.  Between two normalisations a slot takes fewer than 4 warps x 512 drains x 32
+// lanes = 2^16 adds: below 2^31 in every word.  Integer sums are exact and order independent.
+#define SUM_NORM_DRAINS 512
+__device__ __forceinline__ void add_fixed(unsigned *w, const int stride, const long long q)
+{
+    atomicAdd(w, (unsigned)q & 0x7fffu);
+    const long long q1 = q >> 15;  // arithmetic: 44 signed bits
+    const unsigned lo = (unsigned)q1;
+    const unsigned old = atomicAdd(w + stride, lo);
+    atomicAdd(w + 2 * stride, (unsigned)(q1 >> 32) + (old > ~lo ? 1u : 0u));
+}
+// what the wrapping-prone words of one slot hold (exchanged with zero); last: also the middle word (nobody adds any more)
+__device__ __forceinline__ double take_fixed(unsigned *w, const int stride, const bool last)
+{
+    double v = 0.0;
+    if (w[0]) v += (double)atomicExch(w, 0u);
+    if (w[2 * stride]) v += (double)(int)atomicExch(w + 2 * stride, 0u) * 140737488355328.0;  // 2^47
+    if (last) v += (double)w[stride] * 32768.0;
+    return v;
+}
+// 2^k such that |v| * 2^k < 2^59 for every |v| <= vmax
+__device__ __forceinline__ double fixed_scale(const double vmax)
+{
+    int e = 0;
+    if (vmax > 0.0 && vmax < 1.0e300) frexp(vmax, &e);  // vmax < 2^e
+    return ldexp(1.0, 59 - e);
+}
+
+struct SumJob {
+    int start;  // first secondary (index into the sorted arrays, multiple of CFB_PAD)
+    int n;      // secondaries
+    int meta;   // bits 0-5 wrap code | 6-13 first level edge | 14-22 number of levels | flags
+};
+#define SJ_TRI (1 << 23)     // the tile against itself: only secondaries after the primary
+#define SJ_DIRZ (1 << 24)    // primary and secondary lie in different reference cells (one-sided pi cut of wp / DDrppi)
+#define SJ_NEEDLO (1 << 25)  // some pair of the two cells may lie below the first edge
+
+// Per-warp shared memory.  NA = staged arrays (x, y, z and, with weights, w).
+template <typename T, int NA>
+struct SumWarp {
+    alignas(16) T buf[2][NA][SUM_CH];
+    alignas(16) T prim[NA][SUM_TILE];  // the tile's primaries with the current wrap applied (+ weights): gathered by the drain
+    // accepted-pair stack: (primary << 16 | secondary) of every pair that passed the range test.  Four bytes per entry --
+    // the drain recomputes the separation from the positions, which costs it 13 instructions and buys a third more
+    // resident warps than a stack that carries the values.  The last 32 entries are a dump for the lanes that have nothing
+    // to push (branch-free stores).
+    unsigned ring_i[SUM_RING + 32];
+    SumJob q[SUM_QCAP];
+};
+
+// everything the drain needs that does not change within a kernel
+template <typename T>
+struct SumConst {
+    const T *edges;        // shared: T[nedges]
+    const double *scale;   // shared: double[nedges], fixed-point scale of the separation sum per bin
+    unsigned *h_np, *h_sep, *h_w;  // shared histograms: count [slots*copies], sums [3][slots*copies]
+    int hstride;           // nslots * copies
+    int copies_shift;      // log2(copies)
+    int nedges;
+    T pimax, sqr_pimax, inv_dpi, inv_dmu, sqr_mumax, npi_p1, nmu_p1, e_lo, e_hi, sqr_max_sep;
+    float inv_dmu_f;
+    double w_scale;
+    int fast_acos;
+};
+
+// true when value v lies at or above edge e in the binning order (theta: edges are cosines, decreasing)
+template <typename T, int MODE>
+__device__ __forceinline__ bool at_or_above(const T v, const T e)
+{
+    return MODE == CFB_THETA ? (v <= e) : (v >= e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One separation and its range test.  b = second payload value (|dz| for DDrppi, dz^2 for DDsmu).
+template <typename T, int MODE, bool NEEDLO>
+__device__ __forceinline__ bool eval_pair(const T x2, const T y2, const T z2, const T x1, const T y1, const T z1, const T tz,
+                                          const SumConst<T> &K, const bool dirz, T &v, T &b)
+{
+    // second - (first + wrap) (countpairs_kernels.c.src:79-81,178-180)
+    const T dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+    bool acc;
+    b = 0;
+    if (MODE == CFB_DD || MODE == CFB_XI) {
+        v = fma_t<T>(dz, dz, fma_t<T>(dy, dy, dx * dx));  // countpairs_kernels.c.src:188-190
+        acc = v < K.e_hi;
+        if (NEEDLO) acc = acc && v >= K.e_lo;
+    } else if (MODE == CFB_WP) {
+        v = fma_t<T>(dy, dy, dx * dx);  // wp_kernels.c.src:197-198
+        // two reference cells: survivors of the fast-forward over z1 <= zpos - pimax, then the SIGNED dz < pimax
+        // (wp_kernels.c.src:139-142, 207-221); inside one reference cell j follows i in z order (dz >= 0)
+        acc = dirz ? (z2 > tz && dz < K.pimax) : (dz > -K.pimax && dz < K.pimax);
+        acc = acc && v < K.e_hi;
+        if (NEEDLO) acc = acc && v >= K.e_lo;
+    } else if (MODE == CFB_RPPI) {
+        v = fma_t<T>(dy, dy, dx * dx);  // countpairs_rp_pi_kernels.c.src:196-197
+        b = dz < 0 ? -dz : dz;
+        // survivors of the fast-forward (:139-142), then |dz| < pimax (:196-207)
+        acc = (dirz ? (z2 > tz) : (dz > -K.pimax)) && b < K.pimax;
+        acc = acc && v < K.e_hi;
+        if (NEEDLO) acc = acc && v >= K.e_lo;
+    } else if (MODE == CFB_SMU) {
+        b = dz * dz;
+        v = fma_t<T>(dx, dx, fma_t<T>(dy, dy, b));  // countpairs_s_mu_kernels.c.src:212-214
+        acc = v < K.e_hi;
+        if (NEEDLO) acc = acc && v >= K.e_lo;
+    } else if (MODE == CFB_THETA) {
+        // cos(theta) = 1 - chord^2 / 2 (countpairs_theta_mocks_kernels.c.src:1062-1068); edges decrease
+        const T chord2 = fma_t<T>(dz, dz, fma_t<T>(dy, dy, dx * dx));
+        v = (T)1.0 - (T)0.5 * chord2;
+        acc = v > K.e_hi;
+        if (NEEDLO) acc = acc && v <= K.e_lo;
+    } else if (MODE == CFB_RPPI_MOCKS) {
+        v = fma_t<T>(dx, dx, fma_t<T>(dy, dy, dz * dz));  // sqr_sep; the rest of the pair runs in the drain
+        acc = v < K.sqr_max_sep;
+    } else {  // CFB_SMU_MOCKS
+        v = fma_t<T>(dx, dx, fma_t<T>(dy, dy, dz * dz));
+        acc = v < K.e_hi && v >= K.e_lo;
+    }
+    return acc;
+}
+
+// sqrt for the average separation.  double: float reciprocal-square-root seed + one Newton step in double, relative error
+// < 6e-14 (the averages are sums of millions of terms compared at 1e-10; the reference's own sums depend on the thread
+// schedule at the 1e-13 level); IEEE sqrt outside the float range.  float: IEEE.
+__device__ __forceinline__ float sep_sqrt(const float v) { return __fsqrt_rn(v); }
+__device__ __forceinline__ double sep_sqrt(const double v)
+{
+    const float vf = __double2float_rn(v);
+    if (!(vf > 1.0e-30f && vf < 1.0e30f)) return __dsqrt_rn(v);
+    float y0;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(vf));
+    const double y = (double)y0;
+    const double r0 = v * y;
+    const double e = __fma_rn(-r0, r0, v);
+    return __fma_rn(e, 0.5 * y, r0);
+}
+
+// mu * inv_dmu of DDsmu for an accepted pair: b = dz^2, a = s^2.  Only its integer part matters (the mu bin).
+// double: the bin is first located in FLOAT arithmetic (the FP32 pipe is idle in this kernel); if the float estimate is
+// farther from an integer than its error bound, its integer part is the exact one; otherwise (probability ~1e-4) the
+// reference's arithmetic runs: true divide, IEEE sqrt (countpairs_s_mu_kernels.c.src:228-277).  Returned is a value with
+// the same integer part as the reference's mu * inv_dmu and a fraction safely away from 0 and 1, so that adding
+// sbin * (nmu + 1) in floating point and truncating gives the reference's slot.
+__device__ __forceinline__ float mu_coord(const float b, const float a, const SumConst<float> &K)
+{
+    return __fsqrt_rn(__fdiv_rn(b, a)) * K.inv_dmu;
+}
+__device__ __forceinline__ double mu_coord(const double b, const double a, const SumConst<double> &K)
+{
+    const float bf = __double2float_rn(b), af = __double2float_rn(a);
+    float yf;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(__fdividef(bf, af)));
+    yf *= K.inv_dmu_f;
+    const float fl = floorf(yf), fr = yf - fl;
+    const float tol = 4.0e-6f * (yf + 1.0f);  // > 8 x the error bound of the float evaluation
+    if (fr > tol && fr < 1.0f - tol && af > 1.0e-30f && af < 1.0e30f && bf > 1.0e-30f) return (double)fl + 0.5;
+    return __dsqrt_rn(__ddiv_rn(b, a)) * K.inv_dmu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The drain: n (<= 32) accepted pairs from the top of the stack, one per lane.
+// E[l], l < 4: the job's level edges in registers (padded so that the compare is false); nl > 4: binary search.
+template <typename T, int MODE, bool AVG, bool WGT, int NA>
+__device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA> &W, const int bsel, const SumConst<T> &K,
+                                      const T (&E)[8], const int kfirst, const int nl, const int lane)
+{
+    __syncwarp();
+    bool ok = lane < n;
+    const unsigned idx = W.ring_i[head + lane];  // entries head .. head + n - 1 (the top of the stack)
+    const int pidx = (idx >> 16) & (SUM_TILE - 1), j = idx & (SUM_CH - 1);
+    // the pair again, with the arithmetic of the hot loop (same function, same operands)
+    const T x1 = W.prim[0][pidx], y1 = W.prim[1][pidx], z1 = W.prim[2][pidx];
+    const T x2 = W.buf[bsel][0][j], y2 = W.buf[bsel][1][j], z2 = W.buf[bsel][2][j];
+    T a, b;
+    eval_pair<T, MODE, false>(x2, y2, z2, x1, y1, z1, (T)0, K, false, a, b);
+
+    T v = a;      // the quantity that is binned
+    T f2 = 0;     // second-dimension coordinate in bins (pi * inv_dpi or mu * inv_dmu)
+    if (MODE == CFB_RPPI) {
+        f2 = b * K.inv_dpi;
+    } else if (MODE == CFB_SMU) {
+        // keep if dz^2 < s^2 mu_max^2; sqr_mu = dz^2 / s^2 (true divide, fast_divide_and_NR_steps == 0), mu = sqrt
+        // (countpairs_s_mu_kernels.c.src:216-277)
+        if (!(b < a * K.sqr_mumax)) ok = false;
+        f2 = mu_coord(b, a, K);
+    } else if (MODE == CFB_RPPI_MOCKS || MODE == CFB_SMU_MOCKS) {
+        // line of sight = pair midpoint (countpairs_rp_pi_mocks_kernels.c.src:200-290, countpairs_s_mu_mocks_kernels.c.src:196-290)
+        const T dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+        const T parx = x2 + x1, pary = y2 + y1, parz = z2 + z1;
+        const T term1 = parx * dx, term2 = pary * dy;
+        const T s_dot_l = fma_t<T>(parz, dz, term1 + term2);
+        const T sqr_s_dot_l = s_dot_l * s_dot_l;
+        const T sqr_norm_l = fma_t<T>(parx, parx, fma_t<T>(pary, pary, parz * parz));
+        if (MODE == CFB_RPPI_MOCKS) {
+            // a = sqr_sep, already below sqr_max_sep
+            if (!(sqr_s_dot_l < K.sqr_pimax * sqr_norm_l)) ok = false;
+            const T sqr_Dpar = divi_t<T>(sqr_s_dot_l, sqr_norm_l);
+            const T sqr_Dperp = a - sqr_Dpar;
+            if (!(sqr_Dpar < K.sqr_pimax && sqr_Dperp < K.e_hi && sqr_Dperp >= K.e_lo)) ok = false;
+            v = sqr_Dperp;
+            f2 = sqrt_t<T>(sqr_Dpar) * K.inv_dpi;
+        } else {
+            // a = s2, already within [e_lo, e_hi)
+            const T sqr_mu = divi_t<T>(sqr_s_dot_l, sqr_norm_l * a);
+            if (!(sqr_mu < K.sqr_mumax)) ok = false;
+            f2 = sqrt_t<T>(sqr_mu) * K.inv_dmu;
+        }
+    }
+    // separation bin: kfirst + the number of levels at or below the value
+    int kb = kfirst;
+    if (nl <= 4) {
+#pragma unroll
+        for (int l = 0; l < 4; l++) kb += at_or_above<T, MODE>(v, E[l]) ? 1 : 0;
+    } else {
+        int lo = kfirst, hi = kfirst + nl;  // first edge in [lo, hi) the value is not at or above
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (at_or_above<T, MODE>(v, K.edges[mid])) lo = mid + 1; else hi = mid;
+        }
+        kb = lo;
+    }
+    int slot = kb;
+    if (MODE == CFB_RPPI || MODE == CFB_RPPI_MOCKS) {
+        // rpbin*(npibin+1) + pi*inv_dpi evaluated in T, then truncated (countpairs_rp_pi_kernels.c.src:249-256)
+        slot = (int)((T)kb * K.npi_p1 + f2);
+    } else if (MODE == CFB_SMU || MODE == CFB_SMU_MOCKS) {
+        slot = (int)((T)kb * K.nmu_p1 + f2);  // countpairs_s_mu_kernels.c.src:269-277
+    }
+    if (!ok) slot = 0, kb = kfirst;  // idle lanes: any valid address
+    long long qsep = 0, qw = 0;
+    if (AVG) {
+        T sep;
+        if (MODE == CFB_THETA) {
+            const T cc = v >= (T)1.0 ? (T)1.0 : v;
+            const T th = K.fast_acos ? fast_acos_t<T>(cc) : (T)acos(cc);
+            sep = (T)(th * (T)57.29577951308232087679815481410517);
+        } else
+            sep = sep_sqrt(v);
+        qsep = __double2ll_rn((double)sep * K.scale[kb]);
+    }
+    if (WGT) {
+        const T w1 = W.prim[NA - 1][pidx], w2 = W.buf[bsel][NA - 1][j];
+        qw = __double2ll_rn((double)(T)(w1 * w2) * K.w_scale);  // pair_product, weight_functions.h.src:71-91
+    }
+    if (ok) {
+        const int h = (slot << K.copies_shift) + (lane & ((1 << K.copies_shift) - 1));
+        atomicAdd(&K.h_np[h], 1u);
+        if (AVG) add_fixed(&K.h_sep[h], K.hstride, qsep);
+        if (WGT) add_fixed(&K.h_w[h], K.hstride, qw);
+    }
+    __syncwarp();
+}
+
+// Moves what the wrapping-prone words of the block's histogram hold into the global histogram (any warp, any time).
+// last: everything (end of the kernel, after a block barrier).
+template <int MODE, bool AVG, bool WGT, typename T>
+__device__ __forceinline__ void flush_hist(const PairParams &P, const SumConst<T> &K, const int ns, const int first,
+                                           const int step, const bool last)
+{
+    const int copies = 1 << K.copies_shift;
+    for (int i = first; i < ns; i += step) {
+        u64 cnt = 0;
+        double ssep = 0.0, sw = 0.0;
+        for (int c = 0; c < copies; c++) {
+            const int h = (i << K.copies_shift) + c;
+            if (K.h_np[h]) cnt += atomicExch(&K.h_np[h], 0u);
+            if (AVG) ssep += take_fixed(&K.h_sep[h], K.hstride, last);
+            if (WGT) sw += take_fixed(&K.h_w[h], K.hstride, last);
+        }
+        if (cnt) atomicAdd(&P.npairs[i], cnt);
+        if (AVG && ssep != 0.0) {
+            const int kb = (MODE == CFB_RPPI || MODE == CFB_RPPI_MOCKS)
+                               ? i / (P.npibin + 1)
+                               : ((MODE == CFB_SMU || MODE == CFB_SMU_MOCKS) ? i / (P.nmu_bins + 1) : i);
+            atomicAdd(&P.sum_sep[i], ssep / K.scale[kb < K.nedges ? kb : K.nedges - 1]);
+        }
+        if (WGT && sw != 0.0) atomicAdd(&P.sum_w[i], sw / K.w_scale);
+    }
+}
+
+// The hot loop: secondaries k .. m-1 of the staged chunk against the lane's PA primaries, until the chunk ends or the
+// ring holds a full drain.  Four independent separations per lane and iteration (2 secondaries x 2 primaries, or
+// 4 x 1): their FP chains overlap, and one compaction serves the four ballots.  Returns the next secondary.
+// DIRECT (count-only 1-D statistics and DDrppi, jobs with at most 8 levels): no compaction at all -- every lane
+// finishes its own pairs (level count, slot) and only the histogram update is predicated.  Without per-pair sums that is
+// fewer instructions than pushing, popping and binning 0.3 accepted pairs per separation.
+template <typename T, int MODE, bool WGT, int NA, int PA, bool TRI, bool NEEDLO, int DIRECT /* 0 | levels in registers */>
+__device__ __forceinline__ int hot_loop(int k, const int m, SumWarp<T, NA> &W, const int bsel, const T (&xq)[SUM_PA],
+                                        const T (&yq)[SUM_PA], const T (&zq)[SUM_PA], const SumConst<T> &K,
+                                        const bool dirz, const int c0, const int lane, int &tail, const T (&E)[8],
+                                        const int kfirst)
+{
+    const T *sx = W.buf[bsel][0], *sy = W.buf[bsel][1], *sz = W.buf[bsel][2];
+    const unsigned lt = (1u << lane) - 1u;
+    constexpr int NS = 4 / PA;  // secondaries per iteration
+    T tz[PA];
+#pragma unroll
+    for (int p = 0; p < PA; p++) tz[p] = zq[p] - K.pimax;  // target of the reference's fast-forward over z (wp, DDrppi)
+    for (; k < m && tail < 32; k += NS) {
+        T v[4], b[4];
+        bool acc[4];
+        unsigned msk[4];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const T x2 = sx[k + s], y2 = sy[k + s], z2 = sz[k + s];
+#pragma unroll
+            for (int p = 0; p < PA; p++) {
+                const int e = s * PA + p;
+                acc[e] = eval_pair<T, MODE, NEEDLO>(x2, y2, z2, xq[p], yq[p], zq[p], tz[p], K, dirz, v[e], b[e]);
+                if (TRI) acc[e] = acc[e] && (c0 + k + s > lane + 32 * p);
+            }
+        }
+        if (DIRECT) {
+            const int cpy = lane & ((1 << K.copies_shift) - 1);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int kb = kfirst;
+#pragma unroll
+                for (int l = 0; l < DIRECT; l++) kb += at_or_above<T, MODE>(v[e], E[l]) ? 1 : 0;
+                int slot = kb;
+                // rpbin*(npibin+1) + |dz|*inv_dpi evaluated in T, then truncated (countpairs_rp_pi_kernels.c.src:249-256)
+                if (MODE == CFB_RPPI) slot = (int)((T)kb * K.npi_p1 + b[e] * K.inv_dpi);
+                if (acc[e]) atomicAdd(&K.h_np[(slot << K.copies_shift) + cpy], 1u);
+            }
+            continue;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) msk[e] = __ballot_sync(0xffffffffu, acc[e]);
+        if (msk[0] | msk[1] | msk[2] | msk[3]) {
+            int base = tail;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                // lanes with nothing to push store into the dump behind the stack: no divergent code in this loop
+                const int pos = acc[e] ? base + __popc(msk[e] & lt) : SUM_RING + lane;
+                W.ring_i[pos] = ((unsigned)(lane + 32 * (e % PA)) << 16) | (unsigned)(k + e / PA);
+                base += __popc(msk[e]);
+            }
+            tail = base;
+        }
+    }
+    return k;
+}
+
+template <typename T, int NA>
+__device__ __forceinline__ void stage_chunk(SumWarp<T, NA> &W, const int bsel, const SetView<T> &B, const int first,
+                                            const int m4, const int lane)
+{
+    constexpr int EPV = 16 / (int)sizeof(T);
+    for (int v = lane * EPV; v < m4; v += 32 * EPV) {
+        cp_async16(&W.buf[bsel][0][v], B.x + first + v);
+        cp_async16(&W.buf[bsel][1][v], B.y + first + v);
+        cp_async16(&W.buf[bsel][2][v], B.z + first + v);
+        if (NA == 4) cp_async16(&W.buf[bsel][3][v], B.w + first + v);
+    }
+    cp_async_commit();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MODE, bool AVG, bool WGT, bool LIST>
+__global__ void __launch_bounds__(SUM_WARPS * 32, SUM_MINB)
+k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
+{
+    constexpr int NA = WGT ? 4 : 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // dynamic smem: per-warp areas | edges (T) | edges as double, in search order | sep scale per edge | histograms
+    SumWarp<T, NA> *warps = (SumWarp<T, NA> *)smem_raw;
+    const int nedges = P.nedges;
+    size_t off = (sizeof(SumWarp<T, NA>) * SUM_WARPS + 15) & ~(size_t)15;
+    T *s_edges = (T *)(smem_raw + off);
+    off += ((size_t)nedges * sizeof(T) + 15) & ~(size_t)15;
+    double *s_edges_d = (double *)(smem_raw + off);
+    off += (size_t)nedges * 8;
+    double *s_scale = (double *)(smem_raw + off);
+    off += (size_t)nedges * 8;
+    unsigned *s_hist = (unsigned *)(smem_raw + off);
+    const int ns = (int)P.nslots;
+    const int cshift = P.sum_copies_shift;
+    const int hstride = ns << cshift;
+    const int hwords = hstride * (1 + (AVG ? 3 : 0) + (WGT ? 3 : 0));
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < nedges; i += blockDim.x) {
+        const T e = ((const T *)P.edges)[i];
+        s_edges[i] = e;
+        s_edges_d[i] = MODE == CFB_THETA ? -(double)e : (double)e;
+        // largest separation a pair of the bin below edge i can have: sqrt(edge) (edges are squared), or the angle in
+        // degrees whose cosine the edge is
+        double vmax;
+        if (MODE == CFB_THETA) vmax = acos(fmin(1.0, fmax(-1.0, (double)e))) * 57.29577951308232087679815481410517 + 1e-9;
+        else vmax = sqrt(fmax(0.0, (double)e));
+        s_scale[i] = fixed_scale(vmax);
+    }
+    for (int i = tid; i < hwords; i += blockDim.x) s_hist[i] = 0u;
+    SumWarp<T, NA> &W = warps[wid];
+
+    SumConst<T> K;
+    K.edges = s_edges;
+    K.scale = s_scale;
+    K.h_np = s_hist;
+    K.h_sep = s_hist + hstride;
+    K.h_w = s_hist + (1 + (AVG ? 3 : 0)) * hstride;
+    K.hstride = hstride;
+    K.copies_shift = cshift;
+    K.nedges = nedges;
+    K.pimax = (T)P.pimax;
+    K.sqr_pimax = K.pimax * K.pimax;  // rppi mocks (countpairs_rp_pi_mocks_kernels.c.src:56-57)
+    K.inv_dpi = (T)P.inv_dpi;
+    K.inv_dmu = (T)P.inv_dmu;
+    K.inv_dmu_f = (float)P.inv_dmu;
+    K.sqr_mumax = (T)P.sqr_mumax;
+    K.npi_p1 = (T)(P.npibin + 1);
+    K.nmu_p1 = (T)(P.nmu_bins + 1);
+    K.fast_acos = P.fast_acos;
+    K.w_scale = 1.0;
+    if (WGT) K.w_scale = fixed_scale(P.wmax[0] * P.wmax[1]);
+    __syncthreads();
+    K.e_lo = s_edges[0];
+    K.e_hi = s_edges[nedges - 1];
+    K.sqr_max_sep = K.e_hi + K.sqr_pimax;
+    const double sqr_max_sep_d = (double)K.sqr_max_sep;
+
+    u64 my_eval = 0, my_jobs = 0, my_levels = 0;
+    int drains = 0;  // this warp's drains since it last normalised the block's histogram
+    uint32_t it = 0;  // chunks staged so far by this warp (buffer = it & 1)
+    constexpr int SPLIT = CFB_TILE / SUM_TILE;  // the gridlink tile table holds 128-particle tiles
+
+    for (;;) {
+        long long gw = 0;
+        if (lane == 0) gw = (long long)atomicAdd(&P.counters[4], 1ULL);
+        gw = __shfl_sync(0xffffffffu, gw, 0);
+        if (gw >= P.ntiles * SPLIT) break;
+        const int64_t tile = gw / SPLIT;
+        const int cellP = P.tile_cell[tile];
+        if (!cfb_owns_cell(cellP, P.shard_rank, P.shard_n)) continue;  // another rank's cell
+        const int toff = P.tile_off[tile] + (int)(gw % SPLIT) * SUM_TILE;
+        const int nP = A.count[cellP];
+        if (toff >= nP) continue;
+        const int startP = A.start[cellP];
+        const int nv = min(SUM_TILE, nP - toff);  // valid primaries of this tile
+        const int pa = (nv + 31) >> 5;
+        const T nanv = sizeof(T) == 4 ? (T)CUDART_NAN_F : (T)CUDART_NAN;
+        const T *pxg = A.x + startP + toff, *pyg = A.y + startP + toff, *pzg = A.z + startP + toff;
+        const T *pwg = WGT ? A.w + startP + toff : nullptr;
+
+        int gx = 0, gy = 0, gz = 0, rax = 0, ray = 0, raz = 0;
+        long long refA = 0;
+        int nrow = 1, rowlen, wz = 1, rx = 0, ry = 0, rz = 0;
+        int64_t list0 = 0;
+        const int sub2 = LIST ? P.list_sub2 : 1;
+        const int refP = LIST ? cellP / sub2 : 0;
+        if (LIST) {
+            list0 = P.list_off[refP];
+            rowlen = (int)(P.list_off[refP + 1] - list0) * sub2;
+        } else {
+            gz = cellP % P.g.ng[2];
+            gy = (cellP / P.g.ng[2]) % P.g.ng[1];
+            gx = cellP / (P.g.ng[2] * P.g.ng[1]);
+            rax = gx / P.g.s[0];
+            ray = gy / P.g.s[1];
+            raz = gz / P.g.s[2];
+            refA = ((long long)rax * P.g.n[1] + ray) * P.g.n[2] + raz;
+            rx = P.g.reach[0];
+            ry = P.g.reach[1];
+            rz = P.g.reach[2];
+            wz = 2 * rz + 1;
+            nrow = 2 * rx + 1;
+            rowlen = (2 * ry + 1) * wz;
+        }
+        const double eps = sizeof(T) == 4 ? 2.384185791015625e-07 /* 2^-22 */ : 4.440892098500626e-16 /* 2^-51 */;
+
+        int qn = 0;
+        int cur_code = 0;
+        T xq[SUM_PA], yq[SUM_PA], zq[SUM_PA];
+        __syncwarp();  // the previous tile's drains are done with W.prim
+#pragma unroll
+        for (int p = 0; p < SUM_PA; p++) {
+            const int i = lane + 32 * p;
+            const bool ok = i < nv;
+            xq[p] = ok ? pxg[i] : nanv;
+            yq[p] = ok ? pyg[i] : nanv;
+            zq[p] = ok ? pzg[i] : nanv;
+            W.prim[0][i] = xq[p];
+            W.prim[1][i] = yq[p];
+            W.prim[2][i] = zq[p];
+            if (WGT) W.prim[3][i] = ok ? pwg[i] : (T)0;
+        }
+        __syncwarp();
+
+        for (int row = 0; row < nrow; row++) {
+            for (int base = 0; base < rowlen; base += 32) {
+                // ---------------- phase 1: one candidate per lane ----------------
+                const int cand = base + lane;
+                bool keep = cand < rowlen;
+                int cellQ = -1, code = 0, kfirst = 1, nl = 0, flags = 0;
+                int j_start = 0, j_n = 0, j2_start = 0, j2_n = 0;
+                if (keep) {
+                    double offd[3] = {0.0, 0.0, 0.0};
+                    if (LIST) {
+                        const int li = cand / sub2;
+                        const int refQ = P.list_cells[list0 + li];
+                        cellQ = refQ * sub2 + (cand - li * sub2);
+                        // the host lists every unordered pair of reference cells once (and a cell with itself):
+                        // inside one reference cell every unordered pair of fine cells is taken once
+                        if (P.autocorr && refQ == refP && cellQ > cellP) keep = false;
+                        if (!(P.autocorr && refQ == refP)) flags |= SJ_DIRZ;
+                    } else {
+                        const unsigned iy = fdiv((unsigned)cand, P.m_wz);
+                        const int t[3] = {gx + row - rx, gy + (int)iy - ry, gz + (cand - (int)iy * wz) - rz};
+                        const int ra[3] = {rax, ray, raz};
+                        int q[3], rb[3];
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const int ng = P.g.ng[a];
+                            if (P.g.periodic[a]) {
+                                // one image per side at most; further images are exact duplicates the reference
+                                // suppresses (gridlink_utils.h.src:46-72)
+                                if (t[a] < -ng || t[a] >= 2 * ng) keep = false;
+                            } else if (t[a] < 0 || t[a] >= ng)
+                                keep = false;
+                            if (!keep) break;
+                            // neighbour reference cell within +-refine of the primary's (gridlink_impl.c.src:499-518)
+                            const int rt = (int)fdiv((unsigned)(t[a] + ng), P.m_s[a]) - P.g.n[a];
+                            const int dref = rt - ra[a];
+                            if (dref > P.g.refine[a] || dref < -P.g.refine[a]) keep = false;
+                            if (t[a] < 0) {
+                                q[a] = t[a] + ng;
+                                rb[a] = rt + P.g.n[a];
+                                code |= 1 << (2 * a);  // +wrap on the first particle (gridlink_impl.c.src:504)
+                                offd[a] = P.wrap[a];
+                            } else if (t[a] >= ng) {
+                                q[a] = t[a] - ng;
+                                rb[a] = rt - P.g.n[a];
+                                code |= 2 << (2 * a);
+                                offd[a] = -P.wrap[a];
+                            } else {
+                                q[a] = t[a];
+                                rb[a] = rt;
+                            }
+                        }
+                        if (keep) {
+                            cellQ = (q[0] * P.g.ng[1] + q[1]) * P.g.ng[2] + q[2];
+                            if (P.autocorr) {
+                                // reference keeps icell2 <= icell (gridlink_impl.c.src:525); within one reference cell
+                                // every unordered pair of fine cells is taken once
+                                const long long refB = ((long long)rb[0] * P.g.n[1] + rb[1]) * P.g.n[2] + rb[2];
+                                if (refB > refA || (refB == refA && cellQ < cellP)) keep = false;
+                                if (refB != refA) flags |= SJ_DIRZ;
+                                // a cell against its own periodic image: the reference pairs it (all pairs i, j with
+                                // the wrap on i), here every |d| >= L/2 > rmax on that axis: nothing in range
+                                if (cellQ == cellP && code != 0) keep = false;
+                            } else
+                                flags |= SJ_DIRZ;
+                        }
+                    }
+                    int nQ = 0;
+                    if (keep) {
+                        nQ = B.count[cellQ];
+                        if (nQ == 0) keep = false;
+                    }
+                    if (keep) {
+                        // ---- conservative interval of the binned quantity over all pairs of the two cells ----
+                        double dmin[3], dmax[3];
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const double plo = (double)A.bounds[(int64_t)cellP * CFB_NB + 2 * a] + offd[a];
+                            const double phi = (double)A.bounds[(int64_t)cellP * CFB_NB + 2 * a + 1] + offd[a];
+                            const double qlo = (double)B.bounds[(int64_t)cellQ * CFB_NB + 2 * a];
+                            const double qhi = (double)B.bounds[(int64_t)cellQ * CFB_NB + 2 * a + 1];
+                            double lo = 0.0;
+                            if (qlo > phi) lo = qlo - phi;
+                            else if (plo > qhi) lo = plo - qhi;
+                            const double hi = fmax(qhi - plo, phi - qlo);
+                            // rounding of (first + wrap) and of the subtraction
+                            const double del = eps * (fmax(fabs(plo), fabs(phi)) + hi);
+                            dmin[a] = fmax(0.0, lo - del);
+                            dmax[a] = hi + del;
+                        }
+                        double vlo, vhi;
+                        if (MODE == CFB_WP || MODE == CFB_RPPI) {
+                            vlo = dmin[0] * dmin[0] + dmin[1] * dmin[1];
+                            vhi = dmax[0] * dmax[0] + dmax[1] * dmax[1];
+                            if (dmin[2] >= P.pimax) keep = false;  // every |dz| >= pimax
+                        } else {
+                            vlo = dmin[0] * dmin[0] + dmin[1] * dmin[1] + dmin[2] * dmin[2];
+                            vhi = dmax[0] * dmax[0] + dmax[1] * dmax[1] + dmax[2] * dmax[2];
+                        }
+                        vlo *= (1.0 - 2.0 * eps);
+                        vhi *= (1.0 + 2.0 * eps);
+                        if (MODE == CFB_THETA) {  // -cos(theta) = chord^2 / 2 - 1, one more rounding near 1
+                            vlo = (0.5 * vlo - 1.0) - 4.0 * eps;
+                            vhi = (0.5 * vhi - 1.0) + 4.0 * eps;
+                        }
+                        if (MODE == CFB_RPPI_MOCKS) {
+                            // the interval is that of the 3-D separation: it prunes, and it bounds rp^2 from above only
+                            if (vlo >= sqr_max_sep_d) keep = false;
+                            vlo = -1.0;
+                        } else if (vlo >= s_edges_d[nedges - 1])
+                            keep = false;
+                        if (vhi < s_edges_d[0]) keep = false;
+                        if (keep) {
+                            // klo = largest k with E[k] <= vlo, khi = smallest k with E[k] > vhi
+                            int a = 0, b = nedges;
+                            while (a < b) {
+                                const int m = (a + b) >> 1;
+                                if (s_edges_d[m] <= vlo) a = m + 1; else b = m;
+                            }
+                            const int klo = a - 1;
+                            b = nedges;
+                            while (a < b) {
+                                const int m = (a + b) >> 1;
+                                if (s_edges_d[m] <= vhi) a = m + 1; else b = m;
+                            }
+                            const int khi = a;
+                            // the pair's bin is kfirst + #{levels k in [kfirst, kfirst + nl) at or below its value}
+                            kfirst = klo + 1 > 1 ? klo + 1 : 1;
+                            const int klast = khi - 1 < nedges - 2 ? khi - 1 : nedges - 2;
+                            nl = klast - kfirst + 1;
+                            if (nl < 0) nl = 0;
+                            if (klo < 0) flags |= SJ_NEEDLO;
+                            const bool tri = P.autocorr && cellQ == cellP;
+                            const int startQ = B.start[cellQ];
+                            u64 npairs_an;
+                            if (tri) {
+                                // same cell: the tile against itself + the secondaries after this tile
+                                const int after = nP - (toff + SUM_TILE);
+                                j_start = startQ + toff;
+                                j_n = nv;
+                                flags |= SJ_TRI;
+                                if (after > 0) {
+                                    j2_start = startQ + toff + SUM_TILE;
+                                    j2_n = after;
+                                }
+                                npairs_an = (u64)nv * (u64)(nv - 1) / 2 + (u64)nv * (u64)(after > 0 ? after : 0);
+                            } else {
+                                j_start = startQ;
+                                j_n = nQ;
+                                npairs_an = (u64)nv * (u64)nQ;
+                            }
+                            my_eval += npairs_an;
+                            my_levels += npairs_an * (u64)nl;
+                        }
+                    }
+                }
+                // ---------------- push the survivors ----------------
+                {
+                    const unsigned m1 = __ballot_sync(0xffffffffu, keep);
+                    const unsigned m2 = __ballot_sync(0xffffffffu, keep && j2_n > 0);
+                    const unsigned lt = (1u << lane) - 1u;
+                    const int meta = code | (kfirst << 6) | (nl << 14) | flags;
+                    if (keep) {
+                        SumJob jb;
+                        jb.start = j_start;
+                        jb.n = j_n;
+                        jb.meta = meta;
+                        W.q[qn + __popc(m1 & lt)] = jb;
+                        if (j2_n > 0) {
+                            jb.start = j2_start;
+                            jb.n = j2_n;
+                            jb.meta = meta & ~SJ_TRI;
+                            W.q[qn + __popc(m1) + __popc(m2 & lt)] = jb;
+                        }
+                    }
+                    qn += __popc(m1) + __popc(m2);
+                    __syncwarp();
+                }
+                const bool last = (row == nrow - 1) && (base + 32 >= rowlen);
+                if (qn <= SUM_QCAP - 64 && !last) continue;
+
+                // ---------------- phase 2: drain the job queue ----------------
+                my_jobs += qn;
+                int e = 0, c0 = 0;
+                if (qn > 0) {
+                    const SumJob jb = W.q[0];
+                    stage_chunk<T, NA>(W, it & 1, B, jb.start, (min(SUM_CH, jb.n) + 3) & ~3, lane);
+                }
+                while (e < qn) {
+                    const SumJob jb = W.q[e];
+                    const int m4 = (min(SUM_CH, jb.n - c0) + 3) & ~3;
+                    int e2 = e, c2 = c0 + SUM_CH;
+                    if (c2 >= jb.n) {
+                        e2 = e + 1;
+                        c2 = 0;
+                    }
+                    const int bsel = it & 1;
+                    if (e2 < qn) {
+                        const SumJob jn = W.q[e2];
+                        stage_chunk<T, NA>(W, bsel ^ 1, B, jn.start + c2, (min(SUM_CH, jn.n - c2) + 3) & ~3, lane);
+                        cp_async_wait<1>();
+                    } else
+                        cp_async_wait<0>();
+                    __syncwarp();
+
+                    // first particle gets the wrap: xpos = x0 + off_xwrap (countpairs_kernels.c.src:79-81)
+                    const int jcode = jb.meta & 63;
+                    if (jcode != cur_code) {
+                        cur_code = jcode;
+                        const int cx = jcode & 3, cy = (jcode >> 2) & 3, cz = (jcode >> 4) & 3;
+                        const T ox = cx == 1 ? (T)P.wrap[0] : -(T)P.wrap[0];
+                        const T oy = cy == 1 ? (T)P.wrap[1] : -(T)P.wrap[1];
+                        const T oz = cz == 1 ? (T)P.wrap[2] : -(T)P.wrap[2];
+#pragma unroll
+                        for (int p = 0; p < SUM_PA; p++) {
+                            const int i = lane + 32 * p;
+                            if (i < nv) {
+                                const T xr = pxg[i], yr = pyg[i], zr = pzg[i];
+                                xq[p] = cx ? xr + ox : xr;
+                                yq[p] = cy ? yr + oy : yr;
+                                zq[p] = cz ? zr + oz : zr;
+                                W.prim[0][i] = xq[p];
+                                W.prim[1][i] = yq[p];
+                                W.prim[2][i] = zq[p];
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    const int jk = (jb.meta >> 6) & 255, jl = (jb.meta >> 14) & 511;
+                    const bool dirz = (jb.meta & SJ_DIRZ) != 0;
+                    const bool tri = (jb.meta & SJ_TRI) != 0, needlo = (jb.meta & SJ_NEEDLO) != 0;
+                    T E[8];  // the job's level edges; beyond nl: an edge no value is at or above
+#pragma unroll
+                    for (int l = 0; l < 8; l++) {
+                        const T none = MODE == CFB_THETA ? (sizeof(T) == 4 ? (T)-CUDART_INF_F : (T)-CUDART_INF)
+                                                         : (sizeof(T) == 4 ? (T)CUDART_INF_F : (T)CUDART_INF);
+                        E[l] = l < jl ? s_edges[min(jk + l, nedges - 1)] : none;
+                    }
+                    int tail = 0, k = 0;  // the stack is empty at every chunk start: the drain gathers from this chunk's buffer
+                    constexpr bool DIRECT_OK = !AVG && !WGT && (MODE == CFB_DD || MODE == CFB_WP || MODE == CFB_RPPI || MODE == CFB_THETA);
+                    const bool direct = DIRECT_OK && jl <= 8;
+                    for (;;) {
+#define SUM_HOT(PA_, TRI_, LO_, DIR_) \
+    k = hot_loop<T, MODE, WGT, NA, PA_, TRI_, LO_, DIR_>(k, m4, W, bsel, xq, yq, zq, K, dirz, c0, lane, tail, E, jk)
+#define SUM_HOT3(PA_, DIR_)                          \
+    do {                                             \
+        if (tri) SUM_HOT(PA_, true, true, DIR_);     \
+        else if (needlo) SUM_HOT(PA_, false, true, DIR_); \
+        else SUM_HOT(PA_, false, false, DIR_);       \
+    } while (0)
+                        if (DIRECT_OK && direct) {
+                            if (jl <= 4) {
+                                if (pa == 1) SUM_HOT3(1, DIRECT_OK ? 4 : 0);
+                                else SUM_HOT3(2, DIRECT_OK ? 4 : 0);
+                            } else {
+                                if (pa == 1) SUM_HOT3(1, DIRECT_OK ? 8 : 0);
+                                else SUM_HOT3(2, DIRECT_OK ? 8 : 0);
+                            }
+                        } else if (pa == 1)
+                            SUM_HOT3(1, 0);
+                        else
+                            SUM_HOT3(2, 0);
+#undef SUM_HOT3
+#undef SUM_HOT
+                        if (tail >= 32 || (k >= m4 && tail > 0)) {
+                            const int n = tail < 32 ? tail : 32;
+                            drain<T, MODE, AVG, WGT, NA>(n, tail - n, W, bsel, K, E, jk, jl, lane);
+                            tail -= n;
+                            if (++drains >= SUM_NORM_DRAINS) {
+                                flush_hist<MODE, AVG, WGT, T>(P, K, ns, lane, 32, false);
+                                drains = 0;
+                            }
+                            continue;
+                        }
+                        if (k >= m4) break;
+                    }
+                    __syncwarp();  // everyone is done with buf[bsel] before it is staged again
+                    it++;
+                    e = e2;
+                    c0 = c2;
+                }
+                qn = 0;
+            }
+        }
+    }
+    // ---------------- merge ----------------
+    __syncthreads();
+    flush_hist<MODE, AVG, WGT, T>(P, K, ns, tid, blockDim.x, true);
+    for (int o = 16; o > 0; o >>= 1) {
+        my_eval += __shfl_xor_sync(0xffffffffu, my_eval, o);
+        my_jobs += __shfl_xor_sync(0xffffffffu, my_jobs, o);
+        my_levels += __shfl_xor_sync(0xffffffffu, my_levels, o);
+    }
+    if (lane == 0) {
+        if (my_eval) atomicAdd(&P.counters[0], my_eval);
+        if (my_jobs) atomicAdd(&P.counters[1], my_jobs / 32);  // my_jobs is warp-uniform: the shuffle sum counted it 32x
+        if (my_levels) atomicAdd(&P.counters[3], my_levels);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+SetView<T> view_of(const ParticleSet &S)
+{
+    SetView<T> v;
+    v.x = (const T *)S.sorted[0].p;
+    v.y = (const T *)S.sorted[1].p;
+    v.z = (const T *)S.sorted[2].p;
+    v.w = (const T *)S.sorted[3].p;
+    v.count = (const int *)S.count.p;
+    v.start = (const int *)S.start.p;
+    v.bounds = (const T *)S.bounds.p;
+    return v;
+}
+
+template <typename T, bool WGT>
+size_t sum_fixed_smem(int nedges)
+{
+    constexpr int NA = WGT ? 4 : 3;
+    size_t off = (sizeof(SumWarp<T, NA>) * SUM_WARPS + 15) & ~(size_t)15;
+    off += ((size_t)nedges * sizeof(T) + 15) & ~(size_t)15;
+    off += (size_t)nedges * 16;
+    return off;
+}
+
+template <typename T, int MODE, bool AVG, bool WGT, bool LIST>
+int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cudaStream_t st)
+{
+    auto kern = k_pairs_sum<T, MODE, AVG, WGT, LIST>;
+    if (P.ntiles <= 0) return 0;
+    int dev = 0, sms = 0, smem_sm = 0, smem_blk = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    CK(cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t fixed = sum_fixed_smem<T, WGT>(P.nedges);
+    const size_t per_copy = (size_t)P.nslots * 4 * (1 + (AVG ? 3 : 0) + (WGT ? 3 : 0));
+    // histogram copies: as many (1, 2, 4 or 8) as still leave three resident blocks per SM
+    int want_blocks = SUM_MINB, max_shift = 3;
+    if (const char *e = getenv("CORRFUNC_B200_SUM_BLOCKS")) want_blocks = atoi(e) > 0 ? atoi(e) : want_blocks;
+    if (const char *e = getenv("CORRFUNC_B200_SUM_COPIES")) {
+        max_shift = 0;
+        while ((2 << max_shift) <= atoi(e) && max_shift < 5) max_shift++;
+    }
+    const size_t per_block_budget = (size_t)smem_sm / want_blocks - 1024;  // 1 KB per block is reserved by the runtime
+    int shift = 0;
+    while (shift < max_shift && fixed + (per_copy << (shift + 1)) <= per_block_budget &&
+           fixed + (per_copy << (shift + 1)) <= (size_t)smem_blk)
+        shift++;
+    const size_t sm = fixed + (per_copy << shift);
+    if (sm > (size_t)smem_blk) return -1;  // histogram too large for shared memory: the caller falls back
+    P.sum_copies_shift = shift;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SUM_WARPS * 32, sm));
+    if (per_sm < 1) per_sm = 1;
+    constexpr int SPLIT = CFB_TILE / SUM_TILE;
+    int64_t nblk = (P.ntiles * SPLIT / (P.shard_n > 1 ? P.shard_n : 1) + SUM_WARPS - 1) / SUM_WARPS + 1;
+    if (nblk > (int64_t)sms * per_sm) nblk = (int64_t)sms * per_sm;
+    kern<<<(unsigned int)nblk, SUM_WARPS * 32, sm, st>>>(P, view_of<T>(SA), view_of<T>(SB));
+    cfb_ctx().launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int MODE, bool LIST>
+int launch_mode(const cfb_binning *bin, const PairParams &P, const ParticleSet &SA, const ParticleSet &SB, cudaStream_t st)
+{
+    const bool a = bin->need_avg != 0, w = bin->need_weights != 0;
+    if (a && w) return launch_inst<T, MODE, true, true, LIST>(P, SA, SB, st);
+    if (a) return launch_inst<T, MODE, true, false, LIST>(P, SA, SB, st);
+    if (w) return launch_inst<T, MODE, false, true, LIST>(P, SA, SB, st);
+    return launch_inst<T, MODE, false, false, LIST>(P, SA, SB, st);
+}
+
+template <typename T>
+int launch_T(const cfb_binning *bin, const PairParams &P, bool list_mode)
+{
+    Ctx &c = cfb_ctx();
+    const ParticleSet &SA = c.set[0];
+    const ParticleSet &SB = bin->autocorr ? c.set[0] : c.set[1];
+    if (list_mode) {
+        if (bin->mode != CFB_THETA) return cfb_fail("neighbour-list mode is only used by DDtheta");
+        return launch_mode<T, CFB_THETA, true>(bin, P, SA, SB, c.stream);
+    }
+    switch (bin->mode) {
+    case CFB_DD:
+    case CFB_XI: return launch_mode<T, CFB_DD, false>(bin, P, SA, SB, c.stream);
+    case CFB_WP: return launch_mode<T, CFB_WP, false>(bin, P, SA, SB, c.stream);
+    case CFB_RPPI: return launch_mode<T, CFB_RPPI, false>(bin, P, SA, SB, c.stream);
+    case CFB_SMU: return launch_mode<T, CFB_SMU, false>(bin, P, SA, SB, c.stream);
+    case CFB_RPPI_MOCKS: return launch_mode<T, CFB_RPPI_MOCKS, false>(bin, P, SA, SB, c.stream);
+    case CFB_SMU_MOCKS: return launch_mode<T, CFB_SMU_MOCKS, false>(bin, P, SA, SB, c.stream);
+    default: return cfb_fail("unknown mode %d", bin->mode);
+    }
+}
+
+}  // namespace
+
+// 0 = launched, -1 = not applicable (too many edges / histogram too large: use the generic kernel), 1 = error.
+// P.wmax must be set when weights are on (cfb_weight_maxima).
+int cfb_launch_pairs_sum(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode)
+{
+    static_assert(CFB_TILE % SUM_TILE == 0, "sum tiles subdivide the gridlink tiles");
+    if (bin->nedges < 2 || bin->nedges > SUM_MAX_EDGES) return -1;
+    for (int i = 0; i < bin->nedges; i++) {
+        // the level search needs finite, strictly monotonic edges (increasing; theta: decreasing cosines)
+        if (!isfinite(bin->edges[i])) return -1;
+        if (i > 0 && (bin->mode == CFB_THETA ? !(bin->edges[i] < bin->edges[i - 1]) : !(bin->edges[i] > bin->edges[i - 1])))
+            return -1;
+    }
+    if (bin->nslots >= (1 << 20)) return -1;
+    return prec == 4 ? launch_T<float>(bin, P, list_mode) : launch_T<double>(bin, P, list_mode);
+}

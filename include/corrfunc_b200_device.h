@@ -86,7 +86,7 @@ typedef struct {
     int64_t n_cells, n_tiles;
     int fine[3];          /* fine lattice used on the device */
     int kernel_launches;  /* CUDA kernels launched by this call */
-    int kernel_kind;      /* 0 = generic, 1 = fast 1-D */
+    int kernel_kind;      /* 0 = legacy generic, 1 = fast 1-D, 2 = per-pair-sum */
     uint64_t n_analytic;  /* pairs binned from cell bounding boxes alone, without evaluating a separation */
     uint64_t n_levelpairs; /* sum over evaluated pairs of the number of edge compares (levels) each one took */
 } cfb_stats;
@@ -138,7 +138,7 @@ int cfb_count_spheres(int slot, int prec, const double lo[3], const double ext[3
 
 /* Tunables (mostly for tests / benchmarks). */
 void cfb_set_target_occupancy(int particles_per_fine_cell); /* 0 = default */
-void cfb_force_kernel(int kind);                            /* -1 auto, 0 generic, 1 fast */
+void cfb_force_kernel(int kind);                            /* -1 auto, 0 no fast kernel (per-pair-sum, else generic), 1 fast, 3 legacy generic only */
 
 #ifdef __cplusplus
 }

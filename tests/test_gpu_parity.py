@@ -381,7 +381,7 @@ def test_fast_DD_vs_oracle(dtype, periodic, autocorr, edges):
     _force(0)
     try:
         gen = T.DD(autocorr, 4, edges, x, y, z, **kw)
-        assert _lib.last_stats()["kernel_kind"] == 0
+        assert _lib.last_stats()["kernel_kind"] in (0, 2)  # not the fast kernel: per-pair-sum (2) or legacy generic (0)
     finally:
         _force(-1)
     assert np.array_equal(got["npairs"], gen["npairs"])
@@ -630,7 +630,7 @@ def test_DDtheta_refined_lattice(dtype, autocorr, link, occ):
         assert st["kernel_kind"] == 1 and st["n_cells"] >= 1
         assert np.array_equal(got["npairs"], ref["npairs"])
         got = DDtheta_mocks(autocorr, 2, tb, ra1, dec1, **kw_full)
-        assert _lib.last_stats()["kernel_kind"] == 0
+        assert _lib.last_stats()["kernel_kind"] in (0, 2)  # not the fast kernel: per-pair-sum (2) or legacy generic (0)
     finally:
         lib.cfb_set_target_occupancy(0)
     assert np.array_equal(got["npairs"], ref["npairs"])

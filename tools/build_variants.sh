@@ -5,11 +5,11 @@ set -e
 cd "$(dirname "$0")/../corrfunc_b200/csrc"
 mkdir -p variants
 while [ $# -ge 2 ]; do
-  rm -f cuda/pairs_fast.o cuda/pairs_generic.o
+  rm -f cuda/pairs_fast.o cuda/pairs_generic.o cuda/pairs_sum.o
   make -j8 VARIANT_FLAGS="$2" > /dev/null
   cp libcorrfunc_b200.so variants/libcorrfunc_b200_$1.so
   grep -A3 "k_pairs_fastIfLi0ELb0ELb0" cuda/pairs_fast.o.ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $1"
   shift 2
 done
-rm -f cuda/pairs_fast.o cuda/pairs_generic.o
+rm -f cuda/pairs_fast.o cuda/pairs_generic.o cuda/pairs_sum.o
 make -j8 > /dev/null

@@ -1,0 +1,11 @@
+#!/bin/bash
+# exp_sum.py (c3-like, 3 M points) for the default library and the variants given as arguments
+for v in default "$@"; do
+  if [ $v = default ]; then unset CORRFUNC_B200_LIBPATH; else export CORRFUNC_B200_LIBPATH=$PWD/corrfunc_b200/csrc/variants/libcorrfunc_b200_$v.so; fi
+  echo "== $v"
+  python tools/exp_sum.py 3e6 2>&1 | grep -v legacy | tail -7
+done
+unset CORRFUNC_B200_LIBPATH
+for c in c2rppi c2rppi32; do
+  timeout 600 python bench.py --config $c --steps 3 --no-cpu-baseline 2>/dev/null | python tools/bench_summary.py $c
+done
