@@ -53,6 +53,9 @@ CONFIGS = {
                mu_max=1.0, nmu=20, weights=True, avg=True),
     "c5d": dict(stat="xi", N=100_000_000, L=2000.0, bins=("log", 0.1, 150.0, 31), dtype="f64", seed=1006),
     "c5": dict(stat="xi", N=100_000_000, L=2000.0, bins=("log", 0.1, 150.0, 31), dtype="f32", seed=1006),
+    # config 5 is "xi AND DD(autocorr=1, periodic)": the same points through countpairs(), whose lattice
+    # spans the data extent instead of [0, L]
+    "c5DD": dict(stat="DD", N=100_000_000, L=2000.0, bins=("log", 0.1, 150.0, 31), dtype="f32", seed=1006),
 }
 # mocks: up to the first range test of a pair -- 3 sub + 3 add (perp, par), 2 mul + add + fma (s.l), its square,
 # mul + 2 fma (s^2): 14 lane-instructions, 17 FLOP
@@ -180,6 +183,20 @@ def ref_cell_counts(pts, L, nmesh, dtype):
     return np.bincount(lin, minlength=nmesh[0] * nmesh[1] * nmesh[2]).reshape(nmesh)
 
 
+def workload_config(args, cfg, N, input_bytes):
+    """The workload both arms are measured on, as a dict that depends on nothing but the workload itself (the driver
+    compares the two arms' `config` for equality)."""
+    return {"workload": "%s %s: N=%d L=%g bins=%s%s" % (args.config, cfg["stat"], N, cfg["L"], cfg["bins"],
+                                                        "" if not args.npart else " (REDUCED N, not the headline size)"),
+            "dtype": cfg["dtype"],
+            "l2": "inputs larger than L2" if input_bytes >= 256 * 1024 * 1024 else "256 MiB L2 flush between iterations"}
+
+
+def input_bytes_of(cfg, N):
+    per = {"DDtheta": 4, "DDrppi_mocks": 3, "DDsmu_mocks": 3}.get(cfg["stat"], 3) + (1 if cfg.get("weights") else 0)
+    return per * N * (4 if cfg["dtype"] == "f32" else 8)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -238,6 +255,9 @@ def run_ours(args, cfg):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     os.environ["CORRFUNC_B200_DEVICE"] = str(local)
+    if args.inlib and world == 1:
+        # ONE process, ONE C call, args.gpus devices: the sharding happens inside the library (CORRFUNC_B200_NGPUS)
+        os.environ["CORRFUNC_B200_NGPUS"] = str(args.gpus)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -359,7 +379,6 @@ def run_ours(args, cfg):
             n_eval = s["n_eval"]
             launches += s["kernel_launches"]
         barrier()
-        clocks = sampler.stop() if rank == 0 else None
         t_res = t_acc / args.steps
         # ---- timed: end to end from pinned host buffers ----
         barrier()
@@ -380,6 +399,25 @@ def run_ours(args, cfg):
         barrier()
         t_e2e = t_acc / args.steps
         st1 = _lib.last_stats()
+        # ---- end to end from PAGEABLE host buffers (what a numpy caller passes), single process only ----
+        t_page = None
+        if world == 1:
+            t_acc = 0.0
+            for _ in range(min(args.steps, 3)):
+                if need_flush:
+                    flush.zero_()
+                    torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                one_call({k: torch.from_numpy(pts[k]) for k in keys}, bf)
+                t_acc += time.perf_counter() - t0
+            t_page = t_acc / min(args.steps, 3)
+        # small configs finish before nvidia-smi (200 ms period) has reported three times: keep the same workload
+        # running, untimed, until it has -- a clocks line without samples verifies nothing
+        if rank == 0:
+            t_end = time.perf_counter() + 3.0
+            while len(sampler.rows) < 4 and time.perf_counter() < t_end:
+                one_call(resident, bf)
+        clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks (device-synchronised host clock around synchronous calls)
     if world > 1:
@@ -413,18 +451,31 @@ def run_ours(args, cfg):
         pass
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     lanes = 128 if dtype == np.float32 else 64
+    # measured ALU issue rate (tools/ubench.cu: dependent-free FFMA / DFMA streams on every SM, profiles/measured_alu.json)
+    # and DRAM traffic of the pair kernel (one ncu capture per config, profiles/measured_traffic.json)
+    alu, traffic_tab = {}, {}
+    try:
+        alu = json.load(open(os.path.join(ROOT, "profiles", "measured_alu.json")))
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "measured_traffic.json")))
+    except Exception:
+        pass
+    key = "fp32_warp_instr_per_clk_per_sm" if dtype == np.float32 else "fp64_warp_instr_per_clk_per_sm"
+    nominal_wi = lanes / 32.0
+    measured_wi = float(alu.get(key, nominal_wi))
+    traffic = traffic_tab.get(args.config if not args.npart else "", {}).get("dram_bytes_per_launch")
     flop = FLOP_PER_EVAL[stat]
     # ALU roofline of SURVEY.md 8(d): one evaluation costs INSTR_PER_EVAL lane-instructions of the FP32
     # (FP64) pipe, so peak evals/s = SMs x lanes x clock / INSTR_PER_EVAL; in FLOP terms that mix carries
     # FLOP_PER_EVAL per INSTR_PER_EVAL lane-cycles (sub and mul count 1, fma 2)
-    peak_tflops = 148 * lanes * sm_max * 1e6 * flop / INSTR_PER_EVAL[stat] / 1e12
+    peak_tflops = 148 * measured_wi * 32 * sm_max * 1e6 * flop / INSTR_PER_EVAL[stat] / 1e12
     ach_tflops = n_eval_total * flop / (kmean * 1e-3) / 1e12 / max(world, 1)  # per GPU
-    peak_evals = 148 * lanes * sm_max * 1e6 / INSTR_PER_EVAL[stat]
+    peak_evals = 148 * measured_wi * 32 * sm_max * 1e6 / INSTR_PER_EVAL[stat]
+    ngpu_used = max(world, int(lib.cfb_last_device_count()))
     line = {
         "metric": "pair evaluations/sec (reference-equivalent candidate pairs, N_cand/t) and DD wall-time",
         "value": n_cand / t_res,
         "unit": "pair_evals/s",
-        "n_gpus": world,
+        "n_gpus": ngpu_used,
         "steps": args.steps,
         "warmup": max(args.warmup, 3),
         "ms_per_step": t_res * 1e3,
@@ -433,19 +484,22 @@ def run_ours(args, cfg):
         "vs_baseline": None,
         "dtype": cfg["dtype"],
         "data": "synthetic",
-        "config": {"workload": "%s %s: N=%d L=%g bins=%s%s" % (args.config, stat, N, cfg["L"], cfg["bins"],
-                                                              "" if not args.npart else " (REDUCED N, not the headline size)"),
-                   "l2": "inputs larger than L2" if not need_flush else "256 MiB L2 flush between iterations",
-                   "reference_lattice": list(st0["nmesh"]), "refine": list(st0["refine"]), "device_lattice": list(st0["fine"]),
-                   "timing": "host clock around synchronous C-ABI calls (device-synchronised on both sides), max over ranks; kernel time by CUDA events on the launch stream",
-                   "device_ms_per_step": float(np.mean(dev_ms))},
+        "config": workload_config(args, cfg, N, input_bytes),
+        "lattice": {"reference_lattice": list(st0["nmesh"]), "refine": list(st0["refine"]), "device_lattice": list(st0["fine"])},
+        "timing": {"how": "host clock around synchronous C-ABI calls (device-synchronised on both sides), max over ranks; "
+                          "kernel time by CUDA events on the launch stream",
+                   "device_ms_per_step": float(np.mean(dev_ms)),
+                   "process_model": ("one process, one C call, %d devices inside the library" % ngpu_used) if args.inlib
+                   else "one process per GPU"},
         "e2e": {"value": n_cand / t_e2e, "unit": "pair_evals/s", "ms_per_step": t_e2e * 1e3,
-                "h2d_bytes_per_step": int(input_bytes), "d2h_bytes_per_step": int(len(bins) * 24 + 64)},
+                "h2d_bytes_per_step": int(input_bytes), "d2h_bytes_per_step": int(len(bins) * 24 + 64),
+                "host_buffers": "pinned", "ms_per_step_pageable": None if t_page is None else t_page * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "fp32_alu" if dtype == np.float32 else "fp64_alu", "achieved": ach_tflops, "peak": peak_tflops,
-                     "unit": "TFLOP/s", "frac": ach_tflops / peak_tflops, "traffic": None,
-                     "peak_source": "nominal ALU issue rate: 148 SMs x %d lanes x %.0f MHz x %d FLOP / %d instr per evaluation (MEASURED_PEAKS.json has no FP32/FP64 ALU figure; clock = its sm_max_mhz)" % (lanes, sm_max, flop, INSTR_PER_EVAL[stat]),
+                     "unit": "TFLOP/s", "frac": ach_tflops / peak_tflops, "traffic": traffic,
+                     "peak_source": "%s ALU issue rate: 148 SMs x %.2f warp-instr/clk/SM (nominal %.0f) x 32 lanes x %.0f MHz x %d FLOP / %d instr per evaluation (MEASURED_PEAKS.json has no ALU figure; clock = its sm_max_mhz; issue rate from tools/ubench.cu, profiles/measured_alu.json)" % ("measured" if key in alu else "nominal", measured_wi, nominal_wi, sm_max, flop, INSTR_PER_EVAL[stat]),
+                     "frac_of_nominal_peak": ach_tflops / (148 * lanes * sm_max * 1e6 * flop / INSTR_PER_EVAL[stat] / 1e12),
                      "kernel_ms": kmean, "gridlink_ms": float(np.mean(grid_ms)), "n_eval": n_eval_total,
                      "evals_per_s": n_eval_total / (kmean * 1e-3), "peak_evals_per_s_per_gpu": peak_evals,
                      "kernel_share_of_step": kmean * 1e-3 / t_res,
@@ -555,19 +609,92 @@ def cpu_baseline(cfg, args, budget_s=15.0, steps=1, n_cand_full=None):
             "sample": "first %d of the %d points (same box, same bins): reference %s, %d OpenMP threads" % (n_s, n_full, stat, cores)}
 
 
+def n_cand_of(cfg, pts, n, bins):
+    """Candidate pairs of the reference's cell-pair set for the first n points (None when there is no cheap closed form)."""
+    stat = cfg["stat"]
+    dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
+    if stat in ("xi", "wp", "DD", "DDrppi"):
+        nm, rf = ref_lattice_for(cfg, n, bins)
+        return n_cand_box(ref_cell_counts({k: pts[k][:n] for k in "xyz"}, cfg["L"], nm, dtype), rf)
+    if stat in ("DDsmu", "DDrppi_mocks", "DDsmu_mocks"):
+        return n_cand_data_extent(cfg, pts, n, bins)
+    return None
+
+
 def run_reference(args, cfg):
+    """The reference arm: the UNMODIFIED reference (oracle/_ref, AVX-512F kernels, every host thread) on the workload of
+    the GPU arm.  When K full-size steps fit the time budget they are run as they are.  Otherwise (config 5: 100 M points
+    take the reference 10-25 minutes per step) the reference is timed at two sizes of the same box and bins -- K steps at
+    n_small, one at n_large (10 M and 30 M when the budget allows, the sizes SURVEY 8(d) names) -- the exponent of
+    t ~ n^p is fitted from the two, and the full-size time is extrapolated: `ms_per_step` and `value` are those of the
+    FULL workload and carry `extrapolated: true`, the measured seconds and the fit sit beside them."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    cb = cpu_baseline(cfg, args, budget_s=12.0, steps=max(1, args.steps))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
+
+    ref = H.load_ref()
     N = args.npart or cfg["N"]
-    return {"impl": "reference", "metric": "pair evaluations/sec (reference-equivalent candidate pairs, N_cand/t) and DD wall-time",
-            "value": cb["value"], "unit": "pair_evals/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": cb.get("seconds", 0) * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
-            "config": {"workload": "%s %s: N=%d L=%g bins=%s" % (args.config, cfg["stat"], N, cfg["L"], cfg["bins"])},
-            "cpu_baseline": cb,
-            "e2e": {"value": cb["value"], "unit": "pair_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    base = {"impl": "reference", "metric": "pair evaluations/sec (reference-equivalent candidate pairs, N_cand/t) and DD wall-time",
+            "unit": "pair_evals/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": workload_config(args, cfg, N, input_bytes_of(cfg, N))}
+    if ref is None:
+        base.update(value=None, ms_per_step=None, cpu_baseline={"value": None, "kind": "reference", "cores": 0,
+                                                                "sample": "oracle/_ref not built"})
+        return base
+    dtype = np.float32 if cfg["dtype"] == "f32" else np.float64
+    cores = os.cpu_count() or 1
+    bins = make_bins(cfg["bins"])
+    stat = cfg["stat"]
+    K = max(1, args.steps)
+    budget = float(os.environ.get("CORRFUNC_BENCH_REF_BUDGET_S", "200"))
+    pts = gen_points(cfg, N, dtype)
+    n_cal = min(N, 1_000_000 if stat != "DDtheta" else 300_000)
+    t_cal = ref_call(ref, cfg, pts, n_cal, bins, cores)
+    t_full_guess = t_cal * (N / n_cal) ** 2
+    n_cand_full = n_cand_of(cfg, pts, N, bins)
+    isa = "avx512f" if H.ref_variant() == "v4" else "avx"
+    if (K + min(args.warmup, 1)) * t_full_guess <= budget:
+        for _ in range(min(args.warmup, 1)):
+            ref_call(ref, cfg, pts, N, bins, cores)
+        ts = [ref_call(ref, cfg, pts, N, bins, cores) for _ in range(K)]
+        t = float(np.mean(ts))
+        extra = {"extrapolated": False, "seconds_per_step": ts}
+        sample = "the full workload: %d points, reference %s, %d OpenMP threads, %d steps" % (N, stat, cores, K)
+    else:
+        # two sizes: K steps at n_small (45 % of the budget), one at n_large (45 %)
+        n_small = int(min(10_000_000, n_cal * (0.45 * budget / (K * t_cal)) ** 0.5, N))
+        n_large = int(min(30_000_000, n_cal * (0.45 * budget / t_cal) ** 0.5, N))
+        if n_large < 1.5 * n_small:
+            n_small = int(n_large / 1.5)
+        ts = [ref_call(ref, cfg, pts, n_small, bins, cores) for _ in range(K)]
+        t_small = float(np.mean(ts))
+        t_large = ref_call(ref, cfg, pts, n_large, bins, cores)
+        p_fit = float(np.log(t_large / t_small) / np.log(n_large / n_small))
+        t = t_large * (N / n_large) ** p_fit
+        # error bar: the exponent is a two-point fit; +-0.05 on it (the run-to-run spread of the two timings) moves the
+        # extrapolation by the factor (N / n_large)^0.05
+        err = (N / n_large) ** 0.05 - 1.0
+        extra = {"extrapolated": True, "fit": {"n": [n_small, n_large], "seconds": [t_small, t_large], "exponent": p_fit,
+                                                "steps_at_n_small": K, "relative_error_of_extrapolation": err,
+                                                "model": "t = t(n_large) * (N / n_large)^exponent, same box and bins at lower density"}}
+        sample = ("first %d (x%d steps) and first %d (x1) of the %d points, same box and bins; t ~ n^%.2f; full size extrapolated "
+                  "(+-%.0f %%): reference %s, %d OpenMP threads" % (n_small, K, n_large, N, p_fit, 100 * err, stat, cores))
+    value = None if n_cand_full is None else n_cand_full / t
+    if value is None:
+        # no closed form for this lattice (DDtheta): pairs in range per second over the whole catalogue are not comparable
+        # with the GPU arm's unit; report wall time and leave the rate to the GPU arm's own count
+        value = float("nan")
+    cb = {"value": value, "unit": "pair_evals/s", "cores": cores, "kind": "reference", "isa": isa, "seconds": t,
+          "n_cand": n_cand_full, "omp": {"proc_bind": os.environ.get("OMP_PROC_BIND"), "places": os.environ.get("OMP_PLACES")},
+          "sample": sample}
+    cb.update(extra)
+    base.update(value=value, ms_per_step=t * 1e3, cpu_baseline=cb,
+                e2e={"value": value, "unit": "pair_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    base.update({k: v for k, v in extra.items() if k in ("extrapolated", "fit")})
+    return base
 
 
 def main():
@@ -581,6 +708,8 @@ def main():
     ap.add_argument("--occ", type=int, default=0, help="target particles per device cell (0 = default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inlib", action="store_true",
+                    help="single process: let the library shard one call over --gpus devices (CORRFUNC_B200_NGPUS)")
     args = ap.parse_args()
     if args.impl == "reference":
         # the reference's OpenMP threads pinned to cores.  Only this arm: it is a process of its own

@@ -3,13 +3,22 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <thread>
+#include <vector>
+
 #include "cfb_internal.cuh"
 
-static Ctx g_ctx;
+// One context per device.  Context 0 is the one every call starts on (CORRFUNC_B200_DEVICE or the current device); the
+// others exist only while a pair count is sharded over several devices INSIDE one call (count_box_multi below), each
+// driven by its own host thread whose thread-local `tl_ctx` points at it.
+#define CFB_MAX_DEV 16
+static Ctx g_ctxs[CFB_MAX_DEV];
+static thread_local Ctx *tl_ctx = &g_ctxs[0];
+#define g_ctx (*tl_ctx)
 // persistent pinned host buffers handed to the host layer (cfb_host_scratch)
 static void *g_host_scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 static size_t g_host_scratch_cap[6] = {0, 0, 0, 0, 0, 0};
-Ctx &cfb_ctx() { return g_ctx; }
+Ctx &cfb_ctx() { return *tl_ctx; }
 
 int cfb_fail(const char *fmt, ...)
 {
@@ -42,9 +51,22 @@ int cfb_ensure(DevBuf &b, size_t bytes)
     return 0;
 }
 
+static int init_ctx(Ctx &c, int dev)
+{
+    if (c.ready) return 0;
+    CK(cudaSetDevice(dev));
+    c.dev = dev;
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c.ev[i]));
+    c.pinned_cap = 1 << 20;
+    CK(cudaMallocHost(&c.pinned, c.pinned_cap));
+    c.ready = true;
+    return 0;
+}
+
 extern "C" int cfb_init(void)
 {
-    Ctx &c = g_ctx;
+    Ctx &c = g_ctxs[0];
     if (c.ready) return 0;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -58,19 +80,11 @@ extern "C" int cfb_init(void)
     else
         cudaGetDevice(&dev);
     if (dev < 0 || dev >= ndev) return cfb_fail("CORRFUNC_B200_DEVICE=%d out of range (have %d devices)", dev, ndev);
-    CK(cudaSetDevice(dev));
-    c.dev = dev;
-    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; i++) CK(cudaEventCreate(&c.ev[i]));
-    c.pinned_cap = 1 << 20;
-    CK(cudaMallocHost(&c.pinned, c.pinned_cap));
-    c.ready = true;
-    return 0;
+    return init_ctx(c, dev);
 }
 
-extern "C" void cfb_shutdown(void)
+static void release_ctx(Ctx &c)
 {
-    Ctx &c = g_ctx;
     if (!c.ready) return;
     cudaSetDevice(c.dev);
     cudaStreamSynchronize(c.stream);
@@ -87,18 +101,26 @@ extern "C" void cfb_shutdown(void)
         rel(S.tile_cell); rel(S.tile_off);
         S = ParticleSet();
     }
-    cfb_spheres_release();
     rel(c.scratch); rel(c.hist); rel(c.edges); rel(c.list_off); rel(c.list_cells); rel(c.ngrid_ra); rel(c.ra_off);
     if (c.pinned) cudaFreeHost(c.pinned);
     c.pinned = nullptr;
+    for (int i = 0; i < 8; i++) cudaEventDestroy(c.ev[i]);
+    cudaStreamDestroy(c.stream);
+    c.ready = false;
+}
+
+extern "C" void cfb_shutdown(void)
+{
+    if (!g_ctxs[0].ready) return;
+    cudaSetDevice(g_ctxs[0].dev);
+    cfb_spheres_release();
     for (int i = 0; i < 6; i++) {
         if (g_host_scratch[i]) cudaFreeHost(g_host_scratch[i]);
         g_host_scratch[i] = nullptr;
         g_host_scratch_cap[i] = 0;
     }
-    for (int i = 0; i < 8; i++) cudaEventDestroy(c.ev[i]);
-    cudaStreamDestroy(c.stream);
-    c.ready = false;
+    for (int d = CFB_MAX_DEV - 1; d >= 0; d--) release_ctx(g_ctxs[d]);
+    cudaSetDevice(g_ctxs[0].dev);
 }
 
 extern "C" void cfb_set_shard(int rank, int nranks)
@@ -403,7 +425,8 @@ static bool fast_box_plan(const Ctx &c, const cfb_binning *bin, const cfb_box_la
     return true;
 }
 
-extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *out, cfb_stats *stats)
+// One device's share of a box count (all of it when shard_n == 1): gridlink, pair kernel, histogram read-back.
+static int count_box_one(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *out, cfb_stats *stats)
 {
     Ctx &c = g_ctx;
     if (!c.ready) return cfb_fail("cfb_count_box before cfb_upload");
@@ -498,6 +521,151 @@ extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat,
     if (stats) *stats = st;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Several GPUs inside ONE call (SURVEY 8(e) "process model"; the reference shards its cell pairs over OpenMP threads inside
+// the call, theory/DD/countpairs_impl.c.src:452-530).  The public signatures have no slot for a device count, so it comes
+// from the environment: CORRFUNC_B200_NGPUS = n uses n devices; unset, every visible device is used once a particle set
+// holds CFB_MULTI_MIN_N points (below that a second device costs more in replication than it saves).  One process per GPU
+// (torchrun: cfb_set_shard with nranks > 1, or CORRFUNC_B200_DEVICE set) always stays on its own device.
+// Device 0 of the call holds the uploaded arrays; the others receive them by peer copies over NVLink (900 GB/s per
+// direction instead of another trip over PCIe), then every device grids its replica and counts the primary cells it
+// owns (cfb_owns_cell), driven by its own host thread; the partial histograms (<= a few KB) are summed on the host.
+#define CFB_MULTI_MIN_N 4000000
+static int g_multi_devs[CFB_MAX_DEV];
+static int g_multi_last = 1;  // devices the last box count ran on
+
+static int plan_devices(const Ctx &c0, int64_t nmax, int *devs)
+{
+    devs[0] = c0.dev;
+    if (c0.shard_n > 1) return 1;
+    const char *en = getenv("CORRFUNC_B200_NGPUS");
+    const char *ed = getenv("CORRFUNC_B200_DEVICE");
+    int want;
+    if (en && *en) want = atoi(en);
+    else if (ed && *ed) want = 1;
+    else want = nmax >= CFB_MULTI_MIN_N ? CFB_MAX_DEV : 1;
+    if (want <= 1) return 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    int n = 1;
+    for (int d = 0; d < ndev && n < want && n < CFB_MAX_DEV; d++)
+        if (d != c0.dev) devs[n++] = d;
+    return n;
+}
+
+// copies set `slot` of context 0 (device memory there) into context `c` of another device
+static int replicate_set(Ctx &c, const Ctx &c0, int slot)
+{
+    const ParticleSet &S0 = c0.set[slot];
+    ParticleSet &S = c.set[slot];
+    S.prec = S0.prec;
+    S.n = S0.n;
+    S.gridded = false;
+    const size_t bytes = (size_t)S0.n * S0.prec;
+    for (int i = 0; i < 6; i++) {
+        S.raw[i] = nullptr;
+        if (i >= 4 || !S0.raw[i] || S0.n == 0) continue;  // x, y, z, w: what the box statistics use
+        if (cfb_ensure(S.rawbuf[i], bytes)) return 1;
+        CK(cudaMemcpyPeerAsync(S.rawbuf[i].p, c.dev, S0.raw[i], c0.dev, bytes, c.stream));
+        S.raw[i] = S.rawbuf[i].p;
+    }
+    return 0;
+}
+
+static int count_box_multi(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *out, cfb_stats *stats, int nd,
+                           const int *devs)
+{
+    Ctx &c0 = g_ctxs[0];
+    const int nsets = bin->autocorr ? 1 : 2;
+    const int64_t ns = bin->nslots;
+    CK(cudaSetDevice(c0.dev));
+    CK(cudaEventRecord(c0.ev[7], c0.stream));  // the uploads of this call are complete when this event is
+    std::vector<uint64_t> np((size_t)nd * ns, 0);
+    std::vector<double> ss((size_t)nd * ns, 0.0), sw((size_t)nd * ns, 0.0);
+    std::vector<cfb_stats> st(nd);
+    std::vector<int> rc(nd, 0);
+    auto work = [&](int k) {
+        tl_ctx = &g_ctxs[k];
+        Ctx &c = g_ctxs[k];
+        c.err[0] = 0;
+        if (k > 0) {
+            if (init_ctx(c, devs[k])) { rc[k] = 1; return; }
+            if (cudaSetDevice(c.dev) != cudaSuccess) { rc[k] = 1; return; }
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, c.dev, c0.dev) == cudaSuccess && can) {
+                if (cudaDeviceEnablePeerAccess(c0.dev, 0) != cudaSuccess) cudaGetLastError();  // already enabled: fine
+            }
+            if (cudaStreamWaitEvent(c.stream, c0.ev[7], 0) != cudaSuccess) { rc[k] = 1; return; }
+            for (int s = 0; s < nsets; s++)
+                if (replicate_set(c, c0, s)) { rc[k] = 1; return; }
+            c.target_occ = c0.target_occ;
+            c.force_kernel = c0.force_kernel;
+        }
+        c.shard_rank = k;
+        c.shard_n = nd;
+        cfb_hist h = {np.data() + (size_t)k * ns, out->sum_sep ? ss.data() + (size_t)k * ns : nullptr,
+                      out->sum_w ? sw.data() + (size_t)k * ns : nullptr};
+        rc[k] = count_box_one(bin, lat, &h, &st[k]);
+        c.shard_rank = 0;
+        c.shard_n = 1;
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < nd; k++) th.emplace_back(work, k);
+    work(0);
+    for (auto &t : th) t.join();
+    tl_ctx = &g_ctxs[0];
+    cudaSetDevice(c0.dev);
+    for (int k = 0; k < nd; k++)
+        if (rc[k]) {
+            if (k > 0) snprintf(c0.err, sizeof(c0.err), "device %d: %s", devs[k], g_ctxs[k].err);
+            return 1;
+        }
+    cfb_stats tot = st[0];
+    for (int64_t i = 0; i < ns; i++) {
+        uint64_t n = 0;
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < nd; k++) {
+            n += np[(size_t)k * ns + i];
+            a += ss[(size_t)k * ns + i];
+            b += sw[(size_t)k * ns + i];
+        }
+        out->npairs[i] = n;
+        if (out->sum_sep) out->sum_sep[i] = a;
+        if (out->sum_w) out->sum_w[i] = b;
+    }
+    for (int k = 1; k < nd; k++) {  // times: the slowest device; work counters: the sum
+        if (st[k].ms_gridlink > tot.ms_gridlink) tot.ms_gridlink = st[k].ms_gridlink;
+        if (st[k].ms_pairs > tot.ms_pairs) tot.ms_pairs = st[k].ms_pairs;
+        if (st[k].ms_total_device > tot.ms_total_device) tot.ms_total_device = st[k].ms_total_device;
+        tot.n_eval += st[k].n_eval;
+        tot.n_tilepairs += st[k].n_tilepairs;
+        tot.n_analytic += st[k].n_analytic;
+        tot.n_levelpairs += st[k].n_levelpairs;
+        tot.kernel_launches += st[k].kernel_launches;
+    }
+    if (stats) *stats = tot;
+    return 0;
+}
+
+extern "C" int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *out, cfb_stats *stats)
+{
+    tl_ctx = &g_ctxs[0];
+    Ctx &c0 = g_ctxs[0];
+    if (!c0.ready) return cfb_fail("cfb_count_box before cfb_upload");
+    int64_t nmax = c0.set[0].n;
+    if (!bin->autocorr && c0.set[1].n > nmax) nmax = c0.set[1].n;
+    const int nd = plan_devices(c0, nmax, g_multi_devs);
+    g_multi_last = nd;
+    if (nd <= 1) return count_box_one(bin, lat, out, stats);
+    return count_box_multi(bin, lat, out, stats, nd, g_multi_devs);
+}
+
+/* devices the last cfb_count_box ran on */
+extern "C" int cfb_last_device_count(void) { return g_multi_last; }
 
 extern "C" int cfb_theta_subdivision(int64_t nmax, int64_t ncells)
 {

@@ -110,6 +110,9 @@ void cfb_set_shard(int rank, int nranks);
 void cfb_get_shard(int *rank, int *nranks);
 
 int cfb_count_box(const cfb_binning *bin, const cfb_box_lattice *lat, cfb_hist *out, cfb_stats *stats);
+/* Devices the last cfb_count_box ran on.  CORRFUNC_B200_NGPUS = n shards one call over n devices of this process (default:
+ * all visible ones once a particle set holds 4 M points; 1 under cfb_set_shard with nranks > 1 or CORRFUNC_B200_DEVICE). */
+int cfb_last_device_count(void);
 
 /* Theta: two-phase because the reference's neighbour search needs per-cell RA bounds.
  * cfb_theta_gridlink sorts slot(s) into the lattice and returns per-cell counts and bounds (host

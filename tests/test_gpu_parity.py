@@ -699,7 +699,9 @@ def test_float_z_window_case(stat):
     assert not d[:-1].any() and d[-1] == 2, d
 
 
-FULL_SIZE_VERIFIED = ["c1", "c2", "c2wp32", "c2rppi", "c2rppi32", "c3", "c4", "c5sd10M", "c5"]
+# c5dsd10M: config 5 in DOUBLE at the same density (10 M points) -- the double kernel is another code path
+# (compare-and-count instead of the packed sign-bit counters); c5DDsd10M: the same points through DD(autocorr=1, periodic)
+FULL_SIZE_VERIFIED = ["c1", "c2", "c2wp32", "c2rppi", "c2rppi32", "c3", "c4", "c5sd10M", "c5dsd10M", "c5DDsd10M", "c5"]
 
 
 @pytest.mark.parametrize("name", FULL_SIZE_VERIFIED)
@@ -741,3 +743,41 @@ def _check_full_size(name):
         # lost most of its digits, so its float averages are not a standard to hold the GPU to
         if k in g.files and not name.endswith("f32"):
             _close(np.asarray(r[k]).reshape(g[k].shape), g[k], 1e-10, k)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("autocorr", [1, 0])
+@pytest.mark.parametrize("occ", [0, 8])
+def test_DDtheta_fast_acos_vs_oracle(dtype, autocorr, occ):
+    """options.fast_acos = 1: thetaavg from the degree-8 polynomial of utils/fast_acos.h:57-101 (used by the reference at
+    countpairs_theta_mocks_kernels.c.src:153,490,822) instead of libm's acos.  Same counts, and averages equal to the
+    oracle's run with the same flag -- and measurably different from the libm run, so the flag is known to reach the
+    kernel.  occ = 8 forces the sub x sub refinement of the RA/DEC lattice."""
+    from corrfunc_b200 import _lib
+    from corrfunc_b200.mocks import DDtheta_mocks
+
+    ra1, dec1 = H.sphere_points(25, 30000, dtype)
+    ra2, dec2 = H.sphere_points(26, 20000, dtype)
+    w1 = (1.0 - np.random.default_rng(27).random(ra1.size)).astype(dtype)
+    w2 = (1.0 - np.random.default_rng(28).random(ra2.size)).astype(dtype)
+    tb = np.logspace(np.log10(0.05), 1, 16)
+    kw = dict(weights1=w1, weight_type="pair_product", output_thetaavg=True)
+    okw = dict(w1=w1, weight_type="pair_product", need_avg=True, autocorr=bool(autocorr))
+    if not autocorr:
+        kw.update(RA2=ra2, DEC2=dec2, weights2=w2)
+        okw.update(RA2=ra2, DEC2=dec2, w2=w2)
+    lib = _lib.load()
+    lib.cfb_set_target_occupancy(occ)
+    try:
+        fast = DDtheta_mocks(autocorr, 2, tb, ra1, dec1, fast_acos=True, **kw)
+        slow = DDtheta_mocks(autocorr, 2, tb, ra1, dec1, fast_acos=False, **kw)
+    finally:
+        lib.cfb_set_target_occupancy(0)
+    ref = H.oracle_theta(ra1, dec1, tb, fast_acos=True, **okw)
+    assert np.array_equal(fast["npairs"], ref["npairs"]) and np.array_equal(slow["npairs"], ref["npairs"])
+    _close(fast["thetaavg"], ref["ravg"], 1e-9 if dtype == np.float64 else 1e-4, "thetaavg (fast_acos)")
+    _close(fast["weightavg"], ref["weightavg"], TOL[dtype], "weightavg")
+    if dtype == np.float64:
+        # the polynomial is good to 3.7e-9 rad, libm to 1e-16: the two runs differ, but by less than 1e-6 degrees
+        d = np.abs(fast["thetaavg"] - slow["thetaavg"])
+        assert d.max() > 0 and d.max() < 1e-6
