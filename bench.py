@@ -468,9 +468,9 @@ def run_ours(args, cfg):
     # (FP64) pipe, so peak evals/s = SMs x lanes x clock / INSTR_PER_EVAL; in FLOP terms that mix carries
     # FLOP_PER_EVAL per INSTR_PER_EVAL lane-cycles (sub and mul count 1, fma 2)
     peak_tflops = 148 * measured_wi * 32 * sm_max * 1e6 * flop / INSTR_PER_EVAL[stat] / 1e12
-    ach_tflops = n_eval_total * flop / (kmean * 1e-3) / 1e12 / max(world, 1)  # per GPU
-    peak_evals = 148 * measured_wi * 32 * sm_max * 1e6 / INSTR_PER_EVAL[stat]
     ngpu_used = max(world, int(lib.cfb_last_device_count()))
+    ach_tflops = n_eval_total * flop / (kmean * 1e-3) / 1e12 / ngpu_used  # per GPU
+    peak_evals = 148 * measured_wi * 32 * sm_max * 1e6 / INSTR_PER_EVAL[stat]
     line = {
         "metric": "pair evaluations/sec (reference-equivalent candidate pairs, N_cand/t) and DD wall-time",
         "value": n_cand / t_res,

@@ -45,6 +45,10 @@ int main(int argc, char **argv)
     const char *binfile = argv[4];
     const double boxsize = atof(argv[5]);
     const int autocorr = n[1] == 0;
+    if (autocorr) {  /* like the reference's own callers: the first set again (DDtheta returns early on ND2 == 0) */
+        n[1] = n[0];
+        for (int k = 0; k < 4; k++) a[1][k] = a[0][k];
+    }
 
     struct config_options options = get_config_options();
     options.float_type = (uint8_t)prec;
