@@ -49,6 +49,9 @@ def load():
     lib.cfb_set_target_occupancy.argtypes = [C.c_int]
     lib.cfb_force_kernel.argtypes = [C.c_int]
     lib.cfb_init.restype = C.c_int
+    lib.corrfunc_b200_catalog_cache.argtypes = [C.c_int]
+    lib.cfb_catalog_cache_hits.restype = C.c_longlong
+    lib.cfb_last_device_count.restype = C.c_int
     _lib = lib
     return lib
 

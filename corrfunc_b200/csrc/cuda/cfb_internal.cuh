@@ -30,6 +30,12 @@ struct ParticleSet {
     DevBuf tile_cell, tile_off;  // int32 per tile
     int64_t ncells = 0, npad = 0, ntiles = 0;
     bool gridded = false;
+    // catalogue cache (cfb_set_catalog_cache): the caller's pointers this set was uploaded from, and the lattice it was
+    // last sorted into -- an identical request is served without a copy / without a sort
+    const void *src[6] = {0};
+    bool src_valid = false;
+    unsigned char grid_sig[160];
+    bool grid_sig_valid = false;
 };
 
 struct Ctx {

@@ -368,7 +368,21 @@ static int gridlink_box_T(Ctx &c, ParticleSet &S, const cfb_box_lattice *lat, co
 int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3], double scale)
 {
     Ctx &c = cfb_ctx();
-    return S.prec == 4 ? gridlink_box_T<float>(c, S, lat, sub, scale) : gridlink_box_T<double>(c, S, lat, sub, scale);
+    // the sorted form of an unchanged catalogue (catalogue cache) in an unchanged lattice is still good
+    unsigned char sig[sizeof(S.grid_sig)];
+    static_assert(sizeof(cfb_box_lattice) + 3 * sizeof(int) + sizeof(double) <= sizeof(S.grid_sig), "signature buffer");
+    memset(sig, 0, sizeof(sig));
+    memcpy(sig, lat, sizeof(*lat));
+    memcpy(sig + sizeof(*lat), sub, 3 * sizeof(int));
+    memcpy(sig + sizeof(*lat) + 3 * sizeof(int), &scale, sizeof(double));
+    if (S.gridded && S.grid_sig_valid && memcmp(sig, S.grid_sig, sizeof(sig)) == 0) return 0;
+    S.grid_sig_valid = false;
+    const int rc = S.prec == 4 ? gridlink_box_T<float>(c, S, lat, sub, scale) : gridlink_box_T<double>(c, S, lat, sub, scale);
+    if (rc == 0) {
+        memcpy(S.grid_sig, sig, sizeof(sig));
+        S.grid_sig_valid = true;
+    }
+    return rc;
 }
 
 template <typename T>
@@ -416,5 +430,6 @@ static int gridlink_theta_T(Ctx &c, ParticleSet &S, const cfb_theta_lattice *lat
 int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t ncells)
 {
     Ctx &c = cfb_ctx();
+    S.grid_sig_valid = false;
     return S.prec == 4 ? gridlink_theta_T<float>(c, S, lat, ncells) : gridlink_theta_T<double>(c, S, lat, ncells);
 }

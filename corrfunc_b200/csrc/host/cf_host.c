@@ -38,6 +38,7 @@ static void *g_reduce_user = NULL;
 const corrfunc_b200_stats *corrfunc_b200_last_stats(void) { return &g_stats; }
 const char *corrfunc_b200_version(void) { return "corrfunc_b200 0.1.0 (API " CORRFUNC_API_VERSION ")"; }
 void corrfunc_b200_set_shard(int rank, int nranks) { cfb_set_shard(rank, nranks); }
+void corrfunc_b200_catalog_cache(int on) { cfb_set_catalog_cache(on); }
 void corrfunc_b200_set_reduce_hook(corrfunc_b200_reduce_fn fn, void *user)
 {
     g_reduce = fn;

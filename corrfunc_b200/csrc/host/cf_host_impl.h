@@ -67,11 +67,18 @@ static int HFN(cf_mesh_for)(const REAL lo[3], const REAL hi[3], const REAL maxsi
     return EXIT_SUCCESS;
 }
 
-static const void *HFN(host_copy)(const void *p, const int64_t n)
-{ /* the epilogue reads the weights on the host: weight arrays must be host memory (positions may be
-     device memory) */
-    (void)n;
-    return p;
+static const void *HFN(host_copy)(const void *p, const int64_t n, void **tofree)
+{ /* the epilogue reads the weights on the host (self-pair term, weight sums of xi / wp).  Like the positions, the
+     weight arrays may be device memory (cfb_upload borrows device pointers): those are copied back first. */
+    *tofree = NULL;
+    if (!p || n <= 0 || !cfb_is_device_ptr(p)) return p;
+    void *h = malloc((size_t)n * sizeof(REAL));
+    if (!h || cfb_copy_to_host(h, p, (size_t)n * sizeof(REAL))) {
+        free(h);
+        return NULL;
+    }
+    *tofree = h;
+    return h;
 }
 
 static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, void *Z1, const int64_t ND2, void *X2,
@@ -385,8 +392,15 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
             const int64_t first = (mode == CFB_RPPI) ? (npibin + 1) : (mode == CFB_SMU ? (nmu_bins + 1) : 1);
             npairs[first] += (uint64_t)ND1;
             if (need_weightavg) { /* always index 1, also in the 2-D layouts (rp_pi_impl:641, s_mu_impl:648) */
-                const REAL *w = (const REAL *)HFN(host_copy)(W1, ND1);
+                void *tofree = NULL;
+                const REAL *w = (const REAL *)HFN(host_copy)(W1, ND1, &tofree);
+                if (!w) {
+                    fprintf(stderr, "Error: could not read the weights back from the device\n");
+                    free(npairs); free(sum_sep); free(sum_w); free(rupp); free(rupp_sqr);
+                    return EXIT_FAILURE;
+                }
                 for (int64_t j = 0; j < ND1; j++) sum_w[1] += (double)(REAL)(w[j] * w[j]);
+                free(tofree);
             }
         }
     }
@@ -413,12 +427,14 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
         const int64_t ND = ND1;
         REAL weightsum = (REAL)ND, weight_sqr_sum = (REAL)ND;
         if (need_weightavg && extra->weight_method == PAIR_PRODUCT) {
-            const REAL *weights = (const REAL *)HFN(host_copy)(W1, ND1);
+            void *tofree = NULL;
+            const REAL *weights = (const REAL *)HFN(host_copy)(W1, ND1, &tofree);
             weightsum = 0;
-            for (int64_t j = 0; j < ND; j++) {
+            for (int64_t j = 0; weights && j < ND; j++) {
                 weightsum += weights[j];
                 weight_sqr_sum += weights[j] * weights[j];
             }
+            free(tofree);
         }
         const REAL prefac = weightsum * (weightsum - weightsum / ND) / (boxsize * boxsize * boxsize);
         REAL rlow = 0.0;

@@ -31,6 +31,11 @@ const corrfunc_b200_stats *corrfunc_b200_last_stats(void);
 
 const char *corrfunc_b200_version(void);
 
+/* DD / DR / RR in one context: between corrfunc_b200_catalog_cache(1) and (0), catalogues passed again under the same
+ * pointers are uploaded once and sorted once per lattice (see cfb_set_catalog_cache).  The caller must not modify the
+ * arrays in between. */
+void corrfunc_b200_catalog_cache(int on);
+
 /* cz (km/s) -> comoving distance (Mpc/h) exactly as countpairs_mocks / countpairs_mocks_s_mu do it for
  * is_comoving_dist == 0 (mocks/DDrppi_mocks/countpairs_rp_pi_mocks_impl.c.src:326-362): the redshift -> distance table
  * of utils/set_cosmo_dist.c:27-75 (Simpson's rule, 10000 points per unit redshift; plain C despite its GSL include),

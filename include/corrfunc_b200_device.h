@@ -15,6 +15,7 @@
  */
 #ifndef CORRFUNC_B200_DEVICE_H
 #define CORRFUNC_B200_DEVICE_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -100,6 +101,15 @@ const char *cfb_last_error(void);
  * Pointers may be host or device memory (detected with cudaPointerGetAttributes). w/ra/dec may be NULL. */
 int cfb_upload(int slot, int prec, int64_t n, const void *x, const void *y, const void *z, const void *w,
                const void *ra, const void *dec);
+/* 1 when p is device or managed memory (cudaPointerGetAttributes), else 0; blocking device-to-host copy (0 = ok).  The host
+ * layer's epilogue reads weight arrays on the host and uses these when the caller passed device pointers. */
+int cfb_is_device_ptr(const void *p);
+int cfb_copy_to_host(void *dst, const void *src, size_t bytes);
+/* Catalogue cache: while on, a particle set passed again under the same pointers / length / element size is taken to be
+ * unchanged -- it is not copied again (whichever slot it was in) and keeps its sorted form while the lattice stays the
+ * same.  For workflows that count DD, DR and RR over two catalogues (Corrfunc/utils.py:27-165). */
+void cfb_set_catalog_cache(int on);
+long long cfb_catalog_cache_hits(void);
 /* Folds the device-side min/max of slot's x,y,z (or ra,dec when which==1) into lohi[6]={min3,max3}. */
 int cfb_extent(int slot, int which, double lohi[6]);
 

@@ -21,6 +21,11 @@ static void *g_scratch[6];
 
 const char *cfb_last_error(void) { return "stub device layer"; }
 int cfb_init(void) { return 0; }
+int cfb_is_device_ptr(const void *p) { (void)p; return 0; }
+int cfb_copy_to_host(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+int cfb_last_device_count(void) { return 1; }
+void cfb_set_catalog_cache(int on) { (void)on; }
+long long cfb_catalog_cache_hits(void) { return 0; }
 void cfb_shutdown(void) {}
 void cfb_set_target_occupancy(int n) { (void)n; }
 void cfb_force_kernel(int k) { (void)k; }

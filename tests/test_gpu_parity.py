@@ -701,7 +701,8 @@ def test_float_z_window_case(stat):
 
 # c5dsd10M: config 5 in DOUBLE at the same density (10 M points) -- the double kernel is another code path
 # (compare-and-count instead of the packed sign-bit counters); c5DDsd10M: the same points through DD(autocorr=1, periodic)
-FULL_SIZE_VERIFIED = ["c1", "c2", "c2wp32", "c2rppi", "c2rppi32", "c3", "c4", "c5sd10M", "c5dsd10M", "c5DDsd10M", "c5"]
+# c5d: config 5 itself in double, 100 M points (the reference needed 6151 s on 5 cores for this golden)
+FULL_SIZE_VERIFIED = ["c1", "c2", "c2wp32", "c2rppi", "c2rppi32", "c3", "c4", "c5sd10M", "c5dsd10M", "c5DDsd10M", "c5", "c5d"]
 
 
 @pytest.mark.parametrize("name", FULL_SIZE_VERIFIED)
@@ -781,3 +782,98 @@ def test_DDtheta_fast_acos_vs_oracle(dtype, autocorr, occ):
         # the polynomial is good to 3.7e-9 rad, libm to 1e-16: the two runs differ, but by less than 1e-6 degrees
         d = np.abs(fast["thetaavg"] - slow["thetaavg"])
         assert d.max() > 0 and d.max() < 1e-6
+
+
+@pytest.mark.parametrize("stat", ["DD", "xi"])
+def test_device_pointers_including_weights(stat):
+    """Positions AND weights handed over as device memory (cfb_upload borrows device pointers; INTEGRATION.md tells
+    callers with resident catalogues to do that).  The host epilogue needs the weights for the self-pair term (bins
+    starting at 0) and for the weight sums of xi: it reads them back (cfb_is_device_ptr / cfb_copy_to_host) instead of
+    dereferencing a device pointer.  Same results as from host arrays."""
+    import ctypes as C
+
+    import torch
+    from corrfunc_b200 import _capi, _lib
+
+    lib = _lib.load()
+    _capi._declare(lib)
+    L, N = 150.0, 60000
+    x, y, z, w = H.box_points(77, N, L, np.float64)
+    bins = np.linspace(0.0, 12.0, 9)  # rmin = 0: the self pairs and their w*w enter the first bin
+    o = _capi.default_options(np.float64, periodic=True, need_avg_sep=True, boxsize=L)
+    if stat == "DD":
+        host = _capi.call_DD(lib, 1, 1, bins, x, y, z, w1=w, weight_type="pair_product", options=o)
+    else:
+        host = _capi.call_xi(lib, L, 1, bins, x, y, z, w=w, weight_type="pair_product", options=o)
+    d = [torch.from_numpy(a).cuda() for a in (x, y, z, w)]
+    P = [C.c_void_p(t.data_ptr()) for t in d]
+    e = _capi.ExtraOptions()
+    e.weight_method = _capi.WEIGHT_PAIR_PRODUCT
+    for ws in (e.weights0, e.weights1):
+        ws.num_weights = 1
+        ws.weights[0] = d[3].data_ptr()
+    o = _capi.default_options(np.float64, periodic=True, need_avg_sep=True, boxsize=L)
+    with _capi.binfile_for(bins) as bf:
+        if stat == "DD":
+            r = _capi.ResultsDD()
+            st = lib.countpairs(N, P[0], P[1], P[2], N, P[0], P[1], P[2], 1, 1, bf, C.byref(r), C.byref(o), C.byref(e))
+        else:
+            r = _capi.ResultsXi()
+            st = lib.countpairs_xi(N, P[0], P[1], P[2], L, 1, bf, C.byref(r), C.byref(o), C.byref(e))
+    assert st == 0
+    n = r.nbin
+    got_np = np.ctypeslib.as_array(r.npairs, shape=(n,)).copy()[1:]
+    got_w = np.ctypeslib.as_array(r.weightavg, shape=(n,)).copy()[1:]
+    assert np.array_equal(got_np, host["npairs"])
+    _close(got_w, host["weightavg"], 1e-12, "weightavg from device weights")
+    if stat == "xi":
+        _close(np.ctypeslib.as_array(r.xi, shape=(n,)).copy()[1:], host["cf"], 1e-12, "xi from device weights")
+        lib.free_results_xi(C.byref(r))
+    else:
+        lib.free_results(C.byref(r))
+
+
+@pytest.mark.parametrize("stat", ["DD", "DDrppi", "DDsmu"])
+def test_DD_DR_RR_in_one_context(stat):
+    """corrfunc_b200.workflow.DD_DR_RR: data and randoms uploaded once (catalogue cache), three counts -- identical to
+    three separate calls, with the uploads of the second and third count served from the cache; the Landy-Szalay
+    estimate on top equals the reference's converter on the separate counts (Corrfunc/utils.py:27-165)."""
+    from corrfunc_b200 import _lib, workflow
+    from corrfunc_b200.utils import convert_3d_counts_to_cf
+
+    T = _theory()
+    L = 200.0
+    x, y, z, w = H.box_points(81, 50000, L, np.float64)
+    rx, ry, rz, rw = H.box_points(82, 120000, L, np.float64)
+    bins = np.logspace(-0.3, np.log10(18.0), 12)
+    kw = dict(periodic=True, boxsize=L, weight_type="pair_product")
+    extra = dict(DD={}, DDrppi=dict(pimax=20.0), DDsmu=dict(mu_max=1.0, nmu_bins=8))[stat]
+    lib = _lib.load()
+    hits0 = lib.cfb_catalog_cache_hits()
+    dd, dr, rr = workflow.DD_DR_RR(2, bins, x, y, z, rx, ry, rz, weights=w, rweights=rw, stat=stat, **extra, **kw)
+    # DD(D) uploads D; DR finds D, uploads R; RR finds R (in the other slot): 2 hits
+    assert lib.cfb_catalog_cache_hits() - hits0 == 2
+    if stat == "DD":
+        fn = lambda a, A, wa, **k: T.DD(a, 2, bins, A[0], A[1], A[2], weights1=wa, **k, **kw)
+    elif stat == "DDrppi":
+        fn = lambda a, A, wa, **k: T.DDrppi(a, 2, 20.0, bins, A[0], A[1], A[2], weights1=wa, **k, **kw)
+    else:
+        fn = lambda a, A, wa, **k: T.DDsmu(a, 2, bins, 1.0, 8, A[0], A[1], A[2], weights1=wa, **k, **kw)
+    dd2 = fn(1, (x, y, z), w)
+    dr2 = fn(0, (x, y, z), w, X2=rx, Y2=ry, Z2=rz, weights2=rw)
+    rr2 = fn(1, (rx, ry, rz), rw)
+    for a, b in ((dd, dd2), (dr, dr2), (rr, rr2)):
+        assert np.array_equal(a["npairs"], b["npairs"])
+        _close(a["weightavg"], b["weightavg"], 1e-12, "weightavg")
+    if stat == "DD":
+        cf = workflow.xi_from_catalogs(2, bins, x, y, z, rx, ry, rz, periodic=True, boxsize=L)
+        cf2 = convert_3d_counts_to_cf(x.size, x.size, rx.size, rx.size, T.DD(1, 2, bins, x, y, z, periodic=True, boxsize=L),
+                                      T.DD(0, 2, bins, x, y, z, X2=rx, Y2=ry, Z2=rz, periodic=True, boxsize=L),
+                                      T.DD(0, 2, bins, x, y, z, X2=rx, Y2=ry, Z2=rz, periodic=True, boxsize=L),
+                                      T.DD(1, 2, bins, rx, ry, rz, periodic=True, boxsize=L))
+        assert np.allclose(cf, cf2, rtol=0, atol=0)
+    # outside the context every call uploads again
+    h1 = lib.cfb_catalog_cache_hits()
+    fn(1, (x, y, z), w)
+    fn(1, (x, y, z), w)
+    assert lib.cfb_catalog_cache_hits() == h1
