@@ -54,6 +54,7 @@ struct Ctx {
     int target_occ = 0;
     int theta_sub = 1;  // sub x sub fine cells per reference RA/DEC cell of the last theta gridlink
     int force_kernel = -1;
+    bool prefer_legacy = false;  // this count is better served by the legacy generic kernel (set per call)
     int last_kind = 0;  // kernel the last count ran: 0 legacy generic, 1 fast, 2 per-pair-sum
     int launches = 0;
     char err[512];

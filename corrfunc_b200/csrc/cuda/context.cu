@@ -500,7 +500,12 @@ static int count_box_one(const cfb_binning *bin, const cfb_box_lattice *lat, cfb
         const char *e = getenv("CORRFUNC_B200_SUM_OCC");
         sum_occ = (e && atoi(e) > 0) ? atoi(e) : 56;
     }
-    choose_subdivision(c, lat, nmax, sub, fast ? 112 : sum_occ);
+    // count-only DDrppi: the one-thread-per-primary generic kernel (pairs_generic.cu) on 112-particle cells is the fastest
+    // of the three for it -- measured on config 2, double / float: 12.0 / 10.4 ms against 14.7 / 13.2 ms for the
+    // per-pair-sum kernel (its range tests and 2-D slot arithmetic run for every lane anyway, so compaction buys nothing)
+    const bool legacy_rppi = !fast && bin->mode == CFB_RPPI && !bin->need_avg && !bin->need_weights;
+    c.prefer_legacy = legacy_rppi;
+    choose_subdivision(c, lat, nmax, sub, (fast || legacy_rppi) ? 112 : sum_occ);
     for (int s = 0; s < nsets; s++)
         if (cfb_gridlink_box_set(c.set[s], lat, sub, scale)) return 1;
     CK(cudaEventRecord(c.ev[1], c.stream));

@@ -614,7 +614,7 @@ int cfb_launch_pairs_generic(const cfb_binning *bin, const PairParams &P0, int p
         const char *e = getenv("CORRFUNC_B200_LEGACY_GENERIC");
         legacy = (e && atoi(e) > 0) ? 1 : 0;
     }
-    if (!legacy && cfb_ctx().force_kernel != 3) {
+    if (!legacy && cfb_ctx().force_kernel != 3 && !(cfb_ctx().prefer_legacy && cfb_ctx().force_kernel != 0)) {
         const int rc = cfb_launch_pairs_sum(bin, P, prec, list_mode);
         if (rc >= 0) {
             cfb_ctx().last_kind = 2;

@@ -39,6 +39,9 @@ const corrfunc_b200_stats *corrfunc_b200_last_stats(void) { return &g_stats; }
 const char *corrfunc_b200_version(void) { return "corrfunc_b200 0.1.0 (API " CORRFUNC_API_VERSION ")"; }
 void corrfunc_b200_set_shard(int rank, int nranks) { cfb_set_shard(rank, nranks); }
 void corrfunc_b200_catalog_cache(int on) { cfb_set_catalog_cache(on); }
+/* utils/cpu_features.c:19-120: nothing to detect here, the kernels run on the GPU whatever the host CPU is */
+int runtime_instrset_detect(void) { return AVX512F; }
+int get_max_usable_isa(void) { return AVX512F; }
 void corrfunc_b200_set_reduce_hook(corrfunc_b200_reduce_fn fn, void *user)
 {
     g_reduce = fn;
@@ -124,17 +127,27 @@ static int cf_setup_bins(const char *fname, double *rmin, double *rmax, int *nbi
 }
 
 /* raw device histograms -> optional cross-rank sum */
-static int reduce_across_ranks(uint64_t *np, double *ss, double *sw, int64_t nslots)
+/* local_status: what this rank's device count returned.  Every rank enters the collective whatever it returned -- a rank
+ * that failed locally (out of memory, a particle outside the box of its replica) must not leave the others waiting in
+ * the all-reduce for ever -- and announces the failure in slot 0 of the counts, which no statistic ever writes (bins start
+ * at 1); afterwards all ranks fail together. */
+static int reduce_across_ranks(int local_status, uint64_t *np, double *ss, double *sw, int64_t nslots)
 {
     int rank = 0, nranks = 1;
     cfb_get_shard(&rank, &nranks);
-    if (nranks <= 1) return 0;
+    if (nranks <= 1) return local_status;
     if (!g_reduce) {
         fprintf(stderr, "corrfunc_b200> work is sharded over %d ranks but no reduce hook is set; "
                         "results would be partial\n", nranks);
         return 1;
     }
-    return g_reduce(np, ss, sw, nslots, g_reduce_user);
+    const uint64_t failed_mark = (uint64_t)1 << 62;
+    if (nslots > 0) np[0] = local_status ? failed_mark : 0;
+    const int rc = g_reduce(np, ss, sw, nslots, g_reduce_user);
+    const int any_failed = nslots > 0 && np[0] >= failed_mark;
+    if (nslots > 0) np[0] = 0;
+    if (any_failed && !local_status) fprintf(stderr, "corrfunc_b200> another rank failed; this rank's result is discarded too\n");
+    return (rc || any_failed || local_status) ? 1 : 0;
 }
 
 /* what every statistic hands back to its public wrapper (arrays are malloc'ed, caller owns them) */

@@ -375,7 +375,7 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
     cfb_stats dst;
     memset(&dst, 0, sizeof(dst));
     if (ND1 > 0 && (autocorr || ND2 > 0)) status = cfb_count_box(&B, &L, &H, &dst);
-    if (status == 0) status = reduce_across_ranks(npairs, sum_sep, sum_w, nslots);
+    status = reduce_across_ranks(status, npairs, sum_sep, sum_w, nslots);
     if (status) {
         free(npairs); free(sum_sep); free(sum_w); free(rupp); free(rupp_sqr);
         return EXIT_FAILURE;
@@ -642,6 +642,13 @@ static int HFN(cf_vpf_mocks)(const int64_t Ngal, void *vra, void *vdec, void *vc
     }
     if (!(rmax > 0.0)) { fprintf(stderr, "rmax=%lf has to be positive", (double)rmax); return EXIT_FAILURE; }
     if (nbin < 1) { fprintf(stderr, "Number of bins=%d has to be at least 1", nbin); return EXIT_FAILURE; }
+    if (nbin == 1) {
+        /* the reference's vectorised shell loop never runs for a single shell and drops every particle it handles while its
+         * scalar remainder loop counts them (vpf_mocks_kernels.c.src:63-92 vs :100-120): its answer depends on the cell
+         * occupancies modulo the vector width.  Nothing meaningful to reproduce -- refuse instead of returning P0 = 1. */
+        fprintf(stderr, "corrfunc_b200> counts-in-spheres with a single radial bin is not supported (use nbin >= 2)\n");
+        return EXIT_FAILURE;
+    }
     if (nc < 1) { fprintf(stderr, "Number of spheres=%d has to be at least 1", nc); return EXIT_FAILURE; }
     if (num_pN < 1) { fprintf(stderr, "Number of pN's=%d requested must be at least 1", num_pN); return EXIT_FAILURE; }
     if (!(cosmology == 1 || cosmology == 2)) {
@@ -842,6 +849,10 @@ static int HFN(cf_vpf_theory)(const int64_t np, void *vX, void *vY, void *vZ, co
     if (options->float_type != sizeof(REAL)) {
         fprintf(stderr, "ERROR: In %s> Can only handle arrays of size=%zu. Got an array of size = %zu\n", __func__,
                 sizeof(REAL), options->float_type);
+        return EXIT_FAILURE;
+    }
+    if (nbin == 1) {
+        fprintf(stderr, "corrfunc_b200> counts-in-spheres with a single radial bin is not supported (use nbin >= 2)\n");
         return EXIT_FAILURE;
     }
     if (!(rmax > 0.0 && nbin > 0 && nc > 0 && num_pN > 0)) {
@@ -1305,7 +1316,7 @@ static int HFN(cf_theta)(const int64_t ND1, void *vra1, void *vdec1, const int64
             sum_w = calloc((size_t)nthetabin, sizeof(double));
             cfb_hist H = {npairs, sum_sep, sum_w};
             status = cfb_count_theta(&B, ncells, ngb_off, ngb, &H, &dst);
-            if (!status) status = reduce_across_ranks(npairs, sum_sep, sum_w, nthetabin);
+            status = reduce_across_ranks(status, npairs, sum_sep, sum_w, nthetabin);
         }
     }
     for (int s = 0; s < 2; s++) {

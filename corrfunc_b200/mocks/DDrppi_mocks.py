@@ -4,7 +4,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import _capi, _lib
-from ..utils import check_same_dtype, process_weights, translate_isa_string_to_enum
+from ..utils import check_same_dtype, native_inputs, process_weights, translate_isa_string_to_enum
 from .DDtheta_mocks import fix_ra_dec
 
 
@@ -30,8 +30,7 @@ def DDrppi_mocks(autocorr, cosmology, nthreads, pimax, binfile, RA1, DEC1, CZ1, 
     ``int(pimax)`` unit-width pi bins [and the C call's wall time when ``c_api_timer``]."""
     if not autocorr and (RA2 is None or DEC2 is None or CZ2 is None):
         raise ValueError("Must pass valid arrays for RA2/DEC2/CZ2 for computing cross-correlation")
-    dtype = check_same_dtype(RA1, DEC1, CZ1, RA2, DEC2, CZ2, weights1, weights2)
-    weights1, weights2 = process_weights(weights1, weights2, RA1, RA2, weight_type, autocorr)
+    (RA1, DEC1, CZ1, RA2, DEC2, CZ2), weights1, weights2, dtype = native_inputs((RA1, DEC1, CZ1, RA2, DEC2, CZ2), weights1, weights2, RA1, RA2, weight_type, autocorr)
     RA1, DEC1 = fix_ra_dec(RA1, DEC1)
     if autocorr == 0:
         RA2, DEC2 = fix_ra_dec(RA2, DEC2)
@@ -45,6 +44,8 @@ def DDrppi_mocks(autocorr, cosmology, nthreads, pimax, binfile, RA1, DEC1, CZ1, 
     r = _capi.call_DDrppi_mocks(_lib.load(), autocorr, cosmology, nthreads, pimax, binfile, RA1, DEC1, CZ1, w1=w1,
                                 RA2=RA2, DEC2=DEC2, CZ2=CZ2, w2=w2, weight_type=weight_type, options=opt, dtype=dtype)
     nrp, npi = r["npairs"].shape
+    if r["npairs"].size == 0:  # empty particle set: an empty table, like the reference
+        npi = max(npi, 1)
     res = np.zeros(nrp * npi, dtype=[("rmin", np.float64), ("rmax", np.float64), ("rpavg", np.float64),
                                      ("pimax", np.float64), ("npairs", np.uint64), ("weightavg", np.float64)])
     dpi = r["pimax"] / npi  # rows as built in _countpairs_mocks.c (rp-major, upper pi edge per row)

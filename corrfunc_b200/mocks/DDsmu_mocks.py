@@ -4,7 +4,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import _capi, _lib
-from ..utils import check_same_dtype, process_weights
+from ..utils import check_same_dtype, native_inputs, process_weights
 from .DDrppi_mocks import _mock_options
 from .DDtheta_mocks import fix_ra_dec
 
@@ -22,8 +22,7 @@ def DDsmu_mocks(autocorr, cosmology, nthreads, mu_max, nmu_bins, binfile, RA1, D
     if mu_max <= 0.0 or mu_max > 1.0:  # DDsmu_mocks.py: "The parameter `mu_max` (= ...) must be > 0 and <= 1.0"
         raise ValueError("The parameter `mu_max` (= {0}), the max. of cosine of the angle to the line-of-sight (LOS), "
                          "must be > 0 and <= 1.0".format(mu_max))
-    dtype = check_same_dtype(RA1, DEC1, CZ1, RA2, DEC2, CZ2, weights1, weights2)
-    weights1, weights2 = process_weights(weights1, weights2, RA1, RA2, weight_type, autocorr)
+    (RA1, DEC1, CZ1, RA2, DEC2, CZ2), weights1, weights2, dtype = native_inputs((RA1, DEC1, CZ1, RA2, DEC2, CZ2), weights1, weights2, RA1, RA2, weight_type, autocorr)
     RA1, DEC1 = fix_ra_dec(RA1, DEC1)
     if autocorr == 0:
         RA2, DEC2 = fix_ra_dec(RA2, DEC2)
@@ -38,6 +37,8 @@ def DDsmu_mocks(autocorr, cosmology, nthreads, mu_max, nmu_bins, binfile, RA1, D
                                w1=w1, RA2=RA2, DEC2=DEC2, CZ2=CZ2, w2=w2, weight_type=weight_type, options=opt,
                                dtype=dtype)
     ns, nmu = r["npairs"].shape
+    if r["npairs"].size == 0:  # empty particle set: an empty table, like the reference
+        nmu = max(nmu, 1)
     res = np.zeros(ns * nmu, dtype=[("smin", np.float64), ("smax", np.float64), ("savg", np.float64),
                                     ("mumax", np.float64), ("npairs", np.uint64), ("weightavg", np.float64)])
     dmu = r["mu_max"] / nmu

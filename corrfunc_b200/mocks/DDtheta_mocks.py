@@ -4,7 +4,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import _capi, _lib
-from ..utils import check_same_dtype, process_weights, translate_isa_string_to_enum
+from ..utils import check_same_dtype, native_inputs, process_weights, translate_isa_string_to_enum
 
 
 def fix_ra_dec(ra, dec):
@@ -32,8 +32,7 @@ def DDtheta_mocks(autocorr, nthreads, binfile, RA1, DEC1, weights1=None, RA2=Non
     if link_in_ra and not link_in_dec:
         raise ValueError("Linking in RA requires linking in DEC as well")  # mocks.options: LINK_IN_RA needs LINK_IN_DEC
     translate_isa_string_to_enum(isa)
-    dtype = check_same_dtype(RA1, DEC1, RA2, DEC2, weights1, weights2)
-    weights1, weights2 = process_weights(weights1, weights2, RA1, RA2, weight_type, autocorr)
+    (RA1, DEC1, RA2, DEC2), weights1, weights2, dtype = native_inputs((RA1, DEC1, RA2, DEC2), weights1, weights2, RA1, RA2, weight_type, autocorr)
     RA1, DEC1 = fix_ra_dec(RA1, DEC1)
     if autocorr == 0:
         RA2, DEC2 = fix_ra_dec(RA2, DEC2)

@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import _capi, _lib
-from ..utils import check_same_dtype, process_weights, translate_isa_string_to_enum
+from ..utils import check_same_dtype, convert_to_native_endian, native_inputs, translate_isa_string_to_enum
 
 
 def _options(dtype, *, periodic, boxsize, verbose, need_avg, refine, default_refine, max_cells_per_dim,
@@ -37,8 +37,8 @@ def DD(autocorr, nthreads, binfile, X1, Y1, Z1, weights1=None, periodic=True, bo
         raise ValueError("Must pass valid arrays for X2/Y2/Z2 for computing cross-correlation")
     if periodic and boxsize is None:
         raise ValueError("Must specify a boxsize if periodic=True")
-    dtype = check_same_dtype(X1, Y1, Z1, X2, Y2, Z2, weights1, weights2)
-    weights1, weights2 = process_weights(weights1, weights2, X1, X2, weight_type, autocorr)
+    (X1, Y1, Z1, X2, Y2, Z2), weights1, weights2, dtype = native_inputs((X1, Y1, Z1, X2, Y2, Z2), weights1, weights2, X1, X2,
+                                                                        weight_type, autocorr)
     opt = _options(dtype, periodic=periodic, boxsize=boxsize, verbose=verbose, need_avg=output_ravg,
                    refine=(xbin_refine_factor, ybin_refine_factor, zbin_refine_factor), default_refine=(2, 2, 1),
                    max_cells_per_dim=max_cells_per_dim, copy_particles=copy_particles,
@@ -61,8 +61,8 @@ def DDrppi(autocorr, nthreads, pimax, binfile, X1, Y1, Z1, weights1=None, period
         raise ValueError("Must pass valid arrays for X2/Y2/Z2 for computing cross-correlation")
     if periodic and boxsize is None:
         raise ValueError("Must specify a boxsize if periodic=True")
-    dtype = check_same_dtype(X1, Y1, Z1, X2, Y2, Z2, weights1, weights2)
-    weights1, weights2 = process_weights(weights1, weights2, X1, X2, weight_type, autocorr)
+    (X1, Y1, Z1, X2, Y2, Z2), weights1, weights2, dtype = native_inputs((X1, Y1, Z1, X2, Y2, Z2), weights1, weights2, X1, X2,
+                                                                        weight_type, autocorr)
     opt = _options(dtype, periodic=periodic, boxsize=boxsize, verbose=verbose, need_avg=output_rpavg,
                    refine=(xbin_refine_factor, ybin_refine_factor, zbin_refine_factor), default_refine=(2, 2, 1),
                    max_cells_per_dim=max_cells_per_dim, copy_particles=copy_particles,
@@ -94,8 +94,8 @@ def DDsmu(autocorr, nthreads, binfile, mu_max, nmu_bins, X1, Y1, Z1, weights1=No
         raise ValueError("The parameter `mu_max` = {0}, has to be in (0.0, 1.0]".format(mu_max))
     if nmu_bins < 1:
         raise ValueError("Number of mu bins must be at least 1")
-    dtype = check_same_dtype(X1, Y1, Z1, X2, Y2, Z2, weights1, weights2)
-    weights1, weights2 = process_weights(weights1, weights2, X1, X2, weight_type, autocorr)
+    (X1, Y1, Z1, X2, Y2, Z2), weights1, weights2, dtype = native_inputs((X1, Y1, Z1, X2, Y2, Z2), weights1, weights2, X1, X2,
+                                                                        weight_type, autocorr)
     opt = _options(dtype, periodic=periodic, boxsize=boxsize, verbose=verbose, need_avg=output_savg,
                    refine=(xbin_refine_factor, ybin_refine_factor, zbin_refine_factor), default_refine=(2, 2, 1),
                    max_cells_per_dim=max_cells_per_dim, copy_particles=copy_particles,
@@ -119,8 +119,7 @@ def wp(boxsize, pimax, nthreads, binfile, X, Y, Z, weights=None, weight_type=Non
        c_cell_timer=False, isa="fastest"):
     """Projected correlation function wp(rp) in a periodic cube.  ``c_cell_timer`` has no GPU
     equivalent (there is no per-cell-pair CPU kernel call to time): the third return value is None."""
-    dtype = check_same_dtype(X, Y, Z, weights)
-    weights, _ = process_weights(weights, None, X, None, weight_type, True)
+    (X, Y, Z), weights, _, dtype = native_inputs((X, Y, Z), weights, None, X, None, weight_type, True)
     opt = _options(dtype, periodic=True, boxsize=boxsize, verbose=verbose, need_avg=output_rpavg,
                    refine=(xbin_refine_factor, ybin_refine_factor, zbin_refine_factor), default_refine=(2, 2, 1),
                    max_cells_per_dim=max_cells_per_dim, copy_particles=copy_particles,
@@ -140,8 +139,7 @@ def xi(boxsize, nthreads, binfile, X, Y, Z, weights=None, weight_type=None, verb
        xbin_refine_factor=2, ybin_refine_factor=2, zbin_refine_factor=1, max_cells_per_dim=100,
        copy_particles=True, enable_min_sep_opt=True, c_api_timer=False, isa="fastest"):
     """3-D correlation function xi(r) in a periodic cube (analytic randoms)."""
-    dtype = check_same_dtype(X, Y, Z, weights)
-    weights, _ = process_weights(weights, None, X, None, weight_type, True)
+    (X, Y, Z), weights, _, dtype = native_inputs((X, Y, Z), weights, None, X, None, weight_type, True)
     opt = _options(dtype, periodic=True, boxsize=boxsize, verbose=verbose, need_avg=output_ravg,
                    refine=(xbin_refine_factor, ybin_refine_factor, zbin_refine_factor), default_refine=(2, 2, 1),
                    max_cells_per_dim=max_cells_per_dim, copy_particles=copy_particles,
@@ -163,6 +161,7 @@ def vpf(rmax, nbins, nspheres, numpN, seed, X, Y, Z, verbose=False, periodic=Tru
     ``nspheres`` centres drawn with MT19937 seeded by ``seed``.  Returns a structured array (rmax, pN[numpN])."""
     if periodic and boxsize is None:
         raise ValueError("Must specify a boxsize if periodic=True")
+    X, Y, Z = (convert_to_native_endian(a, warn=True) for a in (X, Y, Z))
     dtype = check_same_dtype(X, Y, Z)
     opt = _options(dtype, periodic=periodic, boxsize=boxsize, verbose=verbose, need_avg=False,
                    refine=(xbin_refine_factor, ybin_refine_factor, zbin_refine_factor), default_refine=(1, 1, 1),

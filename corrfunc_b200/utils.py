@@ -26,8 +26,8 @@ def process_weights(weights1, weights2, X1, X2, weight_type, autocorr):
     def prep(w, x):
         if w is None:
             return None
-        if isinstance(w, float):
-            w = np.array(w, dtype=x.dtype)
+        if np.isscalar(w) or (isinstance(w, np.ndarray) and w.ndim == 0):
+            w = np.array(w, dtype=np.asarray(x).dtype)  # a scalar weight takes the particles' dtype (Corrfunc/utils.py:994-1003)
         w = np.atleast_1d(w)
         if w.shape[-1] == 1:
             w = np.tile(w, len(x))
@@ -43,6 +43,18 @@ def process_weights(weights1, weights2, X1, X2, weight_type, autocorr):
         if weights2 is None and weights1 is not None:
             weights2 = np.ones((len(weights1), len(X2)), dtype=X2.dtype)
     return weights1, weights2
+
+
+def native_inputs(positions, weights1, weights2, X1, X2, weight_type, autocorr):
+    """What every wrapper does with its arrays before the C call, in the reference's order (Corrfunc/theory/DD.py:222-247):
+    weights are brought into shape first (scalars take the particles' dtype), every array is converted to the machine's byte
+    order, and only then must they all share one dtype.  Returns (positions, weights1, weights2, dtype)."""
+    weights1, weights2 = process_weights(weights1, weights2, X1, X2, weight_type, autocorr)
+    positions = [convert_to_native_endian(a, warn=True) for a in positions]
+    weights1 = convert_to_native_endian(weights1, warn=True)
+    weights2 = convert_to_native_endian(weights2, warn=True)
+    dtype = check_same_dtype(*positions, weights1, weights2)
+    return positions, weights1, weights2, dtype
 
 
 def check_same_dtype(*arrs):

@@ -66,6 +66,12 @@ typedef enum {
     NUM_ISA
 } isa;
 
+/* utils/cpu_features.h:36-37 -- the reference's extension modules ask which kernels the CPU can run and pass the answer
+ * back as options->instruction_set.  This library has one code path (the GPU's); every value is accepted and ignored, and
+ * the "maximum" reported is the reference's own maximum so that isa="fastest" resolves to a value the reference knows. */
+extern int runtime_instrset_detect(void);
+extern int get_max_usable_isa(void);
+
 struct api_cell_timings {
     int64_t N1;
     int64_t N2;

@@ -65,3 +65,23 @@ def test_compat_package_exposes_the_reference_import_paths():
         sys.path.pop(0)
         for k in [k for k in sys.modules if k == "Corrfunc" or k.startswith("Corrfunc.")]:
             del sys.modules[k]
+
+
+def test_wrapper_input_preparation_follows_the_reference_order():
+    """Corrfunc/theory/DD.py:222-247: weights are shaped first (a Python scalar takes the particles' dtype), then every
+    array is brought to native byte order, and only then must all arrays share one dtype."""
+    import numpy as np
+    from corrfunc_b200.utils import native_inputs
+
+    x = np.linspace(0, 1, 5, dtype=np.float32)
+    (x1, y1, z1), w1, w2, dt = native_inputs((x, x, x), 0.5, None, x, None, "pair_product", True)
+    assert dt == np.float32 and w1.dtype == np.float32 and w1.shape == (1, 5) and w2 is None
+    big = x.astype(">f4")
+    (x1, y1, z1), w1, _, dt = native_inputs((big, big, big), big, None, big, None, "pair_product", True)
+    assert dt == np.float32 and x1.dtype.isnative and w1.dtype.isnative and np.array_equal(x1, x)
+    # cross-correlation with one weight array missing: ones for pair_product
+    (a, b, c, d, e, f), w1, w2, dt = native_inputs((x, x, x, x[:3], x[:3], x[:3]), None, x[:3], x, x[:3], "pair_product", False)
+    assert w1.shape == (1, 5) and np.all(w1 == 1) and w2.shape == (1, 3)
+    import pytest
+    with pytest.raises(TypeError):
+        native_inputs((x, x.astype(np.float64), x), None, None, x, None, None, True)

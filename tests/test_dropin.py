@@ -143,3 +143,93 @@ def test_one_call_many_gpus(tmp_path):
     _close(outn[:, 1], out1[:, 1], 1e-6, "ravg")
     ref = H.oracle_theory("xi", x, y, z, bins, boxsize=L)
     assert np.array_equal(out1[:, 0].astype(np.uint64), ref["npairs"])
+
+
+def _load_ext(name):
+    import importlib.util
+
+    path = os.path.join(BUILD, name + ".so")
+    if not os.path.exists(path):
+        pytest.skip("%s.so is built only where /root/reference exists (tests/c_abi/build.sh)" % name)
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_reference_extension_modules_import():
+    """The reference's CPython extension modules (theory/python_bindings/_countpairs.c,
+    mocks/python_bindings/_countpairs_mocks.c), compiled UNMODIFIED from where they lie and linked against
+    libcorrfunc_b200.so: every symbol they need resolves (incl. get_max_usable_isa, countspheres)."""
+    _ensure_built()
+    th = _load_ext("_countpairs")
+    mk = _load_ext("_countpairs_mocks")
+    assert {"countpairs", "countpairs_rp_pi", "countpairs_s_mu", "countpairs_wp", "countpairs_xi", "countspheres_vpf"} <= set(dir(th))
+    assert {"countpairs_rp_pi_mocks", "countpairs_s_mu_mocks", "countpairs_theta_mocks", "countspheres_vpf_mocks"} <= set(dir(mk))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_reference_extension_modules_count_on_the_gpu(tmp_path, dtype):
+    """Calls them the way Corrfunc/theory/DD.py:249-264, DDrppi.py, DDsmu.py, wp.py, xi.py and
+    Corrfunc/mocks/DDtheta_mocks.py do (same positional and keyword arguments, weights as a (1, N) array, boxsize as a
+    3-tuple, isa = -1 "fastest") and compares the rows they return with the oracle."""
+    th = _load_ext("_countpairs")
+    mk = _load_ext("_countpairs_mocks")
+    L, N = 120.0, 40000
+    x, y, z, w = H.box_points(191, N, L, dtype)
+    bins = np.logspace(-0.5, np.log10(12.0), 11)
+    _, bfile = _write_inputs(tmp_path, dtype, (x, y, z, w), None, bins)
+    W = w.reshape(1, -1)
+    kw = dict(periodic=True, verbose=False, boxsize=(L, L, L), xbin_refine_factor=2, ybin_refine_factor=2,
+              zbin_refine_factor=1, max_cells_per_dim=100, copy_particles=True, enable_min_sep_opt=True, c_api_timer=True,
+              isa=-1, weights1=W, weight_type="pair_product")
+    okw = dict(w1=w, weight_type="pair_product", need_avg=True, periodic=True, boxsize=L)
+    tol = TOL[dtype]
+
+    def rows(res):
+        assert res is not None, "the extension returned None (RuntimeError in the reference's wrapper)"
+        r, api_time = res
+        assert api_time > 0
+        return np.array([tuple(t) for t in r], dtype=np.float64)
+
+    # DD: rows (rmin, rmax, ravg, npairs, weightavg), _countpairs.c:1426-1440
+    r = rows(th.countpairs(1, 2, bfile, x, y, z, output_ravg=True, **kw))
+    ref = H.oracle_theory("DD", x, y, z, bins, **okw)
+    assert np.array_equal(r[:, 3].astype(np.uint64), ref["npairs"])
+    _close(r[:, 2], ref["ravg"], tol, "ravg")
+    _close(r[:, 4], ref["weightavg"], tol, "weightavg")
+    # DDrppi: rows (rmin, rmax, rpavg, pi_upper, npairs, weightavg), :1722-1740
+    r = rows(th.countpairs_rp_pi(1, 2, 30.0, bfile, x, y, z, output_rpavg=True, **kw))
+    ref = H.oracle_theory("DDrppi", x, y, z, bins, pimax=30.0, **okw)
+    assert np.array_equal(r[:, 4].astype(np.uint64), ref["npairs"].ravel())
+    _close(r[:, 5], ref["weightavg"].ravel(), tol, "weightavg")
+    # DDsmu: rows (smin, smax, savg, mu_upper, npairs, weightavg), :2508
+    r = rows(th.countpairs_s_mu(1, 2, bfile, 0.8, 10, x, y, z, output_savg=True, fast_divide_and_NR_steps=0, **kw))
+    ref = H.oracle_theory("DDsmu", x, y, z, bins, mu_max=0.8, nmu_bins=10, **okw)
+    assert np.array_equal(r[:, 4].astype(np.uint64), ref["npairs"].ravel())
+    _close(r[:, 2], ref["ravg"].ravel(), tol, "savg")
+    # xi: rows (rmin, rmax, ravg, xi, npairs, weightavg), :2201
+    kx = {k: v for k, v in kw.items() if k not in ("periodic", "boxsize", "weights1")}
+    r = rows(th.countpairs_xi(L, 2, bfile, x, y, z, weights=W, output_ravg=True, **kx))
+    ref = H.oracle_theory("xi", x, y, z, bins, **okw)
+    assert np.array_equal(r[:, 4].astype(np.uint64), ref["npairs"])
+    assert np.allclose(r[:, 3], ref["cf"], rtol=1e-9 if dtype == np.float64 else 1e-4, atol=1e-12)
+    # wp: rows (rmin, rmax, rpavg, wp, npairs, weightavg) + cell timings, :1965-1983
+    res = th.countpairs_wp(L, 30.0, 2, bfile, x, y, z, weights=W, output_rpavg=True, c_cell_timer=False, **kx)
+    assert res is not None
+    r = np.array([tuple(t) for t in res[0]], dtype=np.float64)
+    ref = H.oracle_theory("wp", x, y, z, bins, pimax=30.0, **okw)
+    assert np.array_equal(r[:, 4].astype(np.uint64), ref["npairs"])
+    # DDtheta_mocks: rows (thetamin, thetamax, thetaavg, npairs, weightavg), _countpairs_mocks.c:2018
+    ra, dec = H.sphere_points(193, 30000, dtype)
+    wt = (1.0 - np.random.default_rng(194).random(ra.size)).astype(dtype)
+    tb = np.logspace(np.log10(0.05), 1, 13)
+    _, tfile = _write_inputs(tmp_path, dtype, (ra, dec, ra, wt), None, tb)
+    r = rows(mk.countpairs_theta_mocks(1, 2, tfile, ra, dec, weights1=wt.reshape(1, -1), weight_type="pair_product",
+                                       link_in_dec=True, link_in_ra=True, verbose=False, output_thetaavg=True, fast_acos=False,
+                                       ra_refine_factor=2, dec_refine_factor=2, max_cells_per_dim=100, copy_particles=True,
+                                       enable_min_sep_opt=True, c_api_timer=True, isa=-1))
+    ref = H.oracle_theta(ra, dec, tb, w1=wt, weight_type="pair_product", need_avg=True)
+    assert np.array_equal(r[:, 3].astype(np.uint64), ref["npairs"])
+    _close(r[:, 4], ref["weightavg"], tol, "weightavg")

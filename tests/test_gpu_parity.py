@@ -827,7 +827,8 @@ def test_device_pointers_including_weights(stat):
     assert np.array_equal(got_np, host["npairs"])
     _close(got_w, host["weightavg"], 1e-12, "weightavg from device weights")
     if stat == "xi":
-        _close(np.ctypeslib.as_array(r.xi, shape=(n,)).copy()[1:], host["cf"], 1e-12, "xi from device weights")
+        # xi = DD/RR - 1 is ~1e-5 here: the 1e-16 run-to-run spread of the weight sums shows up as 1e-11 relative
+        assert np.allclose(np.ctypeslib.as_array(r.xi, shape=(n,)).copy()[1:], host["cf"], rtol=1e-9, atol=1e-13)
         lib.free_results_xi(C.byref(r))
     else:
         lib.free_results(C.byref(r))
