@@ -57,6 +57,9 @@
 #define FAST_MINB_F64 3
 #endif
 #define FAST_PRIM 4     // primaries per lane  (32 * 4 = CFB_TILE)
+#ifndef FAST_SPLIT
+#define FAST_SPLIT 1    // half-warp split of a last primary row that holds <= 16 particles (float DD / xi, <= 3 levels)
+#endif
 
 typedef unsigned long long u64;
 
@@ -180,7 +183,12 @@ struct FastShared {
 
 // ------------------------------------------------------------------------------------------------
 // One chunk of secondaries against the lane's 4 primaries; cnt[l] += #{pairs with v < E[l]}.
-template <int MODE, int NL, int PA, int ZCUT>
+// SPLIT: the last of the PA primary rows holds at most 16 particles (a cell of 97-112 particles: 40 % of the tiles of
+// config 5), so its upper half-warp would evaluate nothing but padding.  The two half-warps then share that row's
+// primaries (lane l and lane l + 16 hold the same one, fetched by a shuffle) and split the SECONDARIES of every
+// iteration between them: the row costs half its instructions.  Every (primary, secondary) pair is still evaluated
+// exactly once, with the same operations.
+template <int MODE, int NL, int PA, int ZCUT, bool SPLIT>
 __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, const float *sz, const int m4,
                                           const float (&xq)[FAST_PRIM], const float (&yq)[FAST_PRIM],
                                           const float (&zq)[FAST_PRIM], const float *Es, const float pimax,
@@ -209,6 +217,16 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
     // line of the 100+ instruction bodies)
     constexpr int SPI = (PA >= FAST_SPI2_PA && NL >= FAST_SPI2_NL) ? 2 : 4;
     constexpr int H = SPI / 2;
+    constexpr int PFULL = SPLIT ? PA - 1 : PA;  // rows evaluated by every lane against every secondary
+    float xl = 0, yl = 0, zl = 0;
+    int hoff = 0;
+    if (SPLIT) {
+        const int lane = threadIdx.x & 31;
+        xl = __shfl_sync(0xffffffffu, xq[PA - 1], lane & 15);
+        yl = __shfl_sync(0xffffffffu, yq[PA - 1], lane & 15);
+        zl = __shfl_sync(0xffffffffu, zq[PA - 1], lane & 15);
+        hoff = lane >> 4;
+    }
 #pragma unroll UNR
     for (int j = 0; j < m4; j += SPI) {
         u64 xs[H], ys[H], zs[H];
@@ -227,8 +245,29 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
             ys[0] = pk(Y.x, Y.y);
             zs[0] = pk(Z.x, Z.y);
         }
+        if (SPLIT) {
+            // the shared last row: this half-warp's half of the iteration's secondaries
+            if constexpr (SPI == 4) {
+                const float2 X = *reinterpret_cast<const float2 *>(sx + j + 2 * hoff);
+                const float2 Y = *reinterpret_cast<const float2 *>(sy + j + 2 * hoff);
+                const float2 Z = *reinterpret_cast<const float2 *>(sz + j + 2 * hoff);
+                const u64 dx = sub2s(pk(X.x, X.y), xl), dy = sub2s(pk(Y.x, Y.y), yl), dz = sub2s(pk(Z.x, Z.y), zl);
+                const u64 v2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
 #pragma unroll
-        for (int p = 0; p < PA; p++) {
+                for (int l = 0; l < NL; l++) {
+                    const u64 d = sub2s(v2, E[l]);
+                    c[l] += (unsigned)d >> 31;
+                    c[l] += (unsigned)(d >> 63);
+                }
+            } else {
+                const float dx = sx[j + hoff] - xl, dy = sy[j + hoff] - yl, dz = sz[j + hoff] - zl;
+                const float v = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+#pragma unroll
+                for (int l = 0; l < NL; l++) c[l] += __float_as_uint(v - E[l]) >> 31;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PFULL; p++) {
 #pragma unroll
             for (int h = 0; h < H; h++) {
                 const u64 dx = sub2s(xs[h], xq[p]), dy = sub2s(ys[h], yq[p]), dz = sub2s(zs[h], zq[p]);
@@ -320,13 +359,13 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
     }
 }
 
-template <typename T, int MODE, int NL, int PA, int ZCUT>
+template <typename T, int MODE, int NL, int PA, int ZCUT, bool SPLIT = false>
 __device__ __forceinline__ void chunk_T(const T *sx, const T *sy, const T *sz, const int m4, const T (&xq)[FAST_PRIM],
                                         const T (&yq)[FAST_PRIM], const T (&zq)[FAST_PRIM], const T *E,
                                         const T pimax, int (&cnt)[FAST_LMAX])
 {
     if constexpr (sizeof(T) == 4)
-        chunk_f32<MODE, NL, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
+        chunk_f32<MODE, NL, PA, ZCUT, SPLIT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
     else
         chunk_f64<MODE, NL, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
 }
@@ -451,6 +490,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         const int startP = A.start[cellP];
         const int nv = min(CFB_TILE, nP - toff);  // valid primaries of this tile
         const int pa = (nv + 31) >> 5;            // primaries per lane in use
+        const bool tsplit = pa == 4 && nv <= 112; // the fourth row fits a half-warp (see chunk_f32, SPLIT)
         const T nanv = sizeof(T) == 4 ? (T)CUDART_NAN_F : (T)CUDART_NAN;
         const T *pxg = A.x + startP + toff, *pyg = A.y + startP + toff, *pzg = A.z + startP + toff;
 
@@ -761,7 +801,18 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                             else
                                 chunk_dispatch<T, MODE, 1>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
                         } else
-                            chunk_dispatch<T, MODE, 0>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                        {
+                            bool done = false;
+                            if constexpr (sizeof(T) == 4 && MODE == CFB_DD && FAST_SPLIT) {
+                                if (tsplit && nlp <= 3) {  // the three bodies that carry 95 % of the iterations
+                                    if (nlp == 1) chunk_T<T, MODE, 1, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                                    else if (nlp == 2) chunk_T<T, MODE, 2, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                                    else chunk_T<T, MODE, 3, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                                    done = true;
+                                }
+                            }
+                            if (!done) chunk_dispatch<T, MODE, 0>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                        }
                         // ---- warp totals -> warp histogram: +C at the level's slot, -C one above ----
                         // a lane counts at most FAST_PRIM * FAST_CH = 512 pairs per level here and the warp 2^14:
                         // two levels share one 32-bit warp reduction
