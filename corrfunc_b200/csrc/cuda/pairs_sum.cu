@@ -46,7 +46,8 @@
 #ifndef SUM_MINB
 #define SUM_MINB 5               // resident blocks per SM the kernel is compiled for (register budget): the kernel is latency bound, measured 25 % faster at 5 blocks than at 4
 #endif
-#define SUM_RING 160            // accepted-pair stack per warp: < 32 left over + up to 4 x 32 new ones per iteration
+#define SUM_RING 352            // accepted-pair stack per warp (16-bit entries): the hot loop runs until fewer than 128 slots
+                                // (one iteration's worth) are free, then the full batches are drained back to back
 #define SUM_MAX_EDGES 256
 
 typedef unsigned long long u64;
@@ -160,11 +161,11 @@ template <typename T, int NA>
 struct SumWarp {
     alignas(16) T buf[2][NA][SUM_CH];
     alignas(16) T prim[NA][SUM_TILE];  // the tile's primaries with the current wrap applied (+ weights): gathered by the drain
-    // accepted-pair stack: (primary << 16 | secondary) of every pair that passed the range test.  Four bytes per entry --
+    // accepted-pair stack: (primary << 8 | secondary) of every pair that passed the range test.  Two bytes per entry --
     // the drain recomputes the separation from the positions, which costs it 13 instructions and buys a third more
     // resident warps than a stack that carries the values.  The last 32 entries are a dump for the lanes that have nothing
     // to push (branch-free stores).
-    unsigned ring_i[SUM_RING + 32];
+    unsigned short ring_i[SUM_RING + 32];
     SumJob q[SUM_QCAP];
 };
 
@@ -287,7 +288,7 @@ __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA
     __syncwarp();
     bool ok = lane < n;
     const unsigned idx = W.ring_i[head + lane];  // entries head .. head + n - 1 (the top of the stack)
-    const int pidx = (idx >> 16) & (SUM_TILE - 1), j = idx & (SUM_CH - 1);
+    const int pidx = (idx >> 8) & (SUM_TILE - 1), j = idx & (SUM_CH - 1);
     // the pair again, with the arithmetic of the hot loop (same function, same operands)
     const T x1 = W.prim[0][pidx], y1 = W.prim[1][pidx], z1 = W.prim[2][pidx];
     const T x2 = W.buf[bsel][0][j], y2 = W.buf[bsel][1][j], z2 = W.buf[bsel][2][j];
@@ -416,7 +417,7 @@ __device__ __forceinline__ int hot_loop(int k, const int m, SumWarp<T, NA> &W, c
     T tz[PA];
 #pragma unroll
     for (int p = 0; p < PA; p++) tz[p] = zq[p] - K.pimax;  // target of the reference's fast-forward over z (wp, DDrppi)
-    for (; k < m && tail < 32; k += NS) {
+    for (; k < m && tail <= SUM_RING - 128; k += NS) {
         T v[4], b[4];
         bool acc[4];
         unsigned msk[4];
@@ -452,7 +453,7 @@ __device__ __forceinline__ int hot_loop(int k, const int m, SumWarp<T, NA> &W, c
             for (int e = 0; e < 4; e++) {
                 // lanes with nothing to push store into the dump behind the stack: no divergent code in this loop
                 const int pos = acc[e] ? base + __popc(msk[e] & lt) : SUM_RING + lane;
-                W.ring_i[pos] = ((unsigned)(lane + 32 * (e % PA)) << 16) | (unsigned)(k + e / PA);
+                W.ring_i[pos] = (unsigned short)(((lane + 32 * (e % PA)) << 8) | (k + e / PA));
                 base += __popc(msk[e]);
             }
             tail = base;
@@ -869,7 +870,10 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
                             SUM_HOT3(2, 0);
 #undef SUM_HOT3
 #undef SUM_HOT
-                        if (tail >= 32 || (k >= m4 && tail > 0)) {
+                        // the stack is (nearly) full or the chunk is done: every full batch, back to back; the remainder too
+                        // at the end of the chunk (the drain gathers from this chunk's buffer)
+                        const bool last = k >= m4;
+                        while (tail >= 32 || (last && tail > 0)) {
                             const int n = tail < 32 ? tail : 32;
                             drain<T, MODE, AVG, WGT, NA>(n, tail - n, W, bsel, K, E, jk, jl, lane);
                             tail -= n;
@@ -877,9 +881,8 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
                                 flush_hist<MODE, AVG, WGT, T>(P, K, ns, lane, 32, false);
                                 drains = 0;
                             }
-                            continue;
                         }
-                        if (k >= m4) break;
+                        if (last) break;
                     }
                     __syncwarp();  // everyone is done with buf[bsel] before it is staged again
                     it++;
@@ -1009,6 +1012,7 @@ int launch_T(const cfb_binning *bin, const PairParams &P, bool list_mode)
 int cfb_launch_pairs_sum(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode)
 {
     static_assert(CFB_TILE % SUM_TILE == 0, "sum tiles subdivide the gridlink tiles");
+    static_assert(SUM_TILE <= 256 && SUM_CH <= 256, "a stack entry is (primary << 8 | secondary) in 16 bits");
     if (bin->nedges < 2 || bin->nedges > SUM_MAX_EDGES) return -1;
     for (int i = 0; i < bin->nedges; i++) {
         // the level search needs finite, strictly monotonic edges (increasing; theta: decreasing cosines)
