@@ -119,6 +119,7 @@ struct PairParams {
     unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs [2]=pairs binned without evaluation [3]=sum of evaluated pairs x levels [4]=next tile (persistent warps)
     int hist_in_smem;
     int sum_copies_shift;  // per-pair-sum kernel: log2 of the number of shared-memory histogram copies
+    int sum_norm_drains;   // per-pair-sum kernel: drains of a warp between two normalisations of the block's histogram
 };
 
 // Multi-rank sharding is by primary CELL, never by tile: every rank sorts its own replica and the order of the

@@ -192,7 +192,7 @@ template <int MODE, int NL, int PA, int ZCUT, bool SPLIT>
 __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, const float *sz, const int m4,
                                           const float (&xq)[FAST_PRIM], const float (&yq)[FAST_PRIM],
                                           const float (&zq)[FAST_PRIM], const float *Es, const float pimax,
-                                          int (&cnt)[FAST_LMAX])
+                                          const bool dirz, int (&cnt)[FAST_LMAX])
 {
     float E[NL];
     unsigned c[NL];
@@ -202,9 +202,14 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
         c[l] = 0u;
     }
     const u64 th_a = pk(8388608.0f, 8388608.0f), th_b = pk(-16777216.0f, -16777216.0f);
-    float tz[PA];  // target_z = zpos - pimax of the reference's fast-forward (ZCUT == 2 only)
+    // pi cut (ZCUT): ONE loop body serves both cases -- a second set of bodies cost the wp kernel a third more code and,
+    // through the instruction cache, 40 % of its speed.  dirz (two reference cells): z2 > target_z = zpos - pimax of the
+    // reference's fast-forward, then the signed dz < pimax; same reference cell: -pimax < dz < pimax.  The test that does
+    // not apply compares against -inf.
+    float tz[PA];
 #pragma unroll
-    for (int p = 0; p < PA; p++) tz[p] = zq[p] - pimax;
+    for (int p = 0; p < PA; p++) tz[p] = dirz ? zq[p] - pimax : -CUDART_INF_F;
+    const float mpm = dirz ? -CUDART_INF_F : -pimax;
     // The kernel holds one loop per (levels, primaries) variant and the warps of an SM run different ones:
     // unrolling them all 4x overflowed the instruction cache (measured: 26 "no instruction" stall cycles per
     // issued instruction, 5x slower).  Only the variants that carry ~95 % of the iterations (3 primaries per
@@ -279,15 +284,8 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
                     // -cos(theta) * 2^24 = chord^2 * 2^23 - 2^24 (countpairs_theta_mocks_kernels.c.src:1062-1066)
                     if (MODE == CFB_THETA) v2 = fma2(v2, th_a, th_b);
                 }
-                if (ZCUT == 1) {  // same reference cell (j after i in z order, dz >= 0): dz < pimax, here as |dz| < pimax
-                    float v0, v1, z0, z1;
-                    upk(v2, v0, v1);
-                    upk(dz, z0, z1);
-                    v0 = fabsf(z0) < pimax ? v0 : CUDART_INF_F;
-                    v1 = fabsf(z1) < pimax ? v1 : CUDART_INF_F;
-                    v2 = pk(v0, v1);
-                }
-                if (ZCUT == 2) {
+                if (ZCUT) {
+                    // same reference cell (j after i in z order, dz >= 0): dz < pimax, here as |dz| < pimax.
                     // two reference cells: the reference fast-forwards over the secondaries with z1 <= zpos - pimax
                     // (wp_kernels.c.src:139-142) and then masks with the SIGNED dz < pimax (:207-221).  A survivor
                     // whose dz rounds to exactly -pimax is therefore counted; |dz| < pimax would drop it.
@@ -295,8 +293,8 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
                     upk(v2, v0, v1);
                     upk(dz, z0, z1);
                     upk(zs[h], s0, s1);
-                    v0 = (s0 > tz[p] && z0 < pimax) ? v0 : CUDART_INF_F;
-                    v1 = (s1 > tz[p] && z1 < pimax) ? v1 : CUDART_INF_F;
+                    v0 = (s0 > tz[p] && z0 > mpm && z0 < pimax) ? v0 : CUDART_INF_F;
+                    v1 = (s1 > tz[p] && z1 > mpm && z1 < pimax) ? v1 : CUDART_INF_F;
                     v2 = pk(v0, v1);
                 }
                 // [v < E] is the sign bit of the rounded difference v - E (x - x = +0; NaN and +inf give
@@ -319,11 +317,15 @@ template <int MODE, int NL, int PA, int ZCUT>
 __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, const double *sz, const int m4,
                                           const double (&xq)[FAST_PRIM], const double (&yq)[FAST_PRIM],
                                           const double (&zq)[FAST_PRIM], const double *Es,
-                                          const double pimax, int (&cnt)[FAST_LMAX])
+                                          const double pimax, const bool dirz, int (&cnt)[FAST_LMAX])
 {
     double E[NL];
 #pragma unroll
     for (int l = 0; l < NL; l++) E[l] = Es[l];
+    double tz[PA];  // see chunk_f32
+#pragma unroll
+    for (int p = 0; p < PA; p++) tz[p] = dirz ? zq[p] - pimax : -CUDART_INF;
+    const double mpm = dirz ? -CUDART_INF : -pimax;
     // one secondary per iteration for the long bodies (many primaries x levels): same instruction-cache
     // consideration as in chunk_f32
     constexpr int SPI = (PA * NL >= FAST_F64_SPI1) ? 1 : 2;
@@ -350,8 +352,7 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
                     v = __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
                     if (MODE == CFB_THETA) v = __fma_rn(v, 0.5, -1.0);  // -(1 - chord^2/2), exactly
                 }
-                if (ZCUT == 1) v = fabs(dz) < pimax ? v : CUDART_INF;
-                if (ZCUT == 2) v = (zs[h] > zq[p] - pimax && dz < pimax) ? v : CUDART_INF;  // see chunk_f32
+                if (ZCUT) v = (zs[h] > tz[p] && dz > mpm && dz < pimax) ? v : CUDART_INF;
 #pragma unroll
                 for (int l = 0; l < NL; l++) cnt[l] += (v < E[l]) ? 1 : 0;
             }
@@ -362,31 +363,31 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
 template <typename T, int MODE, int NL, int PA, int ZCUT, bool SPLIT = false>
 __device__ __forceinline__ void chunk_T(const T *sx, const T *sy, const T *sz, const int m4, const T (&xq)[FAST_PRIM],
                                         const T (&yq)[FAST_PRIM], const T (&zq)[FAST_PRIM], const T *E,
-                                        const T pimax, int (&cnt)[FAST_LMAX])
+                                        const T pimax, const bool dirz, int (&cnt)[FAST_LMAX])
 {
     if constexpr (sizeof(T) == 4)
-        chunk_f32<MODE, NL, PA, ZCUT, SPLIT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
+        chunk_f32<MODE, NL, PA, ZCUT, SPLIT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt);
     else
-        chunk_f64<MODE, NL, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt);
+        chunk_f64<MODE, NL, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt);
 }
 
 template <typename T, int MODE, int PA, int ZCUT>
 __device__ __forceinline__ void chunk_dispatch_nl(const int nl, const T *sx, const T *sy, const T *sz, const int m4,
                                                   const T (&xq)[FAST_PRIM], const T (&yq)[FAST_PRIM],
                                                   const T (&zq)[FAST_PRIM], const T *E, const T pimax,
-                                                  int (&cnt)[FAST_LMAX])
+                                                  const bool dirz, int (&cnt)[FAST_LMAX])
 {
     switch (nl) {
-    case 1: chunk_T<T, MODE, 1, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
-    case 2: chunk_T<T, MODE, 2, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
-    case 3: chunk_T<T, MODE, 3, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 1: chunk_T<T, MODE, 1, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
+    case 2: chunk_T<T, MODE, 2, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
+    case 3: chunk_T<T, MODE, 3, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
 #if FAST_LMAX == 4
-    default: chunk_T<T, MODE, 4, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    default: chunk_T<T, MODE, 4, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
 #else
-    case 4: chunk_T<T, MODE, 4, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
-    case 5: chunk_T<T, MODE, 5, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
-    case 6: chunk_T<T, MODE, 6, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
-    default: chunk_T<T, MODE, 8, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;  // 7 runs as 8 (E[7] = +inf)
+    case 4: chunk_T<T, MODE, 4, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
+    case 5: chunk_T<T, MODE, 5, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
+    case 6: chunk_T<T, MODE, 6, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
+    default: chunk_T<T, MODE, 8, PA, ZCUT>(sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;  // 7 runs as 8 (E[7] = +inf)
 #endif
     }
 }
@@ -396,13 +397,13 @@ template <typename T, int MODE, int ZCUT>
 __device__ __forceinline__ void chunk_dispatch(const int nl, const int pa, const T *sx, const T *sy, const T *sz,
                                                const int m4, const T (&xq)[FAST_PRIM], const T (&yq)[FAST_PRIM],
                                                const T (&zq)[FAST_PRIM], const T *E, const T pimax,
-                                               int (&cnt)[FAST_LMAX])
+                                               const bool dirz, int (&cnt)[FAST_LMAX])
 {
     switch (pa) {
-    case 1: chunk_dispatch_nl<T, MODE, 1, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
-    case 2: chunk_dispatch_nl<T, MODE, 2, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
-    case 3: chunk_dispatch_nl<T, MODE, 3, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
-    default: chunk_dispatch_nl<T, MODE, 4, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, cnt); break;
+    case 1: chunk_dispatch_nl<T, MODE, 1, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
+    case 2: chunk_dispatch_nl<T, MODE, 2, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
+    case 3: chunk_dispatch_nl<T, MODE, 3, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
+    default: chunk_dispatch_nl<T, MODE, 4, ZCUT>(nl, sx, sy, sz, m4, xq, yq, zq, E, pimax, dirz, cnt); break;
     }
 }
 
@@ -796,22 +797,19 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
 #pragma unroll
                         for (int l = 0; l < FAST_LMAX; l++) cnt[l] = 0;
                         if (MODE == CFB_WP && (jb.meta & JOB_ZCUT)) {
-                            if (jb.meta & JOB_DIRZ)
-                                chunk_dispatch<T, MODE, 2>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
-                            else
-                                chunk_dispatch<T, MODE, 1>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                            chunk_dispatch<T, MODE, 1>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, (jb.meta & JOB_DIRZ) != 0, cnt);
                         } else
                         {
                             bool done = false;
                             if constexpr (sizeof(T) == 4 && MODE == CFB_DD && FAST_SPLIT) {
                                 if (tsplit && nlp <= 3) {  // the three bodies that carry 95 % of the iterations
-                                    if (nlp == 1) chunk_T<T, MODE, 1, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
-                                    else if (nlp == 2) chunk_T<T, MODE, 2, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
-                                    else chunk_T<T, MODE, 3, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                                    if (nlp == 1) chunk_T<T, MODE, 1, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, false, cnt);
+                                    else if (nlp == 2) chunk_T<T, MODE, 2, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, false, cnt);
+                                    else chunk_T<T, MODE, 3, 4, 0, true>(sx, sy, sz, m4, xq, yq, zq, Es, pimax, false, cnt);
                                     done = true;
                                 }
                             }
-                            if (!done) chunk_dispatch<T, MODE, 0>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, cnt);
+                            if (!done) chunk_dispatch<T, MODE, 0>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, false, cnt);
                         }
                         // ---- warp totals -> warp histogram: +C at the level's slot, -C one above ----
                         // a lane counts at most FAST_PRIM * FAST_CH = 512 pairs per level here and the warp 2^14:

@@ -22,9 +22,11 @@
 //     evaluated in floating point exactly as the reference does (IEEE divide and square roots), sqrt for the average,
 //     the weight product, and the histogram update.  Only 0.3 drains run per 32 separations, instead of a divergent
 //     accept branch in nearly every iteration;
-//   * histograms: per block in shared memory, 32-bit words updated with native ATOMS.ADD (counts two words, sums 96-bit
-//     fixed point: exact, order independent, reproducible), REPLICATED `copies` times with the copy chosen by the lane, so
-//     that lanes of one drain that hit the same slot or bank mostly do not serialise.
+//   * histograms: per block in shared memory, 32-bit words updated with native ATOMS.ADD (a count word; sums as 64-bit
+//     fixed point in two words with the carry taken from the returned old value: exact, order independent,
+//     reproducible), laid out [slot][copy][word] and REPLICATED `copies` times with the copy chosen by the lane: with 8
+//     copies lanes of different copy index never meet in a bank, and lanes of one drain that hit the same slot mostly do
+//     not serialise (ncu on config 3: the conflicts of these atomics were half of all shared-memory wavefronts).
 //
 // Compiled with -fmad=false: an FMA appears exactly where the reference's AVX-512 kernels have one.
 #include <math_constants.h>
@@ -108,43 +110,43 @@ __device__ __forceinline__ unsigned fdiv(unsigned n, unsigned magic) { return ma
 // Shared-memory accumulation with the native 32-bit integer ATOMS.ADD only (64-bit, float and double shared atomics
 // compile to compare-and-swap loops on sm_100a).  Measured with tools/ubench_atoms.cu: a full-warp ATOMS.ADD to spread
 // addresses sustains 10-15 word updates per clock and SM when the result is not used and 5-10 as a carry chain; an ATOMS
-// with 8 active lanes costs as much as one with 32 -- which is why the accepted pairs are compacted first.  Measured on
-// config 3 (10 M points): 96-bit sums as three carry-chained words 413 ms, four 16-bit limbs without carries 437 ms,
-// two words (44 bits) 307 ms.  What is used:
-//   count: one word, +1 per pair, result unused;
-//   sums : fixed point -- value * 2^k rounded to an integer below 2^59 in magnitude (k from the bin's upper edge, or from the
-//          largest weight product; 59 bits because a bin may hold a single pair whose value is a millionth of the bin's
-//          largest and is still compared at 1e-10) -- in three words: the low 15 bits go to a word of their own (result
-//          unused), bits 15-46 to a word whose returned old value gives the carry, and the signed top 12 bits + that carry to a
-//          third word (result unused).  One atomic per sum waits for its result, and nothing waits for that but one add.
-// The count word, the low word (< 2^15 per add) and the top word (< 2^12 + 1 per add) must not wrap: every warp
-// NORMALISES the block's histogram every SUM_NORM_DRAINS of its drains -- these words are exchanged with zero and what
-// they held goes to the global histogram.  Between two normalisations a slot takes fewer than 4 warps x 512 drains x 32
-// lanes = 2^16 adds: below 2^31 in every word.  Integer sums are exact and order independent.
+// with 8 active lanes costs as much as one with 32 -- which is why the accepted pairs are compacted first -- and lanes
+// that meet in one bank or one word serialise (ncu, config 3, one histogram copy: 6 wavefronts per ATOMS).
+//   count: one word, +1 per pair, result unused (ATOMS.POPC.INC: lanes on one address are merged by the hardware);
+//   sums : fixed point -- value * 2^k rounded to an integer q below 2^46 in magnitude (k from the bin's upper edge, or
+//          from the largest weight product: 1.4e-14 of the bin's largest value per term, sums compared at 1e-10) -- held
+//          in two words as a 64-bit two's-complement number: ATOMS.ADD of the low 32 bits returns the old value, which
+//          gives the carry that is added with the high part.  q is formed by ONE fused multiply-add with the constant
+//          1.5 * 2^52: the low 52 bits of the result are q in two's complement (no F2I.S64, no shifts).
+// The low word wraps by design (every wrap is a carry).  The count word and the high word (|q >> 32| <= 2^14, + carry)
+// must not wrap: every warp NORMALISES the block's histogram every `norm_drains` of its drains -- these words are
+// exchanged with zero and what they held goes to the global histogram.  Between two normalisations one word takes at most
+// warps x norm_drains x (32 / copies) adds; the launch chooses norm_drains so that this stays below 2^16, i.e. below
+// 2^31 in magnitude.  Integer sums are exact and order independent.
 #define SUM_NORM_DRAINS 512
-__device__ __forceinline__ void add_fixed(unsigned *w, const int stride, const long long q)
+#define SUM_MAGIC 6755399441055744.0  // 1.5 * 2^52
+#define SUM_QBITS 46
+__device__ __forceinline__ void add2(unsigned *w, const double m)  // m = fma(value, scale, SUM_MAGIC)
 {
-    atomicAdd(w, (unsigned)q & 0x7fffu);
-    const long long q1 = q >> 15;  // arithmetic: 44 signed bits
-    const unsigned lo = (unsigned)q1;
-    const unsigned old = atomicAdd(w + stride, lo);
-    atomicAdd(w + 2 * stride, (unsigned)(q1 >> 32) + (old > ~lo ? 1u : 0u));
+    const unsigned lo = (unsigned)__double2loint(m);
+    const int hi = __double2hiint(m) - 0x43380000;  // floor(q / 2^32)
+    const unsigned old = atomicAdd(w, lo);
+    atomicAdd(w + 1, (unsigned)hi + (old > ~lo ? 1u : 0u));
 }
-// what the wrapping-prone words of one slot hold (exchanged with zero); last: also the middle word (nobody adds any more)
-__device__ __forceinline__ double take_fixed(unsigned *w, const int stride, const bool last)
+// what the high word of one sum holds (exchanged with zero); last: also the low word (nobody adds any more)
+__device__ __forceinline__ double take2(unsigned *w, const bool last)
 {
     double v = 0.0;
-    if (w[0]) v += (double)atomicExch(w, 0u);
-    if (w[2 * stride]) v += (double)(int)atomicExch(w + 2 * stride, 0u) * 140737488355328.0;  // 2^47
-    if (last) v += (double)w[stride] * 32768.0;
+    if (w[1]) v = (double)(int)atomicExch(w + 1, 0u) * 4294967296.0;
+    if (last) v += (double)w[0];
     return v;
 }
-// 2^k such that |v| * 2^k < 2^59 for every |v| <= vmax
+// 2^k such that |v| * 2^k < 2^SUM_QBITS for every |v| <= vmax
 __device__ __forceinline__ double fixed_scale(const double vmax)
 {
     int e = 0;
     if (vmax > 0.0 && vmax < 1.0e300) frexp(vmax, &e);  // vmax < 2^e
-    return ldexp(1.0, 59 - e);
+    return ldexp(1.0, SUM_QBITS - e);
 }
 
 struct SumJob {
@@ -174,15 +176,26 @@ template <typename T>
 struct SumConst {
     const T *edges;        // shared: T[nedges]
     const double *scale;   // shared: double[nedges], fixed-point scale of the separation sum per bin
-    unsigned *h_np, *h_sep, *h_w;  // shared histograms: count [slots*copies], sums [3][slots*copies]
-    int hstride;           // nslots * copies
+    unsigned *hist;        // shared histogram [slot][copy][word]: word 0 count, then (low, high) of the separation sum and
+                           // of the weight sum; addressed through hword()
     int copies_shift;      // log2(copies)
+    int cl;                // this lane's copy
     int nedges;
+    int nmu, nmu_p1_i;     // DDsmu: number of mu bins, + 1
+    int norm_drains;
+    bool fast_ok;          // the edges lie within the float range: the float estimates of the drain may be used
     T pimax, sqr_pimax, inv_dpi, inv_dmu, sqr_mumax, npi_p1, nmu_p1, e_lo, e_hi, sqr_max_sep;
-    float inv_dmu_f;
+    float inv_dmu_f, mu_tol_b;
     double w_scale;
     int fast_acos;
 };
+// first word of (slot, this lane's copy); NP words per (slot, copy).  NP is odd (1, 3 or 5), so the multiplication permutes
+// the banks: two lanes meet in a bank only if (slot * copies + copy) agrees modulo 32 -- never for different copies of 8.
+template <int NP, typename T>
+__device__ __forceinline__ unsigned *hword(const SumConst<T> &K, const int slot)
+{
+    return K.hist + (unsigned)(((slot << K.copies_shift) + K.cl) * NP);
+}
 
 // true when value v lies at or above edge e in the binning order (theta: edges are cosines, decreasing)
 template <typename T, int MODE>
@@ -240,51 +253,47 @@ __device__ __forceinline__ bool eval_pair(const T x2, const T y2, const T z2, co
     return acc;
 }
 
-// sqrt for the average separation.  double: float reciprocal-square-root seed + one Newton step in double, relative error
-// < 6e-14 (the averages are sums of millions of terms compared at 1e-10; the reference's own sums depend on the thread
-// schedule at the 1e-13 level); IEEE sqrt outside the float range.  float: IEEE.
-__device__ __forceinline__ float sep_sqrt(const float v) { return __fsqrt_rn(v); }
-__device__ __forceinline__ double sep_sqrt(const double v)
+__device__ __forceinline__ float rsqrt_apx(const float v)
 {
-    const float vf = __double2float_rn(v);
-    if (!(vf > 1.0e-30f && vf < 1.0e30f)) return __dsqrt_rn(v);
-    float y0;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(vf));
-    const double y = (double)y0;
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v));
+    return y;
+}
+__device__ __forceinline__ float sqrt_apx(const float v)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v));
+    return y;
+}
+// sqrt for the average separation, rs ~ 1/sqrt(v) in float (relative error < 2^-21).  double: one Newton step in double,
+// relative error < 6e-14 (the averages are sums of millions of terms compared at 1e-10; the reference's own sums depend on
+// the thread schedule at the 1e-13 level).  float: IEEE.
+__device__ __forceinline__ float sep_sqrt(const float v, const float) { return __fsqrt_rn(v); }
+__device__ __forceinline__ double sep_sqrt(const double v, const float rs)
+{
+    const double y = (double)rs;
     const double r0 = v * y;
     const double e = __fma_rn(-r0, r0, v);
     return __fma_rn(e, 0.5 * y, r0);
 }
 
-// mu * inv_dmu of DDsmu for an accepted pair: b = dz^2, a = s^2.  Only its integer part matters (the mu bin).
-// double: the bin is first located in FLOAT arithmetic (the FP32 pipe is idle in this kernel); if the float estimate is
-// farther from an integer than its error bound, its integer part is the exact one; otherwise (probability ~1e-4) the
-// reference's arithmetic runs: true divide, IEEE sqrt (countpairs_s_mu_kernels.c.src:228-277).  Returned is a value with
-// the same integer part as the reference's mu * inv_dmu and a fraction safely away from 0 and 1, so that adding
-// sbin * (nmu + 1) in floating point and truncating gives the reference's slot.
-__device__ __forceinline__ float mu_coord(const float b, const float a, const SumConst<float> &K)
-{
-    return __fsqrt_rn(__fdiv_rn(b, a)) * K.inv_dmu;
-}
-__device__ __forceinline__ double mu_coord(const double b, const double a, const SumConst<double> &K)
-{
-    const float bf = __double2float_rn(b), af = __double2float_rn(a);
-    float yf;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(__fdividef(bf, af)));
-    yf *= K.inv_dmu_f;
-    const float fl = floorf(yf), fr = yf - fl;
-    const float tol = 4.0e-6f * (yf + 1.0f);  // > 8 x the error bound of the float evaluation
-    if (fr > tol && fr < 1.0f - tol && af > 1.0e-30f && af < 1.0e30f && bf > 1.0e-30f) return (double)fl + 0.5;
-    return __dsqrt_rn(__ddiv_rn(b, a)) * K.inv_dmu;
-}
-
 // ------------------------------------------------------------------------------------------------
 // The drain: n (<= 32) accepted pairs from the top of the stack, one per lane.
 // E[l], l < 4: the job's level edges in registers (padded so that the compare is false); nl > 4: binary search.
+//
+// DDsmu: the reference evaluates slot = (int)(sbin * (nmu + 1) + sqrt(dz^2 / s^2) * inv_dmu) with a true divide and an
+// IEEE square root (countpairs_s_mu_kernels.c.src:228-277).  Here the mu bin is first located in FLOAT arithmetic with
+// the approximate MUFU reciprocal square root and square root (the FP32 and XU pipes are idle in this kernel): if the
+// estimate lies farther from an integer than its error bound -- 4e-6 (y + 1) covers the conversions, the two
+// approximations and three multiplications; in float the rounding of the reference's floating-point index sum, half an
+// ulp of the slot count, is added -- its integer part IS the reference's mu bin (or, at nmu and above, the pair fails
+// the reference's dz^2 < s^2 mu_max^2).  Otherwise (about 1e-4 of the batches) the whole batch takes the reference's
+// arithmetic.
 template <typename T, int MODE, bool AVG, bool WGT, int NA>
 __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA> &W, const int bsel, const SumConst<T> &K,
                                       const T (&E)[8], const int kfirst, const int nl, const int lane)
 {
+    constexpr int NP = 1 + (AVG ? 2 : 0) + (WGT ? 2 : 0);
     __syncwarp();
     bool ok = lane < n;
     const unsigned idx = W.ring_i[head + lane];  // entries head .. head + n - 1 (the top of the stack)
@@ -296,14 +305,33 @@ __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA
     eval_pair<T, MODE, false>(x2, y2, z2, x1, y1, z1, (T)0, K, false, a, b);
 
     T v = a;      // the quantity that is binned
-    T f2 = 0;     // second-dimension coordinate in bins (pi * inv_dpi or mu * inv_dmu)
+    T f2 = 0;     // second-dimension coordinate in bins (pi * inv_dpi or mu * inv_dmu), reference arithmetic
+    int mb = 0;   // DDsmu: mu bin from the float estimate
+    bool exact2 = true;  // warp-uniform: the second-dimension bin comes from f2
+    float rs = 0.0f;     // ~ 1 / sqrt(v) in float, when already known
+    bool have_rs = false;
     if (MODE == CFB_RPPI) {
         f2 = b * K.inv_dpi;
     } else if (MODE == CFB_SMU) {
-        // keep if dz^2 < s^2 mu_max^2; sqr_mu = dz^2 / s^2 (true divide, fast_divide_and_NR_steps == 0), mu = sqrt
-        // (countpairs_s_mu_kernels.c.src:216-277)
-        if (!(b < a * K.sqr_mumax)) ok = false;
-        f2 = mu_coord(b, a, K);
+        bool amb = ok;
+        if (K.fast_ok) {
+            const float af = (float)a, bf = (float)b;
+            rs = rsqrt_apx(af);
+            have_rs = true;
+            const float y = sqrt_apx(bf) * rs * K.inv_dmu_f;
+            mb = __float2int_rz(y);
+            const float fr = y - (float)mb;
+            const float tol = __fmaf_rn(4.0e-6f, y, K.mu_tol_b);  // mu_tol_b includes the 4e-6 * 1
+            amb = ok && !(fr > tol && fr < 1.0f - tol);
+        }
+        exact2 = __any_sync(0xffffffffu, amb);
+        if (exact2) {
+            // keep if dz^2 < s^2 mu_max^2; sqr_mu = dz^2 / s^2 (true divide, fast_divide_and_NR_steps == 0), mu = sqrt
+            // (countpairs_s_mu_kernels.c.src:216-277)
+            if (!(b < a * K.sqr_mumax)) ok = false;
+            f2 = sqrt_t<T>(divi_t<T>(b, a)) * K.inv_dmu;
+        } else if (mb >= K.nmu)
+            ok = false;
     } else if (MODE == CFB_RPPI_MOCKS || MODE == CFB_SMU_MOCKS) {
         // line of sight = pair midpoint (countpairs_rp_pi_mocks_kernels.c.src:200-290, countpairs_s_mu_mocks_kernels.c.src:196-290)
         const T dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
@@ -329,7 +357,10 @@ __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA
     }
     // separation bin: kfirst + the number of levels at or below the value
     int kb = kfirst;
-    if (nl <= 4) {
+    if (nl <= 2) {
+#pragma unroll
+        for (int l = 0; l < 2; l++) kb += at_or_above<T, MODE>(v, E[l]) ? 1 : 0;
+    } else if (nl <= 4) {
 #pragma unroll
         for (int l = 0; l < 4; l++) kb += at_or_above<T, MODE>(v, E[l]) ? 1 : 0;
     } else {
@@ -344,30 +375,37 @@ __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA
     if (MODE == CFB_RPPI || MODE == CFB_RPPI_MOCKS) {
         // rpbin*(npibin+1) + pi*inv_dpi evaluated in T, then truncated (countpairs_rp_pi_kernels.c.src:249-256)
         slot = (int)((T)kb * K.npi_p1 + f2);
-    } else if (MODE == CFB_SMU || MODE == CFB_SMU_MOCKS) {
-        slot = (int)((T)kb * K.nmu_p1 + f2);  // countpairs_s_mu_kernels.c.src:269-277
+    } else if (MODE == CFB_SMU_MOCKS) {
+        slot = (int)((T)kb * K.nmu_p1 + f2);  // countpairs_s_mu_mocks_kernels.c.src
+    } else if (MODE == CFB_SMU) {
+        if (exact2) slot = (int)((T)kb * K.nmu_p1 + f2);  // countpairs_s_mu_kernels.c.src:269-277
+        else slot = kb * K.nmu_p1_i + mb;
     }
     if (!ok) slot = 0, kb = kfirst;  // idle lanes: any valid address
-    long long qsep = 0, qw = 0;
+    double msep = 0.0, mw = 0.0;
     if (AVG) {
         T sep;
         if (MODE == CFB_THETA) {
             const T cc = v >= (T)1.0 ? (T)1.0 : v;
             const T th = K.fast_acos ? fast_acos_t<T>(cc) : (T)acos(cc);
             sep = (T)(th * (T)57.29577951308232087679815481410517);
-        } else
-            sep = sep_sqrt(v);
-        qsep = __double2ll_rn((double)sep * K.scale[kb]);
+        } else if (sizeof(T) == 8 && !K.fast_ok) {
+            sep = sqrt_t<T>(v);
+        } else {
+            if (sizeof(T) == 8 && !have_rs) rs = rsqrt_apx((float)v);
+            sep = sep_sqrt(v, rs);
+        }
+        msep = __fma_rn((double)sep, K.scale[kb], SUM_MAGIC);
     }
     if (WGT) {
         const T w1 = W.prim[NA - 1][pidx], w2 = W.buf[bsel][NA - 1][j];
-        qw = __double2ll_rn((double)(T)(w1 * w2) * K.w_scale);  // pair_product, weight_functions.h.src:71-91
+        mw = __fma_rn((double)(T)(w1 * w2), K.w_scale, SUM_MAGIC);  // pair_product, weight_functions.h.src:71-91
     }
     if (ok) {
-        const int h = (slot << K.copies_shift) + (lane & ((1 << K.copies_shift) - 1));
-        atomicAdd(&K.h_np[h], 1u);
-        if (AVG) add_fixed(&K.h_sep[h], K.hstride, qsep);
-        if (WGT) add_fixed(&K.h_w[h], K.hstride, qw);
+        unsigned *h = hword<NP>(K, slot);
+        atomicAdd(h, 1u);
+        if (AVG) add2(h + 1, msep);
+        if (WGT) add2(h + 1 + (AVG ? 2 : 0), mw);
     }
     __syncwarp();
 }
@@ -378,15 +416,16 @@ template <int MODE, bool AVG, bool WGT, typename T>
 __device__ __forceinline__ void flush_hist(const PairParams &P, const SumConst<T> &K, const int ns, const int first,
                                            const int step, const bool last)
 {
+    constexpr int NP = 1 + (AVG ? 2 : 0) + (WGT ? 2 : 0);
     const int copies = 1 << K.copies_shift;
     for (int i = first; i < ns; i += step) {
         u64 cnt = 0;
         double ssep = 0.0, sw = 0.0;
-        for (int c = 0; c < copies; c++) {
-            const int h = (i << K.copies_shift) + c;
-            if (K.h_np[h]) cnt += atomicExch(&K.h_np[h], 0u);
-            if (AVG) ssep += take_fixed(&K.h_sep[h], K.hstride, last);
-            if (WGT) sw += take_fixed(&K.h_w[h], K.hstride, last);
+        unsigned *h = K.hist + (unsigned)((i << K.copies_shift) * NP);
+        for (int c = 0; c < copies; c++, h += NP) {
+            if (h[0]) cnt += atomicExch(h, 0u);
+            if (AVG) ssep += take2(h + 1, last);
+            if (WGT) sw += take2(h + 1 + (AVG ? 2 : 0), last);
         }
         if (cnt) atomicAdd(&P.npairs[i], cnt);
         if (AVG && ssep != 0.0) {
@@ -432,7 +471,6 @@ __device__ __forceinline__ int hot_loop(int k, const int m, SumWarp<T, NA> &W, c
             }
         }
         if (DIRECT) {
-            const int cpy = lane & ((1 << K.copies_shift) - 1);
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 int kb = kfirst;
@@ -441,7 +479,7 @@ __device__ __forceinline__ int hot_loop(int k, const int m, SumWarp<T, NA> &W, c
                 int slot = kb;
                 // rpbin*(npibin+1) + |dz|*inv_dpi evaluated in T, then truncated (countpairs_rp_pi_kernels.c.src:249-256)
                 if (MODE == CFB_RPPI) slot = (int)((T)kb * K.npi_p1 + b[e] * K.inv_dpi);
-                if (acc[e]) atomicAdd(&K.h_np[(slot << K.copies_shift) + cpy], 1u);
+                if (acc[e]) atomicAdd(hword<1>(K, slot), 1u);
             }
             continue;
         }
@@ -496,8 +534,7 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
     unsigned *s_hist = (unsigned *)(smem_raw + off);
     const int ns = (int)P.nslots;
     const int cshift = P.sum_copies_shift;
-    const int hstride = ns << cshift;
-    const int hwords = hstride * (1 + (AVG ? 3 : 0) + (WGT ? 3 : 0));
+    const int hwords = (ns << cshift) * (1 + (AVG ? 2 : 0) + (WGT ? 2 : 0));
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < nedges; i += blockDim.x) {
@@ -517,10 +554,14 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
     SumConst<T> K;
     K.edges = s_edges;
     K.scale = s_scale;
-    K.h_np = s_hist;
-    K.h_sep = s_hist + hstride;
-    K.h_w = s_hist + (1 + (AVG ? 3 : 0)) * hstride;
-    K.hstride = hstride;
+    K.hist = s_hist;
+    K.cl = lane & ((1 << cshift) - 1);
+    K.norm_drains = P.sum_norm_drains;
+    K.nmu = P.nmu_bins;
+    K.nmu_p1_i = P.nmu_bins + 1;
+    // float estimate of the mu bin (drain): 4e-6 for the estimate itself; in float also the rounding of the reference's
+    // floating-point index sum sbin * (nmu + 1) + mu * inv_dmu (half an ulp at the slot count, taken twice over)
+    K.mu_tol_b = 4.0e-6f + (sizeof(T) == 4 ? 2.5e-7f * (float)ns : 0.0f);
     K.copies_shift = cshift;
     K.nedges = nedges;
     K.pimax = (T)P.pimax;
@@ -537,6 +578,7 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
     __syncthreads();
     K.e_lo = s_edges[0];
     K.e_hi = s_edges[nedges - 1];
+    K.fast_ok = (double)K.e_lo >= 1.0e-30 && (double)K.e_hi <= 1.0e30;
     K.sqr_max_sep = K.e_hi + K.sqr_pimax;
     const double sqr_max_sep_d = (double)K.sqr_max_sep;
 
@@ -877,7 +919,7 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
                             const int n = tail < 32 ? tail : 32;
                             drain<T, MODE, AVG, WGT, NA>(n, tail - n, W, bsel, K, E, jk, jl, lane);
                             tail -= n;
-                            if (++drains >= SUM_NORM_DRAINS) {
+                            if (++drains >= K.norm_drains) {
                                 flush_hist<MODE, AVG, WGT, T>(P, K, ns, lane, 32, false);
                                 drains = 0;
                             }
@@ -944,8 +986,8 @@ int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cuda
     CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     CK(cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const size_t fixed = sum_fixed_smem<T, WGT>(P.nedges);
-    const size_t per_copy = (size_t)P.nslots * 4 * (1 + (AVG ? 3 : 0) + (WGT ? 3 : 0));
-    // histogram copies: as many (1, 2, 4 or 8) as still leave three resident blocks per SM
+    const size_t per_copy = (size_t)P.nslots * 4 * (1 + (AVG ? 2 : 0) + (WGT ? 2 : 0));
+    // histogram copies: as many (1, 2, 4 or 8) as still leave SUM_MINB resident blocks per SM
     int want_blocks = SUM_MINB, max_shift = 3;
     if (const char *e = getenv("CORRFUNC_B200_SUM_BLOCKS")) want_blocks = atoi(e) > 0 ? atoi(e) : want_blocks;
     if (const char *e = getenv("CORRFUNC_B200_SUM_COPIES")) {
@@ -960,6 +1002,12 @@ int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cuda
     const size_t sm = fixed + (per_copy << shift);
     if (sm > (size_t)smem_blk) return -1;  // histogram too large for shared memory: the caller falls back
     P.sum_copies_shift = shift;
+    // a word takes at most warps x norm_drains x (32 / copies) adds between two normalisations: keep that below 2^16
+    {
+        const int lanes_per_copy = 32 >> (shift < 5 ? shift : 5);
+        int nd = 65536 / (SUM_WARPS * (lanes_per_copy > 0 ? lanes_per_copy : 1)) - 1;
+        P.sum_norm_drains = nd < SUM_NORM_DRAINS ? (nd > 1 ? nd : 1) : SUM_NORM_DRAINS;
+    }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SUM_WARPS * 32, sm));
