@@ -120,6 +120,11 @@ struct PairParams {
     int hist_in_smem;
     int sum_copies_shift;  // per-pair-sum kernel: log2 of the number of shared-memory histogram copies
     int sum_norm_drains;   // per-pair-sum kernel: drains of a warp between two normalisations of the block's histogram
+    int sum_cmask;           // copies - 1
+    unsigned sum_hstride_b, sum_hist_off;  // bytes from one histogram slot to the next; offset of the histogram in dynamic shared memory
+    float sum_inv_dmu_f;
+    int sum_kmin, sum_nkeys; // per-pair-sum kernel: separation-bin table (first float key, number of keys; 0 = no table)
+    double coord_max;      // largest |coordinate| a particle (with its periodic shift) can have: float-filter margins of the per-pair-sum kernel
 };
 
 // Multi-rank sharding is by primary CELL, never by tile: every rank sorts its own replica and the order of the

@@ -539,6 +539,11 @@ static int count_box_one(const cfb_binning *bin, const cfb_box_lattice *lat, cfb
         P.g.periodic[k] = lat->periodic[k];
         P.wrap[k] = lat->wrap[k] * scale;
         P.max_sep[k] = lat->max_sep[k];
+        {
+            const double hi_k = lat->lo[k] + (lat->inv[k] > 0 ? (double)lat->nmesh[k] / lat->inv[k] : 0.0);
+            const double cm = (fmax(fabs(lat->lo[k]), fabs(hi_k)) * (1.0 + 1e-6) + fabs(lat->wrap[k])) * scale;
+            if (k == 0 || cm > P.coord_max) P.coord_max = cm;
+        }
     }
     P.tile_cell = (const int *)c.set[0].tile_cell.p;
     P.tile_off = (const int *)c.set[0].tile_off.p;
@@ -826,6 +831,7 @@ extern "C" int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int
         const double cmax = bin->edges[bin->nedges - 1];
         P.max_sep[0] = sqrt(fmax(0.0, 2.0 * (1.0 - cmax)));
     }
+    P.coord_max = 1.0 + 1e-6;  // unit vectors
     P.tile_cell = (const int *)c.set[0].tile_cell.p;
     P.tile_off = (const int *)c.set[0].tile_off.p;
     P.ntiles = c.set[0].ntiles;

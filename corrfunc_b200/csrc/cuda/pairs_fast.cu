@@ -202,14 +202,9 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
         c[l] = 0u;
     }
     const u64 th_a = pk(8388608.0f, 8388608.0f), th_b = pk(-16777216.0f, -16777216.0f);
-    // pi cut (ZCUT): ONE loop body serves both cases -- a second set of bodies cost the wp kernel a third more code and,
-    // through the instruction cache, 40 % of its speed.  dirz (two reference cells): z2 > target_z = zpos - pimax of the
-    // reference's fast-forward, then the signed dz < pimax; same reference cell: -pimax < dz < pimax.  The test that does
-    // not apply compares against -inf.
-    float tz[PA];
+    float tz[PA];  // target_z = zpos - pimax of the reference's fast-forward (ZCUT == 2 only)
 #pragma unroll
-    for (int p = 0; p < PA; p++) tz[p] = dirz ? zq[p] - pimax : -CUDART_INF_F;
-    const float mpm = dirz ? -CUDART_INF_F : -pimax;
+    for (int p = 0; p < PA; p++) tz[p] = zq[p] - pimax;
     // The kernel holds one loop per (levels, primaries) variant and the warps of an SM run different ones:
     // unrolling them all 4x overflowed the instruction cache (measured: 26 "no instruction" stall cycles per
     // issued instruction, 5x slower).  Only the variants that carry ~95 % of the iterations (3 primaries per
@@ -284,8 +279,15 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
                     // -cos(theta) * 2^24 = chord^2 * 2^23 - 2^24 (countpairs_theta_mocks_kernels.c.src:1062-1066)
                     if (MODE == CFB_THETA) v2 = fma2(v2, th_a, th_b);
                 }
-                if (ZCUT) {
-                    // same reference cell (j after i in z order, dz >= 0): dz < pimax, here as |dz| < pimax.
+                if (ZCUT == 1) {  // same reference cell (j after i in z order, dz >= 0): dz < pimax, here as |dz| < pimax
+                    float v0, v1, z0, z1;
+                    upk(v2, v0, v1);
+                    upk(dz, z0, z1);
+                    v0 = fabsf(z0) < pimax ? v0 : CUDART_INF_F;
+                    v1 = fabsf(z1) < pimax ? v1 : CUDART_INF_F;
+                    v2 = pk(v0, v1);
+                }
+                if (ZCUT == 2) {
                     // two reference cells: the reference fast-forwards over the secondaries with z1 <= zpos - pimax
                     // (wp_kernels.c.src:139-142) and then masks with the SIGNED dz < pimax (:207-221).  A survivor
                     // whose dz rounds to exactly -pimax is therefore counted; |dz| < pimax would drop it.
@@ -293,8 +295,9 @@ __device__ __forceinline__ void chunk_f32(const float *sx, const float *sy, cons
                     upk(v2, v0, v1);
                     upk(dz, z0, z1);
                     upk(zs[h], s0, s1);
-                    v0 = (s0 > tz[p] && z0 > mpm && z0 < pimax) ? v0 : CUDART_INF_F;
-                    v1 = (s1 > tz[p] && z1 > mpm && z1 < pimax) ? v1 : CUDART_INF_F;
+                    const bool k0 = (s0 > tz[p]) & (z0 < pimax), k1 = (s1 > tz[p]) & (z1 < pimax);
+                    v0 = k0 ? v0 : CUDART_INF_F;
+                    v1 = k1 ? v1 : CUDART_INF_F;
                     v2 = pk(v0, v1);
                 }
                 // [v < E] is the sign bit of the rounded difference v - E (x - x = +0; NaN and +inf give
@@ -322,10 +325,9 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
     double E[NL];
 #pragma unroll
     for (int l = 0; l < NL; l++) E[l] = Es[l];
-    double tz[PA];  // see chunk_f32
+    double tz[PA];  // see chunk_f32 (ZCUT == 2 only)
 #pragma unroll
-    for (int p = 0; p < PA; p++) tz[p] = dirz ? zq[p] - pimax : -CUDART_INF;
-    const double mpm = dirz ? -CUDART_INF : -pimax;
+    for (int p = 0; p < PA; p++) tz[p] = zq[p] - pimax;
     // one secondary per iteration for the long bodies (many primaries x levels): same instruction-cache
     // consideration as in chunk_f32
     constexpr int SPI = (PA * NL >= FAST_F64_SPI1) ? 1 : 2;
@@ -352,7 +354,13 @@ __device__ __forceinline__ void chunk_f64(const double *sx, const double *sy, co
                     v = __fma_rn(dz, dz, __fma_rn(dy, dy, dx * dx));
                     if (MODE == CFB_THETA) v = __fma_rn(v, 0.5, -1.0);  // -(1 - chord^2/2), exactly
                 }
-                if (ZCUT) v = (zs[h] > tz[p] && dz > mpm && dz < pimax) ? v : CUDART_INF;
+                // masked pairs get the high word of +inf (with the old low word that is +inf or a NaN: never below an edge):
+                // one select instead of two
+                if (ZCUT == 1) v = __hiloint2double(fabs(dz) < pimax ? __double2hiint(v) : 0x7ff00000, __double2loint(v));
+                if (ZCUT == 2) {  // see chunk_f32
+                    const bool kz = (zs[h] > tz[p]) & (dz < pimax);
+                    v = __hiloint2double(kz ? __double2hiint(v) : 0x7ff00000, __double2loint(v));
+                }
 #pragma unroll
                 for (int l = 0; l < NL; l++) cnt[l] += (v < E[l]) ? 1 : 0;
             }
@@ -797,7 +805,10 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
 #pragma unroll
                         for (int l = 0; l < FAST_LMAX; l++) cnt[l] = 0;
                         if (MODE == CFB_WP && (jb.meta & JOB_ZCUT)) {
-                            chunk_dispatch<T, MODE, 1>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, (jb.meta & JOB_DIRZ) != 0, cnt);
+                            if (jb.meta & JOB_DIRZ)
+                                chunk_dispatch<T, MODE, 2>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, true, cnt);
+                            else
+                                chunk_dispatch<T, MODE, 1>(nlp, pa, sx, sy, sz, m4, xq, yq, zq, Es, pimax, false, cnt);
                         } else
                         {
                             bool done = false;

@@ -40,7 +40,7 @@
 #define SUM_PA 2                // primaries per lane
 #define SUM_TILE (32 * SUM_PA)  // primaries per tile; divides CFB_TILE
 #ifndef SUM_CH
-#define SUM_CH 64               // secondaries per staged chunk
+#define SUM_CH 32               // secondaries per staged chunk (64 measured 10 % slower on config 3: one resident block fewer)
 #endif
 #ifndef SUM_QCAP
 #define SUM_QCAP 80             // job queue entries per warp
@@ -48,9 +48,12 @@
 #ifndef SUM_MINB
 #define SUM_MINB 5               // resident blocks per SM the kernel is compiled for (register budget): the kernel is latency bound, measured 25 % faster at 5 blocks than at 4
 #endif
-#define SUM_RING 352            // accepted-pair stack per warp (16-bit entries): the hot loop runs until fewer than 128 slots
-                                // (one iteration's worth) are free, then the full batches are drained back to back
+#ifndef SUM_QL
+#define SUM_QL 32               // accepted pairs a lane can queue before the warp compacts and drains (16: 3 % slower on config 3)
+#endif
 #define SUM_MAX_EDGES 256
+#define SUM_KSH 19              // separation-bin table: key = float bits >> 19 (exponent + 4 mantissa bits: 16 keys per octave)
+#define SUM_MAX_KEYS 2048       // more keys than this (edges spanning > 128 octaves in the squared separation): binary search
 
 typedef unsigned long long u64;
 
@@ -126,12 +129,23 @@ __device__ __forceinline__ unsigned fdiv(unsigned n, unsigned magic) { return ma
 #define SUM_NORM_DRAINS 512
 #define SUM_MAGIC 6755399441055744.0  // 1.5 * 2^52
 #define SUM_QBITS 46
-__device__ __forceinline__ void add2(unsigned *w, const double m)  // m = fma(value, scale, SUM_MAGIC)
+// shared-window addresses (32 bit) and explicit .shared atomics: one address register, immediate word offsets
+__device__ __forceinline__ void sh_red_add(const unsigned addr, const unsigned v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned sh_atom_add(const unsigned addr, const unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void add2(const unsigned addr, const double m)  // m = fma(value, scale, SUM_MAGIC)
 {
     const unsigned lo = (unsigned)__double2loint(m);
     const int hi = __double2hiint(m) - 0x43380000;  // floor(q / 2^32)
-    const unsigned old = atomicAdd(w, lo);
-    atomicAdd(w + 1, (unsigned)hi + (old > ~lo ? 1u : 0u));
+    const unsigned old = sh_atom_add(addr, lo);
+    sh_red_add(addr + 4, (unsigned)hi + (old > ~lo ? 1u : 0u));
 }
 // what the high word of one sum holds (exchanged with zero); last: also the low word (nobody adds any more)
 __device__ __forceinline__ double take2(unsigned *w, const bool last)
@@ -162,12 +176,15 @@ struct SumJob {
 template <typename T, int NA>
 struct SumWarp {
     alignas(16) T buf[2][NA][SUM_CH];
+    // double runs: float copies of the current chunk's positions -- the hot loop is a conservative FLOAT filter there
+    alignas(16) float fbuf[sizeof(T) == 8 ? 3 : 1][sizeof(T) == 8 ? SUM_CH : 4];
     alignas(16) T prim[NA][SUM_TILE];  // the tile's primaries with the current wrap applied (+ weights): gathered by the drain
-    // accepted-pair stack: (primary << 8 | secondary) of every pair that passed the range test.  Two bytes per entry --
-    // the drain recomputes the separation from the positions, which costs it 13 instructions and buys a third more
-    // resident warps than a stack that carries the values.  The last 32 entries are a dump for the lanes that have nothing
-    // to push (branch-free stores).
-    unsigned short ring_i[SUM_RING + 32];
+    // accepted pairs, first per LANE (one byte each: secondary | primary row << 6; entry i of lane l at [i][l], so a push is
+    // one predicated byte store and one add, no ballot, no prefix count), then -- when a lane's queue is full or the chunk
+    // ends -- compacted into `ring` (lane << 8 | entry) by one warp scan over the queue lengths: the drain takes 32
+    // consecutive ring entries, all lanes busy whatever the spread of the queue lengths was.
+    unsigned char laneq[SUM_QL][32];
+    unsigned short ring[32 * SUM_QL + 64];  // + 64: the last drain reads full rows (idle lanes decode to valid indices)
     SumJob q[SUM_QCAP];
 };
 
@@ -178,6 +195,10 @@ struct SumConst {
     const double *scale;   // shared: double[nedges], fixed-point scale of the separation sum per bin
     unsigned *hist;        // shared histogram [slot][copy][word]: word 0 count, then (low, high) of the separation sum and
                            // of the weight sum; addressed through hword()
+    unsigned hl;           // shared-window address of this lane's copy of slot 0
+    const unsigned short *ktab;  // separation-bin table (see drain), nkeys entries: lowest | highest possible bin << 8
+    int kmin, nkeys;       // first key, number of keys (0: no table)
+    unsigned hstride_b;    // bytes from one slot to the next
     int copies_shift;      // log2(copies)
     int cl;                // this lane's copy
     int nedges;
@@ -192,9 +213,9 @@ struct SumConst {
 // first word of (slot, this lane's copy); NP words per (slot, copy).  NP is odd (1, 3 or 5), so the multiplication permutes
 // the banks: two lanes meet in a bank only if (slot * copies + copy) agrees modulo 32 -- never for different copies of 8.
 template <int NP, typename T>
-__device__ __forceinline__ unsigned *hword(const SumConst<T> &K, const int slot)
+__device__ __forceinline__ unsigned hword(const SumConst<T> &K, const int slot)
 {
-    return K.hist + (unsigned)(((slot << K.copies_shift) + K.cl) * NP);
+    return K.hl + (unsigned)slot * K.hstride_b;
 }
 
 // true when value v lies at or above edge e in the binning order (theta: edges are cosines, decreasing)
@@ -277,9 +298,23 @@ __device__ __forceinline__ double sep_sqrt(const double v, const float rs)
     return __fma_rn(e, 0.5 * y, r0);
 }
 
+// Separation bin of a value with MANY candidate edges (a pair of close cells spans most of a logarithmic binning, and
+// those jobs hold a large share of all accepted pairs; ncu: the binary search was a quarter of the drain's instructions).
+// The float image of the value, cut to its exponent and four mantissa bits, indexes a small table that holds the lowest
+// and the highest bin a value with that key can have (built with one float ulp of slack on both sides, so the rounding of
+// the conversion cannot leave the range): for any reasonable binning the two differ by at most one, and ONE exact compare
+// against the edge between them decides.  The bin is the number of edges at or below the value, exactly as the level
+// count / binary search give it.
 // ------------------------------------------------------------------------------------------------
-// The drain: n (<= 32) accepted pairs from the top of the stack, one per lane.
-// E[l], l < 4: the job's level edges in registers (padded so that the compare is false); nl > 4: binary search.
+// The drain: n (<= 32 * SUM_NB) queued pairs, ring entries head .. head + n - 1, SUM_NB per lane.  Every pair is
+// evaluated again with the statistic's own arithmetic and its exact range test (in double runs the hot loop was only a
+// float filter).  Separation bin = the number of edges at or below the value: two compares against the job's level
+// edges when the job has at most two levels; otherwise a FLOAT-KEY TABLE (a pair of close cells spans most of a
+// logarithmic binning, and those jobs hold a large share of all accepted pairs -- ncu: the binary search was a quarter
+// of the drain's instructions).  The float image of the value, cut to its exponent and four mantissa bits, indexes a
+// table of the lowest and the highest bin a value with that key can have (built with one float ulp of slack on both
+// sides, so the rounding of the conversion cannot leave the range): for any reasonable binning the two differ by at most
+// one, and ONE exact compare against the edge between them decides (else a binary search between the two).
 //
 // DDsmu: the reference evaluates slot = (int)(sbin * (nmu + 1) + sqrt(dz^2 / s^2) * inv_dmu) with a true divide and an
 // IEEE square root (countpairs_s_mu_kernels.c.src:228-277).  Here the mu bin is first located in FLOAT arithmetic with
@@ -289,125 +324,197 @@ __device__ __forceinline__ double sep_sqrt(const double v, const float rs)
 // ulp of the slot count, is added -- its integer part IS the reference's mu bin (or, at nmu and above, the pair fails
 // the reference's dz^2 < s^2 mu_max^2).  Otherwise (about 1e-4 of the batches) the whole batch takes the reference's
 // arithmetic.
+#ifndef SUM_NB
+#define SUM_NB 2  // batches of 32 pairs a drain call works on at once: the per-pair code is one long dependent chain
+                  // (gather -> 6 DP -> conversions -> MUFU -> table -> compare -> Newton step -> atomics), two of them in
+                  // flight per lane hide each other's latencies
+#endif
 template <typename T, int MODE, bool AVG, bool WGT, int NA>
 __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA> &W, const int bsel, const SumConst<T> &K,
-                                      const T (&E)[8], const int kfirst, const int nl, const int lane)
+                                      const bool dirz, const T (&E)[4], const int kfirst, const int nl, const int lane)
 {
     constexpr int NP = 1 + (AVG ? 2 : 0) + (WGT ? 2 : 0);
-    __syncwarp();
-    bool ok = lane < n;
-    const unsigned idx = W.ring_i[head + lane];  // entries head .. head + n - 1 (the top of the stack)
-    const int pidx = (idx >> 8) & (SUM_TILE - 1), j = idx & (SUM_CH - 1);
-    // the pair again, with the arithmetic of the hot loop (same function, same operands)
-    const T x1 = W.prim[0][pidx], y1 = W.prim[1][pidx], z1 = W.prim[2][pidx];
-    const T x2 = W.buf[bsel][0][j], y2 = W.buf[bsel][1][j], z2 = W.buf[bsel][2][j];
-    T a, b;
-    eval_pair<T, MODE, false>(x2, y2, z2, x1, y1, z1, (T)0, K, false, a, b);
-
-    T v = a;      // the quantity that is binned
-    T f2 = 0;     // second-dimension coordinate in bins (pi * inv_dpi or mu * inv_dmu), reference arithmetic
-    int mb = 0;   // DDsmu: mu bin from the float estimate
-    bool exact2 = true;  // warp-uniform: the second-dimension bin comes from f2
-    float rs = 0.0f;     // ~ 1 / sqrt(v) in float, when already known
-    bool have_rs = false;
-    if (MODE == CFB_RPPI) {
-        f2 = b * K.inv_dpi;
-    } else if (MODE == CFB_SMU) {
-        bool amb = ok;
-        if (K.fast_ok) {
-            const float af = (float)a, bf = (float)b;
-            rs = rsqrt_apx(af);
-            have_rs = true;
-            const float y = sqrt_apx(bf) * rs * K.inv_dmu_f;
-            mb = __float2int_rz(y);
-            const float fr = y - (float)mb;
-            const float tol = __fmaf_rn(4.0e-6f, y, K.mu_tol_b);  // mu_tol_b includes the 4e-6 * 1
-            amb = ok && !(fr > tol && fr < 1.0f - tol);
-        }
-        exact2 = __any_sync(0xffffffffu, amb);
-        if (exact2) {
-            // keep if dz^2 < s^2 mu_max^2; sqr_mu = dz^2 / s^2 (true divide, fast_divide_and_NR_steps == 0), mu = sqrt
-            // (countpairs_s_mu_kernels.c.src:216-277)
-            if (!(b < a * K.sqr_mumax)) ok = false;
-            f2 = sqrt_t<T>(divi_t<T>(b, a)) * K.inv_dmu;
-        } else if (mb >= K.nmu)
-            ok = false;
-    } else if (MODE == CFB_RPPI_MOCKS || MODE == CFB_SMU_MOCKS) {
-        // line of sight = pair midpoint (countpairs_rp_pi_mocks_kernels.c.src:200-290, countpairs_s_mu_mocks_kernels.c.src:196-290)
-        const T dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
-        const T parx = x2 + x1, pary = y2 + y1, parz = z2 + z1;
-        const T term1 = parx * dx, term2 = pary * dy;
-        const T s_dot_l = fma_t<T>(parz, dz, term1 + term2);
-        const T sqr_s_dot_l = s_dot_l * s_dot_l;
-        const T sqr_norm_l = fma_t<T>(parx, parx, fma_t<T>(pary, pary, parz * parz));
-        if (MODE == CFB_RPPI_MOCKS) {
-            // a = sqr_sep, already below sqr_max_sep
-            if (!(sqr_s_dot_l < K.sqr_pimax * sqr_norm_l)) ok = false;
-            const T sqr_Dpar = divi_t<T>(sqr_s_dot_l, sqr_norm_l);
-            const T sqr_Dperp = a - sqr_Dpar;
-            if (!(sqr_Dpar < K.sqr_pimax && sqr_Dperp < K.e_hi && sqr_Dperp >= K.e_lo)) ok = false;
-            v = sqr_Dperp;
-            f2 = sqrt_t<T>(sqr_Dpar) * K.inv_dpi;
-        } else {
-            // a = s2, already within [e_lo, e_hi)
-            const T sqr_mu = divi_t<T>(sqr_s_dot_l, sqr_norm_l * a);
-            if (!(sqr_mu < K.sqr_mumax)) ok = false;
-            f2 = sqrt_t<T>(sqr_mu) * K.inv_dmu;
+    constexpr int NB = SUM_NB;
+    bool ok[NB];
+    int pidx[NB], j[NB];
+    T a[NB], b[NB], v[NB], f2[NB];
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+        ok[u] = 32 * u + lane < n;
+        const unsigned idx = W.ring[head + 32 * u + lane];
+        pidx[u] = ((idx >> 8) & 31) | ((idx & 64) >> 1);
+        j[u] = idx & (SUM_CH - 1) & 63;
+    }
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+        const T x1 = W.prim[0][pidx[u]], y1 = W.prim[1][pidx[u]], z1 = W.prim[2][pidx[u]];
+        const T x2 = W.buf[bsel][0][j[u]], y2 = W.buf[bsel][1][j[u]], z2 = W.buf[bsel][2][j[u]];
+        // float runs: the hot loop applied this very test; double runs: it applied a float filter that passes a superset
+        if (!eval_pair<T, MODE, true>(x2, y2, z2, x1, y1, z1, z1 - K.pimax, K, dirz, a[u], b[u])) ok[u] = false;
+        v[u] = a[u];  // the quantity that is binned
+        f2[u] = 0;    // second-dimension coordinate in bins (pi * inv_dpi or mu * inv_dmu), reference arithmetic
+        if (MODE == CFB_RPPI) {
+            f2[u] = b[u] * K.inv_dpi;
+        } else if (MODE == CFB_RPPI_MOCKS || MODE == CFB_SMU_MOCKS) {
+            // line of sight = pair midpoint (countpairs_rp_pi_mocks_kernels.c.src:200-290, countpairs_s_mu_mocks_kernels.c.src:196-290)
+            const T dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+            const T parx = x2 + x1, pary = y2 + y1, parz = z2 + z1;
+            const T term1 = parx * dx, term2 = pary * dy;
+            const T s_dot_l = fma_t<T>(parz, dz, term1 + term2);
+            const T sqr_s_dot_l = s_dot_l * s_dot_l;
+            const T sqr_norm_l = fma_t<T>(parx, parx, fma_t<T>(pary, pary, parz * parz));
+            if (MODE == CFB_RPPI_MOCKS) {
+                // a = sqr_sep, already below sqr_max_sep
+                if (!(sqr_s_dot_l < K.sqr_pimax * sqr_norm_l)) ok[u] = false;
+                const T sqr_Dpar = divi_t<T>(sqr_s_dot_l, sqr_norm_l);
+                const T sqr_Dperp = a[u] - sqr_Dpar;
+                if (!(sqr_Dpar < K.sqr_pimax && sqr_Dperp < K.e_hi && sqr_Dperp >= K.e_lo)) ok[u] = false;
+                v[u] = sqr_Dperp;
+                f2[u] = sqrt_t<T>(sqr_Dpar) * K.inv_dpi;
+            } else {
+                // a = s2, already within [e_lo, e_hi)
+                const T sqr_mu = divi_t<T>(sqr_s_dot_l, sqr_norm_l * a[u]);
+                if (!(sqr_mu < K.sqr_mumax)) ok[u] = false;
+                f2[u] = sqrt_t<T>(sqr_mu) * K.inv_dmu;
+            }
         }
     }
-    // separation bin: kfirst + the number of levels at or below the value
-    int kb = kfirst;
+    // separation bin: kfirst + the number of levels at or below the value (E beyond the job's levels: never reached)
+    int kb[NB];
+    float vf[NB];
+    bool have_vf = false;
     if (nl <= 2) {
 #pragma unroll
-        for (int l = 0; l < 2; l++) kb += at_or_above<T, MODE>(v, E[l]) ? 1 : 0;
-    } else if (nl <= 4) {
-#pragma unroll
-        for (int l = 0; l < 4; l++) kb += at_or_above<T, MODE>(v, E[l]) ? 1 : 0;
-    } else {
-        int lo = kfirst, hi = kfirst + nl;  // first edge in [lo, hi) the value is not at or above
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (at_or_above<T, MODE>(v, K.edges[mid])) lo = mid + 1; else hi = mid;
+        for (int u = 0; u < NB; u++) {
+            kb[u] = kfirst + (at_or_above<T, MODE>(v[u], E[0]) ? 1 : 0) + (at_or_above<T, MODE>(v[u], E[1]) ? 1 : 0);
+            vf[u] = 0.0f;
         }
-        kb = lo;
+    } else if (MODE != CFB_THETA && K.nkeys > 0) {
+        // float-key table (see drain): lowest and highest possible bin, one exact compare decides between neighbours
+        have_vf = true;
+        int lo[NB], hi[NB];
+        bool wide = false;
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            vf[u] = (float)v[u];
+            int key = (int)(__float_as_uint(vf[u]) >> SUM_KSH) - K.kmin;
+            key = max(0, min(key, K.nkeys - 1));
+            const unsigned lh = K.ktab[key];
+            lo[u] = lh & 255, hi[u] = lh >> 8;
+            wide = wide || hi[u] > lo[u] + 1;
+        }
+        if (__any_sync(0xffffffffu, wide)) {
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                int l = lo[u], h = hi[u];
+                while (l < h) {  // first edge in [l, h) the value is not at or above
+                    const int mid = (l + h) >> 1;
+                    if (v[u] >= K.edges[mid]) l = mid + 1; else h = mid;
+                }
+                kb[u] = l;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NB; u++) kb[u] = lo[u] + ((hi[u] > lo[u] && v[u] >= K.edges[lo[u]]) ? 1 : 0);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            vf[u] = 0.0f;
+            if (nl <= 4) {
+                kb[u] = kfirst;
+#pragma unroll
+                for (int l = 0; l < 4; l++) kb[u] += at_or_above<T, MODE>(v[u], E[l]) ? 1 : 0;
+            } else {
+                int lo = kfirst, hi = kfirst + nl;  // first edge in [lo, hi) the value is not at or above
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (at_or_above<T, MODE>(v[u], K.edges[mid])) lo = mid + 1; else hi = mid;
+                }
+                kb[u] = lo;
+            }
+        }
     }
-    int slot = kb;
+    int slot[NB];
+    float rs[NB];        // ~ 1 / sqrt(v) in float, when already known
+    bool have_rs = false;
+#pragma unroll
+    for (int u = 0; u < NB; u++) slot[u] = kb[u], rs[u] = 0.0f;
     if (MODE == CFB_RPPI || MODE == CFB_RPPI_MOCKS) {
         // rpbin*(npibin+1) + pi*inv_dpi evaluated in T, then truncated (countpairs_rp_pi_kernels.c.src:249-256)
-        slot = (int)((T)kb * K.npi_p1 + f2);
+#pragma unroll
+        for (int u = 0; u < NB; u++) slot[u] = (int)((T)kb[u] * K.npi_p1 + f2[u]);
     } else if (MODE == CFB_SMU_MOCKS) {
-        slot = (int)((T)kb * K.nmu_p1 + f2);  // countpairs_s_mu_mocks_kernels.c.src
+#pragma unroll
+        for (int u = 0; u < NB; u++) slot[u] = (int)((T)kb[u] * K.nmu_p1 + f2[u]);  // countpairs_s_mu_mocks_kernels.c.src
     } else if (MODE == CFB_SMU) {
-        if (exact2) slot = (int)((T)kb * K.nmu_p1 + f2);  // countpairs_s_mu_kernels.c.src:269-277
-        else slot = kb * K.nmu_p1_i + mb;
-    }
-    if (!ok) slot = 0, kb = kfirst;  // idle lanes: any valid address
-    double msep = 0.0, mw = 0.0;
-    if (AVG) {
-        T sep;
-        if (MODE == CFB_THETA) {
-            const T cc = v >= (T)1.0 ? (T)1.0 : v;
-            const T th = K.fast_acos ? fast_acos_t<T>(cc) : (T)acos(cc);
-            sep = (T)(th * (T)57.29577951308232087679815481410517);
-        } else if (sizeof(T) == 8 && !K.fast_ok) {
-            sep = sqrt_t<T>(v);
-        } else {
-            if (sizeof(T) == 8 && !have_rs) rs = rsqrt_apx((float)v);
-            sep = sep_sqrt(v, rs);
+        bool amb = false;
+        int mb[NB];
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            mb[u] = 0;
+            if (K.fast_ok) {
+                const float af = have_vf ? vf[u] : (float)a[u], bf = (float)b[u];  // DDsmu bins a itself
+                rs[u] = rsqrt_apx(af);
+                const float y = sqrt_apx(bf) * rs[u] * K.inv_dmu_f;
+                mb[u] = __float2int_rz(y);
+                const float fr = y - (float)mb[u];
+                const float tol = __fmaf_rn(4.0e-6f, y, K.mu_tol_b);  // mu_tol_b includes the 4e-6 * 1
+                amb = amb || (ok[u] && !(fr > tol && fr < 1.0f - tol));
+            } else
+                amb = amb || ok[u];
         }
-        msep = __fma_rn((double)sep, K.scale[kb], SUM_MAGIC);
+        have_rs = K.fast_ok;
+        if (__any_sync(0xffffffffu, amb)) {
+            // keep if dz^2 < s^2 mu_max^2; sqr_mu = dz^2 / s^2 (true divide, fast_divide_and_NR_steps == 0), mu = sqrt;
+            // slot = (int)(sbin * (nmu + 1) + mu * inv_dmu) in T (countpairs_s_mu_kernels.c.src:216-277)
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                if (!(b[u] < a[u] * K.sqr_mumax)) ok[u] = false;
+                const T f = sqrt_t<T>(divi_t<T>(b[u], a[u])) * K.inv_dmu;
+                slot[u] = (int)((T)kb[u] * K.nmu_p1 + f);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                if (mb[u] >= K.nmu) ok[u] = false;
+                slot[u] = kb[u] * K.nmu_p1_i + mb[u];
+            }
+        }
     }
-    if (WGT) {
-        const T w1 = W.prim[NA - 1][pidx], w2 = W.buf[bsel][NA - 1][j];
-        mw = __fma_rn((double)(T)(w1 * w2), K.w_scale, SUM_MAGIC);  // pair_product, weight_functions.h.src:71-91
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+        if (!ok[u]) slot[u] = 0, kb[u] = kfirst;  // idle lanes: any valid address
+        double msep = 0.0, mw = 0.0;
+        if (AVG) {
+            T sep;
+            if (MODE == CFB_THETA) {
+                const T cc = v[u] >= (T)1.0 ? (T)1.0 : v[u];
+                const T th = K.fast_acos ? fast_acos_t<T>(cc) : (T)acos(cc);
+                sep = (T)(th * (T)57.29577951308232087679815481410517);
+            } else if (sizeof(T) == 8 && !K.fast_ok) {
+                sep = sqrt_t<T>(v[u]);
+            } else {
+                if (sizeof(T) == 8 && !have_rs) rs[u] = rsqrt_apx(have_vf ? vf[u] : (float)v[u]);
+                sep = sep_sqrt(v[u], rs[u]);
+            }
+            msep = __fma_rn((double)sep, K.scale[kb[u]], SUM_MAGIC);
+        }
+        if (WGT) {
+            const T w1 = W.prim[NA - 1][pidx[u]], w2 = W.buf[bsel][NA - 1][j[u]];
+            mw = __fma_rn((double)(T)(w1 * w2), K.w_scale, SUM_MAGIC);  // pair_product, weight_functions.h.src:71-91
+        }
+#ifdef SUM_ABL_NOATOM  // ablation (timing experiments only, results wrong): no histogram update
+        if (ok[u] && slot[u] == -12345) {
+#else
+        if (ok[u]) {
+#endif
+            const unsigned h = hword<NP>(K, slot[u]);
+            sh_red_add(h, 1u);
+            if (AVG) add2(h + 4, msep);
+            if (WGT) add2(h + 4 + (AVG ? 8 : 0), mw);
+        }
     }
-    if (ok) {
-        unsigned *h = hword<NP>(K, slot);
-        atomicAdd(h, 1u);
-        if (AVG) add2(h + 1, msep);
-        if (WGT) add2(h + 1 + (AVG ? 2 : 0), mw);
-    }
-    __syncwarp();
 }
 
 // Moves what the wrapping-prone words of the block's histogram hold into the global histogram (any warp, any time).
@@ -438,28 +545,115 @@ __device__ __forceinline__ void flush_hist(const PairParams &P, const SumConst<T
     }
 }
 
-// The hot loop: secondaries k .. m-1 of the staged chunk against the lane's PA primaries, until the chunk ends or the
-// ring holds a full drain.  Four independent separations per lane and iteration (2 secondaries x 2 primaries, or
-// 4 x 1): their FP chains overlap, and one compaction serves the four ballots.  Returns the next secondary.
-// DIRECT (count-only 1-D statistics and DDrppi, jobs with at most 8 levels): no compaction at all -- every lane
-// finishes its own pairs (level count, slot) and only the histogram update is predicated.  Without per-pair sums that is
-// fewer instructions than pushing, popping and binning 0.3 accepted pairs per separation.
-template <typename T, int MODE, bool WGT, int NA, int PA, bool TRI, bool NEEDLO, int DIRECT /* 0 | levels in registers */>
-__device__ __forceinline__ int hot_loop(int k, const int m, SumWarp<T, NA> &W, const int bsel, const T (&xq)[SUM_PA],
-                                        const T (&yq)[SUM_PA], const T (&zq)[SUM_PA], const SumConst<T> &K,
-                                        const bool dirz, const int c0, const int lane, int &tail, const T (&E)[8],
-                                        const int kfirst)
+// Float thresholds of the double runs' filter (see hot_loop): every pair the statistic accepts passes.
+struct SumFilt {
+    float hi, lo, pimax;
+};
+// bound on |v_float - v| for v = squared separation sqrt(e2)^2 computed in float from coordinates of magnitude <= cm:
+// ed = 2^-21 cm covers the rounding of both coordinates and of the difference twice over; three more roundings in the sum
+__device__ __forceinline__ double filt_margin(const double e2, const double ed)
+{
+    return 3.47 * ed * sqrt(fmax(e2, 0.0)) + 3.0 * ed * ed + 5.0e-7 * e2;
+}
+template <int MODE, bool NEEDLO>
+__device__ __forceinline__ bool filter_pair(const float x2, const float y2, const float z2, const float x1, const float y1,
+                                            const float z1, const SumFilt &F)
+{
+    const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+    bool acc;
+    if (MODE == CFB_WP || MODE == CFB_RPPI) {
+        const float v = __fmaf_rn(dy, dy, dx * dx);
+        acc = v < F.hi && fabsf(dz) < F.pimax;
+        if (NEEDLO) acc = acc && v >= F.lo;
+    } else {
+        // DD / DDsmu: s^2; theta: chord^2 (1 - chord^2 / 2 > cos(theta_max)); mocks: s^2 (3-D)
+        const float v = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+        acc = v < F.hi;
+        if ((NEEDLO && MODE != CFB_RPPI_MOCKS) || MODE == CFB_SMU_MOCKS) acc = acc && v >= F.lo;
+    }
+    return acc;
+}
+
+// The hot loop: secondaries k .. m-1 of the staged chunk against the lane's PA primaries, until the chunk ends or some
+// lane's queue may overflow in the next iteration.  It only decides WHICH pairs go on -- in float runs with the
+// statistic's own arithmetic and range test (same subtraction order, same FMA association), in double runs with a
+// conservative FLOAT filter (float copies of the positions, thresholds widened by a bound on the float error): the FP32
+// pipe runs at twice the FP64 rate with half the latency, the loop needs neither the double primaries nor the level edges
+// in registers, and the drain evaluates every queued pair exactly anyway.  Four independent separations per lane and
+// iteration; a queued pair costs one predicated byte store and one add.  Returns the next secondary.
+template <typename T, int MODE, int PA, bool TRI, bool NEEDLO>
+__device__ __forceinline__ int hot_loop(int k, const int m, const float *sx, const float *sy, const float *sz,
+                                        const float (&xh)[SUM_PA], const float (&yh)[SUM_PA], const float (&zh)[SUM_PA],
+                                        const SumConst<T> &K, const SumFilt &F, const bool dirz, const int c0,
+                                        const int lane, unsigned &qaddr, const unsigned qlimit)
+{
+    constexpr int NS = 4 / PA;  // secondaries per iteration
+    float tz[PA];
+#pragma unroll
+    for (int p = 0; p < PA; p++) tz[p] = zh[p] - (float)K.pimax;  // target of the reference's fast-forward over z (wp, DDrppi)
+    for (; k < m; k += NS) {
+        float x2[NS], y2[NS], z2[NS];
+        if constexpr (NS == 4) {
+            const float4 X = *reinterpret_cast<const float4 *>(sx + k), Y = *reinterpret_cast<const float4 *>(sy + k),
+                         Z = *reinterpret_cast<const float4 *>(sz + k);
+            x2[0] = X.x, x2[1] = X.y, x2[2] = X.z, x2[3] = X.w;
+            y2[0] = Y.x, y2[1] = Y.y, y2[2] = Y.z, y2[3] = Y.w;
+            z2[0] = Z.x, z2[1] = Z.y, z2[2] = Z.z, z2[3] = Z.w;
+        } else {
+            const float2 X = *reinterpret_cast<const float2 *>(sx + k), Y = *reinterpret_cast<const float2 *>(sy + k),
+                         Z = *reinterpret_cast<const float2 *>(sz + k);
+            x2[0] = X.x, x2[1] = X.y, y2[0] = Y.x, y2[1] = Y.y, z2[0] = Z.x, z2[1] = Z.y;
+        }
+        bool acc[4];
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+#pragma unroll
+            for (int p = 0; p < PA; p++) {
+                const int e = s * PA + p;
+                if constexpr (sizeof(T) == 4) {
+                    float v, b;
+                    acc[e] = eval_pair<float, MODE, NEEDLO>(x2[s], y2[s], z2[s], xh[p], yh[p], zh[p], tz[p], K, dirz, v, b);
+                } else
+                    acc[e] = filter_pair<MODE, NEEDLO>(x2[s], y2[s], z2[s], xh[p], yh[p], zh[p], F);
+                if (TRI) acc[e] = acc[e] && (c0 + k + s > lane + 32 * p);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+#pragma unroll
+            for (int p = 0; p < PA; p++) {
+                if (acc[s * PA + p]) {
+                    // one address register (a shared-window address), one predicated store, one predicated add
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(qaddr), "r"((k + s) | (p << 6)) : "memory");
+                    qaddr += 32;
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, qaddr > qlimit)) {
+            k += NS;
+            break;
+        }
+    }
+    return k;
+}
+
+// The direct loop (count-only 1-D statistics and DDrppi, jobs with at most 8 levels): no queue at all -- every lane
+// finishes its own pairs in the run's precision (level count, slot) and only the histogram update is predicated.
+// Without per-pair sums that is fewer instructions than queueing and re-evaluating 0.3 accepted pairs per separation.
+template <typename T, int MODE, int NA, int PA, bool TRI, bool NEEDLO, int DIRECT /* levels in registers */>
+__device__ __forceinline__ void direct_loop(const int m, SumWarp<T, NA> &W, const int bsel, const T (&xq)[SUM_PA],
+                                            const T (&yq)[SUM_PA], const T (&zq)[SUM_PA], const SumConst<T> &K,
+                                            const bool dirz, const int c0, const int lane, const T (&E)[8],
+                                            const int kfirst)
 {
     const T *sx = W.buf[bsel][0], *sy = W.buf[bsel][1], *sz = W.buf[bsel][2];
-    const unsigned lt = (1u << lane) - 1u;
     constexpr int NS = 4 / PA;  // secondaries per iteration
     T tz[PA];
 #pragma unroll
     for (int p = 0; p < PA; p++) tz[p] = zq[p] - K.pimax;  // target of the reference's fast-forward over z (wp, DDrppi)
-    for (; k < m && tail <= SUM_RING - 128; k += NS) {
+    for (int k = 0; k < m; k += NS) {
         T v[4], b[4];
         bool acc[4];
-        unsigned msk[4];
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             const T x2 = sx[k + s], y2 = sy[k + s], z2 = sz[k + s];
@@ -470,34 +664,60 @@ __device__ __forceinline__ int hot_loop(int k, const int m, SumWarp<T, NA> &W, c
                 if (TRI) acc[e] = acc[e] && (c0 + k + s > lane + 32 * p);
             }
         }
-        if (DIRECT) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int kb = kfirst;
+        for (int e = 0; e < 4; e++) {
+            int kb = kfirst;
 #pragma unroll
-                for (int l = 0; l < DIRECT; l++) kb += at_or_above<T, MODE>(v[e], E[l]) ? 1 : 0;
-                int slot = kb;
-                // rpbin*(npibin+1) + |dz|*inv_dpi evaluated in T, then truncated (countpairs_rp_pi_kernels.c.src:249-256)
-                if (MODE == CFB_RPPI) slot = (int)((T)kb * K.npi_p1 + b[e] * K.inv_dpi);
-                if (acc[e]) atomicAdd(hword<1>(K, slot), 1u);
-            }
-            continue;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; e++) msk[e] = __ballot_sync(0xffffffffu, acc[e]);
-        if (msk[0] | msk[1] | msk[2] | msk[3]) {
-            int base = tail;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                // lanes with nothing to push store into the dump behind the stack: no divergent code in this loop
-                const int pos = acc[e] ? base + __popc(msk[e] & lt) : SUM_RING + lane;
-                W.ring_i[pos] = (unsigned short)(((lane + 32 * (e % PA)) << 8) | (k + e / PA));
-                base += __popc(msk[e]);
-            }
-            tail = base;
+            for (int l = 0; l < DIRECT; l++) kb += at_or_above<T, MODE>(v[e], E[l]) ? 1 : 0;
+            int slot = kb;
+            // rpbin*(npibin+1) + |dz|*inv_dpi evaluated in T, then truncated (countpairs_rp_pi_kernels.c.src:249-256)
+            if (MODE == CFB_RPPI) slot = (int)((T)kb * K.npi_p1 + b[e] * K.inv_dpi);
+            if (acc[e]) sh_red_add(hword<1>(K, slot), 1u);
         }
     }
-    return k;
+}
+
+// Compacts the lanes' queues into the ring (one warp scan) and drains it, 32 pairs at a time.
+template <typename T, int MODE, bool AVG, bool WGT, int NA>
+__device__ __forceinline__ void flush_queues(SumWarp<T, NA> &W, const int bsel, const SumConst<T> &K, const PairParams &P,
+                                             const int ns, const bool dirz, const int kfirst, const int nl, const int lane,
+                                             const unsigned char *qbase, const unsigned qaddr0, unsigned &qaddr, int &drains)
+{
+    const int c = (int)(qaddr - qaddr0) >> 5;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    const int excl = incl - c;
+    const int maxc = __reduce_max_sync(0xffffffffu, c);
+    const unsigned lb = (unsigned)lane << 8;
+    for (int i = 0; i < maxc; i++)
+        if (i < c) W.ring[excl + i] = (unsigned short)(lb | qbase[32 * i]);
+    qaddr = qaddr0;
+    __syncwarp();
+    T E[4];  // the job's first level edges; beyond nl: an edge no value is at or above
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        const T none = MODE == CFB_THETA ? (sizeof(T) == 4 ? (T)-CUDART_INF_F : (T)-CUDART_INF)
+                                         : (sizeof(T) == 4 ? (T)CUDART_INF_F : (T)CUDART_INF);
+        E[l] = l < nl ? K.edges[min(kfirst + l, K.nedges - 1)] : none;
+    }
+#ifdef SUM_ABL_NODRAIN  // ablation (timing experiments only, results wrong): queue and compact, never drain
+    if (total < 0)
+#endif
+    for (int head = 0; head < total; head += 32 * SUM_NB) {
+        drain<T, MODE, AVG, WGT, NA>(min(32 * SUM_NB, total - head), head, W, bsel, K, dirz, E, kfirst, nl, lane);
+    }
+    drains += (total + 31) >> 5;  // at most SUM_QL per flush: the launch leaves that much slack in norm_drains
+    if (drains >= K.norm_drains) {
+        flush_hist<MODE, AVG, WGT, T>(P, K, ns, lane, 32, false);
+        drains = 0;
+    }
+    __syncwarp();  // the ring and the queues are free again
 }
 
 template <typename T, int NA>
@@ -531,6 +751,8 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
     off += (size_t)nedges * 8;
     double *s_scale = (double *)(smem_raw + off);
     off += (size_t)nedges * 8;
+    unsigned short *s_ktab = (unsigned short *)(smem_raw + off);
+    off += ((size_t)P.sum_nkeys * 2 + 15) & ~(size_t)15;
     unsigned *s_hist = (unsigned *)(smem_raw + off);
     const int ns = (int)P.nslots;
     const int cshift = P.sum_copies_shift;
@@ -555,7 +777,12 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
     K.edges = s_edges;
     K.scale = s_scale;
     K.hist = s_hist;
-    K.cl = lane & ((1 << cshift) - 1);
+    K.ktab = s_ktab;
+    K.kmin = P.sum_kmin;
+    K.nkeys = P.sum_nkeys;
+    K.cl = lane & P.sum_cmask;
+    K.hl = smem_u32(smem_raw) + P.sum_hist_off + (unsigned)K.cl * (4 * (1 + (AVG ? 2 : 0) + (WGT ? 2 : 0)));
+    K.hstride_b = P.sum_hstride_b;
     K.norm_drains = P.sum_norm_drains;
     K.nmu = P.nmu_bins;
     K.nmu_p1_i = P.nmu_bins + 1;
@@ -568,7 +795,7 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
     K.sqr_pimax = K.pimax * K.pimax;  // rppi mocks (countpairs_rp_pi_mocks_kernels.c.src:56-57)
     K.inv_dpi = (T)P.inv_dpi;
     K.inv_dmu = (T)P.inv_dmu;
-    K.inv_dmu_f = (float)P.inv_dmu;
+    K.inv_dmu_f = P.sum_inv_dmu_f;
     K.sqr_mumax = (T)P.sqr_mumax;
     K.npi_p1 = (T)(P.npibin + 1);
     K.nmu_p1 = (T)(P.nmu_bins + 1);
@@ -576,10 +803,39 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
     K.w_scale = 1.0;
     if (WGT) K.w_scale = fixed_scale(P.wmax[0] * P.wmax[1]);
     __syncthreads();
+    if (MODE != CFB_THETA) {
+        // separation-bin table (see drain): for every key the number of edges at or below the smallest / the largest value
+        // whose float image can carry that key
+        for (int k = tid; k < P.sum_nkeys; k += blockDim.x) {
+            const double vlo = (double)__uint_as_float((unsigned)(k + P.sum_kmin) << SUM_KSH) * (1.0 - 2.4e-7);
+            const double vhi = (double)__uint_as_float((unsigned)(k + P.sum_kmin + 1) << SUM_KSH) * (1.0 + 2.4e-7);
+            int lo = 0, hi = 0;
+            for (int i = 0; i < nedges; i++) {
+                lo += s_edges_d[i] <= vlo ? 1 : 0;
+                hi += s_edges_d[i] <= vhi ? 1 : 0;
+            }
+            if (hi > nedges - 1) hi = nedges - 1;  // keeps every index derived from a bin inside the tables
+            if (lo > hi) lo = hi;
+            s_ktab[k] = (unsigned short)(lo | (hi << 8));
+        }
+        __syncthreads();
+    }
     K.e_lo = s_edges[0];
     K.e_hi = s_edges[nedges - 1];
     K.fast_ok = (double)K.e_lo >= 1.0e-30 && (double)K.e_hi <= 1.0e30;
     K.sqr_max_sep = K.e_hi + K.sqr_pimax;
+    // double runs: thresholds of the hot loop's float filter, widened by the bound on the float error (filt_margin)
+    SumFilt F;
+    F.hi = CUDART_INF_F, F.lo = -CUDART_INF_F, F.pimax = CUDART_INF_F;
+    if (sizeof(T) == 8) {
+        const double ed = 4.76837158203125e-07 * P.coord_max;  // 2^-21 x the largest |coordinate| (periodic shift included)
+        double hi2 = (double)K.e_hi, lo2 = (double)K.e_lo;
+        if (MODE == CFB_THETA) hi2 = 2.0 * (1.0 - (double)K.e_hi) + 1e-15, lo2 = 2.0 * (1.0 - (double)K.e_lo) - 1e-15;
+        if (MODE == CFB_RPPI_MOCKS) hi2 = (double)K.sqr_max_sep;
+        F.hi = __double2float_ru(hi2 + filt_margin(hi2, ed));
+        if (lo2 > 0.0 && sqrt(lo2) > 4.0 * ed) F.lo = __double2float_rd(lo2 - filt_margin(lo2, ed));
+        F.pimax = __double2float_ru((double)K.pimax * (1.0 + 1e-6) + 2.0 * ed);
+    }
     const double sqr_max_sep_d = (double)K.sqr_max_sep;
 
     u64 my_eval = 0, my_jobs = 0, my_levels = 0;
@@ -634,6 +890,7 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
         int qn = 0;
         int cur_code = 0;
         T xq[SUM_PA], yq[SUM_PA], zq[SUM_PA];
+        float xh[SUM_PA], yh[SUM_PA], zh[SUM_PA];  // what the hot loop works with: the primaries (float runs) / their float copies
         __syncwarp();  // the previous tile's drains are done with W.prim
 #pragma unroll
         for (int p = 0; p < SUM_PA; p++) {
@@ -642,6 +899,7 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
             xq[p] = ok ? pxg[i] : nanv;
             yq[p] = ok ? pyg[i] : nanv;
             zq[p] = ok ? pzg[i] : nanv;
+            xh[p] = (float)xq[p], yh[p] = (float)yq[p], zh[p] = (float)zq[p];
             W.prim[0][i] = xq[p];
             W.prim[1][i] = yq[p];
             W.prim[2][i] = zq[p];
@@ -869,6 +1127,7 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
                                 xq[p] = cx ? xr + ox : xr;
                                 yq[p] = cy ? yr + oy : yr;
                                 zq[p] = cz ? zr + oz : zr;
+                                xh[p] = (float)xq[p], yh[p] = (float)yq[p], zh[p] = (float)zq[p];
                                 W.prim[0][i] = xq[p];
                                 W.prim[1][i] = yq[p];
                                 W.prim[2][i] = zq[p];
@@ -879,52 +1138,68 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
                     const int jk = (jb.meta >> 6) & 255, jl = (jb.meta >> 14) & 511;
                     const bool dirz = (jb.meta & SJ_DIRZ) != 0;
                     const bool tri = (jb.meta & SJ_TRI) != 0, needlo = (jb.meta & SJ_NEEDLO) != 0;
-                    T E[8];  // the job's level edges; beyond nl: an edge no value is at or above
-#pragma unroll
-                    for (int l = 0; l < 8; l++) {
-                        const T none = MODE == CFB_THETA ? (sizeof(T) == 4 ? (T)-CUDART_INF_F : (T)-CUDART_INF)
-                                                         : (sizeof(T) == 4 ? (T)CUDART_INF_F : (T)CUDART_INF);
-                        E[l] = l < jl ? s_edges[min(jk + l, nedges - 1)] : none;
-                    }
-                    int tail = 0, k = 0;  // the stack is empty at every chunk start: the drain gathers from this chunk's buffer
                     constexpr bool DIRECT_OK = !AVG && !WGT && (MODE == CFB_DD || MODE == CFB_WP || MODE == CFB_RPPI || MODE == CFB_THETA);
-                    const bool direct = DIRECT_OK && jl <= 8;
-                    for (;;) {
-#define SUM_HOT(PA_, TRI_, LO_, DIR_) \
-    k = hot_loop<T, MODE, WGT, NA, PA_, TRI_, LO_, DIR_>(k, m4, W, bsel, xq, yq, zq, K, dirz, c0, lane, tail, E, jk)
-#define SUM_HOT3(PA_, DIR_)                          \
+                    if (DIRECT_OK && jl <= 8) {
+                        T E[8];  // the job's level edges; beyond nl: an edge no value is at or above
+#pragma unroll
+                        for (int l = 0; l < 8; l++) {
+                            const T none = MODE == CFB_THETA ? (sizeof(T) == 4 ? (T)-CUDART_INF_F : (T)-CUDART_INF)
+                                                             : (sizeof(T) == 4 ? (T)CUDART_INF_F : (T)CUDART_INF);
+                            E[l] = l < jl ? s_edges[min(jk + l, nedges - 1)] : none;
+                        }
+#define SUM_DIR(PA_, TRI_, LO_, NL_) \
+    direct_loop<T, MODE, NA, PA_, TRI_, LO_, NL_>(m4, W, bsel, xq, yq, zq, K, dirz, c0, lane, E, jk)
+#define SUM_DIR3(PA_, NL_)                           \
     do {                                             \
-        if (tri) SUM_HOT(PA_, true, true, DIR_);     \
-        else if (needlo) SUM_HOT(PA_, false, true, DIR_); \
-        else SUM_HOT(PA_, false, false, DIR_);       \
+        if (tri) SUM_DIR(PA_, true, true, NL_);      \
+        else if (needlo) SUM_DIR(PA_, false, true, NL_); \
+        else SUM_DIR(PA_, false, false, NL_);        \
     } while (0)
-                        if (DIRECT_OK && direct) {
-                            if (jl <= 4) {
-                                if (pa == 1) SUM_HOT3(1, DIRECT_OK ? 4 : 0);
-                                else SUM_HOT3(2, DIRECT_OK ? 4 : 0);
-                            } else {
-                                if (pa == 1) SUM_HOT3(1, DIRECT_OK ? 8 : 0);
-                                else SUM_HOT3(2, DIRECT_OK ? 8 : 0);
+                        if (jl <= 4) {
+                            if (pa == 1) SUM_DIR3(1, DIRECT_OK ? 4 : 1);
+                            else SUM_DIR3(2, DIRECT_OK ? 4 : 1);
+                        } else {
+                            if (pa == 1) SUM_DIR3(1, DIRECT_OK ? 8 : 1);
+                            else SUM_DIR3(2, DIRECT_OK ? 8 : 1);
+                        }
+#undef SUM_DIR3
+#undef SUM_DIR
+                    } else {
+                        const float *sx, *sy, *sz;
+                        if constexpr (sizeof(T) == 8) {
+                            // float copies of the chunk's positions for the filter
+                            for (int v = lane; v < m4; v += 32) {
+                                W.fbuf[0][v] = (float)W.buf[bsel][0][v];
+                                W.fbuf[1][v] = (float)W.buf[bsel][1][v];
+                                W.fbuf[2][v] = (float)W.buf[bsel][2][v];
                             }
-                        } else if (pa == 1)
-                            SUM_HOT3(1, 0);
-                        else
-                            SUM_HOT3(2, 0);
+                            __syncwarp();
+                            sx = W.fbuf[0], sy = W.fbuf[1], sz = W.fbuf[2];
+                        } else {
+                            sx = (const float *)W.buf[bsel][0], sy = (const float *)W.buf[bsel][1], sz = (const float *)W.buf[bsel][2];
+                        }
+                        const unsigned char *const qbase = &W.laneq[0][lane];
+                        const unsigned qaddr0 = smem_u32(qbase);
+                        unsigned qaddr = qaddr0;
+                        const unsigned qlimit = qaddr0 + 32 * (SUM_QL - 4);  // an iteration queues at most 4 pairs per lane
+                        int k = 0;
+                        for (;;) {
+#define SUM_HOT(PA_, TRI_, LO_) \
+    k = hot_loop<T, MODE, PA_, TRI_, LO_>(k, m4, sx, sy, sz, xh, yh, zh, K, F, dirz, c0, lane, qaddr, qlimit)
+#define SUM_HOT3(PA_)                          \
+    do {                                       \
+        if (tri) SUM_HOT(PA_, true, true);     \
+        else if (needlo) SUM_HOT(PA_, false, true); \
+        else SUM_HOT(PA_, false, false);       \
+    } while (0)
+                            if (pa == 1) SUM_HOT3(1);
+                            else SUM_HOT3(2);
 #undef SUM_HOT3
 #undef SUM_HOT
-                        // the stack is (nearly) full or the chunk is done: every full batch, back to back; the remainder too
-                        // at the end of the chunk (the drain gathers from this chunk's buffer)
-                        const bool last = k >= m4;
-                        while (tail >= 32 || (last && tail > 0)) {
-                            const int n = tail < 32 ? tail : 32;
-                            drain<T, MODE, AVG, WGT, NA>(n, tail - n, W, bsel, K, E, jk, jl, lane);
-                            tail -= n;
-                            if (++drains >= K.norm_drains) {
-                                flush_hist<MODE, AVG, WGT, T>(P, K, ns, lane, 32, false);
-                                drains = 0;
-                            }
+                            // some lane's queue is full or the chunk is done (the drain gathers from this chunk's buffer)
+                            flush_queues<T, MODE, AVG, WGT, NA>(W, bsel, K, P, ns, dirz, jk, jl, lane, qbase, qaddr0, qaddr, drains);
+                            if (k >= m4) break;
                         }
-                        if (last) break;
                     }
                     __syncwarp();  // everyone is done with buf[bsel] before it is staged again
                     it++;
@@ -966,12 +1241,13 @@ SetView<T> view_of(const ParticleSet &S)
 }
 
 template <typename T, bool WGT>
-size_t sum_fixed_smem(int nedges)
+size_t sum_fixed_smem(int nedges, int nkeys)
 {
     constexpr int NA = WGT ? 4 : 3;
     size_t off = (sizeof(SumWarp<T, NA>) * SUM_WARPS + 15) & ~(size_t)15;
     off += ((size_t)nedges * sizeof(T) + 15) & ~(size_t)15;
     off += (size_t)nedges * 16;
+    off += ((size_t)nkeys * 2 + 15) & ~(size_t)15;
     return off;
 }
 
@@ -985,7 +1261,7 @@ int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cuda
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     CK(cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t fixed = sum_fixed_smem<T, WGT>(P.nedges);
+    const size_t fixed = sum_fixed_smem<T, WGT>(P.nedges, P.sum_nkeys);
     const size_t per_copy = (size_t)P.nslots * 4 * (1 + (AVG ? 2 : 0) + (WGT ? 2 : 0));
     // histogram copies: as many (1, 2, 4 or 8) as still leave SUM_MINB resident blocks per SM
     int want_blocks = SUM_MINB, max_shift = 3;
@@ -1002,10 +1278,14 @@ int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cuda
     const size_t sm = fixed + (per_copy << shift);
     if (sm > (size_t)smem_blk) return -1;  // histogram too large for shared memory: the caller falls back
     P.sum_copies_shift = shift;
+    P.sum_cmask = (1 << shift) - 1;
+    P.sum_hstride_b = (unsigned)((4 * (1 + (AVG ? 2 : 0) + (WGT ? 2 : 0))) << shift);
+    P.sum_hist_off = (unsigned)fixed;
+    P.sum_inv_dmu_f = (float)P.inv_dmu;
     // a word takes at most warps x norm_drains x (32 / copies) adds between two normalisations: keep that below 2^16
     {
         const int lanes_per_copy = 32 >> (shift < 5 ? shift : 5);
-        int nd = 65536 / (SUM_WARPS * (lanes_per_copy > 0 ? lanes_per_copy : 1)) - 1;
+        int nd = 65536 / (SUM_WARPS * (lanes_per_copy > 0 ? lanes_per_copy : 1)) - 1 - SUM_QL;
         P.sum_norm_drains = nd < SUM_NORM_DRAINS ? (nd > 1 ? nd : 1) : SUM_NORM_DRAINS;
     }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -1057,8 +1337,9 @@ int launch_T(const cfb_binning *bin, const PairParams &P, bool list_mode)
 
 // 0 = launched, -1 = not applicable (too many edges / histogram too large: use the generic kernel), 1 = error.
 // P.wmax must be set when weights are on (cfb_weight_maxima).
-int cfb_launch_pairs_sum(const cfb_binning *bin, const PairParams &P, int prec, bool list_mode)
+int cfb_launch_pairs_sum(const cfb_binning *bin, const PairParams &P0, int prec, bool list_mode)
 {
+    PairParams P = P0;
     static_assert(CFB_TILE % SUM_TILE == 0, "sum tiles subdivide the gridlink tiles");
     static_assert(SUM_TILE <= 256 && SUM_CH <= 256, "a stack entry is (primary << 8 | secondary) in 16 bits");
     if (bin->nedges < 2 || bin->nedges > SUM_MAX_EDGES) return -1;
@@ -1069,5 +1350,19 @@ int cfb_launch_pairs_sum(const cfb_binning *bin, const PairParams &P, int prec, 
             return -1;
     }
     if (bin->nslots >= (1 << 20)) return -1;
+    // separation-bin table (see drain): keys of the float images of [first edge, last edge]
+    P.sum_kmin = 0;
+    P.sum_nkeys = 0;
+    if (bin->mode != CFB_THETA && bin->edges[0] > 1.0e-30 && bin->edges[bin->nedges - 1] < 1.0e30) {
+        const float flo = (float)(bin->edges[0] * (1.0 - 1e-6)), fhi = (float)(bin->edges[bin->nedges - 1] * (1.0 + 1e-6));
+        unsigned blo, bhi;
+        memcpy(&blo, &flo, 4);
+        memcpy(&bhi, &fhi, 4);
+        const int kmin = (int)(blo >> SUM_KSH), kmax = (int)(bhi >> SUM_KSH);
+        if (kmax - kmin + 1 <= SUM_MAX_KEYS) {
+            P.sum_kmin = kmin;
+            P.sum_nkeys = kmax - kmin + 1;
+        }
+    }
     return prec == 4 ? launch_T<float>(bin, P, list_mode) : launch_T<double>(bin, P, list_mode);
 }
