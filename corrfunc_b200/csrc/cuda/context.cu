@@ -407,9 +407,32 @@ static int upload_edges(Ctx &c, const cfb_binning *bin, const double *edges)
     return 0;
 }
 
+// One int in mapped, portable pinned memory: the host layer's signal handler writes it, every device reads it.
+static volatile int g_abort_fallback = 0;
+static volatile int *g_abort_host = nullptr;
+static const volatile int *g_abort_dev = nullptr;
+extern "C" volatile int *cfb_abort_flag(void)
+{
+    if (g_abort_host) return g_abort_host;
+    void *h = nullptr, *d = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+        cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+        memset(h, 0, 64);
+        g_abort_host = (volatile int *)h;
+        g_abort_dev = (const volatile int *)d;
+    } else {
+        cudaGetLastError();
+        g_abort_host = &g_abort_fallback;  // no device: nothing will poll it
+        g_abort_dev = nullptr;
+    }
+    return g_abort_host;
+}
+
 static void fill_common(PairParams &P, Ctx &c, const cfb_binning *bin, int64_t nslots)
 {
     memset(&P, 0, sizeof(P));
+    cfb_abort_flag();
+    P.abort = g_abort_dev;
     P.mode = bin->mode;
     P.nedges = bin->nedges;
     P.npibin = bin->npibin;

@@ -488,7 +488,11 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
 
     for (;;) {
         long long gw = 0;
-        if (lane == 0) gw = (long long)atomicAdd(&P.counters[4], 1ULL);
+        if (lane == 0) {
+            gw = (long long)atomicAdd(&P.counters[4], 1ULL);
+            // interrupt (SIGINT / SIGTERM / SIGHUP caught by the host layer, cf. countpairs_impl.c.src:475-477): no further tiles
+            if (P.abort && *P.abort) gw = (long long)1 << 62;
+        }
         gw = __shfl_sync(0xffffffffu, gw, 0);
         if (gw >= P.ntiles) break;
         const int64_t tile = gw;

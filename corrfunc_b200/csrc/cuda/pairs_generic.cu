@@ -112,6 +112,13 @@ __global__ void __launch_bounds__(CFB_TILE)
 k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    {
+        // interrupt (see cfb_abort_flag): blocks that start after the signal do nothing
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = (P.abort && *P.abort) ? 1 : 0;
+        __syncthreads();
+        if (s_abort) return;
+    }
     // dynamic smem layout: edges | sep scale per edge (double) | npairs (2 words) | sum_sep (3 words) | sum_w (3 words)
     T *s_edges = (T *)smem_raw;
     const int nedges = P.nedges;

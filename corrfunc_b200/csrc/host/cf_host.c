@@ -126,6 +126,45 @@ static int cf_setup_bins(const char *fname, double *rmin, double *rmax, int *nbi
     return EXIT_SUCCESS;
 }
 
+/* ---- interrupts (utils/macros.h:145-167; theory/DD/countpairs_impl.c.src:31-37, 193, 475-477, 554-569, 695) ----
+ * The reference installs handlers for SIGTERM, SIGINT and SIGHUP for the duration of a call ("mostly useful during the
+ * python execution"), its loop over cell pairs polls the flag they set, and an interrupted call returns EXIT_FAILURE.
+ * Here the flag lives in mapped pinned memory (cfb_abort_flag): the persistent pair kernels read it at every tile fetch. */
+#include <signal.h>
+typedef void (*cf_sig_t)(int);
+static const int cf_signals[3] = {SIGTERM, SIGINT, SIGHUP};
+static volatile sig_atomic_t cf_interrupt_status = 0;
+static volatile int *cf_abort = NULL;
+static void cf_interrupt_handler(int signo)
+{
+    fprintf(stderr, "Received signal = `%s' (signo = %d). Aborting \n", strsignal(signo), signo);
+    cf_interrupt_status = 1;
+    if (cf_abort) *cf_abort = 1;
+}
+static void cf_signals_install(cf_sig_t prev[3])
+{
+    cf_abort = cfb_abort_flag();
+    *cf_abort = 0;
+    cf_interrupt_status = 0;
+    for (int i = 0; i < 3; i++) {
+        prev[i] = signal(cf_signals[i], cf_interrupt_handler);
+        if (prev[i] == SIG_ERR) fprintf(stderr, "Can not handle signal = %d\n", cf_signals[i]);
+    }
+}
+/* returns 1 when the call was interrupted */
+static int cf_signals_restore(const cf_sig_t prev[3])
+{
+    for (int i = 0; i < 3; i++) {
+        if (prev[i] == SIG_IGN || prev[i] == SIG_ERR) continue;
+        if (signal(cf_signals[i], prev[i]) == SIG_ERR)
+            fprintf(stderr, "Could not reset signal handler to default for signal = %d\n", cf_signals[i]);
+    }
+    const int hit = cf_interrupt_status != 0;
+    if (cf_abort) *cf_abort = 0;
+    cf_interrupt_status = 0;
+    return hit;
+}
+
 /* raw device histograms -> optional cross-rank sum */
 /* local_status: what this rank's device count returned.  Every rank enters the collective whatever it returned -- a rank
  * that failed locally (out of memory, a particle outside the box of its replica) must not leave the others waiting in

@@ -374,7 +374,12 @@ static int HFN(cf_box)(const int mode, const int64_t ND1, void *X1, void *Y1, vo
     cfb_hist H = {npairs, sum_sep, sum_w};
     cfb_stats dst;
     memset(&dst, 0, sizeof(dst));
-    if (ND1 > 0 && (autocorr || ND2 > 0)) status = cfb_count_box(&B, &L, &H, &dst);
+    {
+        cf_sig_t prev_handlers[3];
+        cf_signals_install(prev_handlers);
+        if (ND1 > 0 && (autocorr || ND2 > 0)) status = cfb_count_box(&B, &L, &H, &dst);
+        if (cf_signals_restore(prev_handlers)) status = 1; /* interrupted: EXIT_FAILURE (countpairs_impl.c.src:554-569) */
+    }
     status = reduce_across_ranks(status, npairs, sum_sep, sum_w, nslots);
     if (status) {
         free(npairs); free(sum_sep); free(sum_w); free(rupp); free(rupp_sqr);
@@ -1315,7 +1320,12 @@ static int HFN(cf_theta)(const int64_t ND1, void *vra1, void *vdec1, const int64
             sum_sep = calloc((size_t)nthetabin, sizeof(double));
             sum_w = calloc((size_t)nthetabin, sizeof(double));
             cfb_hist H = {npairs, sum_sep, sum_w};
-            status = cfb_count_theta(&B, ncells, ngb_off, ngb, &H, &dst);
+            {
+                cf_sig_t prev_handlers[3];
+                cf_signals_install(prev_handlers);
+                status = cfb_count_theta(&B, ncells, ngb_off, ngb, &H, &dst);
+                if (cf_signals_restore(prev_handlers)) status = 1; /* interrupted: EXIT_FAILURE */
+            }
             status = reduce_across_ranks(status, npairs, sum_sep, sum_w, nthetabin);
         }
     }

@@ -108,6 +108,11 @@ int cfb_copy_to_host(void *dst, const void *src, size_t bytes);
 /* Catalogue cache: while on, a particle set passed again under the same pointers / length / element size is taken to be
  * unchanged -- it is not copied again (whichever slot it was in) and keeps its sorted form while the lattice stays the
  * same.  For workflows that count DD, DR and RR over two catalogues (Corrfunc/utils.py:27-165). */
+/* Interrupt flag (utils/macros.h:145-167, theory/DD/countpairs_impl.c.src:31-37,475-477: the reference installs SIGINT /
+ * SIGTERM / SIGHUP handlers for the duration of a call and its loop over cell pairs polls the flag they set).  Returns the
+ * HOST address of one int in mapped pinned memory (a plain static int without a CUDA device): the host layer's signal
+ * handler stores 1 there, the persistent pair kernels read it whenever a warp fetches its next tile and stop early. */
+volatile int *cfb_abort_flag(void);
 void cfb_set_catalog_cache(int on);
 long long cfb_catalog_cache_hits(void);
 /* Folds the device-side min/max of slot's x,y,z (or ra,dec when which==1) into lohi[6]={min3,max3}. */

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <signal.h>
 #include <string.h>
 
 #include "corrfunc_b200_device.h"
@@ -24,6 +25,8 @@ int cfb_init(void) { return 0; }
 int cfb_is_device_ptr(const void *p) { (void)p; return 0; }
 int cfb_copy_to_host(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
 int cfb_last_device_count(void) { return 1; }
+static volatile int stub_abort;
+volatile int *cfb_abort_flag(void) { return &stub_abort; }
 void cfb_set_catalog_cache(int on) { (void)on; }
 long long cfb_catalog_cache_hits(void) { return 0; }
 void cfb_shutdown(void) {}
@@ -121,6 +124,8 @@ int cfb_count_box(const cfb_binning *b, const cfb_box_lattice *l, cfb_hist *o, c
 {
     (void)l;
     if (s) memset(s, 0, sizeof(*s));
+    /* test hook: a signal arrives while the device counts (tests/test_cpu_host_layer.py::test_host_layer_interrupt) */
+    if (getenv("CFB_STUB_RAISE")) raise(atoi(getenv("CFB_STUB_RAISE")));
     if (!(b->mode == CFB_RPPI_MOCKS || b->mode == CFB_SMU_MOCKS) || b->nedges > 4096) return 1;
     const int s1 = b->autocorr ? 0 : 1;
     if (b->prec == 4) MOCKS_PAIRS(float, fmaf, sqrtf)

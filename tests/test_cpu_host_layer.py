@@ -162,3 +162,30 @@ def test_host_layer_mocks_error_behaviour(hostlib):
     assert r["npairs"].size == 0  # the reference returns EXIT_SUCCESS and leaves the results untouched
     with pytest.raises(RuntimeError):  # vpf: nonsense parameters
         _capi.call_vpf(hostlib, -1.0, 4, 10, 3, 1, ra, dec, d, options=ok(periodic=False))
+
+
+def test_host_layer_interrupt(hostlib, capfd, monkeypatch):
+    """utils/macros.h:145-167, theory/DD/countpairs_impl.c.src:31-37,554-569: a SIGINT / SIGTERM / SIGHUP that arrives during
+    a call is caught by the library's own handler (message on stderr, flag for the device), the call returns
+    EXIT_FAILURE, and the caller's handlers are back in place afterwards."""
+    import signal
+
+    ra, dec, d, _ = H.mock_points(5, 2000, np.float64)
+    bins = np.logspace(-1, 1, 6)
+    o = _capi.default_options(np.float64, is_comoving_dist=True)
+    ok = _capi.call_DDrppi_mocks(hostlib, 1, 1, 1, 10.0, bins, ra, dec, d, options=o)
+    assert ok["npairs"].sum() > 0
+    for signo in (signal.SIGINT, signal.SIGTERM, signal.SIGHUP):
+        monkeypatch.setenv("CFB_STUB_RAISE", str(int(signo)))
+        with pytest.raises(RuntimeError):
+            _capi.call_DDrppi_mocks(hostlib, 1, 1, 1, 10.0, bins, ra, dec, d, options=_capi.default_options(np.float64, is_comoving_dist=True))
+        err = capfd.readouterr().err
+        assert "Received signal" in err and "Aborting" in err and "signo = %d" % int(signo) in err
+    monkeypatch.delenv("CFB_STUB_RAISE")
+    # the flag is cleared and the handlers are restored: the next call succeeds, and Python sees its own SIGINT again
+    again = _capi.call_DDrppi_mocks(hostlib, 1, 1, 1, 10.0, bins, ra, dec, d, options=_capi.default_options(np.float64, is_comoving_dist=True))
+    assert np.array_equal(again["npairs"], ok["npairs"])
+    with pytest.raises(KeyboardInterrupt):
+        signal.raise_signal(signal.SIGINT)
+        import time
+        time.sleep(0.01)

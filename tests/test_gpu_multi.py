@@ -82,3 +82,43 @@ def test_c5sd10M_golden_one_process_per_gpu_torchrun(tmp_path):
                        capture_output=True, text=True, env=env, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.count("OK=1") == n
+
+
+@pytest.mark.gpu
+def test_interrupt_stops_a_running_count(tmp_path):
+    """SIGINT during a long count (utils/macros.h:145-167, theory/DD/countpairs_impl.c.src:475-477,554-569): the library's
+    handler prints the reference's message and sets the mapped flag, the persistent warps stop fetching tiles, the call
+    returns EXIT_FAILURE (RuntimeError in the wrapper) well before the count would have finished."""
+    import signal
+    import time
+
+    script = tmp_path / "long_count.py"
+    script.write_text(
+        "import os, sys, time\n"
+        "import numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from corrfunc_b200.theory import xi\n"
+        "N, L = 40_000_000, 1473.0\n"  # config 5's density: about 2 s of pair counting
+        "rng = np.random.default_rng(5)\n"
+        "x, y, z = (rng.random(N, dtype=np.float32) * np.float32(L) for _ in range(3))\n"
+        "bins = np.logspace(-1, np.log10(150.0), 31)\n"
+        "xi(L, 1, bins, x[:100000], y[:100000], z[:100000])\n"  # context, kernels loaded
+        "print('START', flush=True)\n"
+        "t0 = time.time()\n"
+        "try:\n"
+        "    xi(L, 1, bins, x, y, z)\n"
+        "    print('FINISHED %%.3f' %% (time.time() - t0), flush=True)\n"
+        "except RuntimeError as e:\n"
+        "    print('INTERRUPTED %%.3f' %% (time.time() - t0), flush=True)\n" % H.ROOT)
+    env = dict(os.environ, CORRFUNC_B200_NGPUS="1")
+    p = subprocess.Popen([sys.executable, str(script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    line = p.stdout.readline()
+    assert line.startswith("START"), line + p.stderr.read()
+    time.sleep(0.8)  # copies, upload and gridlink take 0.2-0.4 s; the pair kernel (about 2 s) is running now
+    p.send_signal(signal.SIGINT)
+    t_sig = time.time()
+    out, err = p.communicate(timeout=120)
+    waited = time.time() - t_sig
+    assert "INTERRUPTED" in out, out + err
+    assert "Received signal" in err and "Aborting" in err
+    assert waited < 1.0, "the count did not stop early: %.2f s after the signal" % waited
