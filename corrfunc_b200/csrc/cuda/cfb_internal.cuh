@@ -117,7 +117,7 @@ struct PairParams {
     double *sum_sep, *sum_w;
     const double *wmax;  // device: max |weight| of the first and of the second set (generic kernel, weights on)
     unsigned long long *counters;  // [0]=n_eval [1]=n_tilepairs [2]=pairs binned without evaluation [3]=sum of evaluated pairs x levels [4]=next tile (persistent warps)
-    const volatile int *abort;  // mapped host flag set by the host layer's signal handler (cfb_abort_flag); polled at every tile fetch
+    const volatile int *abort;  // mapped host flag set by the host layer's signal handler (cfb_abort_flag); polled at every 64th tile fetch
     int hist_in_smem;
     int sum_copies_shift;  // per-pair-sum kernel: log2 of the number of shared-memory histogram copies
     int sum_norm_drains;   // per-pair-sum kernel: drains of a warp between two normalisations of the block's histogram

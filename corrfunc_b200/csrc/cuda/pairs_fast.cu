@@ -490,8 +490,10 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
         long long gw = 0;
         if (lane == 0) {
             gw = (long long)atomicAdd(&P.counters[4], 1ULL);
-            // interrupt (SIGINT / SIGTERM / SIGHUP caught by the host layer, cf. countpairs_impl.c.src:475-477): no further tiles
-            if (P.abort && *P.abort) gw = (long long)1 << 62;
+            // interrupt (SIGINT / SIGTERM / SIGHUP caught by the host layer, cf. countpairs_impl.c.src:475-477): every 64th
+            // fetch also reads the host's flag (a read over PCIe: doing it at every fetch cost config 1 a factor of four)
+            // and, when it is set, pushes the tile counter past the end -- every later fetch of every warp then ends its loop
+            if ((gw & 63) == 0 && P.abort && *P.abort) gw = (long long)atomicAdd(&P.counters[4], 1ULL << 40) + ((long long)1 << 40);
         }
         gw = __shfl_sync(0xffffffffu, gw, 0);
         if (gw >= P.ntiles) break;

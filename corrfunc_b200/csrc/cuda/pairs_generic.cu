@@ -114,8 +114,12 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     {
         // interrupt (see cfb_abort_flag): blocks that start after the signal do nothing
+        // every 64th block reads the host's flag (over PCIe) and latches it in device memory, all blocks read the latch
         __shared__ int s_abort;
-        if (threadIdx.x == 0) s_abort = (P.abort && *P.abort) ? 1 : 0;
+        if (threadIdx.x == 0) {
+            if ((blockIdx.x & 63) == 0 && P.abort && *P.abort) atomicExch(&P.counters[5], 1ULL);
+            s_abort = *(volatile unsigned long long *)&P.counters[5] != 0ULL;
+        }
         __syncthreads();
         if (s_abort) return;
     }

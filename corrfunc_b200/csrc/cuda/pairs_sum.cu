@@ -695,8 +695,18 @@ __device__ __forceinline__ void flush_queues(SumWarp<T, NA> &W, const int bsel, 
     const int excl = incl - c;
     const int maxc = __reduce_max_sync(0xffffffffu, c);
     const unsigned lb = (unsigned)lane << 8;
-    for (int i = 0; i < maxc; i++)
-        if (i < c) W.ring[excl + i] = (unsigned short)(lb | qbase[32 * i]);
+#ifndef SUM_COPY_UNROLL
+#define SUM_COPY_UNROLL 4
+#endif
+    // four independent load -> store pairs in flight per lane (the loop is pure latency)
+    for (int i0 = 0; i0 < maxc; i0 += SUM_COPY_UNROLL) {
+        unsigned e[SUM_COPY_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SUM_COPY_UNROLL; u++) e[u] = qbase[32 * min(i0 + u, SUM_QL - 1)];
+#pragma unroll
+        for (int u = 0; u < SUM_COPY_UNROLL; u++)
+            if (i0 + u < c) W.ring[excl + i0 + u] = (unsigned short)(lb | e[u]);
+    }
     qaddr = qaddr0;
     __syncwarp();
     T E[4];  // the job's first level edges; beyond nl: an edge no value is at or above
@@ -847,8 +857,10 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
         long long gw = 0;
         if (lane == 0) {
             gw = (long long)atomicAdd(&P.counters[4], 1ULL);
-            // interrupt (SIGINT / SIGTERM / SIGHUP caught by the host layer, cf. countpairs_impl.c.src:475-477): no further tiles
-            if (P.abort && *P.abort) gw = (long long)1 << 62;
+            // interrupt (SIGINT / SIGTERM / SIGHUP caught by the host layer, cf. countpairs_impl.c.src:475-477): every 64th
+            // fetch also reads the host's flag (a read over PCIe: doing it at every fetch cost config 1 a factor of four)
+            // and, when it is set, pushes the tile counter past the end -- every later fetch of every warp then ends its loop
+            if ((gw & 63) == 0 && P.abort && *P.abort) gw = (long long)atomicAdd(&P.counters[4], 1ULL << 40) + ((long long)1 << 40);
         }
         gw = __shfl_sync(0xffffffffu, gw, 0);
         if (gw >= P.ntiles * SPLIT) break;

@@ -111,7 +111,8 @@ int cfb_copy_to_host(void *dst, const void *src, size_t bytes);
 /* Interrupt flag (utils/macros.h:145-167, theory/DD/countpairs_impl.c.src:31-37,475-477: the reference installs SIGINT /
  * SIGTERM / SIGHUP handlers for the duration of a call and its loop over cell pairs polls the flag they set).  Returns the
  * HOST address of one int in mapped pinned memory (a plain static int without a CUDA device): the host layer's signal
- * handler stores 1 there, the persistent pair kernels read it whenever a warp fetches its next tile and stop early. */
+ * handler stores 1 there; the persistent pair kernels read it at every 64th tile fetch (a read over PCIe) and, when it is
+ * set, push the tile counter past the end, which stops every warp at its next fetch. */
 volatile int *cfb_abort_flag(void);
 void cfb_set_catalog_cache(int on);
 long long cfb_catalog_cache_hits(void);
