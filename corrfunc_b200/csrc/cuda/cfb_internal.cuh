@@ -45,6 +45,7 @@ struct Ctx {
     cudaEvent_t ev[8];
     ParticleSet set[2];
     DevBuf scratch;  // reductions, scalars
+    DevBuf sort_rec, sort_cid, sort_cur;  // two-pass scatter of large sets (gridlink.cu): records, their cells, cursors
     DevBuf hist;     // npairs | sum_sep | sum_w | n_eval, n_tilepairs
     DevBuf edges;
     DevBuf list_off, list_cells, ngrid_ra, ra_off;

@@ -103,6 +103,7 @@ static void release_ctx(Ctx &c)
         S = ParticleSet();
     }
     rel(c.scratch); rel(c.hist); rel(c.edges); rel(c.list_off); rel(c.list_cells); rel(c.ngrid_ra); rel(c.ra_off);
+    rel(c.sort_rec); rel(c.sort_cid); rel(c.sort_cur);
     if (c.pinned) cudaFreeHost(c.pinned);
     c.pinned = nullptr;
     for (int i = 0; i < 8; i++) cudaEventDestroy(c.ev[i]);

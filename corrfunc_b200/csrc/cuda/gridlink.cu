@@ -11,6 +11,8 @@
 //                  and NaN fill of the padding slots
 //   k_fill_tiles   (cell, offset) table of primary tiles
 // All of it is HBM-bound byte shuffling: coalesced streaming reads, one scattered write per value.
+#include <stdlib.h>
+
 #include "cfb_internal.cuh"
 
 template <typename T>
@@ -126,18 +128,31 @@ __global__ void k_scan_cells(const int64_t ncells, const int *__restrict__ count
             sa += va[k];
             sb += vb[k];
         }
-        s_a[threadIdx.x] = sa;
-        s_b[threadIdx.x] = sb;
-        __syncthreads();
-        for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of the thread sums
-            long long ta = 0, tb = 0;
-            if ((int)threadIdx.x >= off) {
-                ta = s_a[threadIdx.x - off];
-                tb = s_b[threadIdx.x - off];
+        // inclusive scan of the 1024 thread sums: shuffles within the warps, then over the 32 warp totals
+        {
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            long long ia = sa, ib = sb;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const long long ta = __shfl_up_sync(0xffffffffu, ia, off), tb = __shfl_up_sync(0xffffffffu, ib, off);
+                if (lane >= off) ia += ta, ib += tb;
+            }
+            if (lane == 31) s_a[wid] = ia, s_b[wid] = ib;  // warp totals
+            __syncthreads();
+            if (wid == 0) {
+                long long wa = s_a[lane], wb = s_b[lane];
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const long long ta = __shfl_up_sync(0xffffffffu, wa, off), tb = __shfl_up_sync(0xffffffffu, wb, off);
+                    if (lane >= off) wa += ta, wb += tb;
+                }
+                s_a[32 + lane] = wa, s_b[32 + lane] = wb;  // inclusive scan of the warp totals
             }
             __syncthreads();
-            s_a[threadIdx.x] += ta;
-            s_b[threadIdx.x] += tb;
+            const long long pa = wid ? s_a[32 + wid - 1] : 0, pb = wid ? s_b[32 + wid - 1] : 0;
+            __syncthreads();
+            s_a[threadIdx.x] = ia + pa;
+            s_b[threadIdx.x] = ib + pb;
             __syncthreads();
         }
         long long ea = carry_a + s_a[threadIdx.x] - sa, eb = carry_b + s_b[threadIdx.x] - sb;
@@ -180,6 +195,88 @@ __global__ void k_scatter(const int64_t n, const T *__restrict__ x, const T *__r
     ys[p] = y[i] * scale;
     zs[p] = z[i] * scale;
     if (w) ws[p] = w[i];
+}
+
+// ---- two-pass scatter for large sets -------------------------------------------------------------------------------
+// k_scatter writes every particle's three 4-byte coordinates to random places of a 1.2 GB target (config 5): the L2
+// cannot hold the partially written 32-byte sectors, and ncu counts 8.9 GB read + 8.4 GB written for 1.2 GB of payload
+// (10.6 of the 13.3 ms of the whole gridlink).  Large sets therefore go through a coarse partition first:
+//   pass 1 (k_partition): buckets of 2^shift consecutive cells (<= 512 buckets).  A block takes 4096 particles, ranks them
+//          within their buckets in shared memory, reserves one run per bucket with a single global atomic and writes
+//          {x, y, z, w} records (16 / 32 bytes) + the cell index into the bucket's region of a temporary array that has
+//          the layout of the final one: runs of ~10 records, sector-sized writes;
+//   pass 2 (k_place): walks the temporary array in order -- at any time the blocks in flight work on a few neighbouring
+//          buckets, whose final positions (a few MB) stay in L2 until their sectors are complete -- and places every
+//          record at start[cell] + arrival rank.
+// The order of the particles inside a cell is, as before, the order of arrival.
+#define CFB_PART_CHUNK 4096
+#define CFB_PART_MAXB 512
+template <typename T>
+struct alignas(4 * sizeof(T)) Rec4 {
+    T x, y, z, w;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_partition(const int64_t n, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
+            const T *__restrict__ w, const int *__restrict__ cidx, const int shift, const int nbuckets,
+            const int *__restrict__ start, int *__restrict__ bcursor, Rec4<T> *__restrict__ rec, int *__restrict__ rcid,
+            const T scale)
+{
+    __shared__ int s_cnt[CFB_PART_MAXB], s_base[CFB_PART_MAXB];
+    constexpr int PER = CFB_PART_CHUNK / 256;
+    for (int64_t chunk = blockIdx.x; chunk * CFB_PART_CHUNK < n; chunk += gridDim.x) {
+        for (int b = threadIdx.x; b < nbuckets; b += 256) s_cnt[b] = 0;
+        __syncthreads();
+        int c[PER], lr[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int64_t i = chunk * CFB_PART_CHUNK + k * 256 + threadIdx.x;
+            c[k] = i < n ? cidx[i] : -1;
+            lr[k] = c[k] >= 0 ? atomicAdd(&s_cnt[c[k] >> shift], 1) : 0;
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbuckets; b += 256) {
+            const int cnt = s_cnt[b];
+            if (cnt) s_base[b] = start[(int64_t)b << shift] + atomicAdd(&bcursor[b], cnt);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            if (c[k] < 0) continue;
+            const int64_t i = chunk * CFB_PART_CHUNK + k * 256 + threadIdx.x;
+            const int p = s_base[c[k] >> shift] + lr[k];
+            Rec4<T> r;
+            // scale is a power of two (exact): the fast float kernel works on pre-scaled positions
+            r.x = x[i] * scale, r.y = y[i] * scale, r.z = z[i] * scale, r.w = w ? w[i] : (T)0;
+            rec[p] = r;
+            rcid[p] = c[k];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_place(const int64_t npad, const Rec4<T> *__restrict__ rec, const int *__restrict__ rcid, const int *__restrict__ start,
+        int *__restrict__ cur, T *__restrict__ xs, T *__restrict__ ys, T *__restrict__ zs, T *__restrict__ ws)
+{
+    constexpr int PER = CFB_PART_CHUNK / 256;
+    for (int64_t chunk = blockIdx.x; chunk * CFB_PART_CHUNK < npad; chunk += gridDim.x) {
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int64_t p = chunk * CFB_PART_CHUNK + k * 256 + threadIdx.x;
+            if (p >= npad) continue;
+            const int c = rcid[p];
+            if (c < 0) continue;  // padding between the buckets' runs
+            const Rec4<T> r = rec[p];
+            const int q = start[c] + atomicAdd(&cur[c], 1);
+            xs[q] = r.x;
+            ys[q] = r.y;
+            zs[q] = r.z;
+            if (ws) ws[q] = r.w;
+        }
+    }
 }
 
 // One warp per cell: min/max bounds of x,y,z (and of a fourth, unsorted-by-value array `ra` given
@@ -310,7 +407,37 @@ static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells, double scale)
     const bool hasw = S.raw[3] != nullptr;
     for (int a = 0; a < (hasw ? 4 : 3); a++)
         if (cfb_ensure(S.sorted[a], sb)) return 1;
-    if (S.n > 0) {
+    static int64_t sort2_min = -1;  // sets at least this large take the two-pass scatter
+    if (sort2_min < 0) {
+        const char *e = getenv("CORRFUNC_B200_SORT2_MIN");
+        sort2_min = (e && *e) ? atoll(e) : 4000000;
+    }
+    if (S.n > 0 && S.n >= sort2_min && S.npad > 0) {
+        int shift = 0;
+        while (((ncells + ((int64_t)1 << shift) - 1) >> shift) > CFB_PART_MAXB) shift++;
+        const int nbuckets = (int)((ncells + ((int64_t)1 << shift) - 1) >> shift);
+        if (cfb_ensure(c.sort_rec, (size_t)S.npad * sizeof(Rec4<T>))) return 1;
+        if (cfb_ensure(c.sort_cid, (size_t)S.npad * 4)) return 1;
+        if (cfb_ensure(c.sort_cur, (size_t)(ncells + CFB_PART_MAXB) * 4)) return 1;
+        CK(cudaMemsetAsync(c.sort_cid.p, 0xFF, (size_t)S.npad * 4, c.stream));
+        CK(cudaMemsetAsync(c.sort_cur.p, 0, (size_t)(ncells + CFB_PART_MAXB) * 4, c.stream));
+        int *bcursor = (int *)c.sort_cur.p, *ccursor = (int *)c.sort_cur.p + CFB_PART_MAXB;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned g1 = (unsigned)min((int64_t)nblocks(S.n, CFB_PART_CHUNK), (int64_t)sms * 8);
+        k_partition<T><<<g1, 256, 0, c.stream>>>(S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2],
+                                                  (const T *)S.raw[3], (const int *)S.cidx.p, shift, nbuckets,
+                                                  (const int *)S.start.p, bcursor, (Rec4<T> *)c.sort_rec.p,
+                                                  (int *)c.sort_cid.p, (T)scale);
+        // few blocks in flight: their targets (a few neighbouring buckets) must stay L2-resident until complete
+        const unsigned g2 = (unsigned)min((int64_t)nblocks(S.npad, CFB_PART_CHUNK), (int64_t)sms * 2);
+        k_place<T><<<g2, 256, 0, c.stream>>>(S.npad, (const Rec4<T> *)c.sort_rec.p, (const int *)c.sort_cid.p,
+                                              (const int *)S.start.p, ccursor, (T *)S.sorted[0].p, (T *)S.sorted[1].p,
+                                              (T *)S.sorted[2].p, hasw ? (T *)S.sorted[3].p : nullptr);
+        c.launches += 2;
+        CK(cudaGetLastError());
+    } else if (S.n > 0) {
         k_scatter<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(
             S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2], (const T *)S.raw[3],
             (const int *)S.cidx.p, (const int *)S.rank.p, (const int *)S.start.p, (T *)S.sorted[0].p,
