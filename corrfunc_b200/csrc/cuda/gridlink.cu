@@ -59,7 +59,8 @@ __global__ void k_cellindex_box(const int64_t n, const T *__restrict__ x, const 
     }
     const int c = (gx * G.ng[1] + gy) * G.ng[2] + gz;
     cidx[i] = c;
-    rank[i] = atomicAdd(&count[c], 1);
+    if (rank) rank[i] = atomicAdd(&count[c], 1);
+    else atomicAdd(&count[c], 1);  // the two-pass scatter ranks by arrival itself: no return value, no second array
 }
 
 // DDtheta lattice: idec=(int)(ngrid_dec*(DEC-dec_min)*inv_dec_diff); if(idec>=ngrid_dec) idec--;
@@ -103,26 +104,71 @@ __global__ void k_cellindex_theta(const int64_t n, const T *__restrict__ ra, con
     rank[i] = atomicAdd(&count[c], 1);
 }
 
-// Single-block exclusive scan of padded counts (-> start) and tile counts (-> tstart).
-// totals[0] = padded particle total, totals[1] = tile total.
-__global__ void k_scan_cells(const int64_t ncells, const int *__restrict__ count, int *__restrict__ start,
-                             int *__restrict__ tstart, long long *totals)
+// Exclusive scan of padded counts (-> start) and tile counts (-> tstart) in two launches: every block owns `seg`
+// consecutive cells; k_scan_sums leaves the segment totals, k_scan_cells adds up the totals of the segments before its
+// own and scans its segment (1024 threads x 8 cells at a time, warp shuffles).  totals[0] = padded particle total,
+// totals[1] = tile total.  (One block over all cells took 1.15 ms of config 5's gridlink for 3.5 MB of counts.)
+#define CFB_SCAN_ITEMS 8
+__global__ void __launch_bounds__(1024)
+k_scan_sums(const int64_t ncells, const int64_t seg, const int *__restrict__ count, long long *__restrict__ bsum)
+{
+    __shared__ long long s_a[32], s_b[32];
+    const int64_t lo = blockIdx.x * seg, hi = min(ncells, lo + seg);
+    long long sa = 0, sb = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 1024) {
+        const int cnt = count[i];
+        sa += (cnt + CFB_PAD - 1) / CFB_PAD * CFB_PAD;
+        sb += (cnt + CFB_TILE - 1) / CFB_TILE;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, off);
+        sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    }
+    if ((threadIdx.x & 31) == 0) s_a[threadIdx.x >> 5] = sa, s_b[threadIdx.x >> 5] = sb;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        sa = s_a[threadIdx.x], sb = s_b[threadIdx.x];
+        for (int off = 16; off > 0; off >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, off);
+            sb += __shfl_xor_sync(0xffffffffu, sb, off);
+        }
+        if (threadIdx.x == 0) bsum[2 * blockIdx.x] = sa, bsum[2 * blockIdx.x + 1] = sb;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_cells(const int64_t ncells, const int64_t seg, const int *__restrict__ count, int *__restrict__ start,
+             int *__restrict__ tstart, const long long *__restrict__ bsum, long long *totals)
 {
     __shared__ long long s_a[1024], s_b[1024];
     __shared__ long long carry_a, carry_b;
-    if (threadIdx.x == 0) {
-        carry_a = 0;
-        carry_b = 0;
+    {
+        // totals of the segments before this one
+        long long pa = 0, pb = 0;
+        for (int j = threadIdx.x; j < (int)blockIdx.x; j += 1024) pa += bsum[2 * j], pb += bsum[2 * j + 1];
+        for (int off = 16; off > 0; off >>= 1) {
+            pa += __shfl_xor_sync(0xffffffffu, pa, off);
+            pb += __shfl_xor_sync(0xffffffffu, pb, off);
+        }
+        if ((threadIdx.x & 31) == 0) s_a[threadIdx.x >> 5] = pa, s_b[threadIdx.x >> 5] = pb;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            pa = 0, pb = 0;
+            for (int w = 0; w < 32; w++) pa += s_a[w], pb += s_b[w];
+            carry_a = pa;
+            carry_b = pb;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int ITEMS = 8;
-    for (int64_t base = 0; base < ncells; base += 1024 * ITEMS) {
+    const int ITEMS = CFB_SCAN_ITEMS;
+    const int64_t lo = blockIdx.x * seg, hi = min(ncells, lo + seg);
+    for (int64_t base = lo; base < hi; base += 1024 * ITEMS) {
         long long va[ITEMS], vb[ITEMS], sa = 0, sb = 0;
         const int64_t i0 = base + (int64_t)threadIdx.x * ITEMS;
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
             const int64_t i = i0 + k;
-            const int cnt = i < ncells ? count[i] : 0;
+            const int cnt = i < hi ? count[i] : 0;
             va[k] = (cnt + CFB_PAD - 1) / CFB_PAD * CFB_PAD;
             vb[k] = (cnt + CFB_TILE - 1) / CFB_TILE;
             sa += va[k];
@@ -159,7 +205,7 @@ __global__ void k_scan_cells(const int64_t ncells, const int *__restrict__ count
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
             const int64_t i = i0 + k;
-            if (i < ncells) {
+            if (i < hi) {
                 start[i] = (int)ea;
                 tstart[i] = (int)eb;
             }
@@ -173,7 +219,7 @@ __global__ void k_scan_cells(const int64_t ncells, const int *__restrict__ count
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
         totals[0] = carry_a;
         totals[1] = carry_b;
     }
@@ -201,80 +247,159 @@ __global__ void k_scatter(const int64_t n, const T *__restrict__ x, const T *__r
 // k_scatter writes every particle's three 4-byte coordinates to random places of a 1.2 GB target (config 5): the L2
 // cannot hold the partially written 32-byte sectors, and ncu counts 8.9 GB read + 8.4 GB written for 1.2 GB of payload
 // (10.6 of the 13.3 ms of the whole gridlink).  Large sets therefore go through a coarse partition first:
-//   pass 1 (k_partition): buckets of 2^shift consecutive cells (<= 512 buckets).  A block takes 4096 particles, ranks them
-//          within their buckets in shared memory, reserves one run per bucket with a single global atomic and writes
-//          {x, y, z, w} records (16 / 32 bytes) + the cell index into the bucket's region of a temporary array that has
-//          the layout of the final one: runs of ~10 records, sector-sized writes;
+//   pass 1 (k_partition): buckets of 2^shift consecutive cells (<= 512 buckets).  A block takes a chunk of particles
+//          (64 KB of records), ranks them within their buckets with shared-memory atomics, orders the records by bucket
+//          in shared memory (one block scan of the bucket counts), reserves one run per bucket with a single global
+//          atomic and writes the staged records out in order -- consecutive threads, consecutive 16-byte records of one
+//          run -- into the bucket's region of a temporary array that has the layout of the final one.  A record is
+//          {x, y, z, cell} (without weights: one 16-byte store per particle, nothing else) or {x, y, z, w} + the cell in a
+//          second array;
 //   pass 2 (k_place): walks the temporary array in order -- at any time the blocks in flight work on a few neighbouring
 //          buckets, whose final positions (a few MB) stay in L2 until their sectors are complete -- and places every
-//          record at start[cell] + arrival rank.
+//          record at start[cell] + arrival rank.  Which slots of the temporary array hold a record follows from the
+//          position alone (a bucket's records are contiguous from its base; the padding is at its end): nothing is cleared.
 // The order of the particles inside a cell is, as before, the order of arrival.
-#define CFB_PART_CHUNK 4096
 #define CFB_PART_MAXB 512
 template <typename T>
 struct alignas(4 * sizeof(T)) Rec4 {
     T x, y, z, w;
 };
-
 template <typename T>
+__host__ __device__ constexpr int part_chunk() { return 65536 / (int)sizeof(Rec4<T>); }  // records per block and round: 4096 / 2048
+__device__ __forceinline__ float cell_as_real(const int c, float) { return __int_as_float(c); }
+__device__ __forceinline__ double cell_as_real(const int c, double) { return __longlong_as_double((long long)c); }
+__device__ __forceinline__ int real_as_cell(const float v) { return __float_as_int(v); }
+__device__ __forceinline__ int real_as_cell(const double v) { return (int)__double_as_longlong(v); }
+template <typename T, bool WGT>
+__host__ __device__ constexpr size_t part_smem() { return (size_t)part_chunk<T>() * (sizeof(Rec4<T>) + 2 + (WGT ? 4 : 0)); }
+
+template <typename T, bool WGT>
 __global__ void __launch_bounds__(256)
 k_partition(const int64_t n, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
             const T *__restrict__ w, const int *__restrict__ cidx, const int shift, const int nbuckets,
             const int *__restrict__ start, int *__restrict__ bcursor, Rec4<T> *__restrict__ rec, int *__restrict__ rcid,
             const T scale)
 {
-    __shared__ int s_cnt[CFB_PART_MAXB], s_base[CFB_PART_MAXB];
-    constexpr int PER = CFB_PART_CHUNK / 256;
-    for (int64_t chunk = blockIdx.x; chunk * CFB_PART_CHUNK < n; chunk += gridDim.x) {
-        for (int b = threadIdx.x; b < nbuckets; b += 256) s_cnt[b] = 0;
+    constexpr int CH = part_chunk<T>(), PER = CH / 256;
+    extern __shared__ __align__(16) unsigned char part_sm[];
+    Rec4<T> *s_rec = (Rec4<T> *)part_sm;
+    unsigned short *s_bk = (unsigned short *)(part_sm + (size_t)CH * sizeof(Rec4<T>));
+    int *s_cid = (int *)(part_sm + (size_t)CH * (sizeof(Rec4<T>) + 2));
+    __shared__ int s_cnt[CFB_PART_MAXB], s_off[CFB_PART_MAXB], s_base[CFB_PART_MAXB], s_wsum[8], s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int64_t chunk = blockIdx.x; chunk * CH < n; chunk += gridDim.x) {
+        for (int b = tid; b < CFB_PART_MAXB; b += 256) s_cnt[b] = 0;
         __syncthreads();
         int c[PER], lr[PER];
 #pragma unroll
         for (int k = 0; k < PER; k++) {
-            const int64_t i = chunk * CFB_PART_CHUNK + k * 256 + threadIdx.x;
-            c[k] = i < n ? cidx[i] : -1;
+            const int64_t i = chunk * CH + k * 256 + tid;
+            c[k] = i < n ? __ldcs(cidx + i) : -1;
             lr[k] = c[k] >= 0 ? atomicAdd(&s_cnt[c[k] >> shift], 1) : 0;
         }
         __syncthreads();
-        for (int b = threadIdx.x; b < nbuckets; b += 256) {
-            const int cnt = s_cnt[b];
-            if (cnt) s_base[b] = start[(int64_t)b << shift] + atomicAdd(&bcursor[b], cnt);
+        {
+            // exclusive scan of the 512 bucket counts (two per thread) -> the buckets' offsets in the staging area;
+            // one global atomic per non-empty bucket reserves its run
+            const int c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
+            int incl = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_wsum[wid] = incl;
+            __syncthreads();
+            int pre = 0;
+#pragma unroll
+            for (int v = 0; v < 8; v++) pre += v < wid ? s_wsum[v] : 0;
+            const int excl = pre + incl - (c0 + c1);
+            s_off[2 * tid] = excl;
+            s_off[2 * tid + 1] = excl + c0;
+            if (c0) s_base[2 * tid] = start[(int64_t)(2 * tid) << shift] + atomicAdd(&bcursor[2 * tid], c0);
+            if (c1) s_base[2 * tid + 1] = start[(int64_t)(2 * tid + 1) << shift] + atomicAdd(&bcursor[2 * tid + 1], c1);
+            if (tid == 255) s_total = pre + incl;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             if (c[k] < 0) continue;
-            const int64_t i = chunk * CFB_PART_CHUNK + k * 256 + threadIdx.x;
-            const int p = s_base[c[k] >> shift] + lr[k];
+            const int64_t i = chunk * CH + k * 256 + tid;
+            const int bk = c[k] >> shift;
+            const int slot = s_off[bk] + lr[k];
             Rec4<T> r;
             // scale is a power of two (exact): the fast float kernel works on pre-scaled positions
-            r.x = x[i] * scale, r.y = y[i] * scale, r.z = z[i] * scale, r.w = w ? w[i] : (T)0;
-            rec[p] = r;
-            rcid[p] = c[k];
+            r.x = __ldcs(x + i) * scale, r.y = __ldcs(y + i) * scale, r.z = __ldcs(z + i) * scale;
+            r.w = WGT ? __ldcs(w + i) : cell_as_real(c[k], (T)0);
+            s_rec[slot] = r;
+            s_bk[slot] = (unsigned short)bk;
+            if (WGT) s_cid[slot] = c[k];
+        }
+        __syncthreads();
+        const int total = s_total;
+        for (int idx = tid; idx < total; idx += 256) {
+            const int bk = s_bk[idx];
+            const int p = s_base[bk] + (idx - s_off[bk]);
+            rec[p] = s_rec[idx];
+            if (WGT) rcid[p] = s_cid[idx];
         }
         __syncthreads();
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_place(const int64_t npad, const Rec4<T> *__restrict__ rec, const int *__restrict__ rcid, const int *__restrict__ start,
-        int *__restrict__ cur, T *__restrict__ xs, T *__restrict__ ys, T *__restrict__ zs, T *__restrict__ ws)
+// cur[c] starts as start[c] (a device copy): the atomic's return value is the record's final position.  (1024 threads per
+// block over the same window of records measured 0.7 ms slower than 256 on config 5: the pass is bound by the L2's
+// handling of the scattered 4-byte stores, not by latency.)
+#ifndef CFB_PLACE_THREADS
+#define CFB_PLACE_THREADS 256
+#endif
+// streaming (evict-first) load of a record: the 1.6 GB of records pass through the L2 once and must not push out the
+// partially written target sectors
+__device__ __forceinline__ Rec4<float> load_rec_cs(const Rec4<float> *p)
 {
-    constexpr int PER = CFB_PART_CHUNK / 256;
-    for (int64_t chunk = blockIdx.x; chunk * CFB_PART_CHUNK < npad; chunk += gridDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));
+    Rec4<float> r;
+    r.x = v.x, r.y = v.y, r.z = v.z, r.w = v.w;
+    return r;
+}
+__device__ __forceinline__ Rec4<double> load_rec_cs(const Rec4<double> *p)
+{
+    const double2 a = __ldcs(reinterpret_cast<const double2 *>(p)), b = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
+    Rec4<double> r;
+    r.x = a.x, r.y = a.y, r.z = b.x, r.w = b.y;
+    return r;
+}
+template <typename T, bool WGT>
+__global__ void __launch_bounds__(CFB_PLACE_THREADS)
+k_place(const int64_t npad, const Rec4<T> *__restrict__ rec, const int *__restrict__ rcid, const int *__restrict__ start,
+        const int shift, const int nbuckets, const int *__restrict__ bcount, int *__restrict__ cur, T *__restrict__ xs,
+        T *__restrict__ ys, T *__restrict__ zs, T *__restrict__ ws)
+{
+    constexpr int CH = 4096, PER = CH / CFB_PLACE_THREADS;
+    __shared__ int s_base[CFB_PART_MAXB], s_cnt[CFB_PART_MAXB];
+    for (int b = threadIdx.x; b < nbuckets; b += CFB_PLACE_THREADS) {
+        s_base[b] = start[(int64_t)b << shift];
+        s_cnt[b] = bcount[b];
+    }
+    __syncthreads();
+    for (int64_t chunk = blockIdx.x; chunk * CH < npad; chunk += gridDim.x) {
 #pragma unroll
         for (int k = 0; k < PER; k++) {
-            const int64_t p = chunk * CFB_PART_CHUNK + k * 256 + threadIdx.x;
+            const int64_t p = chunk * CH + k * CFB_PLACE_THREADS + threadIdx.x;
             if (p >= npad) continue;
-            const int c = rcid[p];
-            if (c < 0) continue;  // padding between the buckets' runs
-            const Rec4<T> r = rec[p];
-            const int q = start[c] + atomicAdd(&cur[c], 1);
+            int lo = 0, hi = nbuckets;  // last bucket whose base is <= p (of equal bases the last: the others are empty)
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)s_base[mid] <= p) lo = mid; else hi = mid;
+            }
+            if (p - s_base[lo] >= s_cnt[lo]) continue;  // padding at the end of the bucket's region
+            const Rec4<T> r = load_rec_cs(rec + p);
+            const int c = WGT ? __ldcs(rcid + p) : real_as_cell(r.w);
+            const int q = atomicAdd(&cur[c], 1);
             xs[q] = r.x;
             ys[q] = r.y;
             zs[q] = r.z;
-            if (ws) ws[q] = r.w;
+            if (WGT) ws[q] = r.w;
         }
     }
 }
@@ -383,16 +508,74 @@ __global__ void k_fill_tiles(const int64_t ncells, const int *__restrict__ count
 
 static inline unsigned int nblocks(int64_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
 
+static int64_t sort2_min()
+{
+    static int64_t v = -1;  // sets at least this large take the two-pass scatter
+    if (v < 0) {
+        const char *e = getenv("CORRFUNC_B200_SORT2_MIN");
+        v = (e && *e) ? atoll(e) : 4000000;
+    }
+    return v;
+}
+
+template <typename T, bool WGT>
+static int scatter_two_pass(Ctx &c, ParticleSet &S, int64_t ncells, double scale)
+{
+    int shift = 0;
+    while (((ncells + ((int64_t)1 << shift) - 1) >> shift) > CFB_PART_MAXB) shift++;
+    const int nbuckets = (int)((ncells + ((int64_t)1 << shift) - 1) >> shift);
+    if (cfb_ensure(c.sort_rec, (size_t)S.npad * sizeof(Rec4<T>))) return 1;
+    if (WGT && cfb_ensure(c.sort_cid, (size_t)S.npad * 4)) return 1;
+    if (cfb_ensure(c.sort_cur, (size_t)(ncells + CFB_PART_MAXB) * 4)) return 1;
+    int *bcursor = (int *)c.sort_cur.p, *ccursor = (int *)c.sort_cur.p + CFB_PART_MAXB;
+    CK(cudaMemsetAsync(bcursor, 0, (size_t)CFB_PART_MAXB * 4, c.stream));
+    CK(cudaMemcpyAsync(ccursor, S.start.p, (size_t)ncells * 4, cudaMemcpyDeviceToDevice, c.stream));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kp = k_partition<T, WGT>;
+    constexpr size_t sm = part_smem<T, WGT>();
+    CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const unsigned g1 = (unsigned)min((int64_t)nblocks(S.n, part_chunk<T>()), (int64_t)sms * 8);
+    kp<<<g1, 256, sm, c.stream>>>(S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2], (const T *)S.raw[3],
+                                  (const int *)S.cidx.p, shift, nbuckets, (const int *)S.start.p, bcursor,
+                                  (Rec4<T> *)c.sort_rec.p, (int *)c.sort_cid.p, (T)scale);
+    // few blocks in flight: their targets (a few neighbouring buckets) must stay L2-resident until complete
+    static int place_blocks = -1;
+    if (place_blocks < 0) {
+        const char *e = getenv("CORRFUNC_B200_PLACE_BLOCKS");
+        place_blocks = (e && atoi(e) > 0) ? atoi(e) : 2;
+    }
+    const unsigned g2 = (unsigned)min((int64_t)nblocks(S.npad, 4096), (int64_t)sms * place_blocks);
+    k_place<T, WGT><<<g2, CFB_PLACE_THREADS, 0, c.stream>>>(S.npad, (const Rec4<T> *)c.sort_rec.p, (const int *)c.sort_cid.p,
+                                               (const int *)S.start.p, shift, nbuckets, bcursor, ccursor,
+                                               (T *)S.sorted[0].p, (T *)S.sorted[1].p, (T *)S.sorted[2].p,
+                                               WGT ? (T *)S.sorted[3].p : nullptr);
+    c.launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// have_rank: the cell-index kernel left every particle's arrival rank in S.rank (needed by the one-pass scatter)
 template <typename T>
-static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells, double scale)
+static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells, double scale, bool have_rank)
 {
     // scan -> starts / tile ids
     if (cfb_ensure(S.start, (size_t)ncells * 4)) return 1;
     if (cfb_ensure(S.tstart, (size_t)ncells * 4)) return 1;
-    // scratch: [0] out-of-bounds counter (written by the cell-index kernel), +64: {padded total, tile total}
-    long long *totals = (long long *)((char *)c.scratch.p + 64);
-    k_scan_cells<<<1, 1024, 0, c.stream>>>(ncells, (const int *)S.count.p, (int *)S.start.p, (int *)S.tstart.p, totals);
-    c.launches++;
+    // scratch: [0] out-of-bounds counter (written by the cell-index kernel), +64: {padded total, tile total},
+    // +1024: segment totals of the scan (2 x 64)
+    long long *totals = (long long *)((char *)c.scratch.p + 64), *bsum = (long long *)((char *)c.scratch.p + 1024);
+    {
+        const int64_t per = 1024 * CFB_SCAN_ITEMS;
+        int64_t seg = (ncells + 63) / 64;
+        seg = (seg + per - 1) / per * per;
+        const unsigned g = (unsigned)((ncells + seg - 1) / seg);  // <= 64
+        k_scan_sums<<<g, 1024, 0, c.stream>>>(ncells, seg, (const int *)S.count.p, bsum);
+        k_scan_cells<<<g, 1024, 0, c.stream>>>(ncells, seg, (const int *)S.count.p, (int *)S.start.p, (int *)S.tstart.p,
+                                               bsum, totals);
+        c.launches += 2;
+    }
     CK(cudaGetLastError());
     long long *h = (long long *)c.pinned;
     CK(cudaMemcpyAsync(h, c.scratch.p, 64 + 16, cudaMemcpyDeviceToHost, c.stream));
@@ -407,36 +590,8 @@ static int finish_sort(Ctx &c, ParticleSet &S, int64_t ncells, double scale)
     const bool hasw = S.raw[3] != nullptr;
     for (int a = 0; a < (hasw ? 4 : 3); a++)
         if (cfb_ensure(S.sorted[a], sb)) return 1;
-    static int64_t sort2_min = -1;  // sets at least this large take the two-pass scatter
-    if (sort2_min < 0) {
-        const char *e = getenv("CORRFUNC_B200_SORT2_MIN");
-        sort2_min = (e && *e) ? atoll(e) : 4000000;
-    }
-    if (S.n > 0 && S.n >= sort2_min && S.npad > 0) {
-        int shift = 0;
-        while (((ncells + ((int64_t)1 << shift) - 1) >> shift) > CFB_PART_MAXB) shift++;
-        const int nbuckets = (int)((ncells + ((int64_t)1 << shift) - 1) >> shift);
-        if (cfb_ensure(c.sort_rec, (size_t)S.npad * sizeof(Rec4<T>))) return 1;
-        if (cfb_ensure(c.sort_cid, (size_t)S.npad * 4)) return 1;
-        if (cfb_ensure(c.sort_cur, (size_t)(ncells + CFB_PART_MAXB) * 4)) return 1;
-        CK(cudaMemsetAsync(c.sort_cid.p, 0xFF, (size_t)S.npad * 4, c.stream));
-        CK(cudaMemsetAsync(c.sort_cur.p, 0, (size_t)(ncells + CFB_PART_MAXB) * 4, c.stream));
-        int *bcursor = (int *)c.sort_cur.p, *ccursor = (int *)c.sort_cur.p + CFB_PART_MAXB;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const unsigned g1 = (unsigned)min((int64_t)nblocks(S.n, CFB_PART_CHUNK), (int64_t)sms * 8);
-        k_partition<T><<<g1, 256, 0, c.stream>>>(S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2],
-                                                  (const T *)S.raw[3], (const int *)S.cidx.p, shift, nbuckets,
-                                                  (const int *)S.start.p, bcursor, (Rec4<T> *)c.sort_rec.p,
-                                                  (int *)c.sort_cid.p, (T)scale);
-        // few blocks in flight: their targets (a few neighbouring buckets) must stay L2-resident until complete
-        const unsigned g2 = (unsigned)min((int64_t)nblocks(S.npad, CFB_PART_CHUNK), (int64_t)sms * 2);
-        k_place<T><<<g2, 256, 0, c.stream>>>(S.npad, (const Rec4<T> *)c.sort_rec.p, (const int *)c.sort_cid.p,
-                                              (const int *)S.start.p, ccursor, (T *)S.sorted[0].p, (T *)S.sorted[1].p,
-                                              (T *)S.sorted[2].p, hasw ? (T *)S.sorted[3].p : nullptr);
-        c.launches += 2;
-        CK(cudaGetLastError());
+    if (S.n > 0 && (S.n >= sort2_min() || !have_rank)) {
+        if (hasw ? scatter_two_pass<T, true>(c, S, ncells, scale) : scatter_two_pass<T, false>(c, S, ncells, scale)) return 1;
     } else if (S.n > 0) {
         k_scatter<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(
             S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2], (const T *)S.raw[3],
@@ -479,17 +634,19 @@ static int gridlink_box_T(Ctx &c, ParticleSet &S, const cfb_box_lattice *lat, co
     if (cfb_ensure(S.count, (size_t)ncells * 4)) return 1;
     if (cfb_ensure(S.bounds, (size_t)ncells * CFB_NB * sizeof(T))) return 1;
     if (cfb_ensure(S.cidx, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
-    if (cfb_ensure(S.rank, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
+    // large sets take the two-pass scatter, which ranks by arrival itself: no rank array (400 MB at 100 M points)
+    const bool want_rank = S.n < sort2_min();
+    if (want_rank && cfb_ensure(S.rank, (size_t)(S.n > 0 ? S.n : 1) * 4)) return 1;
     CK(cudaMemsetAsync(S.count.p, 0, (size_t)ncells * 4, c.stream));
     CK(cudaMemsetAsync(c.scratch.p, 0, 256, c.stream));
     if (S.n > 0) {
         k_cellindex_box<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(
-            S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2], G, (int *)S.cidx.p, (int *)S.rank.p,
-            (int *)S.count.p, (unsigned long long *)c.scratch.p);
+            S.n, (const T *)S.raw[0], (const T *)S.raw[1], (const T *)S.raw[2], G, (int *)S.cidx.p,
+            want_rank ? (int *)S.rank.p : nullptr, (int *)S.count.p, (unsigned long long *)c.scratch.p);
         c.launches++;
         CK(cudaGetLastError());
     }
-    return finish_sort<T>(c, S, ncells, scale);
+    return finish_sort<T>(c, S, ncells, scale, want_rank);
 }
 
 int cfb_gridlink_box_set(ParticleSet &S, const cfb_box_lattice *lat, const int sub[3], double scale)
@@ -545,7 +702,7 @@ static int gridlink_theta_T(Ctx &c, ParticleSet &S, const cfb_theta_lattice *lat
     c.launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c.stream));  // pinned staging reused by finish_sort
-    if (finish_sort<T>(c, S, nfine, 1.0)) return 1;
+    if (finish_sort<T>(c, S, nfine, 1.0, true)) return 1;
     k_ra_bounds_init<T><<<nblocks(nfine, 256), 256, 0, c.stream>>>(nfine, (T *)S.bounds.p);
     k_ra_bounds<T><<<nblocks(S.n, 256), 256, 0, c.stream>>>(S.n, (const T *)S.raw[4], (const int *)S.cidx.p,
                                                            (T *)S.bounds.p);
@@ -559,4 +716,68 @@ int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t
     Ctx &c = cfb_ctx();
     S.grid_sig_valid = false;
     return S.prec == 4 ? gridlink_theta_T<float>(c, S, lat, ncells) : gridlink_theta_T<double>(c, S, lat, ncells);
+}
+
+// ---- multi-rank sharding: this rank's contiguous tile range (cfb_internal.cuh) ---------------------------------------
+// One block: every thread sums the cost of its run of consecutive cells, a block scan gives the prefix at the start of
+// every run, and the thread whose run holds the cell where the prefix first reaches k / nranks of the total writes that
+// boundary.  out[0 .. 1] = first tile of the rank, first tile of the next rank.
+__global__ void __launch_bounds__(1024)
+k_shard_bounds(const int64_t ncells, const int *__restrict__ cnt1, const int *__restrict__ cnt2,
+               const int *__restrict__ tstart, const long long ntiles, const int rank, const int nranks, long long *out)
+{
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t seg = (ncells + 1023) / 1024;
+    const int64_t lo = min(ncells, tid * seg), hi = min(ncells, lo + seg);
+    unsigned long long sum = 0;
+    for (int64_t c = lo; c < hi; c++) sum += (unsigned long long)cnt1[c] * (unsigned long long)(cnt2[c] + 1);
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[wid] = incl;
+    if (tid < 2) out[tid] = tid == 0 ? 0 : ntiles;  // rank 0 starts at the first tile, the last rank ends at the last
+    __syncthreads();
+    unsigned long long pre = 0;
+    for (int v = 0; v < wid; v++) pre += s_w[v];
+    if (tid == 1023) s_total = pre + incl;
+    __syncthreads();
+    const unsigned long long total = s_total;
+    unsigned long long before = pre + incl - sum;
+    // boundary k: the first cell after the one where the running cost reaches total * k / nranks
+    const unsigned long long t0 = (unsigned long long)((double)total * ((double)rank / (double)nranks));
+    const unsigned long long t1 = (unsigned long long)((double)total * ((double)(rank + 1) / (double)nranks));
+    for (int64_t c = lo; c < hi; c++) {
+        const unsigned long long after = before + (unsigned long long)cnt1[c] * (unsigned long long)(cnt2[c] + 1);
+        const long long tnext = c + 1 < ncells ? (long long)tstart[c + 1] : ntiles;
+        if (rank > 0 && before < t0 && t0 <= after) out[0] = tnext;
+        if (rank + 1 < nranks && before < t1 && t1 <= after) out[1] = tnext;
+        before = after;
+    }
+}
+
+int cfb_shard_tile_range(const ParticleSet &SA, const ParticleSet &SB, int rank, int nranks, int64_t *tile_lo, int64_t *tile_hi)
+{
+    *tile_lo = 0;
+    *tile_hi = SA.ntiles;
+    if (nranks <= 1 || SA.ntiles <= 0) return 0;
+    Ctx &c = cfb_ctx();
+    if (SB.ncells != SA.ncells) return cfb_fail("sharding: the two particle sets are on different lattices");
+    if (cfb_ensure(c.scratch, 4096)) return 1;
+    long long *out = (long long *)((char *)c.scratch.p + 3072);
+    k_shard_bounds<<<1, 1024, 0, c.stream>>>(SA.ncells, (const int *)SA.count.p, (const int *)SB.count.p,
+                                              (const int *)SA.tstart.p, (long long)SA.ntiles, rank, nranks, out);
+    c.launches++;
+    CK(cudaGetLastError());
+    long long h[2];
+    CK(cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    if (h[0] < 0 || h[1] < h[0] || h[1] > SA.ntiles) return cfb_fail("sharding: bad tile range [%lld, %lld)", h[0], h[1]);
+    *tile_lo = h[0];
+    *tile_hi = h[1];
+    return 0;
 }

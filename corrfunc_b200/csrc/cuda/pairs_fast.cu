@@ -481,7 +481,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
 
     // Persistent warps: every warp pulls its next primary tile from a global counter (tiles differ in
     // work by the cell occupancies; one tile per warp left 7 % of the warp time waiting at the block's
-    // final barrier).  Across ranks the work is sharded by primary cell (cfb_owns_cell).
+    // final barrier).  Across ranks the work is sharded by primary cell (cfb_shard_tile_range).
     u64 my_eval = 0, my_jobs = 0, my_analytic = 0, my_levels = 0;
     unsigned wbound = 0;  // warp-uniform bound on the magnitude of any slot of W.wh
     uint32_t it = 0;  // chunks staged so far by this warp (buffer = it & 1, TMA parity = (it >> 1) & 1)
@@ -495,11 +495,10 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
             // and, when it is set, pushes the tile counter past the end -- every later fetch of every warp then ends its loop
             if ((gw & 63) == 0 && P.abort && *P.abort) gw = (long long)atomicAdd(&P.counters[4], 1ULL << 40) + ((long long)1 << 40);
         }
-        gw = __shfl_sync(0xffffffffu, gw, 0);
-        if (gw >= P.ntiles) break;
+        gw = __shfl_sync(0xffffffffu, gw, 0) + P.tile_lo;  // this rank's tiles: [tile_lo, tile_hi) (cfb_shard_tile_range)
+        if (gw >= P.tile_hi) break;
         const int64_t tile = gw;
         const int cellP = P.tile_cell[tile];
-        if (!cfb_owns_cell(cellP, P.shard_rank, P.shard_n)) continue;  // another rank's cell (see cfb_owns_cell)
         const int toff = P.tile_off[tile];
         const int nP = A.count[cellP];
         const int startP = A.start[cellP];
@@ -926,7 +925,7 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
         if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
         res = sms * (per_sm > 0 ? per_sm : 1);
     }
-    int64_t nblk = (Q.ntiles / (Q.shard_n > 1 ? Q.shard_n : 1) + FAST_WARPS - 1) / FAST_WARPS + 1;
+    int64_t nblk = ((Q.tile_hi - Q.tile_lo) + FAST_WARPS - 1) / FAST_WARPS + 1;
     if (nblk > res) nblk = res;
     if (use_tma)
         k_pairs_fast<T, MODE, LIST, true><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q, view_of<T>(SA), view_of<T>(SB));

@@ -147,6 +147,13 @@ __device__ __forceinline__ void add2(const unsigned addr, const double m)  // m 
     const unsigned old = sh_atom_add(addr, lo);
     sh_red_add(addr + 4, (unsigned)hi + (old > ~lo ? 1u : 0u));
 }
+// second half of add2: the high word + the carry of the low word's add (old = what the low word held before it)
+__device__ __forceinline__ void add2_hi(const unsigned addr_hi, const double m, const unsigned old)
+{
+    const unsigned lo = (unsigned)__double2loint(m);
+    const int hi = __double2hiint(m) - 0x43380000;  // floor(q / 2^32)
+    sh_red_add(addr_hi, (unsigned)hi + (old > ~lo ? 1u : 0u));
+}
 // what the high word of one sum holds (exchanged with zero); last: also the low word (nobody adds any more)
 __device__ __forceinline__ double take2(unsigned *w, const bool last)
 {
@@ -178,7 +185,10 @@ struct SumWarp {
     alignas(16) T buf[2][NA][SUM_CH];
     // double runs: float copies of the current chunk's positions -- the hot loop is a conservative FLOAT filter there
     alignas(16) float fbuf[sizeof(T) == 8 ? 3 : 1][sizeof(T) == 8 ? SUM_CH : 4];
-    alignas(16) T prim[NA][SUM_TILE];  // the tile's primaries with the current wrap applied (+ weights): gathered by the drain
+    // the tile's primaries with the current wrap applied (+ weights), gathered by the drain.  Primary `lane + 32 p` lives at
+    // [2 lane + p]: a batch of the drain holds the two primaries of two or three neighbouring lanes, and at [lane + 32 p]
+    // the two rows of one lane shared their banks (ncu: 3.6 wavefronts per gather against 1.9 ideal)
+    alignas(16) T prim[NA][SUM_TILE];
     // accepted pairs, first per LANE (one byte each: secondary | primary row << 6; entry i of lane l at [i][l], so a push is
     // one predicated byte store and one add, no ballot, no prefix count), then -- when a lane's queue is full or the chunk
     // ends -- compacted into `ring` (lane << 8 | entry) by one warp scan over the queue lengths: the drain takes 32
@@ -342,7 +352,7 @@ __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA
     for (int u = 0; u < NB; u++) {
         ok[u] = 32 * u + lane < n;
         const unsigned idx = W.ring[head + 32 * u + lane];
-        pidx[u] = ((idx >> 8) & 31) | ((idx & 64) >> 1);
+        pidx[u] = ((idx >> 7) & 62) | ((idx >> 6) & 1);  // 2 lane + p
         j[u] = idx & (SUM_CH - 1) & 63;
     }
 #pragma unroll
@@ -482,10 +492,14 @@ __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA
             }
         }
     }
+    // the sums' fixed-point images first, for all batches; then every low-word atomic of the call (their old values come
+    // back independently -- issued one after the other's carry, the four round trips of a call were 7 % of all warp
+    // samples), then the high words with the carries
+    double msep[NB], mw[NB];
 #pragma unroll
     for (int u = 0; u < NB; u++) {
         if (!ok[u]) slot[u] = 0, kb[u] = kfirst;  // idle lanes: any valid address
-        double msep = 0.0, mw = 0.0;
+        msep[u] = 0.0, mw[u] = 0.0;
         if (AVG) {
             T sep;
             if (MODE == CFB_THETA) {
@@ -498,21 +512,37 @@ __device__ __forceinline__ void drain(const int n, const int head, SumWarp<T, NA
                 if (sizeof(T) == 8 && !have_rs) rs[u] = rsqrt_apx(have_vf ? vf[u] : (float)v[u]);
                 sep = sep_sqrt(v[u], rs[u]);
             }
-            msep = __fma_rn((double)sep, K.scale[kb[u]], SUM_MAGIC);
+            msep[u] = __fma_rn((double)sep, K.scale[kb[u]], SUM_MAGIC);
         }
         if (WGT) {
             const T w1 = W.prim[NA - 1][pidx[u]], w2 = W.buf[bsel][NA - 1][j[u]];
-            mw = __fma_rn((double)(T)(w1 * w2), K.w_scale, SUM_MAGIC);  // pair_product, weight_functions.h.src:71-91
+            mw[u] = __fma_rn((double)(T)(w1 * w2), K.w_scale, SUM_MAGIC);  // pair_product, weight_functions.h.src:71-91
         }
+    }
+    unsigned hw[NB], old_s[NB], old_w[NB];
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+        hw[u] = hword<NP>(K, slot[u]);
+        old_s[u] = 0u, old_w[u] = 0u;
 #ifdef SUM_ABL_NOATOM  // ablation (timing experiments only, results wrong): no histogram update
         if (ok[u] && slot[u] == -12345) {
 #else
         if (ok[u]) {
 #endif
-            const unsigned h = hword<NP>(K, slot[u]);
-            sh_red_add(h, 1u);
-            if (AVG) add2(h + 4, msep);
-            if (WGT) add2(h + 4 + (AVG ? 8 : 0), mw);
+            sh_red_add(hw[u], 1u);
+            if (AVG) old_s[u] = sh_atom_add(hw[u] + 4, (unsigned)__double2loint(msep[u]));
+            if (WGT) old_w[u] = sh_atom_add(hw[u] + 4 + (AVG ? 8 : 0), (unsigned)__double2loint(mw[u]));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+#ifdef SUM_ABL_NOATOM
+        if (ok[u] && slot[u] == -12345) {
+#else
+        if (ok[u]) {
+#endif
+            if (AVG) add2_hi(hw[u] + 8, msep[u], old_s[u]);
+            if (WGT) add2_hi(hw[u] + 8 + (AVG ? 8 : 0), mw[u], old_w[u]);
         }
     }
 }
@@ -695,17 +725,20 @@ __device__ __forceinline__ void flush_queues(SumWarp<T, NA> &W, const int bsel, 
     const int excl = incl - c;
     const int maxc = __reduce_max_sync(0xffffffffu, c);
     const unsigned lb = (unsigned)lane << 8;
-#ifndef SUM_COPY_UNROLL
-#define SUM_COPY_UNROLL 4
-#endif
-    // four independent load -> store pairs in flight per lane (the loop is pure latency)
-    for (int i0 = 0; i0 < maxc; i0 += SUM_COPY_UNROLL) {
-        unsigned e[SUM_COPY_UNROLL];
+    // fully unrolled over the queue depth, four entries per (warp-uniform) exit test: every load and store has an immediate
+    // offset (the rolled loop spent 18 instructions per entry on index arithmetic, 6 % of the kernel's instructions)
+    {
+        unsigned short *const rdst = W.ring + excl;
 #pragma unroll
-        for (int u = 0; u < SUM_COPY_UNROLL; u++) e[u] = qbase[32 * min(i0 + u, SUM_QL - 1)];
+        for (int i0 = 0; i0 < SUM_QL; i0 += 4) {
+            if (i0 >= maxc) break;
+            unsigned e[4];
 #pragma unroll
-        for (int u = 0; u < SUM_COPY_UNROLL; u++)
-            if (i0 + u < c) W.ring[excl + i0 + u] = (unsigned short)(lb | e[u]);
+            for (int u = 0; u < 4; u++) e[u] = qbase[32 * (i0 + u)];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i0 + u < c) rdst[i0 + u] = (unsigned short)(lb | e[u]);
+        }
     }
     qaddr = qaddr0;
     __syncwarp();
@@ -862,11 +895,10 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
             // and, when it is set, pushes the tile counter past the end -- every later fetch of every warp then ends its loop
             if ((gw & 63) == 0 && P.abort && *P.abort) gw = (long long)atomicAdd(&P.counters[4], 1ULL << 40) + ((long long)1 << 40);
         }
-        gw = __shfl_sync(0xffffffffu, gw, 0);
-        if (gw >= P.ntiles * SPLIT) break;
+        gw = __shfl_sync(0xffffffffu, gw, 0) + P.tile_lo * SPLIT;  // this rank's tiles: [tile_lo, tile_hi) (cfb_shard_tile_range)
+        if (gw >= P.tile_hi * SPLIT) break;
         const int64_t tile = gw / SPLIT;
         const int cellP = P.tile_cell[tile];
-        if (!cfb_owns_cell(cellP, P.shard_rank, P.shard_n)) continue;  // another rank's cell
         const int toff = P.tile_off[tile] + (int)(gw % SPLIT) * SUM_TILE;
         const int nP = A.count[cellP];
         if (toff >= nP) continue;
@@ -916,10 +948,10 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
             yq[p] = ok ? pyg[i] : nanv;
             zq[p] = ok ? pzg[i] : nanv;
             xh[p] = (float)xq[p], yh[p] = (float)yq[p], zh[p] = (float)zq[p];
-            W.prim[0][i] = xq[p];
-            W.prim[1][i] = yq[p];
-            W.prim[2][i] = zq[p];
-            if (WGT) W.prim[3][i] = ok ? pwg[i] : (T)0;
+            W.prim[0][2 * lane + p] = xq[p];
+            W.prim[1][2 * lane + p] = yq[p];
+            W.prim[2][2 * lane + p] = zq[p];
+            if (WGT) W.prim[3][2 * lane + p] = ok ? pwg[i] : (T)0;
         }
         __syncwarp();
 
@@ -1144,9 +1176,9 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
                                 yq[p] = cy ? yr + oy : yr;
                                 zq[p] = cz ? zr + oz : zr;
                                 xh[p] = (float)xq[p], yh[p] = (float)yq[p], zh[p] = (float)zq[p];
-                                W.prim[0][i] = xq[p];
-                                W.prim[1][i] = yq[p];
-                                W.prim[2][i] = zq[p];
+                                W.prim[0][2 * lane + p] = xq[p];
+                                W.prim[1][2 * lane + p] = yq[p];
+                                W.prim[2][2 * lane + p] = zq[p];
                             }
                         }
                         __syncwarp();
@@ -1309,7 +1341,7 @@ int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cuda
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SUM_WARPS * 32, sm));
     if (per_sm < 1) per_sm = 1;
     constexpr int SPLIT = CFB_TILE / SUM_TILE;
-    int64_t nblk = (P.ntiles * SPLIT / (P.shard_n > 1 ? P.shard_n : 1) + SUM_WARPS - 1) / SUM_WARPS + 1;
+    int64_t nblk = ((P.tile_hi - P.tile_lo) * SPLIT + SUM_WARPS - 1) / SUM_WARPS + 1;
     if (nblk > (int64_t)sms * per_sm) nblk = (int64_t)sms * per_sm;
     kern<<<(unsigned int)nblk, SUM_WARPS * 32, sm, st>>>(P, view_of<T>(SA), view_of<T>(SB));
     cfb_ctx().launches++;
@@ -1357,6 +1389,7 @@ int cfb_launch_pairs_sum(const cfb_binning *bin, const PairParams &P0, int prec,
 {
     PairParams P = P0;
     static_assert(CFB_TILE % SUM_TILE == 0, "sum tiles subdivide the gridlink tiles");
+    static_assert(SUM_QL % 4 == 0 && SUM_PA == 2, "queue compaction is unrolled by four; the primaries of a lane are interleaved in pairs");
     static_assert(SUM_TILE <= 256 && SUM_CH <= 256, "a stack entry is (primary << 8 | secondary) in 16 bits");
     if (bin->nedges < 2 || bin->nedges > SUM_MAX_EDGES) return -1;
     for (int i = 0; i < bin->nedges; i++) {
