@@ -7,6 +7,7 @@
 
 #include "corrfunc_b200_device.h"
 
+#define CFB_SHARD_GROUP 8    // fine cells per shard group: rank r owns the cells c with (c / 8) % nranks == r
 #define CFB_PAD 4            // every fine cell's run in the sorted SoA starts at a multiple of this (16 B for float)
 #define CFB_TILE 128         // primaries per tile in the generic kernel (one per thread)
 #define CFB_FAST_MAX_EDGES 64 // the fast kernel keeps edges and the block histogram in static shared memory
@@ -111,8 +112,9 @@ struct PairParams {
     // tiles of the primary set
     const int *tile_cell, *tile_off;
     int64_t ntiles;
+    int64_t tail_first;  // fast kernel: tiles from this one on are handed out in tail_parts pieces (groups of neighbour rows)
+    int tail_parts;
     int shard_rank, shard_n;
-    int64_t tile_lo, tile_hi;  // this rank's tiles (all of them with one rank): see cfb_shard_tile_range
     // outputs
     unsigned long long *npairs;
     double *sum_sep, *sum_w;
@@ -130,15 +132,17 @@ struct PairParams {
 };
 
 // Multi-rank sharding is by primary CELL, never by tile: every rank sorts its own replica and the order of the
-// particles inside a cell (atomic arrival ranks) differs from rank to rank, so the tiles of one cell only partition its
-// particles consistently when one rank handles all of them.  A rank owns a CONTIGUOUS range of cells -- tiles are in cell
-// order, so a contiguous range of tiles [tile_lo, tile_hi) -- chosen so that the ranks' shares of
-// sum(count1[c] * (count2[c] + 1)) are equal (the work of a cell grows with its own occupancy times the local density).
-// Every rank derives the same boundaries from the same cell counts.  Round 1 interleaved groups of 8 cells over the ranks:
-// balanced for any input, but the resident warps of one device then walk a region n times as wide and their neighbour
-// cells no longer fit the L2 -- rank 0 of 8 emulated on one GPU took 1.5 % longer than an eighth of the full kernel
-// (tools/exp_shard.py), which was most of the 8-GPU efficiency loss.
-int cfb_shard_tile_range(const ParticleSet &SA, const ParticleSet &SB, int rank, int nranks, int64_t *tile_lo, int64_t *tile_hi);
+// particles inside a cell (atomic arrival ranks) differs from rank to rank, so the tiles of one cell only
+// partition its particles consistently when one rank handles all of them.  Groups of 8 consecutive cells are dealt to the
+// ranks in turn: every rank sees the same mix of cells whatever the catalogue and whatever the reference's role filter
+// does to the cells near the ends of the index range (contiguous cost-balanced cell ranges were tried in round 2: the
+// filter gives the low-index cells a fraction of the pairs of the high-index ones, a neighbour-sum cost model still left
+// rank 0 of 8 with 0.119 and rank 7 with 0.131 of config 5's evaluations, and the interleaving itself costs nothing --
+// tools/exp_shard.py: what a rank loses against an n-th of the full kernel is the tail of its last tiles).
+__host__ __device__ __forceinline__ bool cfb_owns_cell(const int cell, const int rank, const int nranks)
+{
+    return nranks <= 1 || (cell / CFB_SHARD_GROUP) % nranks == rank;
+}
 
 // gridlink entry points (gridlink.cu)
 // scale: power of two applied to the sorted copy of the positions (1 unless the fast float kernel runs)

@@ -572,7 +572,6 @@ static int count_box_one(const cfb_binning *bin, const cfb_box_lattice *lat, cfb
     P.tile_cell = (const int *)c.set[0].tile_cell.p;
     P.tile_off = (const int *)c.set[0].tile_off.p;
     P.ntiles = c.set[0].ntiles;
-    if (cfb_shard_tile_range(c.set[0], c.set[nsets - 1], c.shard_rank, c.shard_n, &P.tile_lo, &P.tile_hi)) return 1;
     {
         const unsigned wy = 2 * P.g.reach[1] + 1, wz = 2 * P.g.reach[2] + 1;
         P.m_wz = div_magic(wz);
@@ -611,7 +610,7 @@ static int count_box_one(const cfb_binning *bin, const cfb_box_lattice *lat, cfb
 // (torchrun: cfb_set_shard with nranks > 1, or CORRFUNC_B200_DEVICE set) always stays on its own device.
 // Device 0 of the call holds the uploaded arrays; the others receive them by peer copies over NVLink (900 GB/s per
 // direction instead of another trip over PCIe), then every device grids its replica and counts the primary cells it
-// owns (cfb_shard_tile_range), driven by its own host thread; the partial histograms (<= a few KB) are summed on the host.
+// owns (cfb_owns_cell), driven by its own host thread; the partial histograms (<= a few KB) are summed on the host.
 #define CFB_MULTI_MIN_N 4000000
 static int g_multi_devs[CFB_MAX_DEV];
 static int g_multi_last = 1;  // devices the last box count ran on
@@ -860,7 +859,6 @@ extern "C" int cfb_count_theta(const cfb_binning *bin, int64_t ncells, const int
     P.tile_cell = (const int *)c.set[0].tile_cell.p;
     P.tile_off = (const int *)c.set[0].tile_off.p;
     P.ntiles = c.set[0].ntiles;
-    if (cfb_shard_tile_range(c.set[0], c.set[bin->autocorr ? 0 : 1], c.shard_rank, c.shard_n, &P.tile_lo, &P.tile_hi)) return 1;
     if (P.ntiles > 0 && nlist > 0) {
         if (fast ? cfb_launch_pairs_fast(bin, P, bin->prec, true) : cfb_launch_pairs_generic(bin, P, bin->prec, true))
             return 1;

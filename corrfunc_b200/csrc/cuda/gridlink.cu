@@ -717,67 +717,3 @@ int cfb_gridlink_theta_set(ParticleSet &S, const cfb_theta_lattice *lat, int64_t
     S.grid_sig_valid = false;
     return S.prec == 4 ? gridlink_theta_T<float>(c, S, lat, ncells) : gridlink_theta_T<double>(c, S, lat, ncells);
 }
-
-// ---- multi-rank sharding: this rank's contiguous tile range (cfb_internal.cuh) ---------------------------------------
-// One block: every thread sums the cost of its run of consecutive cells, a block scan gives the prefix at the start of
-// every run, and the thread whose run holds the cell where the prefix first reaches k / nranks of the total writes that
-// boundary.  out[0 .. 1] = first tile of the rank, first tile of the next rank.
-__global__ void __launch_bounds__(1024)
-k_shard_bounds(const int64_t ncells, const int *__restrict__ cnt1, const int *__restrict__ cnt2,
-               const int *__restrict__ tstart, const long long ntiles, const int rank, const int nranks, long long *out)
-{
-    __shared__ unsigned long long s_w[32];
-    __shared__ unsigned long long s_total;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t seg = (ncells + 1023) / 1024;
-    const int64_t lo = min(ncells, tid * seg), hi = min(ncells, lo + seg);
-    unsigned long long sum = 0;
-    for (int64_t c = lo; c < hi; c++) sum += (unsigned long long)cnt1[c] * (unsigned long long)(cnt2[c] + 1);
-    unsigned long long incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_w[wid] = incl;
-    if (tid < 2) out[tid] = tid == 0 ? 0 : ntiles;  // rank 0 starts at the first tile, the last rank ends at the last
-    __syncthreads();
-    unsigned long long pre = 0;
-    for (int v = 0; v < wid; v++) pre += s_w[v];
-    if (tid == 1023) s_total = pre + incl;
-    __syncthreads();
-    const unsigned long long total = s_total;
-    unsigned long long before = pre + incl - sum;
-    // boundary k: the first cell after the one where the running cost reaches total * k / nranks
-    const unsigned long long t0 = (unsigned long long)((double)total * ((double)rank / (double)nranks));
-    const unsigned long long t1 = (unsigned long long)((double)total * ((double)(rank + 1) / (double)nranks));
-    for (int64_t c = lo; c < hi; c++) {
-        const unsigned long long after = before + (unsigned long long)cnt1[c] * (unsigned long long)(cnt2[c] + 1);
-        const long long tnext = c + 1 < ncells ? (long long)tstart[c + 1] : ntiles;
-        if (rank > 0 && before < t0 && t0 <= after) out[0] = tnext;
-        if (rank + 1 < nranks && before < t1 && t1 <= after) out[1] = tnext;
-        before = after;
-    }
-}
-
-int cfb_shard_tile_range(const ParticleSet &SA, const ParticleSet &SB, int rank, int nranks, int64_t *tile_lo, int64_t *tile_hi)
-{
-    *tile_lo = 0;
-    *tile_hi = SA.ntiles;
-    if (nranks <= 1 || SA.ntiles <= 0) return 0;
-    Ctx &c = cfb_ctx();
-    if (SB.ncells != SA.ncells) return cfb_fail("sharding: the two particle sets are on different lattices");
-    if (cfb_ensure(c.scratch, 4096)) return 1;
-    long long *out = (long long *)((char *)c.scratch.p + 3072);
-    k_shard_bounds<<<1, 1024, 0, c.stream>>>(SA.ncells, (const int *)SA.count.p, (const int *)SB.count.p,
-                                              (const int *)SA.tstart.p, (long long)SA.ntiles, rank, nranks, out);
-    c.launches++;
-    CK(cudaGetLastError());
-    long long h[2];
-    CK(cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, c.stream));
-    CK(cudaStreamSynchronize(c.stream));
-    if (h[0] < 0 || h[1] < h[0] || h[1] > SA.ntiles) return cfb_fail("sharding: bad tile range [%lld, %lld)", h[0], h[1]);
-    *tile_lo = h[0];
-    *tile_hi = h[1];
-    return 0;
-}

@@ -481,7 +481,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
 
     // Persistent warps: every warp pulls its next primary tile from a global counter (tiles differ in
     // work by the cell occupancies; one tile per warp left 7 % of the warp time waiting at the block's
-    // final barrier).  Across ranks the work is sharded by primary cell (cfb_shard_tile_range).
+    // final barrier).  Across ranks the work is sharded by primary cell (cfb_owns_cell).
     u64 my_eval = 0, my_jobs = 0, my_analytic = 0, my_levels = 0;
     unsigned wbound = 0;  // warp-uniform bound on the magnitude of any slot of W.wh
     uint32_t it = 0;  // chunks staged so far by this warp (buffer = it & 1, TMA parity = (it >> 1) & 1)
@@ -495,10 +495,23 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
             // and, when it is set, pushes the tile counter past the end -- every later fetch of every warp then ends its loop
             if ((gw & 63) == 0 && P.abort && *P.abort) gw = (long long)atomicAdd(&P.counters[4], 1ULL << 40) + ((long long)1 << 40);
         }
-        gw = __shfl_sync(0xffffffffu, gw, 0) + P.tile_lo;  // this rank's tiles: [tile_lo, tile_hi) (cfb_shard_tile_range)
-        if (gw >= P.tile_hi) break;
-        const int64_t tile = gw;
+        gw = __shfl_sync(0xffffffffu, gw, 0);
+        // Work units: whole tiles, except that the last tiles of the list are handed out in pieces (groups of neighbour
+        // rows).  A tile of config 5 is 12 ms of one warp's time; when the list runs out the warps stop at random points
+        // of their last tile, and the kernel ends with its slowest warp: ~6 ms of idle SMs per launch -- 0.1 % of a 5-s
+        // launch, but 1 % of the 640 ms an eighth of the work takes (tools/exp_shard.py: rank r of 8 emulated on one GPU
+        // took 1.2-1.5 % longer than an eighth of the full kernel, whichever way the cells were dealt to the ranks).
+        if (gw >= P.tail_first + (P.ntiles - P.tail_first) * P.tail_parts) break;
+        int64_t tile = gw;
+        int part = 0, parts = 1;
+        if (gw >= P.tail_first) {
+            const int64_t u = gw - P.tail_first;
+            tile = P.tail_first + u / P.tail_parts;
+            part = (int)(u % P.tail_parts);
+            parts = P.tail_parts;
+        }
         const int cellP = P.tile_cell[tile];
+        if (!cfb_owns_cell(cellP, P.shard_rank, P.shard_n)) continue;  // another rank's cell (see cfb_owns_cell)
         const int toff = P.tile_off[tile];
         const int nP = A.count[cellP];
         const int startP = A.start[cellP];
@@ -549,7 +562,10 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
             zq[p] = ok ? pzg[i] : nanv;
         }
 
-        for (int row = 0; row < nrow; row++) {
+        // this unit's neighbour rows (all of them for a whole tile)
+        const int row_lo = parts > 1 ? (int)((long long)part * nrow / parts) : 0;
+        const int row_hi = parts > 1 ? (int)((long long)(part + 1) * nrow / parts) : nrow;
+        for (int row = row_lo; row < row_hi; row++) {
             for (int base = 0; base < rowlen; base += 32) {
                 // ---------------- phase 1: one candidate per lane ----------------
                 const int cand = base + lane;
@@ -749,7 +765,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                     wbound = 0;
                 }
                 // at most 2 * 32 new jobs per round: drain before another round could overflow the queue
-                const bool last = (row == nrow - 1) && (base + 32 >= rowlen);
+                const bool last = (row == row_hi - 1) && (base + 32 >= rowlen);
                 if (qn <= FAST_QCAP - 64 && !last) continue;
 
                 // ---------------- phase 2: drain the queue ----------------
@@ -925,12 +941,26 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
         if (cap && atoi(cap) > 0 && atoi(cap) < per_sm) per_sm = atoi(cap);
         res = sms * (per_sm > 0 ? per_sm : 1);
     }
-    int64_t nblk = ((Q.tile_hi - Q.tile_lo) + FAST_WARPS - 1) / FAST_WARPS + 1;
+    int64_t nblk = (Q.ntiles / (Q.shard_n > 1 ? Q.shard_n : 1) + FAST_WARPS - 1) / FAST_WARPS + 1;
     if (nblk > res) nblk = res;
+    // the last tail_k tiles of every resident warp (of every rank) go out row by row (see the kernel's work units)
+    PairParams Qt = P;
+    {
+        static int tail_k = -1;
+        if (tail_k < 0) {
+            const char *e = getenv("CORRFUNC_B200_TAIL_TILES_PER_WARP");
+            tail_k = (e && *e) ? atoi(e) : 2;
+        }
+        const int nrow = 2 * Qt.g.reach[0] + 1;
+        Qt.tail_parts = (LIST || nrow < 2 || tail_k <= 0) ? 1 : nrow;
+        const int64_t tail_tiles = (int64_t)tail_k * res * FAST_WARPS * (Qt.shard_n > 1 ? Qt.shard_n : 1);
+        Qt.tail_first = Qt.tail_parts > 1 ? (Qt.ntiles > tail_tiles ? Qt.ntiles - tail_tiles : 0) : Qt.ntiles;
+    }
+    const PairParams &Q2 = Qt;
     if (use_tma)
-        k_pairs_fast<T, MODE, LIST, true><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q, view_of<T>(SA), view_of<T>(SB));
+        k_pairs_fast<T, MODE, LIST, true><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q2, view_of<T>(SA), view_of<T>(SB));
     else
-        k_pairs_fast<T, MODE, LIST, false><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q, view_of<T>(SA), view_of<T>(SB));
+        k_pairs_fast<T, MODE, LIST, false><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q2, view_of<T>(SA), view_of<T>(SB));
     cfb_ctx().launches++;
     CK(cudaGetLastError());
     return 0;

@@ -142,9 +142,10 @@ k_pairs_generic(const PairParams P, const SetView<T> A, const SetView<T> B)
     }
     __shared__ GenShared<T> S;
 
-    // one block per primary tile of this rank's range [tile_lo, tile_hi) (cfb_shard_tile_range)
-    const int64_t tile = P.tile_lo + blockIdx.x;
-    if (tile >= P.tile_hi) return;
+    // one block per primary tile; across ranks the work is sharded by primary cell (cfb_owns_cell)
+    const int64_t tile = blockIdx.x;
+    if (tile >= P.ntiles) return;
+    if (!cfb_owns_cell(P.tile_cell[tile], P.shard_rank, P.shard_n)) return;
     const int tid = threadIdx.x;
 
     for (int i = tid; i < nedges; i += CFB_TILE) {
@@ -546,7 +547,7 @@ static int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &S
     P.hist_in_smem = (sm + hist <= budget) ? 1 : 0;
     sm += P.hist_in_smem ? hist : 8;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 16384));
-    const int64_t nblk = P.tile_hi - P.tile_lo;
+    const int64_t nblk = P.ntiles;
     if (nblk <= 0) return 0;
     if (nblk >= 2147483647LL) return cfb_fail("too many tiles (%lld)", (long long)nblk);
     kern<<<(unsigned int)nblk, CFB_TILE, sm, st>>>(P, view_of<T>(SA), view_of<T>(SB));

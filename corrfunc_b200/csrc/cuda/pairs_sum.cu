@@ -895,10 +895,11 @@ k_pairs_sum(const PairParams P, const SetView<T> A, const SetView<T> B)
             // and, when it is set, pushes the tile counter past the end -- every later fetch of every warp then ends its loop
             if ((gw & 63) == 0 && P.abort && *P.abort) gw = (long long)atomicAdd(&P.counters[4], 1ULL << 40) + ((long long)1 << 40);
         }
-        gw = __shfl_sync(0xffffffffu, gw, 0) + P.tile_lo * SPLIT;  // this rank's tiles: [tile_lo, tile_hi) (cfb_shard_tile_range)
-        if (gw >= P.tile_hi * SPLIT) break;
+        gw = __shfl_sync(0xffffffffu, gw, 0);
+        if (gw >= P.ntiles * SPLIT) break;
         const int64_t tile = gw / SPLIT;
         const int cellP = P.tile_cell[tile];
+        if (!cfb_owns_cell(cellP, P.shard_rank, P.shard_n)) continue;  // another rank's cell
         const int toff = P.tile_off[tile] + (int)(gw % SPLIT) * SUM_TILE;
         const int nP = A.count[cellP];
         if (toff >= nP) continue;
@@ -1341,7 +1342,7 @@ int launch_inst(PairParams P, const ParticleSet &SA, const ParticleSet &SB, cuda
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SUM_WARPS * 32, sm));
     if (per_sm < 1) per_sm = 1;
     constexpr int SPLIT = CFB_TILE / SUM_TILE;
-    int64_t nblk = ((P.tile_hi - P.tile_lo) * SPLIT + SUM_WARPS - 1) / SUM_WARPS + 1;
+    int64_t nblk = (P.ntiles * SPLIT / (P.shard_n > 1 ? P.shard_n : 1) + SUM_WARPS - 1) / SUM_WARPS + 1;
     if (nblk > (int64_t)sms * per_sm) nblk = (int64_t)sms * per_sm;
     kern<<<(unsigned int)nblk, SUM_WARPS * 32, sm, st>>>(P, view_of<T>(SA), view_of<T>(SB));
     cfb_ctx().launches++;

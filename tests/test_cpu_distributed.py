@@ -5,58 +5,31 @@ import os
 import numpy as np
 import torch.multiprocessing as mp
 
-def shard_tile_range(cnt1, cnt2, tstart, ntiles, rank, nranks):
-    """Python restatement of k_shard_bounds (corrfunc_b200/csrc/cuda/gridlink.cu): rank r owns the tiles of a contiguous
-    range of cells; boundary k is the first cell after the one where the running cost sum(cnt1 * (cnt2 + 1)) reaches
-    total * k / nranks."""
-    cost = cnt1.astype(np.uint64) * (cnt2.astype(np.uint64) + np.uint64(1))
-    after = np.cumsum(cost, dtype=np.uint64)
-    before = after - cost
-    total = int(after[-1]) if len(after) else 0
-    tnext = np.append(tstart[1:], ntiles)
-    out = [0, ntiles]
-    for side, k in ((0, rank), (1, rank + 1)):
-        if k == 0 or k == nranks:
-            continue
-        t = np.uint64(int(float(total) * (float(k) / float(nranks))))
-        hit = np.nonzero((before < t) & (t <= after))[0]
-        if len(hit):
-            out[side] = int(tnext[hit[0]])
-    return out
+SHARD_GROUP = 8  # CFB_SHARD_GROUP in corrfunc_b200/csrc/cuda/cfb_internal.cuh
+
+
+def owner_of_cell(cell, nranks):
+    """Python restatement of cfb_owns_cell (cfb_internal.cuh): rank r owns the cells c with (c / 8) % nranks == r."""
+    return (cell // SHARD_GROUP) % nranks if nranks > 1 else 0
 
 
 def test_shard_map_is_a_partition_by_cell():
     """Sharding is by primary cell: every tile of a cell goes to the same rank (the order of the particles inside
     a cell differs between the ranks' replicas, so tiles of one cell must not be split across ranks), every tile is
-    owned by exactly one rank (contiguous ranges that tile [0, ntiles)), and the ranks' shares of the cost are balanced."""
+    owned by exactly one rank, and the ranks' shares are balanced."""
     rng = np.random.default_rng(5)
     for ncells in (1, 7, 8, 9, 64, 1000, 17424):
-        for clustered in (False, True):
-            lam = 114.0 * (np.exp(rng.normal(0.0, 1.0, size=ncells)) if clustered else np.ones(ncells))
-            counts = rng.poisson(lam)
-            if ncells > 8:
-                counts[rng.integers(0, ncells, size=ncells // 8)] = 0  # empty cells hold no tile
-            ntile = (counts + 127) // 128
-            tstart = np.concatenate(([0], np.cumsum(ntile)[:-1]))
-            ntiles = int(ntile.sum())
-            tile_cell = np.repeat(np.arange(ncells), ntile)
-            for nranks in (1, 2, 3, 4, 8):
-                ranges = [shard_tile_range(counts, counts, tstart, ntiles, r, nranks) for r in range(nranks)]
-                assert ranges[0][0] == 0 and ranges[-1][1] == ntiles
-                for r in range(nranks):
-                    lo, hi = ranges[r]
-                    assert 0 <= lo <= hi <= ntiles
-                    if r + 1 < nranks:
-                        assert hi == ranges[r + 1][0]  # the ranges tile [0, ntiles) without gap or overlap
-                    # a boundary never falls inside a cell
-                    if 0 < lo < ntiles:
-                        assert tile_cell[lo] != tile_cell[lo - 1]
-                # every boundary sits within one cell of its target: a share misses the mean by at most one cell's cost
-                cost = counts.astype(np.float64) * (counts + 1)
-                share = np.array([cost[np.unique(tile_cell[lo:hi])].sum() for lo, hi in ranges])
-                assert np.abs(share - share.mean()).max() <= cost.max() + 2.0
-                if ncells >= 1000 and not clustered:
-                    assert share.max() / share.mean() < 1.01
+        counts = rng.poisson(114, size=ncells)
+        ntile = (counts + 127) // 128
+        tile_cell = np.repeat(np.arange(ncells), ntile)
+        for nranks in (1, 2, 3, 4, 8):
+            owner = np.array([owner_of_cell(c, nranks) for c in tile_cell])
+            assert owner.min() >= 0 and owner.max() < nranks
+            for c in np.unique(tile_cell[:200]):
+                assert len(set(owner[tile_cell == c])) == 1
+            if ncells >= 1000:
+                share = np.bincount(owner, weights=counts[tile_cell] / np.maximum(ntile[tile_cell], 1), minlength=nranks)
+                assert share.max() / share.mean() < 1.05
 
 
 def _worker(rank, world, port, q):
