@@ -878,3 +878,19 @@ def test_DD_DR_RR_in_one_context(stat):
     fn(1, (x, y, z), w)
     fn(1, (x, y, z), w)
     assert lib.cfb_catalog_cache_hits() == h1
+
+
+def test_two_pass_scatter_forced_on_small_sets():
+    """Sets of 4 M points and more are sorted by the two-pass scatter (gridlink.cu: k_partition / k_place); the
+    full-size goldens cover it for box lattices.  Here the threshold is lowered to zero in a fresh process, so the
+    driver's smoke cases -- weighted DD + ravg in double, xi in float, DDtheta on the RA/DEC lattice, each against the
+    oracle -- run through it on small inputs as well (records with weights, both precisions, the theta lattice)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CORRFUNC_B200_SORT2_MIN="0")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "smoke OK" in r.stdout
