@@ -956,6 +956,12 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
         const int64_t tail_tiles = (int64_t)tail_k * res * FAST_WARPS * (Qt.shard_n > 1 ? Qt.shard_n : 1);
         Qt.tail_first = Qt.tail_parts > 1 ? (Qt.ntiles > tail_tiles ? Qt.ntiles - tail_tiles : 0) : Qt.ntiles;
     }
+    {
+        // blocks for the units, not the tiles: a small input whose tiles all go out row by row can use more warps
+        const int64_t units = Qt.tail_first + (Qt.ntiles - Qt.tail_first) * Qt.tail_parts;
+        nblk = (units / (Qt.shard_n > 1 ? Qt.shard_n : 1) + FAST_WARPS - 1) / FAST_WARPS + 1;
+        if (nblk > res) nblk = res;
+    }
     const PairParams &Q2 = Qt;
     if (use_tma)
         k_pairs_fast<T, MODE, LIST, true><<<(unsigned int)nblk, FAST_WARPS * 32, 0, st>>>(Q2, view_of<T>(SA), view_of<T>(SB));
