@@ -3,14 +3,16 @@
 // Replaces gridlink_DOUBLE (utils/gridlink_impl.c.src:65-436) and the particle-assignment part of
 // gridlink_mocks_theta_ra_dec_DOUBLE (utils/gridlink_mocks_impl.c.src:1246-1350):
 //   k_cellindex_*  cell index per particle (the reference's truncating formula, bit-for-bit)
-//                  + per-cell histogram; the atomic's return value is the particle's rank in its cell
-//   k_scan_cells   exclusive scan of the (padded) cell counts -> cell start offsets, and of the
-//                  per-cell tile counts -> tile ids
-//   k_scatter      SoA scatter x|y|z|w into cell order
+//                  + per-cell histogram; for small sets the atomic's return value is the particle's rank in its cell
+//   k_scan_sums / k_scan_cells   exclusive scan of the (padded) cell counts -> cell start offsets, and of the
+//                  per-cell tile counts -> tile ids (<= 64 blocks, one segment of cells each)
+//   k_partition / k_place   sets of 4 M points and more: bucket partition of {x, y, z, cell} records staged in shared
+//                  memory, then in-order placement at start[cell] + arrival rank (see "two-pass scatter" below)
+//   k_scatter      smaller sets: SoA scatter x|y|z|w into cell order, one pass
 //   k_bounds_pad   per-cell min/max bounds (the reference's xbounds/ybounds/zbounds/ra_bounds)
 //                  and NaN fill of the padding slots
 //   k_fill_tiles   (cell, offset) table of primary tiles
-// All of it is HBM-bound byte shuffling: coalesced streaming reads, one scattered write per value.
+// All of it is HBM-bound byte shuffling; DESIGN.md section 3a has the per-kernel times and DRAM traffic at 100 M points.
 #include <stdlib.h>
 
 #include "cfb_internal.cuh"
