@@ -562,11 +562,21 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
             zq[p] = ok ? pzg[i] : nanv;
         }
 
-        // this unit's neighbour rows (all of them for a whole tile)
-        const int row_lo = parts > 1 ? (int)((long long)part * nrow / parts) : 0;
-        const int row_hi = parts > 1 ? (int)((long long)(part + 1) * nrow / parts) : nrow;
+        // this unit's candidates (all of them for a whole tile).  Box lattices: tail_parts = the number of rows, a piece is
+        // one row of neighbour cells; neighbour lists (DDtheta, one "row"): a piece is an eighth of the list's rounds
+        int row_lo = 0, row_hi = nrow, base_lo = 0, base_hi = rowlen;
+        if (parts > 1) {
+            if (LIST) {
+                const int nch = (rowlen + 31) >> 5;  // rounds of 32 candidates
+                base_lo = (int)((long long)part * nch / parts) << 5;
+                base_hi = min(rowlen, (int)((long long)(part + 1) * nch / parts) << 5);
+            } else {
+                row_lo = (int)((long long)part * nrow / parts);
+                row_hi = (int)((long long)(part + 1) * nrow / parts);
+            }
+        }
         for (int row = row_lo; row < row_hi; row++) {
-            for (int base = 0; base < rowlen; base += 32) {
+            for (int base = base_lo; base < base_hi; base += 32) {
                 // ---------------- phase 1: one candidate per lane ----------------
                 const int cand = base + lane;
                 bool keep = cand < rowlen;
@@ -765,7 +775,7 @@ k_pairs_fast(const PairParams P, const SetView<T> A, const SetView<T> B)
                     wbound = 0;
                 }
                 // at most 2 * 32 new jobs per round: drain before another round could overflow the queue
-                const bool last = (row == row_hi - 1) && (base + 32 >= rowlen);
+                const bool last = (row == row_hi - 1) && (base + 32 >= base_hi);
                 if (qn <= FAST_QCAP - 64 && !last) continue;
 
                 // ---------------- phase 2: drain the queue ----------------
@@ -943,7 +953,7 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
     }
     int64_t nblk = (Q.ntiles / (Q.shard_n > 1 ? Q.shard_n : 1) + FAST_WARPS - 1) / FAST_WARPS + 1;
     if (nblk > res) nblk = res;
-    // the last tail_k tiles of every resident warp (of every rank) go out row by row (see the kernel's work units)
+    // the last tail_k tiles of every resident warp (of every rank) go out in pieces (see the kernel's work units)
     PairParams Qt = P;
     {
         static int tail_k = -1;
@@ -952,7 +962,7 @@ static int launch_fast(const PairParams &P, const ParticleSet &SA, const Particl
             tail_k = (e && *e) ? atoi(e) : 2;
         }
         const int nrow = 2 * Qt.g.reach[0] + 1;
-        Qt.tail_parts = (LIST || nrow < 2 || tail_k <= 0) ? 1 : nrow;
+        Qt.tail_parts = tail_k <= 0 ? 1 : (LIST ? 8 : nrow);
         const int64_t tail_tiles = (int64_t)tail_k * res * FAST_WARPS * (Qt.shard_n > 1 ? Qt.shard_n : 1);
         Qt.tail_first = Qt.tail_parts > 1 ? (Qt.ntiles > tail_tiles ? Qt.ntiles - tail_tiles : 0) : Qt.ntiles;
     }
