@@ -101,3 +101,37 @@ def test_sharded_upload_allgather_gloo_world2():
         p.join(timeout=60)
     assert sorted(r for r, _ in res) == [0, 1]
     assert all(ok for _, ok in res)
+
+
+def _fast_units(ntiles, tail_first, parts, nrow, rowlen, list_mode):
+    """Python restatement of the fast kernel's work units (corrfunc_b200/csrc/cuda/pairs_fast.cu: k_pairs_fast, "Work
+    units"): whole tiles up to tail_first, then every tile in `parts` pieces -- one row of neighbour cells each on a box
+    lattice (parts = nrow), a share of the neighbour list's rounds of 32 candidates on the RA/DEC lattice."""
+    nunits = tail_first + (ntiles - tail_first) * parts
+    for gw in range(nunits):
+        tile, part, p = gw, 0, 1
+        if gw >= tail_first:
+            u = gw - tail_first
+            tile, part, p = tail_first + u // parts, u % parts, parts
+        row_lo, row_hi, base_lo, base_hi = 0, nrow, 0, rowlen
+        if p > 1:
+            if list_mode:
+                nch = (rowlen + 31) >> 5
+                base_lo = (part * nch // p) << 5
+                base_hi = min(rowlen, ((part + 1) * nch // p) << 5)
+            else:
+                row_lo, row_hi = part * nrow // p, (part + 1) * nrow // p
+        for row in range(row_lo, row_hi):
+            for base in range(base_lo, base_hi, 32):
+                yield tile, row, base
+
+
+def test_fast_kernel_work_units_cover_every_round_once():
+    """Handing the last tiles out in pieces must not lose or repeat a (tile, row, round of 32 candidates)."""
+    for list_mode, nrow, rowlen, parts in ((False, 13, 285, 13), (False, 3, 9, 3), (False, 1, 40, 1), (True, 1, 700, 8),
+                                           (True, 1, 33, 8), (True, 1, 0, 8)):
+        for ntiles, tail in ((1, 5), (7, 3), (40, 16), (40, 0)):
+            tail_first = max(0, ntiles - tail) if parts > 1 else ntiles
+            got = sorted(_fast_units(ntiles, tail_first, parts, nrow, rowlen, list_mode))
+            want = sorted((t, r, b) for t in range(ntiles) for r in range(nrow) for b in range(0, rowlen, 32))
+            assert got == want, (list_mode, nrow, rowlen, parts, ntiles, tail)
