@@ -135,3 +135,54 @@ def test_fast_kernel_work_units_cover_every_round_once():
             got = sorted(_fast_units(ntiles, tail_first, parts, nrow, rowlen, list_mode))
             want = sorted((t, r, b) for t in range(ntiles) for r in range(nrow) for b in range(0, rowlen, 32))
             assert got == want, (list_mode, nrow, rowlen, parts, ntiles, tail)
+
+
+def test_two_pass_sort_bucket_layout_and_validity_rule():
+    """numpy restatement of the two-pass counting sort's bookkeeping (corrfunc_b200/csrc/cuda/gridlink.cu: k_partition /
+    k_place): records of bucket b (2^shift consecutive cells) are written contiguously from start[b << shift]; pass 2
+    decides from the position alone whether a slot of the temporary array holds a record -- the last bucket whose base is
+    <= p, and p - base < count -- also when buckets are empty or share a base.  Every particle must land in its cell's
+    run of the final array exactly once."""
+    rng = np.random.default_rng(11)
+    PAD, MAXB = 4, 512
+    for ncells, n in ((1, 10), (5, 0), (700, 3000), (5000, 20000), (5000, 300)):
+        cidx = rng.integers(0, ncells, size=n)
+        if ncells >= 700:
+            cidx[cidx % 7 == 3] = 0  # runs of empty cells and empty buckets
+        count = np.bincount(cidx, minlength=ncells)
+        padded = (count + PAD - 1) // PAD * PAD
+        start = np.concatenate(([0], np.cumsum(padded)[:-1]))
+        npad = int(padded.sum())
+        shift = 0
+        while ((ncells + (1 << shift) - 1) >> shift) > MAXB:
+            shift += 1
+        nb = (ncells + (1 << shift) - 1) >> shift
+        base = start[(np.arange(nb) << shift)]
+        # pass 1: arrival order within the bucket
+        rec = np.full(npad, -1)
+        bcur = np.zeros(nb, dtype=np.int64)
+        for i in rng.permutation(n):
+            b = cidx[i] >> shift
+            rec[base[b] + bcur[b]] = i
+            bcur[b] += 1
+        # pass 2: validity from the position
+        cur = start.copy()
+        final = np.full(max(npad, 1), -1)
+        for p in range(npad):
+            lo, hi = 0, nb
+            while hi - lo > 1:
+                mid = (lo + hi) >> 1
+                if base[mid] <= p:
+                    lo = mid
+                else:
+                    hi = mid
+            valid = p - base[lo] < bcur[lo]
+            assert valid == (rec[p] >= 0), (ncells, n, p)
+            if valid:
+                c = cidx[rec[p]]
+                final[cur[c]] = rec[p]
+                cur[c] += 1
+        for c in range(ncells):
+            run = final[start[c]:start[c] + count[c]]
+            assert np.all(run >= 0) and np.all(cidx[run] == c)
+        assert np.count_nonzero(final >= 0) == n
